@@ -1,0 +1,140 @@
+/* t8gpu_b200 -- C ABI of the B200-native finite-volume solver core.
+ *
+ * This is the drop-in boundary for t8gpu's hot path (per-face numerical flux + SSP-RK3 stage update + CFL
+ * wave-speed reduction).  The reference has no FFI for this path: user solvers launch `__global__` kernels on
+ * accessor PODs obtained from t8gpu::MeshManager / MemoryManager.  The entry points below are what the header-only
+ * template shim in include/t8gpu/ (same class and member names as the reference) binds to; each comment cites the
+ * reference interface it replaces (paths relative to the t8gpu repository).
+ *
+ * Conventions
+ *   - every pointer documented "device" must be dereferenceable by the current CUDA device (own or peer-mapped),
+ *     "host" pointers by the CPU.  No C++ or torch types cross this boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous unless stated.
+ *   - return value: 0 on success, otherwise a cudaError_t value (cudaErrorInvalidValue for bad arguments).
+ *     The C++ shim feeds it to T8GPU_CUDA_CHECK_ERROR to keep the reference's abort-on-error behaviour
+ *     (t8gpu/utils/cuda.h:7-15).
+ *   - precision suffix: _f32 / _f64 = variable_traits<...>::float_type (t8gpu/memory/memory_manager.h:29).
+ *   - five conserved variables in the order of the examples' VariableList {Rho, Rho_v1, Rho_v2, Rho_v3, Rho_e}
+ *     (examples/compressible_euler/solver.h, examples/subgrid/solver.h:12-20).
+ */
+#ifndef T8GPU_B200_H
+#define T8GPU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T8B200_NVAR 5
+
+/* ABI / build identification: returns 100 * major + minor. */
+int t8b200_version(void);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * 1. Reference-shaped kernels (same inputs, same outputs, same side effects as the reference's launches)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Replaces kepes_compute_fluxes<<<>>> + reflective_boundary_condition<<<>>>
+ *   (examples/compressible_euler/kernels.cu:135-309, :311-469; launched at solver.cu:81-96).
+ * Connectivity arrays are exactly those behind MeshConnectivityAccessor<float_type,3>
+ *   (t8gpu/mesh/mesh_manager.h:159-166): ranks/indices[n_local+n_ghost], face_neighbors[2*nf+nb],
+ *   face_normals[3*(nf+nb)] interleaved, face_surfaces[nf+nb].
+ * vars_all / flux_all: HOST arrays of 5 DEVICE tables; table k holds one device pointer per rank
+ *   (what MemoryAccessorAll<VariableList>::get(k) returns, memory_manager.h:240-246).
+ * Accumulates -F into the left and +F into the right element with atomics, writes speed[f] = |uHat|+aHat for
+ * f in [0, nf+nb).  speed may be NULL. */
+int t8b200_flux_faces_f32(int32_t nf, int32_t nb, const int32_t* ranks, const int32_t* indices,
+                          const int32_t* face_neighbors, const float* face_normals, const float* face_surfaces,
+                          const float* const* const* vars_all, float* const* const* flux_all, float* speed,
+                          void* stream);
+int t8b200_flux_faces_f64(int32_t nf, int32_t nb, const int32_t* ranks, const int32_t* indices,
+                          const int32_t* face_neighbors, const double* face_normals, const double* face_surfaces,
+                          const double* const* const* vars_all, double* const* const* flux_all, double* speed,
+                          void* stream);
+
+/* Replaces timestepping::SSP_3RK_step{1,2,3}<VariableType> and timestepping::subgrid::SSP_3RK_step{1,2,3}
+ *   (t8gpu/timestepping/ssp_runge_kutta.inl:30-99, :101-221).  stage in {1,2,3}.
+ * prev/in/out/flux: HOST arrays of nvar DEVICE pointers (MemoryAccessorOwn<VariableType>::get(k)); `in` is the
+ * previous stage (ignored for stage 1).  n = number of cells; volume of cell i = vol[i / cells_per_vol] / cells_per_vol
+ * (cells_per_vol = 1 for elements, Subgrid::size for subgrids, ssp_runge_kutta.inl:116).  Zeroes flux. */
+int t8b200_rk3_stage_f32(int stage, int64_t n, int nvar, const float* const* prev, const float* const* in,
+                         float* const* out, float* const* flux, const float* vol, int cells_per_vol, float dt,
+                         void* stream);
+int t8b200_rk3_stage_f64(int stage, int64_t n, int nvar, const double* const* prev, const double* const* in,
+                         double* const* out, double* const* flux, const double* vol, int cells_per_vol, double dt,
+                         void* stream);
+
+/* Replaces thrust::reduce(speed_estimates, 0, maximum) (examples/compressible_euler/solver.cu:214-217):
+ * *out_dev = max(0, max_i speed[i]).  out_dev is a device scalar. */
+int t8b200_max_speed_f32(const float* speed, int64_t n, float* out_dev, void* stream);
+int t8b200_max_speed_f64(const double* speed, int64_t n, double* out_dev, void* stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * 2. B200-native fused path: connectivity re-laid out into per-chunk tiles ("plan"), one kernel per RK stage that
+ *    stages a chunk of elements + halo in shared memory, evaluates every face of the chunk once, gathers the
+ *    fluxes per element without atomics and applies the RK combination.  The flux accumulators never touch HBM.
+ *    Replaces one stage of CompressibleEulerSolver::iterate (examples/compressible_euler/solver.cu:78-112).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct t8b200_plan t8b200_plan;
+
+/* Builds the tile plan from the reference-layout connectivity (HOST pointers; same arrays as above, normals/areas
+ * in the precision selected by is_f64).  ranks/indices may be NULL for a single rank without ghosts.
+ * x_*: optional extra partition-boundary faces (ghost neighbour owned by a LOWER rank, which the reference assigns
+ * to that rank, mesh_manager.inl:397); with them every rank evaluates all faces of its own elements
+ * ("owner computes") and no remote atomics are needed.  n_xfaces may be 0. */
+int t8b200_plan_create(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
+                       const int32_t* face_neighbors, const void* face_normals, const void* face_surfaces,
+                       const int32_t* ranks, const int32_t* indices, int32_t n_xfaces,
+                       const int32_t* x_face_neighbors, const void* x_face_normals, const void* x_face_surfaces);
+void t8b200_plan_destroy(t8b200_plan* plan);
+/* info[0]=n_chunks, [1]=max halo per chunk, [2]=max faces per chunk, [3]=shared memory bytes per CTA,
+ * [4]=device bytes held by the plan, [5]=face records (faces counted once per chunk they touch),
+ * [6]=total halo entries, [7]=elements per chunk */
+int t8b200_plan_info(const t8b200_plan* plan, int64_t info[8]);
+
+/* One fused RK stage.  in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's arrays (stage input, U^n, stage
+ * output).  in_all: HOST array of 5 DEVICE tables (one pointer per rank) for ghost reads, or NULL when the plan has
+ * no ghosts.  vol: device, per element.  speed_max_dev: device scalar receiving max(|uHat|+aHat) over the faces of
+ * this stage (zeroed by the call, then max-ed into by the kernel), or NULL. */
+int t8b200_fused_stage_f32(const t8b200_plan* plan, int stage, const float* const* in,
+                           const float* const* const* in_all, const float* const* prev, float* const* out,
+                           const float* vol, float dt, float* speed_max_dev, void* stream);
+int t8b200_fused_stage_f64(const t8b200_plan* plan, int stage, const double* const* in,
+                           const double* const* const* in_all, const double* const* prev, double* const* out,
+                           const double* vol, double dt, double* speed_max_dev, void* stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * 3. Device-side connectivity for uniform Cartesian periodic forests (quad / hex, one tree, Morton order):
+ *    produces, bit for bit, the arrays MeshManager::compute_connectivity_information
+ *    (t8gpu/mesh/mesh_manager.inl:332-481) uploads for t8_cmesh_new_periodic + t8_forest_new_uniform(level),
+ *    for rank `rank` of `nranks` (contiguous SFC ranges, first element of rank p = floor(N p / P)).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t  n_local, n_ghost, n_faces, n_bfaces, n_xfaces;
+  int32_t* ranks;          /* device, n_local + n_ghost */
+  int32_t* indices;        /* device, n_local + n_ghost */
+  int32_t* face_neighbors; /* device, 2 * n_faces */
+  void*    face_normals;   /* device, 3 * n_faces, float or double */
+  void*    face_surfaces;  /* device, n_faces */
+  void*    volumes;        /* device, n_local */
+  void*    centroids;      /* device, 3 * n_local (z = 0 in 2-D), already cast to float_type */
+  int32_t* x_face_neighbors; /* device, 2 * n_xfaces: faces whose ghost neighbour is owned by a lower rank */
+  void*    x_face_normals;
+  void*    x_face_surfaces;
+} t8b200_cart_conn;
+
+int  t8b200_cartesian_uniform_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int level, int nranks, int rank,
+                                           void* stream);
+void t8b200_cartesian_connectivity_free(t8b200_cart_conn* c);
+
+/* Cartesian Kelvin-Helmholtz initial state (examples/subgrid/solver.inl:36-56 / :82-103) sampled at n points
+ * (device, 3 per point, float_type).  u: HOST array of 5 device pointers. */
+int t8b200_init_kelvin_helmholtz_f32(int dim, int64_t n, const float* centers, float* const* u, void* stream);
+int t8b200_init_kelvin_helmholtz_f64(int dim, int64_t n, const double* centers, double* const* u, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T8GPU_B200_H */

@@ -1,0 +1,267 @@
+"""t8gpu_b200 -- B200-native finite-volume solver core behind t8gpu's hot path.
+
+The product is the CUDA library ``libt8gpu_b200.so`` (sources in ``csrc/``, C ABI in ``include/t8gpu_b200.h``) and the
+header-only C++ mirror of the reference's template API in ``include/t8gpu/``.  This Python package is harness glue for
+tests and ``bench.py``: it binds the C ABI with ctypes and uses torch only for device memory and streams.  There is no
+CPU fallback: importing works without a GPU (so that the symbol table can be checked), but every compute entry point
+needs the library and a CUDA device and raises otherwise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt8gpu_b200.so")
+_LIB = None
+
+NVAR = 5
+
+
+class MissingExtension(RuntimeError):
+    pass
+
+
+def lib():
+    """The C-ABI library.  Raises loudly if it has not been built (no fallback path exists)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise MissingExtension(
+                "t8gpu_b200/libt8gpu_b200.so is missing: run `python -m t8gpu_b200.build` (needs nvcc, sm_100a). "
+                "There is no CPU fallback for this path.")
+        _LIB = C.CDLL(LIB_PATH)
+        _LIB.t8b200_plan_destroy.restype = None
+        _LIB.t8b200_cartesian_connectivity_free.restype = None
+        if hasattr(_LIB, "t8b200_solver_destroy"):
+            _LIB.t8b200_solver_destroy.restype = None
+        if hasattr(_LIB, "t8b200_subgrid_plan_destroy"):
+            _LIB.t8b200_subgrid_plan_destroy.restype = None
+    return _LIB
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise CudaError("t8gpu_b200: %s failed with cudaError %d" % (what, rc))
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise MissingExtension("t8gpu_b200 needs a CUDA device; there is no CPU fallback for this path.")
+    return torch
+
+
+def _sfx(dtype):
+    import torch
+    if dtype in (torch.float32, "f32"):
+        return "f32", C.c_float
+    if dtype in (torch.float64, "f64"):
+        return "f64", C.c_double
+    raise TypeError("float_type must be float32 or float64, got %r" % (dtype,))
+
+
+def ptrs(tensors):
+    """Host array of device pointers (one per variable), as MemoryAccessorOwn holds them."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def stream_ptr(stream=None):
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+class RankTables:
+    """Device tables `[var][rank] -> pointer` (what MemoryAccessorAll<VariableList> holds, memory_manager.h:300).
+
+    `per_rank_vars`: list over ranks of lists of NVAR tensors (peer-accessible)."""
+
+    def __init__(self, per_rank_vars, device):
+        torch = _torch()
+        nranks = len(per_rank_vars)
+        host = torch.empty((NVAR, nranks), dtype=torch.int64)
+        for r, vs in enumerate(per_rank_vars):
+            for k in range(NVAR):
+                host[k, r] = vs[k].data_ptr()
+        self.table = host.to(device)
+        self._keep = per_rank_vars
+        self.host = (C.c_void_p * NVAR)()
+        for k in range(NVAR):
+            self.host[k] = self.table[k].data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------ reference-shaped
+
+def flux_faces(conn, vars_all, flux_all, speed=None, stream=None):
+    """kepes_compute_fluxes + reflective_boundary_condition.  conn: dict of device tensors in the reference layout
+    (ranks, indices may be None for one rank); vars_all / flux_all: RankTables."""
+    normals = conn["face_normals"]
+    s, _ = _sfx(normals.dtype)
+    fn = getattr(lib(), "t8b200_flux_faces_" + s)
+    rk, ix = conn.get("ranks"), conn.get("indices")
+    check(fn(int(conn["n_faces"]), int(conn["n_bfaces"]),
+             C.c_void_p(rk.data_ptr() if rk is not None else None),
+             C.c_void_p(ix.data_ptr() if ix is not None else None),
+             C.c_void_p(conn["face_neighbors"].data_ptr()), C.c_void_p(normals.data_ptr()),
+             C.c_void_p(conn["face_areas"].data_ptr()), vars_all.host, flux_all.host,
+             C.c_void_p(speed.data_ptr() if speed is not None else None), stream_ptr(stream)), "flux_faces")
+
+
+def rk3_stage(stage, prev, inp, out, flux, vol, dt, cells_per_vol=1, stream=None):
+    """SSP_3RK_step{stage}; prev/inp/out/flux: lists of per-variable device tensors."""
+    s, ft = _sfx(prev[0].dtype)
+    fn = getattr(lib(), "t8b200_rk3_stage_" + s)
+    n = prev[0].numel()
+    check(fn(stage, C.c_int64(n), len(prev), ptrs(prev), ptrs(inp) if inp is not None else None, ptrs(out),
+             ptrs(flux), C.c_void_p(vol.data_ptr()), cells_per_vol, ft(dt), stream_ptr(stream)), "rk3_stage")
+
+
+def max_speed(speed, out=None, stream=None):
+    torch = _torch()
+    s, _ = _sfx(speed.dtype)
+    if out is None:
+        out = torch.zeros(1, dtype=speed.dtype, device=speed.device)
+    check(getattr(lib(), "t8b200_max_speed_" + s)(C.c_void_p(speed.data_ptr()), C.c_int64(speed.numel()),
+                                                   C.c_void_p(out.data_ptr()), stream_ptr(stream)), "max_speed")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ fused tile plan
+
+class Plan:
+    """Tile plan: the reference-layout connectivity re-laid out per chunk of elements."""
+
+    def __init__(self, conn, dtype):
+        """conn: dict of HOST numpy arrays in the reference layout (as MeshManager::compute_connectivity_information
+        builds them): n_local, n_ghost, n_faces, n_bfaces, face_neighbors, face_normals, face_areas, and for
+        multi-rank ranks, indices, optionally x_face_* (faces whose ghost neighbour belongs to a lower rank)."""
+        import numpy as np
+        _torch()
+        s, _ = _sfx(dtype)
+        npdt = np.float64 if s == "f64" else np.float32
+        self.dtype = dtype
+        nrm = np.ascontiguousarray(conn["face_normals"], dtype=npdt)
+        ar = np.ascontiguousarray(conn["face_areas"], dtype=npdt)
+        nbr = np.ascontiguousarray(conn["face_neighbors"], dtype=np.int32)
+        rk = conn.get("ranks")
+        ix = conn.get("indices")
+        rk = None if rk is None else np.ascontiguousarray(rk, dtype=np.int32)
+        ix = None if ix is None else np.ascontiguousarray(ix, dtype=np.int32)
+        nx = int(conn.get("n_xfaces", 0))
+        xn = np.ascontiguousarray(conn["x_face_neighbors"], dtype=np.int32) if nx else None
+        xr = np.ascontiguousarray(conn["x_face_normals"], dtype=npdt) if nx else None
+        xa = np.ascontiguousarray(conn["x_face_areas"], dtype=npdt) if nx else None
+
+        def p(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+        h = C.c_void_p()
+        check(lib().t8b200_plan_create(C.byref(h), int(s == "f64"), C.c_int64(int(conn["n_local"])),
+                                       C.c_int64(int(conn.get("n_ghost", 0))), int(conn["n_faces"]),
+                                       int(conn["n_bfaces"]), p(nbr), p(nrm), p(ar), p(rk), p(ix), nx, p(xn), p(xr),
+                                       p(xa)), "plan_create")
+        self._h = h
+        info = (C.c_int64 * 8)()
+        check(lib().t8b200_plan_info(self._h, info), "plan_info")
+        self.info = dict(n_chunks=info[0], max_halo=info[1], max_faces=info[2], smem_bytes=info[3],
+                         device_bytes=info[4], face_records=info[5], halo_entries=info[6], chunk=info[7])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().t8b200_plan_destroy(self._h)
+            self._h = None
+
+    def stage(self, stage, inp, prev, out, vol, dt, in_all=None, speed_max=None, stream=None):
+        s, ft = _sfx(self.dtype)
+        fn = getattr(lib(), "t8b200_fused_stage_" + s)
+        check(fn(self._h, stage, ptrs(inp), in_all.host if in_all is not None else None,
+                 ptrs(prev) if prev is not None else None, ptrs(out), C.c_void_p(vol.data_ptr()), ft(dt),
+                 C.c_void_p(speed_max.data_ptr() if speed_max is not None else None), stream_ptr(stream)),
+              "fused_stage")
+
+
+# ------------------------------------------------------------------------------------------------ Cartesian meshes
+
+class _RawDeviceArray:
+    """Exposes a library-owned device buffer through __cuda_array_interface__ so torch can copy it."""
+    _TYPESTR = {"torch.int32": "<i4", "torch.float32": "<f4", "torch.float64": "<f8", "torch.int64": "<i8"}
+
+    def __init__(self, ptr, n, dtype):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr=self._TYPESTR[str(dtype)],
+                                             data=(int(ptr), False), version=2, strides=None)
+
+
+class _CartConn(C.Structure):
+    _fields_ = [("n_local", C.c_int64), ("n_ghost", C.c_int64), ("n_faces", C.c_int64), ("n_bfaces", C.c_int64),
+                ("n_xfaces", C.c_int64), ("ranks", C.c_void_p), ("indices", C.c_void_p),
+                ("face_neighbors", C.c_void_p), ("face_normals", C.c_void_p), ("face_surfaces", C.c_void_p),
+                ("volumes", C.c_void_p), ("centroids", C.c_void_p), ("x_face_neighbors", C.c_void_p),
+                ("x_face_normals", C.c_void_p), ("x_face_surfaces", C.c_void_p)]
+
+
+def cartesian_uniform_connectivity(dim, level, dtype, nranks=1, rank=0, device=None):
+    """Device-built connectivity of a uniform periodic quad/hex forest in the reference layout -> dict of torch
+    tensors (copied out of the library-owned buffers)."""
+    torch = _torch()
+    s, _ = _sfx(dtype)
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    c = _CartConn()
+    check(lib().t8b200_cartesian_uniform_connectivity(C.byref(c), int(s == "f64"), dim, level, nranks, rank,
+                                                      stream_ptr()), "cartesian_uniform_connectivity")
+
+    def grab(ptr, n, dt):
+        if n == 0:
+            return torch.empty(0, dtype=dt, device=device)
+        return torch.as_tensor(_RawDeviceArray(ptr, n, dt), device=device).clone()
+
+    nl, ng, nf, nx = c.n_local, c.n_ghost, c.n_faces, c.n_xfaces
+    out = dict(dim=dim, level=level, n_local=nl, n_ghost=ng, n_faces=nf, n_bfaces=0, n_xfaces=nx, rank=rank,
+               nranks=nranks,
+               ranks=grab(c.ranks, nl + ng, torch.int32), indices=grab(c.indices, nl + ng, torch.int32),
+               face_neighbors=grab(c.face_neighbors, 2 * nf, torch.int32),
+               face_normals=grab(c.face_normals, 3 * nf, dtype), face_areas=grab(c.face_surfaces, nf, dtype),
+               volumes=grab(c.volumes, nl, dtype), centroids=grab(c.centroids, 3 * nl, dtype),
+               x_face_neighbors=grab(c.x_face_neighbors, 2 * nx, torch.int32),
+               x_face_normals=grab(c.x_face_normals, 3 * nx, dtype), x_face_areas=grab(c.x_face_surfaces, nx, dtype))
+    torch.cuda.synchronize()
+    lib().t8b200_cartesian_connectivity_free(C.byref(c))
+    return out
+
+
+def init_kelvin_helmholtz(dim, centers, u, stream=None):
+    """Cartesian Kelvin-Helmholtz state at `centers` (device tensor, 3 per point) into the 5 tensors `u`."""
+    s, _ = _sfx(centers.dtype)
+    n = centers.numel() // 3
+    check(getattr(lib(), "t8b200_init_kelvin_helmholtz_" + s)(dim, C.c_int64(n), C.c_void_p(centers.data_ptr()),
+                                                               ptrs(u), stream_ptr(stream)), "init_kh")
+
+
+def conn_to_host(conn):
+    """torch-tensor connectivity dict -> numpy dict (for Plan)."""
+    import torch
+    return {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in conn.items()}
+
+
+def conn_to_device(conn, dtype, device):
+    """numpy connectivity dict (oracle layout) -> torch tensors on device, float arrays cast to dtype."""
+    import numpy as np
+    torch = _torch()
+    out = {}
+    for k, v in conn.items():
+        if isinstance(v, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(v))
+            if t.dtype in (torch.float32, torch.float64):
+                t = t.to(dtype)
+            out[k] = t.to(device)
+        else:
+            out[k] = v
+    return out
+
+
+from .solver import EulerSolver  # noqa: E402,F401

@@ -1,0 +1,104 @@
+"""Harness-side mirror of the reference's example solver `CompressibleEulerSolver`
+(examples/compressible_euler/solver.h:33-102, solver.cu:75-229) on top of the C ABI.
+
+Storage follows t8gpu::MemoryManager (memory_manager.inl:3-106): one device allocation of
+(nb_variables * nb_steps + 1) arrays of `capacity` elements, array index = step * nb_variables + variable, volume last.
+"""
+import ctypes as C
+
+NVAR = 5
+# StepList of the examples: Step0..Step3 + Fluxes (examples/compressible_euler/solver.h)
+STEP0, STEP1, STEP2, STEP3, FLUXES, NB_STEPS = 0, 1, 2, 3, 4, 5
+
+
+class EulerSolver:
+    """One rank of the unstructured compressible-Euler solver.
+
+    mode = "fused": one tile-plan kernel per RK stage (flux accumulators never reach HBM).
+    mode = "unfused": the reference's schedule (face kernel with atomics, then SSP_3RK_step*), through the
+                      reference-shaped C-ABI entry points.
+    """
+
+    cfl = 0.7  # solver.h:37
+
+    def __init__(self, conn_host, volumes, dtype, device=None, mode="fused", max_level=4):
+        import numpy as np
+        import torch
+        from . import Plan, RankTables, conn_to_device
+        self.torch = torch
+        self.dtype = dtype
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.mode = mode
+        self.max_level = max_level
+        self.n = int(conn_host["n_local"])
+        self.nf = int(conn_host["n_faces"])
+        self.nb = int(conn_host["n_bfaces"])
+        # 128-byte aligned rows: capacity padded to a multiple of 32 elements
+        self.capacity = max(32, (self.n + 31) // 32 * 32)
+        self.buffer = torch.zeros((NVAR * NB_STEPS + 1, self.capacity), dtype=dtype, device=self.device)
+        vol = torch.as_tensor(np.ascontiguousarray(volumes)).to(dtype).to(self.device)
+        self.buffer[NVAR * NB_STEPS, :self.n] = vol
+        self.next, self.prev = STEP0, STEP3
+        self.speed = torch.zeros(max(1, self.nf + self.nb), dtype=dtype, device=self.device)
+        self.speed_max = torch.zeros(1, dtype=dtype, device=self.device)
+        self.plan = None
+        if mode == "fused":
+            self.plan = Plan(conn_host, dtype)
+        else:
+            self.conn = conn_to_device({k: conn_host[k] for k in
+                                        ("face_neighbors", "face_normals", "face_areas")}, dtype, self.device)
+            self.conn.update(n_faces=self.nf, n_bfaces=self.nb, ranks=None, indices=None)
+            self._tables = {s: RankTables([self.variables(s)], self.device) for s in range(NB_STEPS)}
+
+    # --- MemoryManager accessors -----------------------------------------------------------------------
+    def variables(self, step):
+        """get_own_variables(step): list of NVAR 1-D tensors of length n (views)."""
+        return [self.buffer[step * NVAR + k, :self.n] for k in range(NVAR)]
+
+    def volume(self):
+        return self.buffer[NVAR * NB_STEPS, :self.n]
+
+    def set_state(self, u):
+        """u: (5, n) tensor or array -> variables of step `next`."""
+        t = self.torch.as_tensor(u).to(self.dtype).to(self.device)
+        self.buffer[self.next * NVAR:(self.next + 1) * NVAR, :self.n] = t
+
+    def state(self):
+        return self.buffer[self.next * NVAR:(self.next + 1) * NVAR, :self.n]
+
+    # --- CompressibleEulerSolver::iterate (solver.cu:75-175) -------------------------------------------
+    def iterate(self, dt, stream=None):
+        from . import flux_faces, rk3_stage
+        self.next, self.prev = self.prev, self.next
+        prev = self.variables(self.prev)
+        s1, s2, nxt = self.variables(STEP1), self.variables(STEP2), self.variables(self.next)
+        vol = self.volume()
+        if self.mode == "fused":
+            self.plan.stage(1, prev, None, s1, vol, dt, stream=stream)
+            self.plan.stage(2, s1, prev, s2, vol, dt, stream=stream)
+            self.plan.stage(3, s2, prev, nxt, vol, dt, speed_max=self.speed_max, stream=stream)
+            return 3
+        fl = self.variables(FLUXES)
+        T = self._tables
+        flux_faces(self.conn, T[self.prev], T[FLUXES], self.speed, stream)
+        rk3_stage(1, prev, None, s1, fl, vol, dt, stream=stream)
+        flux_faces(self.conn, T[STEP1], T[FLUXES], self.speed, stream)
+        rk3_stage(2, prev, s1, s2, fl, vol, dt, stream=stream)
+        flux_faces(self.conn, T[STEP2], T[FLUXES], self.speed, stream)
+        rk3_stage(3, prev, s2, nxt, fl, vol, dt, stream=stream)
+        return 6
+
+    # --- CompressibleEulerSolver::compute_timestep (solver.cu:213-229) ---------------------------------
+    def max_wave_speed(self):
+        """Device scalar with the stage-3 maximum of |uHat| + aHat."""
+        from . import max_speed
+        if self.mode == "fused":
+            return self.speed_max
+        return max_speed(self.speed, self.speed_max)
+
+    def compute_timestep(self):
+        vmax = float(self.max_wave_speed().item())
+        ft = self.torch.float32 if self.dtype == self.torch.float32 else self.torch.float64
+        half_pow = float(self.torch.tensor(0.5, dtype=ft) ** self.max_level)
+        return float(self.torch.tensor(self.cfl, dtype=ft) * self.torch.tensor(half_pow, dtype=ft) /
+                     self.torch.tensor(vmax, dtype=ft))

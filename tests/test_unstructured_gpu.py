@@ -1,0 +1,180 @@
+"""GPU parity: the CUDA product (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import TOL, perturbed_kh, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+DT = {np.float64: torch.float64, np.float32: torch.float32}
+
+
+def make_forest(kind):
+    if kind == "quad6":      # BASELINE configs[0]: periodic quad level 6, MeshManager<...,3> normals
+        return oracle.Forest(2, 6), 6
+    if kind == "hex4":
+        return oracle.Forest(3, 4), 4
+    if kind == "hex3_walls":  # non-periodic: reflective boundary faces
+        return oracle.Forest(3, 3, periodic=False), 3
+    if kind == "hex_amr":    # hanging faces (2:1)
+        f = oracle.Forest(3, 3)
+        lv, cent, vol, _ = f.elements()
+        crit = np.where(np.abs(cent[:, 2] - 0.5) < 0.2, 20.0, 0.0)
+        return f.adapt(crit, 10.0, 1, 4), 4
+    if kind == "quad_amr_walls":
+        f = oracle.Forest(2, 4, periodic=False)
+        lv, cent, vol, _ = f.elements()
+        crit = np.where(np.abs(cent[:, 1] - 0.5) < 0.2, 20.0, 0.0)
+        return f.adapt(crit, 10.0, 1, 6), 5
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("mode", ["fused", "unfused"])
+@pytest.mark.parametrize("kind", ["quad6", "hex4", "hex3_walls", "hex_amr", "quad_amr_walls"])
+def test_iterate_matches_oracle(cuda, kind, mode, dtype):
+    import t8gpu_b200
+    forest, lvl = make_forest(kind)
+    conn = forest.connectivity(dtype=dtype)
+    u0, vol = perturbed_kh(forest, dtype, seed=1)
+    dt = 0.1 * 2.0 ** -lvl
+    sol = t8gpu_b200.EulerSolver(conn, vol, DT[dtype], device=cuda, mode=mode)
+    sol.set_state(u0)
+    u = u0
+    nsteps = 10
+    for it in range(nsteps):
+        sp = np.zeros(conn["n_faces"] + conn["n_bfaces"], dtype)
+        u, s1, s2 = oracle.iterate(conn, vol, u, dt, speed=sp)
+        sol.iterate(dt)
+        got = sol.state().cpu().numpy()
+        err = rel_linf(got, u)
+        # per-step tolerance of the north star; both sides advance from their own previous state, so allow the
+        # accumulated bound it * tol
+        assert err <= (it + 1) * TOL[np.dtype(dtype)], (kind, mode, it, err)
+        vmax = float(sol.max_wave_speed().item())
+        assert abs(vmax - oracle.max_speed(sp)) <= 4 * np.finfo(dtype).eps * vmax * (10 if dtype == np.float32 else 1e3)
+    dt_ref = oracle.compute_timestep(sp, dtype(0.7), 4)
+    assert abs(sol.compute_timestep() - dt_ref) <= 1e-5 * dt_ref
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_single_step_from_identical_state(cuda, dtype):
+    """One step from bit-identical input: the pure per-step error (no accumulation)."""
+    import t8gpu_b200
+    forest, lvl = make_forest("hex_amr")
+    conn = forest.connectivity(dtype=dtype)
+    u0, vol = perturbed_kh(forest, dtype, seed=2)
+    dt = 0.1 * 2.0 ** -lvl
+    ref, _, _ = oracle.iterate(conn, vol, u0, dt)
+    for mode in ("fused", "unfused"):
+        sol = t8gpu_b200.EulerSolver(conn, vol, DT[dtype], device=cuda, mode=mode)
+        sol.set_state(u0)
+        sol.iterate(dt)
+        assert rel_linf(sol.state().cpu().numpy(), ref) <= TOL[np.dtype(dtype)]
+
+
+def test_hundred_steps_fp64(cuda):
+    """north_star: within 1e-12 relative L-infinity per step over 100 steps (fp64), here on the level-6 quad mesh of
+    configs[0] with the unperturbed Kelvin-Helmholtz data and the reference's dt = 0.1 * 2^-6."""
+    import t8gpu_b200
+    forest = oracle.Forest(2, 6)
+    conn = forest.connectivity(dtype=np.float64)
+    lv, cent, vol, _ = forest.elements()
+    u = oracle.init_kh_points(2, cent, np.float64)
+    sol = t8gpu_b200.EulerSolver(conn, vol, torch.float64, device=cuda, mode="fused")
+    sol.set_state(u)
+    dt = 0.1 * 2.0 ** -6
+    worst = 0.0
+    for it in range(100):
+        # restart the oracle from the product's state each step: measures the per-step difference
+        cur = sol.state().cpu().numpy().copy()
+        ref, _, _ = oracle.iterate(conn, vol, cur, dt)
+        sol.iterate(dt)
+        worst = max(worst, rel_linf(sol.state().cpu().numpy(), ref))
+    assert worst <= 1e-12, worst
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dim,level,P", [(2, 6, 1), (3, 4, 1), (3, 4, 2), (3, 3, 3), (2, 5, 4), (3, 1, 1), (3, 0, 1)])
+def test_device_cartesian_connectivity_bit_exact(cuda, dim, level, P, dtype):
+    """The device-built connectivity equals, bit for bit, the mini-forest restatement of
+    MeshManager::compute_connectivity_information for every rank."""
+    import t8gpu_b200
+    forest = oracle.Forest(dim, level)
+    lv, cent, vol, _ = forest.elements()
+    off = forest.partition_offsets(P)
+    for r in range(P):
+        ref = forest.connectivity(P, r, dtype=dtype)
+        got = t8gpu_b200.conn_to_host(t8gpu_b200.cartesian_uniform_connectivity(dim, level, DT[dtype], P, r))
+        for key in ("n_local", "n_ghost", "n_faces", "n_bfaces", "n_xfaces"):
+            assert got[key] == ref[key], (key, r)
+        for key in ("ranks", "indices", "face_neighbors", "face_normals", "face_areas", "x_face_neighbors",
+                    "x_face_normals", "x_face_areas"):
+            assert got[key].dtype == ref[key].dtype, key
+            assert np.array_equal(got[key], ref[key]), (key, r)
+        assert np.array_equal(got["volumes"], vol[off[r]:off[r + 1]].astype(dtype))
+        assert np.array_equal(got["centroids"].reshape(-1, 3), cent[off[r]:off[r + 1]].astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_kelvin_helmholtz_initial_state(cuda, dtype):
+    import t8gpu_b200
+    for dim, level in ((2, 5), (3, 3)):
+        forest = oracle.Forest(dim, level)
+        lv, cent, vol, _ = forest.elements()
+        c = torch.as_tensor(cent.astype(dtype)).to(cuda).contiguous()
+        u = [torch.empty(len(cent), dtype=DT[dtype], device=cuda) for _ in range(5)]
+        t8gpu_b200.init_kelvin_helmholtz(dim, c, u)
+        got = torch.stack(u).cpu().numpy()
+        ref = oracle.init_kh_points(dim, cent.astype(dtype), dtype)
+        assert rel_linf(got, ref) <= 4 * np.finfo(dtype).eps
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,P", [("hex4", 2), ("hex_amr", 3), ("quad6", 4)])
+@pytest.mark.parametrize("mode", ["fused", "unfused"])
+def test_multi_rank_on_one_gpu(cuda, kind, P, mode, dtype):
+    """P ranks emulated on one device (no kernel waits on another: stage s of every rank is launched before stage
+    s+1 of any).  Ghost reads go through the (rank, index) tables exactly as across GPUs."""
+    from multirank import MultiRankEuler
+    forest, lvl = make_forest(kind)
+    conn1 = forest.connectivity(dtype=dtype)
+    u0, vol = perturbed_kh(forest, dtype, seed=3)
+    dt = 0.1 * 2.0 ** -lvl
+    mr = MultiRankEuler(forest, P, DT[dtype], cuda, mode=mode)
+    mr.set_global_state(u0)
+    u = u0
+    for it in range(5):
+        u, _, _ = oracle.iterate(conn1, vol, u, dt)
+        mr.iterate(dt)
+        err = rel_linf(mr.global_state(), u)
+        assert err <= (it + 1) * TOL[np.dtype(dtype)], (it, err)
+
+
+def test_ragged_and_empty_inputs(cuda):
+    import t8gpu_b200
+    # element count not a multiple of the chunk size, and a mesh smaller than one chunk
+    for kind in ("hex3_walls", "quad_amr_walls"):
+        forest, lvl = make_forest(kind)
+        assert forest.num_elements % 256 != 0 or kind == "hex3_walls"
+    forest = oracle.Forest(3, 1)   # 8 elements, every face pair appears twice (periodic, 2 cells per axis)
+    conn = forest.connectivity(dtype=np.float64)
+    u0, vol = perturbed_kh(forest, np.float64, seed=4)
+    ref, _, _ = oracle.iterate(conn, vol, u0, 0.01)
+    sol = t8gpu_b200.EulerSolver(conn, vol, torch.float64, device=cuda)
+    sol.set_state(u0)
+    sol.iterate(0.01)
+    assert rel_linf(sol.state().cpu().numpy(), ref) <= 1e-12
+    # level 0: one element, no faces at all -> state only rescaled by the RK coefficients
+    forest = oracle.Forest(3, 0)
+    conn = forest.connectivity(dtype=np.float64)
+    assert conn["n_faces"] == 0
+    u0, vol = perturbed_kh(forest, np.float64, seed=5)
+    ref, _, _ = oracle.iterate(conn, vol, u0, 0.01)
+    for mode in ("fused", "unfused"):
+        sol = t8gpu_b200.EulerSolver(conn, vol, torch.float64, device=cuda, mode=mode)
+        sol.set_state(u0)
+        sol.iterate(0.01)
+        assert rel_linf(sol.state().cpu().numpy(), ref) <= 1e-12
