@@ -50,9 +50,9 @@ flux_faces_kernel(int nf, int nb, const int32_t* __restrict__ ranks, const int32
   T nx = normals[3 * f], ny = normals[3 * f + 1], nz = normals[3 * f + 2];
   T a  = areas[f];
 
-  Prim<T> L = to_prim(u.p[0][lr][li], u.p[1][lr][li], u.p[2][lr][li], u.p[3][lr][li], u.p[4][lr][li]);
-  Prim<T> R = boundary ? mirror(L, nx, ny, nz)
-                       : to_prim(u.p[0][rr][ri], u.p[1][rr][ri], u.p[2][rr][ri], u.p[3][rr][ri], u.p[4][rr][ri]);
+  Cell<T> L = to_cell(u.p[0][lr][li], u.p[1][lr][li], u.p[2][lr][li], u.p[3][lr][li], u.p[4][lr][li]);
+  Cell<T> R = boundary ? mirror(L, nx, ny, nz)
+                       : to_cell(u.p[0][rr][ri], u.p[1][rr][ri], u.p[2][rr][ri], u.p[3][rr][ri], u.p[4][rr][ri]);
   T F[5];
   T s = kepes_flux(L, R, nx, ny, nz, F);
   if (speed) speed[f] = s;
@@ -106,8 +106,9 @@ template <typename T>
 static int flux_faces_impl(int32_t nf, int32_t nb, const int32_t* ranks, const int32_t* indices, const int32_t* nbr,
                            const T* normals, const T* areas, const T* const* const* vars_all,
                            T* const* const* flux_all, T* speed, void* stream) {
-  if (nf < 0 || nb < 0 || !nbr || !normals || !areas || !vars_all || !flux_all) return cudaErrorInvalidValue;
+  if (nf < 0 || nb < 0 || !vars_all || !flux_all) return cudaErrorInvalidValue;
   if (nf + nb == 0) return cudaSuccess;
+  if (!nbr || !normals || !areas) return cudaErrorInvalidValue;
   TablesC<T> u;
   Tables<T>  f;
   for (int k = 0; k < 5; k++) {
@@ -172,6 +173,7 @@ struct t8b200_plan {
   int     max_faces  = 0;
   int     multi      = 0;  // has ghosts -> needs rank tables
   size_t  smem_bytes = 0;
+  int     ms = 0, mf = 0;  // compile-time stride variant selected for the kernel
   int64_t dev_bytes = 0, n_records = 0, n_halo = 0;
   // device arrays
   int32_t*  halo_off  = nullptr;  // n_chunks + 1
@@ -204,67 +206,67 @@ struct FusedArgs {
   T               dt;
   T*              speed_max;
   int64_t         n_local;
-  int             max_slots;
-  int             max_faces;
+  int             stage;
+  int             multi;
 };
 
-// CTA = one chunk of EC consecutive elements.
-//   phase 0: conserved -> primitive for the chunk's own elements (coalesced) and its halo (gather), into smem
-//   phase 1: every face touching the chunk: flux from smem primitives -> smem (area-scaled)
+template <typename T, int MS>
+__device__ __forceinline__ void store_cell(T* cq, int s, const Cell<T>& q) {
+  cq[0 * MS + s] = q.rho; cq[1 * MS + s] = q.vx; cq[2 * MS + s] = q.vy; cq[3 * MS + s] = q.vz;
+  cq[4 * MS + s] = q.p;   cq[5 * MS + s] = q.B;  cq[6 * MS + s] = q.w;
+}
+template <typename T, int MS>
+__device__ __forceinline__ Cell<T> load_cell(const T* cq, int s) {
+  Cell<T> q;
+  q.rho = cq[0 * MS + s]; q.vx = cq[1 * MS + s]; q.vy = cq[2 * MS + s]; q.vz = cq[3 * MS + s];
+  q.p   = cq[4 * MS + s]; q.B  = cq[5 * MS + s]; q.w  = cq[6 * MS + s];
+  return q;
+}
+
+// CTA = one chunk of EC consecutive elements.  MS / MF: compile-time strides of the shared-memory SoA arrays
+// (slots = EC own + halo; faces), so every shared access is base + index*sizeof(T) + immediate.
+//   phase 0: conserved -> per-cell quantities for the chunk's own elements (coalesced) and its halo (gather)
+//   phase 1: every face touching the chunk: flux from the staged cells -> smem (area-scaled)
 //   phase 2: per element: signed gather of its faces' fluxes (fixed order: deterministic), RK combination, store
-template <typename T, int STAGE, bool MULTI>
-__global__ void __launch_bounds__(EC) fused_stage_kernel(const __grid_constant__ FusedArgs<T> A) {
+template <typename T, int MS, int MF, int MINB>
+__global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_constant__ FusedArgs<T> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* prim = reinterpret_cast<T*>(smem_raw);            // [6][max_slots]
-  T* fl   = prim + 6 * (size_t)A.max_slots;            // [5][max_faces]
+  T* cq = reinterpret_cast<T*>(smem_raw);  // [7][MS]
+  T* fl = cq + NCELLQ * MS;                // [5][MF]
   const int     c   = blockIdx.x;
   const int     tid = threadIdx.x;
   const int64_t e   = (int64_t)c * EC + tid;
-  const int     MS  = A.max_slots;
 
   // ---- phase 0
   T u0 = T(1), u1 = T(0), u2 = T(0), u3 = T(0), u4 = T(1);
   if (e < A.n_local) {
     u0 = A.in[0][e]; u1 = A.in[1][e]; u2 = A.in[2][e]; u3 = A.in[3][e]; u4 = A.in[4][e];
-    Prim<T> q = to_prim(u0, u1, u2, u3, u4);
-    prim[0 * MS + tid] = q.rho; prim[1 * MS + tid] = q.vx; prim[2 * MS + tid] = q.vy;
-    prim[3 * MS + tid] = q.vz;  prim[4 * MS + tid] = q.p;  prim[5 * MS + tid] = q.beta;
   }
   const int h0 = A.halo_off[c], nh = A.halo_off[c + 1] - h0;
+  const int f0 = A.face_off[c], nfc = A.face_off[c + 1] - f0;
+  if (e < A.n_local) store_cell<T, MS>(cq, tid, to_cell(u0, u1, u2, u3, u4));
   for (int h = tid; h < nh; h += EC) {
     int idx = A.halo_elem[h0 + h];
     T   a0, a1, a2, a3, a4;
-    if (MULTI) {
+    if (A.multi) {
       int rk = A.halo_rank[h0 + h];
       a0 = A.in_all[0][rk][idx]; a1 = A.in_all[1][rk][idx]; a2 = A.in_all[2][rk][idx];
       a3 = A.in_all[3][rk][idx]; a4 = A.in_all[4][rk][idx];
     } else {
       a0 = A.in[0][idx]; a1 = A.in[1][idx]; a2 = A.in[2][idx]; a3 = A.in[3][idx]; a4 = A.in[4][idx];
     }
-    Prim<T> q = to_prim(a0, a1, a2, a3, a4);
-    int     s = EC + h;
-    prim[0 * MS + s] = q.rho; prim[1 * MS + s] = q.vx; prim[2 * MS + s] = q.vy;
-    prim[3 * MS + s] = q.vz;  prim[4 * MS + s] = q.p;  prim[5 * MS + s] = q.beta;
+    store_cell<T, MS>(cq, EC + h, to_cell(a0, a1, a2, a3, a4));
   }
   __syncthreads();
 
   // ---- phase 1
-  const int f0 = A.face_off[c], nfc = A.face_off[c + 1] - f0;
-  const int MF = A.max_faces;
-  T         smax = T(0);
+  T smax = T(0);
   for (int j = tid; j < nfc; j += EC) {
     uint32_t lr = A.face_lr[f0 + j];
     int      sl = lr & 0xFFFFu, sr = lr >> 16;
     T nx = A.fnx[f0 + j], ny = A.fny[f0 + j], nz = A.fnz[f0 + j], ar = A.farea[f0 + j];
-    Prim<T> L, R;
-    L.rho = prim[0 * MS + sl]; L.vx = prim[1 * MS + sl]; L.vy = prim[2 * MS + sl];
-    L.vz  = prim[3 * MS + sl]; L.p  = prim[4 * MS + sl]; L.beta = prim[5 * MS + sl];
-    if (sr == 0xFFFF) {
-      R = mirror(L, nx, ny, nz);
-    } else {
-      R.rho = prim[0 * MS + sr]; R.vx = prim[1 * MS + sr]; R.vy = prim[2 * MS + sr];
-      R.vz  = prim[3 * MS + sr]; R.p  = prim[4 * MS + sr]; R.beta = prim[5 * MS + sr];
-    }
+    Cell<T> L = load_cell<T, MS>(cq, sl);
+    Cell<T> R = sr == 0xFFFF ? mirror(L, nx, ny, nz) : load_cell<T, MS>(cq, sr);
     T F[5];
     T s  = kepes_flux(L, R, nx, ny, nz, F);
     smax = fmax_(smax, s);
@@ -282,20 +284,17 @@ __global__ void __launch_bounds__(EC) fused_stage_kernel(const __grid_constant__
     for (int q = q0; q < q1; q++) {
       int en = ent[q];
       int j  = en >> 1;
-      if (en & 1) {
+      T   sg = (en & 1) ? T(1) : T(-1);
 #pragma unroll
-        for (int k = 0; k < 5; k++) acc[k] += fl[k * MF + j];
-      } else {
-#pragma unroll
-        for (int k = 0; k < 5; k++) acc[k] -= fl[k * MF + j];
-      }
+      for (int k = 0; k < 5; k++) acc[k] = fma(sg, fl[k * MF + j], acc[k]);
     }
-    T v = A.vol[e];
+    const int stage = A.stage;
+    T sc = rk_scale<T>(stage, A.dt, A.vol[e]);
     T uin[5] = {u0, u1, u2, u3, u4};
 #pragma unroll
     for (int k = 0; k < 5; k++) {
-      T p = STAGE == 1 ? uin[k] : A.prev[k][e];
-      A.out[k][e] = rk_combine<T, STAGE>(p, uin[k], acc[k], A.dt, v);
+      T p = stage == 1 ? uin[k] : A.prev[k][e];
+      A.out[k][e] = rk_apply<T>(stage, p, uin[k], acc[k], sc);
     }
   }
 
@@ -439,7 +438,11 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
   P->max_faces  = max_faces;
   P->n_records  = nrec;
   P->n_halo     = (int64_t)halo_elem.size();
-  P->smem_bytes = sizeof(T) * (6 * (size_t)(EC + max_halo) + 5 * (size_t)max_faces);
+  // stride variants compiled into the library (slots, faces)
+  P->ms = EC + max_halo <= 512 ? 512 : (EC + max_halo <= 768 ? 768 : 1280);
+  P->mf = max_faces <= 1024 ? 1024 : (max_faces <= 1536 ? 1536 : 2560);
+  if (EC + max_halo > P->ms || max_faces > P->mf) return cudaErrorInvalidValue;  // chunk too irregular for one CTA
+  P->smem_bytes = sizeof(T) * ((size_t)NCELLQ * P->ms + 5 * (size_t)P->mf);
   if (P->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
 
   cudaError_t err = cudaSuccess;
@@ -458,21 +461,27 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
   return err;
 }
 
-template <typename T, int STAGE>
-static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
-  cudaError_t e;
-  if (P->multi) {
-    auto k = fused_stage_kernel<T, STAGE, true>;
-    e      = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes);
-    if (e != cudaSuccess) return e;
-    k<<<P->n_chunks, EC, P->smem_bytes, st>>>(A);
-  } else {
-    auto k = fused_stage_kernel<T, STAGE, false>;
-    e      = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes);
-    if (e != cudaSuccess) return e;
-    k<<<P->n_chunks, EC, P->smem_bytes, st>>>(A);
-  }
+template <typename T, int MS, int MF, int MINB>
+static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
+  auto k = fused_stage_kernel<T, MS, MF, MINB>;
+  T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
+  k<<<P->n_chunks, EC, P->smem_bytes, st>>>(A);
   return cudaGetLastError();
+}
+
+template <typename T>
+static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
+  // resident CTAs per SM are bounded by shared memory; tell ptxas so it can size the register budget
+  constexpr int B0 = sizeof(T) == 8 ? 3 : 6;
+  if (P->ms == 512 && P->mf == 1024) return launch_variant<T, 512, 1024, B0>(P, A, st);
+  if (P->ms == 512 && P->mf == 1536) return launch_variant<T, 512, 1536, 2>(P, A, st);
+  if (P->ms == 768 && P->mf == 1024) return launch_variant<T, 768, 1024, 2>(P, A, st);
+  if (P->ms == 768 && P->mf == 1536) return launch_variant<T, 768, 1536, 2>(P, A, st);
+  if (P->ms == 768 && P->mf == 2560) return launch_variant<T, 768, 2560, 1>(P, A, st);
+  if (P->ms == 512 && P->mf == 2560) return launch_variant<T, 512, 2560, 1>(P, A, st);
+  if (P->ms == 1280 && P->mf == 1024) return launch_variant<T, 1280, 1024, 1>(P, A, st);
+  if (P->ms == 1280 && P->mf == 1536) return launch_variant<T, 1280, 1536, 1>(P, A, st);
+  return launch_variant<T, 1280, 2560, 1>(P, A, st);
 }
 
 template <typename T>
@@ -494,12 +503,10 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
     A.out[k]    = out[k];
   }
   A.vol = vol; A.dt = dt; A.speed_max = speed_max; A.n_local = P->n_local;
-  A.max_slots = EC + P->max_halo; A.max_faces = P->max_faces;
+  A.stage = stage; A.multi = P->multi;
   cudaStream_t st = (cudaStream_t)stream;
   if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), st));
-  if (stage == 1) return launch_fused<T, 1>(P, A, st);
-  if (stage == 2) return launch_fused<T, 2>(P, A, st);
-  return launch_fused<T, 3>(P, A, st);
+  return launch_fused<T>(P, A, st);
 }
 
 // ============================================================================================================

@@ -4,8 +4,8 @@
 using namespace t8b200;
 template <typename T>
 static T run(const T* uL, const T* uR, const T* n, int reflect, T* F) {
-  Prim<T> L = to_prim(uL[0], uL[1], uL[2], uL[3], uL[4]);
-  Prim<T> R = reflect ? mirror(L, n[0], n[1], n[2]) : to_prim(uR[0], uR[1], uR[2], uR[3], uR[4]);
+  Cell<T> L = to_cell(uL[0], uL[1], uL[2], uL[3], uL[4]);
+  Cell<T> R = reflect ? mirror(L, n[0], n[1], n[2]) : to_cell(uR[0], uR[1], uR[2], uR[3], uR[4]);
   return kepes_flux(L, R, n[0], n[1], n[2], F);
 }
 extern "C" double hostcheck_flux_f64(const double* uL, const double* uR, const double* n, int reflect, double* F) {
