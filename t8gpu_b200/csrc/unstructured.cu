@@ -181,7 +181,12 @@ struct t8b200_plan {
   int32_t*  halo_rank = nullptr;  // owner rank (multi only)
   int32_t*  face_off  = nullptr;  // n_chunks + 1
   uint32_t* face_lr   = nullptr;  // slotL | slotR << 16 ; slotR == 0xFFFF -> wall
-  void *    fnx = nullptr, *fny = nullptr, *fnz = nullptr, *farea = nullptr;
+  void *    fnx = nullptr, *fny = nullptr, *fnz = nullptr, *farea = nullptr;  // general geometry (cmp == 0)
+  // compressed geometry (cmp == 1): every normal is +-e_axis and there are <= 256 distinct areas
+  int       cmp      = 0;
+  int       n_areas  = 0;
+  uint2*    face_lg  = nullptr;  // .x = slotL | slotR << 16, .y = axis*2+sign | area index << 3
+  void*     area_tab = nullptr;
   int32_t*  csr_base = nullptr;  // n_chunks + 1
   uint16_t* csr_off  = nullptr;  // n_chunks * (EC + 1), relative to csr_base[c]
   uint16_t* csr_ent  = nullptr;  // face_local << 1 | (1 if this element is the right side)
@@ -195,6 +200,9 @@ struct FusedArgs {
   const int32_t*  face_off;
   const uint32_t* face_lr;
   const T *       fnx, *fny, *fnz, *farea;
+  const uint2*    face_lg;
+  const T*        area_tab;
+  int             n_areas;
   const int32_t*  csr_base;
   const uint16_t* csr_off;
   const uint16_t* csr_ent;
@@ -228,23 +236,50 @@ __device__ __forceinline__ Cell<T> load_cell(const T* cq, int s) {
 //   phase 0: conserved -> per-cell quantities for the chunk's own elements (coalesced) and its halo (gather)
 //   phase 1: every face touching the chunk: flux from the staged cells -> smem (area-scaled)
 //   phase 2: per element: signed gather of its faces' fluxes (fixed order: deterministic), RK combination, store
-template <typename T, int MS, int MF, int MINB>
+// per-face plan record as the kernel consumes it
+template <typename T>
+struct FaceRec {
+  uint32_t lr;
+  T        nx, ny, nz, ar;
+};
+template <typename T, bool CMP>
+__device__ __forceinline__ void load_face_raw(const FusedArgs<T>& A, int g, uint32_t& lr, uint32_t& geo, T& nx, T& ny,
+                                              T& nz, T& ar) {
+  if (CMP) {
+    uint2 v = A.face_lg[g];
+    lr  = v.x;
+    geo = v.y;
+  } else {
+    lr = A.face_lr[g];
+    nx = A.fnx[g]; ny = A.fny[g]; nz = A.fnz[g]; ar = A.farea[g];
+  }
+}
+
+template <typename T, int MS, int MF, int MINB, bool CMP>
 __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_constant__ FusedArgs<T> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* cq = reinterpret_cast<T*>(smem_raw);  // [7][MS]
   T* fl = cq + NCELLQ * MS;                // [5][MF]
+  __shared__ T atab[CMP ? 256 : 1];
   const int     c   = blockIdx.x;
   const int     tid = threadIdx.x;
   const int64_t e   = (int64_t)c * EC + tid;
+  const bool    own = e < A.n_local;
 
-  // ---- phase 0
+  // ---- phase 0: issue every independent global load of the prologue first
   T u0 = T(1), u1 = T(0), u2 = T(0), u3 = T(0), u4 = T(1);
-  if (e < A.n_local) {
+  if (own) {
     u0 = A.in[0][e]; u1 = A.in[1][e]; u2 = A.in[2][e]; u3 = A.in[3][e]; u4 = A.in[4][e];
   }
   const int h0 = A.halo_off[c], nh = A.halo_off[c + 1] - h0;
   const int f0 = A.face_off[c], nfc = A.face_off[c + 1] - f0;
-  if (e < A.n_local) store_cell<T, MS>(cq, tid, to_cell(u0, u1, u2, u3, u4));
+  // first face record of this thread (consumed in phase 1; its latency hides behind phase 0)
+  uint32_t lr_n = 0, geo_n = 0;
+  T        nx_n = T(0), ny_n = T(0), nz_n = T(0), ar_n = T(0);
+  if (tid < nfc) load_face_raw<T, CMP>(A, f0 + tid, lr_n, geo_n, nx_n, ny_n, nz_n, ar_n);
+  if (CMP && tid < A.n_areas) atab[tid] = A.area_tab[tid];
+
+  if (own) store_cell<T, MS>(cq, tid, to_cell(u0, u1, u2, u3, u4));
   for (int h = tid; h < nh; h += EC) {
     int idx = A.halo_elem[h0 + h];
     T   a0, a1, a2, a3, a4;
@@ -259,12 +294,19 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   }
   __syncthreads();
 
-  // ---- phase 1
+  // ---- phase 1: software-pipelined over this thread's faces (record j+EC is in flight while j is evaluated)
   T smax = T(0);
   for (int j = tid; j < nfc; j += EC) {
-    uint32_t lr = A.face_lr[f0 + j];
-    int      sl = lr & 0xFFFFu, sr = lr >> 16;
-    T nx = A.fnx[f0 + j], ny = A.fny[f0 + j], nz = A.fnz[f0 + j], ar = A.farea[f0 + j];
+    uint32_t lr = lr_n, geo = geo_n;
+    T        nx = nx_n, ny = ny_n, nz = nz_n, ar = ar_n;
+    if (j + EC < nfc) load_face_raw<T, CMP>(A, f0 + j + EC, lr_n, geo_n, nx_n, ny_n, nz_n, ar_n);
+    if (CMP) {
+      T sg = (geo & 1u) ? T(1) : T(-1);
+      int ax = (geo >> 1) & 3;
+      nx = ax == 0 ? sg : T(0); ny = ax == 1 ? sg : T(0); nz = ax == 2 ? sg : T(0);
+      ar = atab[geo >> 3];
+    }
+    int     sl = lr & 0xFFFFu, sr = lr >> 16;
     Cell<T> L = load_cell<T, MS>(cq, sl);
     Cell<T> R = sr == 0xFFFF ? mirror(L, nx, ny, nz) : load_cell<T, MS>(cq, sr);
     T F[5];
@@ -273,14 +315,26 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < 5; k++) fl[k * MF + j] = ar * F[k];
   }
+
+  // ---- phase 2 operands are requested BEFORE the barrier so their latency overlaps the wait
+  const int stage = A.stage;
+  int q0 = 0, q1 = 0;
+  T   vol = T(1), pv[5] = {u0, u1, u2, u3, u4};
+  const uint16_t* ent = A.csr_ent + A.csr_base[c];
+  if (own) {
+    const uint16_t* off = A.csr_off + (size_t)c * (EC + 1);
+    q0  = off[tid];
+    q1  = off[tid + 1];
+    vol = A.vol[e];
+    if (stage != 1) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) pv[k] = A.prev[k][e];
+    }
+  }
   __syncthreads();
 
-  // ---- phase 2
-  if (e < A.n_local) {
-    const uint16_t* off = A.csr_off + (size_t)c * (EC + 1);
-    const uint16_t* ent = A.csr_ent + A.csr_base[c];
-    int q0 = off[tid], q1 = off[tid + 1];
-    T   acc[5] = {T(0), T(0), T(0), T(0), T(0)};
+  if (own) {
+    T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
     for (int q = q0; q < q1; q++) {
       int en = ent[q];
       int j  = en >> 1;
@@ -288,14 +342,10 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 #pragma unroll
       for (int k = 0; k < 5; k++) acc[k] = fma(sg, fl[k * MF + j], acc[k]);
     }
-    const int stage = A.stage;
-    T sc = rk_scale<T>(stage, A.dt, A.vol[e]);
+    T sc = rk_scale<T>(stage, A.dt, vol);
     T uin[5] = {u0, u1, u2, u3, u4};
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-      T p = stage == 1 ? uin[k] : A.prev[k][e];
-      A.out[k][e] = rk_apply<T>(stage, p, uin[k], acc[k], sc);
-    }
+    for (int k = 0; k < 5; k++) A.out[k][e] = rk_apply<T>(stage, pv[k], uin[k], acc[k], sc);
   }
 
   if (A.speed_max) {
@@ -368,6 +418,10 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
   std::vector<uint32_t> face_lr(nrec);
   std::vector<T>        fnx(nrec), fny(nrec), fnz(nrec), far(nrec);
   std::vector<uint16_t> csr_off((size_t)nchunks * (EC + 1)), csr_ent;
+  // compressed geometry: all normals +-e_axis, few distinct areas
+  std::vector<uint32_t> face_geo(nrec);
+  std::vector<T>        area_tab;
+  bool                  cmp = true;
   csr_ent.reserve(2 * nrec);
   std::vector<int32_t> halo_tmp, deg(EC + 1);
   int max_halo = 0, max_faces = 0;
@@ -417,6 +471,18 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
       if (f < (int64_t)nf + nb) { nrm = normals + 3 * f; a = areas[f]; }
       else { int64_t g = f - nf - nb; nrm = xnormals + 3 * g; a = xareas[g]; }
       fnx[q] = nrm[0]; fny[q] = nrm[1]; fnz[q] = nrm[2]; far[q] = a;
+      if (cmp) {
+        int code = -1;
+        for (int d = 0; d < 3; d++) {
+          T o1 = nrm[(d + 1) % 3], o2 = nrm[(d + 2) % 3];
+          if (o1 == T(0) && o2 == T(0) && (nrm[d] == T(1) || nrm[d] == T(-1))) code = 2 * d + (nrm[d] > T(0) ? 1 : 0);
+        }
+        int ai = -1;
+        for (size_t t = 0; t < area_tab.size(); t++)
+          if (area_tab[t] == a) ai = (int)t;
+        if (ai < 0 && area_tab.size() < 256) { ai = (int)area_tab.size(); area_tab.push_back(a); }
+        if (code < 0 || ai < 0) cmp = false; else face_geo[q] = (uint32_t)code | ((uint32_t)ai << 3);
+      }
       if (sl < EC) deg[sl + 1]++;
       if (sr < EC) deg[sr + 1]++;
     }
@@ -439,8 +505,8 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
   P->n_records  = nrec;
   P->n_halo     = (int64_t)halo_elem.size();
   // stride variants compiled into the library (slots, faces)
-  P->ms = EC + max_halo <= 512 ? 512 : (EC + max_halo <= 768 ? 768 : 1280);
-  P->mf = max_faces <= 1024 ? 1024 : (max_faces <= 1536 ? 1536 : 2560);
+  P->ms = EC + max_halo <= 512 ? 512 : 1280;
+  P->mf = max_faces <= 1024 ? 1024 : 2560;
   if (EC + max_halo > P->ms || max_faces > P->mf) return cudaErrorInvalidValue;  // chunk too irregular for one CTA
   P->smem_bytes = sizeof(T) * ((size_t)NCELLQ * P->ms + 5 * (size_t)P->mf);
   if (P->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
@@ -450,38 +516,42 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
   P->halo_elem = upload(halo_elem, P->dev_bytes, err);
   if (P->multi) P->halo_rank = upload(halo_rank, P->dev_bytes, err);
   P->face_off = upload(face_off, P->dev_bytes, err);
-  P->face_lr  = upload(face_lr, P->dev_bytes, err);
-  P->fnx      = upload(fnx, P->dev_bytes, err);
-  P->fny      = upload(fny, P->dev_bytes, err);
-  P->fnz      = upload(fnz, P->dev_bytes, err);
-  P->farea    = upload(far, P->dev_bytes, err);
+  P->cmp = cmp ? 1 : 0;
+  if (cmp) {
+    std::vector<uint2> lg(nrec);
+    for (int64_t q = 0; q < nrec; q++) lg[q] = make_uint2(face_lr[q], face_geo[q]);
+    P->face_lg  = upload(lg, P->dev_bytes, err);
+    P->area_tab = upload(area_tab, P->dev_bytes, err);
+    P->n_areas  = (int)area_tab.size();
+  } else {
+    P->face_lr = upload(face_lr, P->dev_bytes, err);
+    P->fnx     = upload(fnx, P->dev_bytes, err);
+    P->fny     = upload(fny, P->dev_bytes, err);
+    P->fnz     = upload(fnz, P->dev_bytes, err);
+    P->farea   = upload(far, P->dev_bytes, err);
+  }
   P->csr_base = upload(csr_base, P->dev_bytes, err);
   P->csr_off  = upload(csr_off, P->dev_bytes, err);
   P->csr_ent  = upload(csr_ent, P->dev_bytes, err);
   return err;
 }
 
-template <typename T, int MS, int MF, int MINB>
+template <typename T, int MS, int MF, int MINB, bool CMP>
 static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
-  auto k = fused_stage_kernel<T, MS, MF, MINB>;
+  auto k = fused_stage_kernel<T, MS, MF, MINB, CMP>;
   T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
   k<<<P->n_chunks, EC, P->smem_bytes, st>>>(A);
   return cudaGetLastError();
 }
 
-template <typename T>
+template <typename T, bool CMP>
 static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
   // resident CTAs per SM are bounded by shared memory; tell ptxas so it can size the register budget
   constexpr int B0 = sizeof(T) == 8 ? 3 : 6;
-  if (P->ms == 512 && P->mf == 1024) return launch_variant<T, 512, 1024, B0>(P, A, st);
-  if (P->ms == 512 && P->mf == 1536) return launch_variant<T, 512, 1536, 2>(P, A, st);
-  if (P->ms == 768 && P->mf == 1024) return launch_variant<T, 768, 1024, 2>(P, A, st);
-  if (P->ms == 768 && P->mf == 1536) return launch_variant<T, 768, 1536, 2>(P, A, st);
-  if (P->ms == 768 && P->mf == 2560) return launch_variant<T, 768, 2560, 1>(P, A, st);
-  if (P->ms == 512 && P->mf == 2560) return launch_variant<T, 512, 2560, 1>(P, A, st);
-  if (P->ms == 1280 && P->mf == 1024) return launch_variant<T, 1280, 1024, 1>(P, A, st);
-  if (P->ms == 1280 && P->mf == 1536) return launch_variant<T, 1280, 1536, 1>(P, A, st);
-  return launch_variant<T, 1280, 2560, 1>(P, A, st);
+  if (P->ms == 512 && P->mf == 1024) return launch_variant<T, 512, 1024, B0, CMP>(P, A, st);
+  if (P->ms == 512 && P->mf == 2560) return launch_variant<T, 512, 2560, 1, CMP>(P, A, st);
+  if (P->ms == 1280 && P->mf == 1024) return launch_variant<T, 1280, 1024, 1, CMP>(P, A, st);
+  return launch_variant<T, 1280, 2560, 1, CMP>(P, A, st);
 }
 
 template <typename T>
@@ -495,6 +565,7 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
   A.halo_off = P->halo_off; A.halo_elem = P->halo_elem; A.halo_rank = P->halo_rank;
   A.face_off = P->face_off; A.face_lr = P->face_lr;
   A.fnx = (const T*)P->fnx; A.fny = (const T*)P->fny; A.fnz = (const T*)P->fnz; A.farea = (const T*)P->farea;
+  A.face_lg = P->face_lg; A.area_tab = (const T*)P->area_tab; A.n_areas = P->n_areas;
   A.csr_base = P->csr_base; A.csr_off = P->csr_off; A.csr_ent = P->csr_ent;
   for (int k = 0; k < 5; k++) {
     A.in[k]     = in[k];
@@ -506,7 +577,7 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
   A.stage = stage; A.multi = P->multi;
   cudaStream_t st = (cudaStream_t)stream;
   if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), st));
-  return launch_fused<T>(P, A, st);
+  return P->cmp ? launch_fused<T, true>(P, A, st) : launch_fused<T, false>(P, A, st);
 }
 
 // ============================================================================================================
@@ -567,6 +638,7 @@ void t8b200_plan_destroy(t8b200_plan* P) {
   if (!P) return;
   cudaFree(P->halo_off); cudaFree(P->halo_elem); cudaFree(P->halo_rank); cudaFree(P->face_off);
   cudaFree(P->face_lr); cudaFree(P->fnx); cudaFree(P->fny); cudaFree(P->fnz); cudaFree(P->farea);
+  cudaFree(P->face_lg); cudaFree(P->area_tab);
   cudaFree(P->csr_base); cudaFree(P->csr_off); cudaFree(P->csr_ent);
   delete P;
 }

@@ -31,6 +31,38 @@ def make_forest(kind):
     raise KeyError(kind)
 
 
+def rotated(conn, seed=7):
+    """Same topology, but the mesh is rotated in space (general unit normals) and the face areas are perturbed:
+    exercises the uncompressed-geometry path of the tile plan."""
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    c = dict(conn)
+    dt = conn["face_normals"].dtype
+    n = conn["face_normals"].reshape(-1, 3).astype(np.float64) @ q.T
+    c["face_normals"] = np.ascontiguousarray(n.reshape(-1).astype(dt))
+    c["face_areas"] = (conn["face_areas"].astype(np.float64) * rng.uniform(0.8, 1.2, conn["face_areas"].shape)).astype(dt)
+    return c
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("mode", ["fused", "unfused"])
+@pytest.mark.parametrize("kind", ["hex3_walls", "hex_amr"])
+def test_general_normals(cuda, kind, mode, dtype):
+    import t8gpu_b200
+    forest, lvl = make_forest(kind)
+    conn = rotated(forest.connectivity(dtype=dtype))
+    u0, vol = perturbed_kh(forest, dtype, seed=11)
+    dt = 0.05 * 2.0 ** -lvl
+    sol = t8gpu_b200.EulerSolver(conn, vol, DT[dtype], device=cuda, mode=mode)
+    sol.set_state(u0)
+    u = u0
+    for it in range(5):
+        u, _, _ = oracle.iterate(conn, vol, u, dt)
+        sol.iterate(dt)
+        err = rel_linf(sol.state().cpu().numpy(), u)
+        assert err <= (it + 1) * TOL[np.dtype(dtype)], (kind, mode, it, err)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("mode", ["fused", "unfused"])
 @pytest.mark.parametrize("kind", ["quad6", "hex4", "hex3_walls", "hex_amr", "quad_amr_walls"])
