@@ -196,12 +196,32 @@ static mf_forest* balance(mf_forest* f) {
   }
 }
 
-/* t8_forest_set_adapt(non-recursive) + set_balance, with the reference's callback (mesh_manager.inl:125-162 ==
- * subgrid_mesh_manager.inl:198-235): refine if level < max_level and crit > b; coarsen a family if level > min_level
- * and mean over the FIRST FOUR siblings (sic, also in 3-D) < b.  rank_offsets (P+1 entries, may be NULL for P=1):
- * a family is only offered for coarsening when it is entirely on one rank.  crit is float or double (is_f64). */
-mf_forest* mf_adapt(const mf_forest* f, const void* crit, int is_f64, double b, int min_level, int max_level,
-                    const int64_t* rank_offsets, int nranks) {
+/* exported views used by oracle/ref_shim/t8mini.cpp (the t8code-API facade over this forest) */
+int mf_face_neighbors(const mf_forest* f, int64_t e, int face, int64_t out[4]) { return face_neighbors(f, e, face, out); }
+int mf_periodic(const mf_forest* f) { return f->periodic; }
+void mf_element(const mf_forest* f, int64_t e, int* level, uint32_t coord[3]) {
+  *level = f->level[e];
+  unmorton(f->key[e], f->dim, coord);
+}
+
+/* do elements i .. i+2^d-1 form a family (same parent, all leaves of the same level, i is child 0)?
+ * rank_offsets (may be NULL): a family split across ranks is not offered for coarsening. */
+int mf_is_family(const mf_forest* f, int64_t i, const int64_t* rank_offsets, int nranks) {
+  int dim = f->dim, nch = 1 << dim, l = f->level[i];
+  if (l == 0 || i + nch > f->n) return 0;
+  uint64_t pmask = ~(((uint64_t)1 << (dim * (MAXL - l + 1))) - 1);
+  if (((f->key[i] >> (dim * (MAXL - l))) & (uint64_t)(nch - 1)) != 0) return 0;
+  for (int c = 1; c < nch; c++)
+    if (f->level[i + c] != l || (f->key[i + c] & pmask) != (f->key[i] & pmask)) return 0;
+  if (rank_offsets)
+    for (int p = 1; p < nranks; p++)
+      if (rank_offsets[p] > i && rank_offsets[p] < i + nch) return 0;
+  return 1;
+}
+
+/* apply per-element adapt results (1 refine, -1 coarsen the family starting here, 0 keep; entries of the other
+ * family members are ignored when a family is coarsened), then 2:1 face balance (t8_forest_set_balance). */
+mf_forest* mf_apply_adapt(const mf_forest* f, const int8_t* res) {
   int        dim = f->dim, nch = 1 << dim;
   mf_forest* g   = (mf_forest*)calloc(1, sizeof(mf_forest));
   g->dim         = dim;
@@ -209,44 +229,16 @@ mf_forest* mf_adapt(const mf_forest* f, const void* crit, int is_f64, double b, 
   g->key         = (uint64_t*)malloc(sizeof(uint64_t) * f->n * nch);
   g->level       = (int8_t*)malloc(f->n * nch);
   int64_t o      = 0;
-#define CRIT(i) (is_f64 ? ((const double*)crit)[i] : (double)((const float*)crit)[i])
   for (int64_t i = 0; i < f->n;) {
     int l = f->level[i];
-    /* family test */
-    int is_family = 0;
-    if (l > 0 && i + nch <= f->n) {
-      uint64_t pmask = ~(((uint64_t)1 << (dim * (MAXL - l + 1))) - 1);
-      is_family      = ((f->key[i] >> (dim * (MAXL - l))) & (nch - 1)) == 0;
-      for (int c = 1; c < nch && is_family; c++)
-        is_family = f->level[i + c] == l && (f->key[i + c] & pmask) == (f->key[i] & pmask);
-      if (is_family && rank_offsets) {
-        for (int p = 1; p < nranks; p++)
-          if (rank_offsets[p] > i && rank_offsets[p] < i + nch) is_family = 0;
-      }
-    }
-    int res = 0;
-    if (l < max_level) {
-      if (is_f64 ? (CRIT(i) > b) : ((float)CRIT(i) > (float)b)) res = 1;
-    }
-    if (!res && l > min_level && is_family) {
-      if (is_f64) {
-        double c = 0.0;
-        for (int s = 0; s < 4; s++) c += ((const double*)crit)[i + s] / 4.0;
-        if (c < b) res = -1;
-      } else {
-        float c = 0.0f;
-        for (int s = 0; s < 4; s++) c += ((const float*)crit)[i + s] / 4.0f;
-        if (c < (float)b) res = -1;
-      }
-    }
-    if (res > 0) {
+    if (res[i] > 0) {
       for (int ch = 0; ch < nch; ch++) {
         g->key[o]   = f->key[i] | ((uint64_t)ch << (dim * (MAXL - l - 1)));
         g->level[o] = (int8_t)(l + 1);
         o++;
       }
       i += 1;
-    } else if (res < 0) {
+    } else if (res[i] < 0) {
       g->key[o]   = f->key[i];
       g->level[o] = (int8_t)(l - 1);
       o++;
@@ -258,9 +250,41 @@ mf_forest* mf_adapt(const mf_forest* f, const void* crit, int is_f64, double b, 
       i += 1;
     }
   }
-#undef CRIT
   g->n = o;
   return balance(g);
+}
+
+/* t8_forest_set_adapt(non-recursive) + set_balance, with the reference's callback (mesh_manager.inl:125-162 ==
+ * subgrid_mesh_manager.inl:198-235): refine if level < max_level and crit > b; coarsen a family if level > min_level
+ * and mean over the FIRST FOUR siblings (sic, also in 3-D) < b.  crit is float or double (is_f64). */
+mf_forest* mf_adapt(const mf_forest* f, const void* crit, int is_f64, double b, int min_level, int max_level,
+                    const int64_t* rank_offsets, int nranks) {
+  int     nch = 1 << f->dim;
+  int8_t* res = (int8_t*)calloc(f->n, 1);
+  for (int64_t i = 0; i < f->n;) {
+    int l = f->level[i];
+    int is_family = mf_is_family(f, i, rank_offsets, nranks);
+    int r = 0;
+    if (l < max_level) {
+      if (is_f64 ? (((const double*)crit)[i] > b) : (((const float*)crit)[i] > (float)b)) r = 1;
+    }
+    if (!r && l > min_level && is_family) {
+      if (is_f64) {
+        double c = 0.0;
+        for (int s = 0; s < 4; s++) c += ((const double*)crit)[i + s] / 4.0;
+        if (c < b) r = -1;
+      } else {
+        float c = 0.0f;
+        for (int s = 0; s < 4; s++) c += ((const float*)crit)[i + s] / 4.0f;
+        if (c < (float)b) r = -1;
+      }
+    }
+    res[i] = (int8_t)r;
+    i += r < 0 ? nch : 1;
+  }
+  mf_forest* g = mf_apply_adapt(f, res);
+  free(res);
+  return g;
 }
 
 /* mesh_manager.inl:258-281 (== subgrid_mesh_manager.inl:487-510): old->new element map from levels only.
