@@ -71,6 +71,40 @@ int t8b200_rk3_stage_f64(int stage, int64_t n, int nvar, const double* const* pr
 int t8b200_max_speed_f32(const float* speed, int64_t n, float* out_dev, void* stream);
 int t8b200_max_speed_f64(const double* speed, int64_t n, double* out_dev, void* stream);
 
+/* Subgrid path (Subgrid<4,4,4> when dim = 3, Subgrid<4,4> when dim = 2; cell (e,i,j,k) at e*S + i + 4j + 16k,
+ * t8gpu/memory/subgrid_memory_manager.h:35-135).
+ * Replaces compute_inner_fluxes<<<N,(4,4,4)>>> (examples/subgrid/kernels.inl:335-662, launched at solver.inl:166):
+ * fluxes between the cells of one element, accumulated non-atomically into this rank's flux arrays.
+ * vars / flux: HOST arrays of 5 DEVICE pointers (SubgridMemoryAccessorOwn::get(k)); vol: device, per element. */
+int t8b200_subgrid_inner_flux_f32(int dim, int64_t n_elements, const float* vol, const float* const* vars,
+                                  float* const* flux, void* stream);
+int t8b200_subgrid_inner_flux_f64(int dim, int64_t n_elements, const double* vol, const double* const* vars,
+                                  double* const* flux, void* stream);
+/* Replaces compute_outer_fluxes<<<Faces,(4,4)>>> (kernels.inl:664-911, solver.inl:181): fluxes across the faces
+ * between elements, 2:1 hanging faces through level_difference / offset, atomics into both sides (possibly on
+ * another rank).  Arrays are those behind SubgridMeshConnectivityAccessor (t8gpu/mesh/subgrid_mesh_manager.h:29-216):
+ * normals have `dim` components per face, offsets `dim` per face.  vars_all / flux_all as in t8b200_flux_faces. */
+int t8b200_subgrid_outer_flux_f32(int dim, int32_t nf, const int32_t* ranks, const int32_t* indices,
+                                  const int32_t* face_neighbors, const float* face_normals, const float* face_surfaces,
+                                  const int32_t* face_level_difference, const int32_t* face_neighbor_offset,
+                                  const float* const* const* vars_all, float* const* const* flux_all, void* stream);
+int t8b200_subgrid_outer_flux_f64(int dim, int32_t nf, const int32_t* ranks, const int32_t* indices,
+                                  const int32_t* face_neighbors, const double* face_normals,
+                                  const double* face_surfaces, const int32_t* face_level_difference,
+                                  const int32_t* face_neighbor_offset, const double* const* const* vars_all,
+                                  double* const* const* flux_all, void* stream);
+/* Replaces compute_boundary_fluxes<<<B,(4,4)>>> (kernels.inl:913-1107, solver.inl:172): wall flux on the nb boundary
+ * faces stored after the nf interior ones.  vars_own_tab / flux_own_tab: HOST arrays of 5 DEVICE one-entry tables
+ * (this rank's pointer). */
+int t8b200_subgrid_boundary_flux_f32(int dim, int32_t nf, int32_t nb, const int32_t* face_neighbors,
+                                     const float* face_normals, const float* face_surfaces,
+                                     const float* const* const* vars_own_tab, float* const* const* flux_own_tab,
+                                     void* stream);
+int t8b200_subgrid_boundary_flux_f64(int dim, int32_t nf, int32_t nb, const int32_t* face_neighbors,
+                                     const double* face_normals, const double* face_surfaces,
+                                     const double* const* const* vars_own_tab, double* const* const* flux_own_tab,
+                                     void* stream);
+
 /* -------------------------------------------------------------------------------------------------------------
  * 2. B200-native fused path: connectivity re-laid out into per-chunk tiles ("plan"), one kernel per RK stage that
  *    stages a chunk of elements + halo in shared memory, evaluates every face of the chunk once, gathers the
@@ -104,6 +138,29 @@ int t8b200_fused_stage_f32(const t8b200_plan* plan, int stage, const float* cons
 int t8b200_fused_stage_f64(const t8b200_plan* plan, int stage, const double* const* in,
                            const double* const* const* in_all, const double* const* prev, double* const* out,
                            const double* vol, double dt, double* speed_max_dev, void* stream);
+
+/* Fused Subgrid<4,4,4> stage (3-D): replaces compute_inner_fluxes + compute_boundary_fluxes + compute_outer_fluxes +
+ * subgrid::SSP_3RK_step{1,2,3} of one stage (examples/subgrid/solver.inl:156-194) by ONE kernel without atomics.
+ * The plan is built from the SubgridMeshConnectivityAccessor arrays (HOST pointers; normals with 3 components per
+ * face, offsets 3 per face; x_*: optional faces whose ghost neighbour is owned by a lower rank, as in
+ * t8b200_plan_create). */
+typedef struct t8b200_subgrid_plan t8b200_subgrid_plan;
+int  t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
+                                int32_t nb, const int32_t* face_neighbors, const void* face_normals,
+                                const void* face_surfaces, const int32_t* face_level_difference,
+                                const int32_t* face_neighbor_offset, const int32_t* ranks, const int32_t* indices,
+                                int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
+                                const void* x_face_surfaces, const int32_t* x_level_difference,
+                                const int32_t* x_neighbor_offset);
+void t8b200_subgrid_plan_destroy(t8b200_subgrid_plan* plan);
+/* in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's cell arrays; in_all: tables for ghost reads or NULL;
+ * vol: device, per ELEMENT (cell volume = vol/64, ssp_runge_kutta.inl:116). */
+int t8b200_subgrid_fused_stage_f32(const t8b200_subgrid_plan* plan, int stage, const float* const* in,
+                                   const float* const* const* in_all, const float* const* prev, float* const* out,
+                                   const float* vol, float dt, void* stream);
+int t8b200_subgrid_fused_stage_f64(const t8b200_subgrid_plan* plan, int stage, const double* const* in,
+                                   const double* const* const* in_all, const double* const* prev, double* const* out,
+                                   const double* vol, double dt, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
  * 3. Device-side connectivity for uniform Cartesian periodic forests (quad / hex, one tree, Morton order):

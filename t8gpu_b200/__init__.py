@@ -132,6 +132,36 @@ def max_speed(speed, out=None, stream=None):
     return out
 
 
+def subgrid_inner_flux(dim, vol, vars_own, flux_own, stream=None):
+    """compute_inner_fluxes<Subgrid<4,4[,4]>>; vars_own / flux_own: lists of 5 per-variable cell tensors."""
+    s, _ = _sfx(vol.dtype)
+    check(getattr(lib(), "t8b200_subgrid_inner_flux_" + s)(dim, C.c_int64(vol.numel()), C.c_void_p(vol.data_ptr()),
+                                                            ptrs(vars_own), ptrs(flux_own), stream_ptr(stream)),
+          "subgrid_inner_flux")
+
+
+def _opt(t):
+    return C.c_void_p(t.data_ptr() if t is not None else None)
+
+
+def subgrid_outer_flux(conn, vars_all, flux_all, stream=None):
+    """compute_outer_fluxes; conn: dict of device tensors in the SubgridMeshConnectivityAccessor layout."""
+    s, _ = _sfx(conn["face_normals"].dtype)
+    check(getattr(lib(), "t8b200_subgrid_outer_flux_" + s)(
+        int(conn["dim"]), int(conn["n_faces"]), _opt(conn.get("ranks")), _opt(conn.get("indices")),
+        _opt(conn["face_neighbors"]), _opt(conn["face_normals"]), _opt(conn["face_areas"]), _opt(conn["level_diff"]),
+        _opt(conn["offsets"]), vars_all.host, flux_all.host, stream_ptr(stream)), "subgrid_outer_flux")
+
+
+def subgrid_boundary_flux(conn, vars_own_tab, flux_own_tab, stream=None):
+    """compute_boundary_fluxes on the n_bfaces wall faces; *_tab: RankTables of this rank only."""
+    s, _ = _sfx(conn["face_normals"].dtype)
+    check(getattr(lib(), "t8b200_subgrid_boundary_flux_" + s)(
+        int(conn["dim"]), int(conn["n_faces"]), int(conn["n_bfaces"]), _opt(conn["face_neighbors"]),
+        _opt(conn["face_normals"]), _opt(conn["face_areas"]), vars_own_tab.host, flux_own_tab.host,
+        stream_ptr(stream)), "subgrid_boundary_flux")
+
+
 # ------------------------------------------------------------------------------------------------ fused tile plan
 
 class Plan:
@@ -184,6 +214,50 @@ class Plan:
                  ptrs(prev) if prev is not None else None, ptrs(out), C.c_void_p(vol.data_ptr()), ft(dt),
                  C.c_void_p(speed_max.data_ptr() if speed_max is not None else None), stream_ptr(stream)),
               "fused_stage")
+
+
+class SubgridPlan:
+    """Per-element neighbour tables for the fused Subgrid<4,4,4> stage kernel (3-D)."""
+
+    def __init__(self, conn, volumes, dtype):
+        import numpy as np
+        _torch()
+        s, _ = _sfx(dtype)
+        npdt = np.float64 if s == "f64" else np.float32
+        self.dtype = dtype
+        if int(conn["dim"]) != 3:
+            raise ValueError("the fused subgrid kernel is 3-D (Subgrid<4,4,4>); use mode='unfused' for Subgrid<4,4>")
+
+        def arr(k, dt):
+            v = conn.get(k)
+            return None if v is None or len(v) == 0 else np.ascontiguousarray(v, dtype=dt)
+
+        def p(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+        keep = [arr("face_neighbors", np.int32), arr("face_normals", npdt), arr("face_areas", npdt),
+                arr("level_diff", np.int32), arr("offsets", np.int32), arr("ranks", np.int32),
+                arr("indices", np.int32), arr("x_face_neighbors", np.int32), arr("x_face_normals", npdt),
+                arr("x_face_areas", npdt), arr("x_level_diff", np.int32), arr("x_offsets", np.int32)]
+        h = C.c_void_p()
+        check(lib().t8b200_subgrid_plan_create(
+            C.byref(h), int(s == "f64"), C.c_int64(int(conn["n_local"])), C.c_int64(int(conn.get("n_ghost", 0))),
+            int(conn["n_faces"]), int(conn["n_bfaces"]), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]), p(keep[4]),
+            p(keep[5]), p(keep[6]), int(conn.get("n_xfaces", 0)), p(keep[7]), p(keep[8]), p(keep[9]), p(keep[10]),
+            p(keep[11])), "subgrid_plan_create")
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().t8b200_subgrid_plan_destroy(self._h)
+            self._h = None
+
+    def stage(self, stage, inp, prev, out, vol, dt, in_all=None, stream=None):
+        s, ft = _sfx(self.dtype)
+        check(getattr(lib(), "t8b200_subgrid_fused_stage_" + s)(
+            self._h, stage, ptrs(inp), in_all.host if in_all is not None else None,
+            ptrs(prev) if prev is not None else None, ptrs(out), C.c_void_p(vol.data_ptr()), ft(dt),
+            stream_ptr(stream)), "subgrid_fused_stage")
 
 
 # ------------------------------------------------------------------------------------------------ Cartesian meshes
@@ -264,4 +338,4 @@ def conn_to_device(conn, dtype, device):
     return out
 
 
-from .solver import EulerSolver  # noqa: E402,F401
+from .solver import EulerSolver, SubgridEulerSolver  # noqa: E402,F401

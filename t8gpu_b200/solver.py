@@ -102,3 +102,73 @@ class EulerSolver:
         half_pow = float(self.torch.tensor(0.5, dtype=ft) ** self.max_level)
         return float(self.torch.tensor(self.cfl, dtype=ft) * self.torch.tensor(half_pow, dtype=ft) /
                      self.torch.tensor(vmax, dtype=ft))
+
+
+class SubgridEulerSolver:
+    """Harness-side mirror of `SubgridCompressibleEulerSolver<Subgrid<4,4,4>>` / `<Subgrid<4,4>>`
+    (examples/subgrid/solver.h:31-108, solver.inl:152-266) for one rank.
+
+    Storage follows t8gpu::SubgridMemoryManager (subgrid_memory_manager.inl:3-106): nb_variables * nb_steps arrays of
+    capacity * Subgrid::size cells, per-element volumes in a separate vector.
+    mode = "unfused": the reference's schedule through the reference-shaped entry points;
+    mode = "fused": one kernel per RK stage (3-D only), fluxes never reach HBM.
+    """
+
+    def __init__(self, conn_host, volumes, dtype, device=None, mode="unfused"):
+        import numpy as np
+        import torch
+        from . import RankTables, conn_to_device
+        self.torch = torch
+        self.dtype = dtype
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.mode = mode
+        self.dim = int(conn_host["dim"])
+        self.S = 64 if self.dim == 3 else 16
+        self.ne = int(conn_host["n_local"])
+        self.nc = self.ne * self.S
+        self.buffer = torch.zeros((NVAR * NB_STEPS, max(self.nc, 32)), dtype=dtype, device=self.device)
+        self.vol = torch.as_tensor(np.ascontiguousarray(volumes)).to(dtype).to(self.device)
+        self.next, self.prev = STEP0, STEP3
+        keys = ("face_neighbors", "face_normals", "face_areas", "level_diff", "offsets")
+        self.conn = conn_to_device({k: conn_host[k] for k in keys}, dtype, self.device)
+        self.conn.update(dim=self.dim, n_faces=int(conn_host["n_faces"]), n_bfaces=int(conn_host["n_bfaces"]),
+                         ranks=None, indices=None)
+        self._tables = {s: RankTables([self.variables(s)], self.device) for s in range(NB_STEPS)}
+        self.plan = None
+        if mode == "fused":
+            from . import SubgridPlan
+            self.plan = SubgridPlan(conn_host, volumes, dtype)
+
+    def variables(self, step):
+        return [self.buffer[step * NVAR + k, :self.nc] for k in range(NVAR)]
+
+    def set_state(self, u):
+        t = self.torch.as_tensor(u).to(self.dtype).to(self.device)
+        self.buffer[self.next * NVAR:(self.next + 1) * NVAR, :self.nc] = t
+
+    def state(self):
+        return self.buffer[self.next * NVAR:(self.next + 1) * NVAR, :self.nc]
+
+    def iterate(self, dt, stream=None):
+        from . import rk3_stage, subgrid_boundary_flux, subgrid_inner_flux, subgrid_outer_flux
+        self.next, self.prev = self.prev, self.next
+        prev = self.variables(self.prev)
+        s1, s2, nxt = self.variables(STEP1), self.variables(STEP2), self.variables(self.next)
+        if self.mode == "fused":
+            self.plan.stage(1, prev, None, s1, self.vol, dt, stream=stream)
+            self.plan.stage(2, s1, prev, s2, self.vol, dt, stream=stream)
+            self.plan.stage(3, s2, prev, nxt, self.vol, dt, stream=stream)
+            return 3
+        fl = self.variables(FLUXES)
+        T = self._tables
+        launches = 0
+        for stage, sin, vin, vout in ((1, self.prev, prev, s1), (2, STEP1, s1, s2), (3, STEP2, s2, nxt)):
+            subgrid_inner_flux(self.dim, self.vol, vin, fl, stream)
+            if self.conn["n_bfaces"] > 0:
+                subgrid_boundary_flux(self.conn, T[sin], T[FLUXES], stream)
+                launches += 1
+            subgrid_outer_flux(self.conn, T[sin], T[FLUXES], stream)
+            rk3_stage(stage, prev, vin if stage > 1 else None, vout, fl, self.vol, dt, cells_per_vol=self.S,
+                      stream=stream)
+            launches += 3
+        return launches
