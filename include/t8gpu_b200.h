@@ -184,7 +184,22 @@ typedef struct {
 
 int  t8b200_cartesian_uniform_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int level, int nranks, int rank,
                                            void* stream);
+/* Same for a periodic "brick" of bx*by*bz unit trees (tree id = x + bx (y + by z), elements ordered by tree, Morton
+ * inside a tree): the weak-scaling meshes, one tree per GPU.  brick (2,2,2) at level L equals the level L+1 cube. */
+int  t8b200_cartesian_brick_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int level, int bx, int by, int bz,
+                                         int nranks, int rank, void* stream);
 void t8b200_cartesian_connectivity_free(t8b200_cart_conn* c);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * 4. Cross-GPU sharing of the variable buffers, one process per GPU.  Replaces the MPI_Allgather of
+ *    cudaIpcMemHandle_t in SharedDeviceVector (t8gpu/memory/shared_device_vector.inl:171-198): the 64-byte handles are
+ *    exchanged by the caller (torch.distributed / NCCL here), the mapped pointers are peer pointers reached over
+ *    NVLink.  All calls are synchronous.
+ * ------------------------------------------------------------------------------------------------------------- */
+int t8b200_shared_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]);
+int t8b200_shared_open(const unsigned char handle[64], void** dev_ptr);
+int t8b200_shared_close(void* dev_ptr);
+int t8b200_shared_free(void* dev_ptr);
 
 /* Cartesian Kelvin-Helmholtz initial state (examples/subgrid/solver.inl:36-56 / :82-103) sampled at n points
  * (device, 3 per point, float_type).  u: HOST array of 5 device pointers. */

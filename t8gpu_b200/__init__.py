@@ -279,15 +279,16 @@ class _CartConn(C.Structure):
                 ("x_face_normals", C.c_void_p), ("x_face_surfaces", C.c_void_p)]
 
 
-def cartesian_uniform_connectivity(dim, level, dtype, nranks=1, rank=0, device=None):
-    """Device-built connectivity of a uniform periodic quad/hex forest in the reference layout -> dict of torch
-    tensors (copied out of the library-owned buffers)."""
+def cartesian_uniform_connectivity(dim, level, dtype, nranks=1, rank=0, device=None, brick=(1, 1, 1)):
+    """Device-built connectivity of a uniform periodic quad/hex forest (a brick of unit trees, default one tree) in
+    the reference layout -> dict of torch tensors (copied out of the library-owned buffers)."""
     torch = _torch()
     s, _ = _sfx(dtype)
     device = device or torch.device("cuda", torch.cuda.current_device())
     c = _CartConn()
-    check(lib().t8b200_cartesian_uniform_connectivity(C.byref(c), int(s == "f64"), dim, level, nranks, rank,
-                                                      stream_ptr()), "cartesian_uniform_connectivity")
+    check(lib().t8b200_cartesian_brick_connectivity(C.byref(c), int(s == "f64"), dim, level, int(brick[0]),
+                                                    int(brick[1]), int(brick[2]), nranks, rank, stream_ptr()),
+          "cartesian_brick_connectivity")
 
     def grab(ptr, n, dt):
         if n == 0:
@@ -306,6 +307,62 @@ def cartesian_uniform_connectivity(dim, level, dtype, nranks=1, rank=0, device=N
     torch.cuda.synchronize()
     lib().t8b200_cartesian_connectivity_free(C.byref(c))
     return out
+
+
+class SharedBuffer:
+    """A device allocation that other processes on this node can map (cudaIpc handle exchange is up to the caller).
+    `.tensor(shape, dtype)` views it as a torch tensor; `.handle` is the 64-byte IPC handle."""
+
+    def __init__(self, nbytes, device):
+        torch = _torch()
+        self.device = device
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            check(lib().t8b200_shared_alloc(C.c_size_t(self.nbytes), C.byref(p), h), "shared_alloc")
+        self.ptr = p.value
+        self.handle = bytes(h)
+        self._peers = []
+
+    def tensor(self, shape, dtype):
+        torch = _torch()
+        n = 1
+        for d in shape:
+            n *= int(d)
+        t = torch.as_tensor(_RawDeviceArray(self.ptr, n, dtype), device=self.device)
+        return t.view(*shape)
+
+    def open_peer(self, handle):
+        """Map another process's buffer; returns the peer device pointer (int)."""
+        torch = _torch()
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        with torch.cuda.device(self.device):
+            check(lib().t8b200_shared_open(h, C.byref(p)), "shared_open")
+        self._peers.append(p.value)
+        return p.value
+
+    def close(self):
+        for p in self._peers:
+            lib().t8b200_shared_close(C.c_void_p(p))
+        self._peers = []
+        if self.ptr:
+            lib().t8b200_shared_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class PointerTables:
+    """`[var][rank] -> pointer` device tables built from raw integer pointers (peer-mapped or own)."""
+
+    def __init__(self, ptrs_by_var_rank, device):
+        torch = _torch()
+        host = torch.tensor(ptrs_by_var_rank, dtype=torch.int64)
+        assert host.shape[0] == NVAR
+        self.table = host.to(device)
+        self.host = (C.c_void_p * NVAR)()
+        for k in range(NVAR):
+            self.host[k] = self.table[k].data_ptr()
 
 
 def init_kelvin_helmholtz(dim, centers, u, stream=None):

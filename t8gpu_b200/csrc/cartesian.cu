@@ -19,7 +19,8 @@ namespace {
 
 struct Geo {
   int     dim, level, nranks, rank;
-  int64_t N, lo, hi;
+  int     b[3];       // trees per axis ("brick" of unit trees, periodic over the whole brick); tree id = x + bx (y + by z)
+  int64_t N, lo, hi;  // N = global element count; elements are ordered by tree, Morton inside a tree
 };
 
 __host__ __device__ inline int64_t part_off(int64_t N, int P, int p) {
@@ -44,18 +45,35 @@ __device__ inline int64_t encode(const int c[3], int dim, int level) {
     for (int d = 0; d < dim; d++) m |= (int64_t)((c[d] >> b) & 1) << (dim * b + d);
   return m;
 }
+// global element id -> brick-global cell coordinates
+__device__ inline void gdecode(const Geo& g, int64_t m, int c[3]) {
+  const int64_t per = (int64_t)1 << (g.dim * g.level);
+  int64_t       t   = m / per;
+  decode(m - t * per, g.dim, g.level, c);
+  int tc[3] = {(int)(t % g.b[0]), (int)((t / g.b[0]) % g.b[1]), (int)(t / ((int64_t)g.b[0] * g.b[1]))};
+  for (int d = 0; d < g.dim; d++) c[d] += tc[d] << g.level;
+}
+__device__ inline int64_t gencode(const Geo& g, const int c[3]) {
+  const int ext = 1 << g.level;
+  int       tc[3] = {0, 0, 0}, lc[3] = {0, 0, 0};
+  for (int d = 0; d < g.dim; d++) { tc[d] = c[d] >> g.level; lc[d] = c[d] & (ext - 1); }
+  int64_t t = tc[0] + (int64_t)g.b[0] * (tc[1] + (int64_t)g.b[1] * tc[2]);
+  return (t << (g.dim * g.level)) + encode(lc, g.dim, g.level);
+}
 __device__ inline int64_t neighbor(const Geo& g, const int c[3], int face) {
   int n[3] = {c[0], c[1], c[2]};
-  int ax = face >> 1, ext = 1 << g.level;
-  n[ax]  = (n[ax] + ((face & 1) ? 1 : ext - 1)) & (ext - 1);
-  return encode(n, g.dim, g.level);
+  int ax = face >> 1, ext = g.b[ax] << g.level;
+  n[ax] += (face & 1) ? 1 : -1;
+  if (n[ax] < 0) n[ax] += ext;
+  if (n[ax] >= ext) n[ax] -= ext;
+  return gencode(g, n);
 }
 
 __global__ void count_ghost_candidates(Geo g, unsigned long long* counter, int64_t* cand) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.hi - g.lo) return;
   int c[3];
-  decode(g.lo + e, g.dim, g.level, c);
+  gdecode(g, g.lo + e, c);
   for (int f = 0; f < 2 * g.dim; f++) {
     int64_t n = neighbor(g, c, f);
     if (n < g.lo || n >= g.hi) {
@@ -82,7 +100,7 @@ __global__ void faces_kernel(Geo g, const int64_t* __restrict__ ghosts, int64_t 
   int64_t e  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nl) return;
   int c[3];
-  decode(g.lo + e, g.dim, g.level, c);
+  gdecode(g, g.lo + e, c);
   int64_t o = MODE ? cnt[e] : 0, xo = MODE ? xcnt[e] : 0;
   double  h    = ldexp(1.0, -g.level);
   T       area = (T)(g.dim == 3 ? h * h : h);
@@ -126,7 +144,7 @@ __global__ void elements_kernel(Geo g, const int64_t* __restrict__ ghosts, int64
   int64_t i  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nl) {
     int c[3];
-    decode(g.lo + i, g.dim, g.level, c);
+    gdecode(g, g.lo + i, c);
     double h = ldexp(1.0, -g.level);
     ranks[i]   = g.rank;
     indices[i] = (int32_t)i;
@@ -241,20 +259,27 @@ int kh_impl(int dim, int64_t n, const T* centers, T* const* u, void* stream) {
 
 extern "C" {
 
-int t8b200_cartesian_uniform_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int level, int nranks, int rank,
-                                          void* stream) {
-  if (!out || (dim != 2 && dim != 3) || level < 0 || dim * level > 40 || nranks < 1 || rank < 0 || rank >= nranks)
+int t8b200_cartesian_brick_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int level, int bx, int by, int bz,
+                                        int nranks, int rank, void* stream) {
+  if (!out || (dim != 2 && dim != 3) || level < 0 || dim * level > 40 || nranks < 1 || rank < 0 || rank >= nranks ||
+      bx < 1 || by < 1 || bz < 1 || (dim == 2 && bz != 1) || bx > 1024 || by > 1024 || bz > 1024)
     return cudaErrorInvalidValue;
   *out = t8b200_cart_conn{};
   Geo g;
   g.dim = dim; g.level = level; g.nranks = nranks; g.rank = rank;
-  g.N  = (int64_t)1 << (dim * level);
+  g.b[0] = bx; g.b[1] = by; g.b[2] = bz;
+  g.N  = ((int64_t)bx * by * bz) << (dim * level);
   g.lo = part_off(g.N, nranks, rank);
   g.hi = part_off(g.N, nranks, rank + 1);
   if (g.hi - g.lo > 0x7fffffff / 8) return cudaErrorInvalidValue;  // t8_locidx_t is 32 bit
   int rc = is_f64 ? build<double>(out, g, (cudaStream_t)stream) : build<float>(out, g, (cudaStream_t)stream);
   if (rc != 0) t8b200_cartesian_connectivity_free(out);
   return rc;
+}
+
+int t8b200_cartesian_uniform_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int level, int nranks, int rank,
+                                          void* stream) {
+  return t8b200_cartesian_brick_connectivity(out, is_f64, dim, level, 1, 1, 1, nranks, rank, stream);
 }
 
 void t8b200_cartesian_connectivity_free(t8b200_cart_conn* c) {

@@ -210,3 +210,57 @@ def test_ragged_and_empty_inputs(cuda):
         sol.set_state(u0)
         sol.iterate(0.01)
         assert rel_linf(sol.state().cpu().numpy(), ref) <= 1e-12
+
+
+def test_brick_2x2x2_equals_cube_one_level_up(cuda):
+    """A (2,2,2) brick of level-L trees is the level-(L+1) cube in the same element order: checks the multi-tree
+    neighbour arithmetic of the device builder against the mini-forest, rank by rank."""
+    import t8gpu_b200
+    L = 3
+    forest = oracle.Forest(3, L + 1)
+    for P in (1, 8):
+        for r in range(P):
+            ref = forest.connectivity(P, r, dtype=np.float64)
+            got = t8gpu_b200.conn_to_host(t8gpu_b200.cartesian_uniform_connectivity(3, L, torch.float64, P, r,
+                                                                                      brick=(2, 2, 2)))
+            for key in ("ranks", "indices", "face_neighbors", "face_normals", "x_face_neighbors", "x_face_normals"):
+                assert np.array_equal(got[key], ref[key]), (key, P, r)
+            # geometry differs by the unit: brick trees are unit cubes, the cube's octants have edge 1/2
+            assert np.array_equal(got["face_areas"], ref["face_areas"] * 4)
+
+
+@pytest.mark.parametrize("brick,P", [((2, 1, 1), 2), ((2, 2, 1), 4)])
+def test_brick_partitions_agree_with_single_rank(cuda, brick, P):
+    """Weak-scaling meshes: P ranks (one tree each, emulated on one device) vs the same brick on one rank."""
+    import t8gpu_b200
+    from t8gpu_b200.solver import NB_STEPS, NVAR
+    L, dt = 3, 0.1 * 2.0 ** -3
+    c1 = t8gpu_b200.cartesian_uniform_connectivity(3, L, torch.float64, 1, 0, brick=brick)
+    n1 = int(c1["n_local"])
+    one = t8gpu_b200.EulerSolver(t8gpu_b200.conn_to_host(c1), c1["volumes"].cpu().numpy(), torch.float64, device=cuda)
+    t8gpu_b200.init_kelvin_helmholtz(3, c1["centroids"], one.variables(one.next))
+    rng = np.random.default_rng(9)
+    u0 = one.state().cpu().numpy() * (1 + 0.02 * rng.uniform(-1, 1, (5, n1)))
+    one.set_state(u0)
+    conns = [t8gpu_b200.cartesian_uniform_connectivity(3, L, torch.float64, P, r, brick=brick) for r in range(P)]
+    ns = [int(c["n_local"]) for c in conns]
+    off = np.concatenate([[0], np.cumsum(ns)])
+    bufs = []
+    for r in range(P):
+        b = torch.zeros((NVAR * NB_STEPS + 1, ns[r]), dtype=torch.float64, device=cuda)
+        b[NVAR * NB_STEPS] = conns[r]["volumes"]
+        b[0:5] = torch.as_tensor(u0[:, off[r]:off[r + 1]]).to(cuda)
+        bufs.append(b)
+    tabs = {s: t8gpu_b200.RankTables([[bufs[r][s * NVAR + k] for k in range(NVAR)] for r in range(P)], cuda)
+            for s in range(NB_STEPS)}
+    plans = [t8gpu_b200.Plan(t8gpu_b200.conn_to_host(c), torch.float64) for c in conns]
+    nxt, prv = 0, 3
+    for it in range(4):
+        one.iterate(dt)
+        nxt, prv = prv, nxt
+        for stage, sin, sout in ((1, prv, 1), (2, 1, 2), (3, 2, nxt)):
+            for r in range(P):
+                v = lambda s: [bufs[r][s * NVAR + k] for k in range(NVAR)]  # noqa: E731
+                plans[r].stage(stage, v(sin), v(prv), v(sout), bufs[r][NVAR * NB_STEPS], dt, in_all=tabs[sin])
+        got = np.concatenate([bufs[r][nxt * NVAR:(nxt + 1) * NVAR].cpu().numpy() for r in range(P)], axis=1)
+        assert rel_linf(got, one.state().cpu().numpy()) <= 1e-12
