@@ -3,26 +3,32 @@
 //   examples/compressible_euler/kernels.cu:24-133,174-290   (ln_mean, kepes_compute_flux, diffusion matrix, rotation)
 //   examples/subgrid/kernels.inl:21-261
 //
-// The reference spends ~680 FP64-pipe instructions per face, which on B200 (64 FP64 lanes / SM /
-// clock) is ~3x above the HBM floor.  This formulation needs ~150, all algebraically exact rewrites (results agree
-// with the reference's evaluation order to rounding, far inside the 1e-12 / 1e-5 tolerances):
+// The reference spends ~680 FP64-pipe instructions per face.  B200 sustains ~57 FP64 FMA lanes per
+// SM per clock (measured, tools/fp64_peak.cu: 16.5 TFMA/s), so at that count the path sits ~4x above its HBM floor and
+// the FP64 pipe, not HBM, is the binding roofline.  This formulation needs ~115 FP64 instructions per axis-aligned
+// face (~125 for a general normal); every rewrite is algebraically exact (results agree with the reference's
+// evaluation order to rounding, far inside the 1e-12 / 1e-5 tolerances):
 //  * rotation-free: the reference builds an orthonormal frame (n,t1,t2) per face (1 sqrt + 3 divides), rotates both
 //    states, evaluates the flux in that frame and rotates back.  Every term of F* and of R D R^T (wR - wL) is either
 //    rotation invariant or a multiple of n / of a vector already known in xyz, so we evaluate directly in xyz with
-//    dot products against n.
-//  * per-cell quantities (rho, v, p, B = rho/p = 2 beta, w = B |v|^2 / 2) are computed once per cell per stage
-//    (one reciprocal) and staged in shared memory instead of being recomputed, with 4 divides, by each face.
+//    dot products against n; for a normal +e_axis (Cartesian forests) the dot products disappear altogether.
+//  * per-cell quantities are computed once per cell per stage (one reciprocal) and staged in shared memory instead
+//    of being recomputed, with 4 divides, by each face.  They are chosen so that no face-level rescaling is left:
+//        rho,  h = v/2,  kp = kappa p,  b = rho/(2p) (the reference's beta),  q = b |v|^2 / 2.
 //  * no log() for the entropy-variable jump: s = log p - kappa log rho is only needed as sR - sL, and
 //    log(aR/aL) = (aR - aL) / ln_mean(aL, aR) is a by-product of the two logarithmic means the flux needs anyway.
 //    The reference calls log 4x per face (kernels.cu:236-237).
 //  * the Ismail-Roe series branch of ln_mean, (aL+aR) * 52.5 / (105 + 35u + 21u^2 + 15u^3) with u = f^2 < 1e-4,
 //    f = (aR-aL)/(aR+aL), is evaluated without its divide: with x = u/3 + u^2/5 + u^3/7 <= 3.4e-5,
-//    mean = (s/2)(1 - x + x^2 - x^3), 1/mean = (2/s)(1 + x), log(aR/aL) = 2 f (1 + x); truncation x^4 < 2e-18.
-//  * the two remaining reciprocals per face, 1/(rhoL+rhoR) and 1/(BL+BR), come from ONE reciprocal of their product;
-//    1/betaMean is 4/(BL+BR) (same quantity), so p1Hat = (rhoL+rhoR)/(BL+BR).
-//  * Fs4's  1/2 (1/((k-1) betaHat) - |vL|^2/2 - |vR|^2/2) + |vbar|^2  collapses to 1/(2 (k-1) betaHat) + vL.vR/2.
+//    mean = (s/2)(1 - x + x^2 - x^3), 1/(2 mean) = (1 + x)/s, log(aR/aL)/2 = f (1 + x); truncation x^4 < 2e-18.
+//    The log branch (strong jumps) is out of line (cold), one test per face for both means.
+//  * the two reciprocals per face, 1/(rhoL+rhoR) and 1/(bL+bR), come from ONE reciprocal of their product.
+//  * the dissipation is linear in the jump J of the entropy variables: it is evaluated on J/2, which removes the
+//    factor 1/2 of  F = F* - 1/2 R D R^T J  and every halving of a half-jump.
+//  * Fs4's  1/2 (1/((k-1) betaHat) - |vL|^2/2 - |vR|^2/2) + |vbar|^2  collapses to 1/(2 (k-1) betaHat) + vL.vR/2,
+//    and HHat = that + 1/(2 betaHat).
 //  * reciprocal / rsqrt seeds from MUFU (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64) + 2 Newton steps: no slow-path
-//    branches; relative error <= ~2 ulp.
+//    branches, no IEEE divide anywhere on the path; relative error <= ~2 ulp.
 //  * the sparse eigenvector matrix R (11 of 25 entries are 0/1) is expanded by hand.
 #pragma once
 #include <cuda_runtime.h>
@@ -36,16 +42,16 @@ namespace t8b200 {
 // Per-cell quantities staged in shared memory (7 values).
 template <typename T>
 struct Cell {
-  T rho, vx, vy, vz, p, B, w;  // B = rho / p ( = 2 beta ),  w = B * |v|^2 / 2
+  T rho, hx, hy, hz, kp, b, q;  // h = v/2, kp = kappa*p, b = rho/(2p), q = b |v|^2 / 2 = 2 b |h|^2
 };
 constexpr int NCELLQ = 7;
 
-template <typename T>
-T8B_HD T fabs_(T x) { return x < T(0) ? -x : x; }
+T8B_HD double fabs_(double x) { return ::fabs(x); }
+T8B_HD float  fabs_(float x) { return ::fabsf(x); }
 template <typename T>
 T8B_HD T fmax_(T a, T b) { return a > b ? a : b; }
 
-// ---- fast reciprocal / rsqrt ------------------------------------------------------------------------------
+// ---- fast reciprocal / sqrt -------------------------------------------------------------------------------
 T8B_HD double fast_rcp(double x) {
 #ifdef __CUDA_ARCH__
   double r;
@@ -61,7 +67,9 @@ T8B_HD double fast_rcp(double x) {
 }
 T8B_HD float fast_rcp(float x) {
 #ifdef __CUDA_ARCH__
-  return __frcp_rn(x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
 #else
   return 1.0f / x;
 #endif
@@ -75,139 +83,163 @@ T8B_HD double fast_sqrt(double x) {
   y         = fma(y, t, y);
   t         = fma(-xh * y, y, 0.5);
   y         = fma(y, t, y);
-  double s  = x * y;
-  return fma(fma(-s, s, x), 0.5 * y, s);
+  return x * y;
 #else
   return std::sqrt(x);
 #endif
 }
 T8B_HD float fast_sqrt(float x) {
 #ifdef __CUDA_ARCH__
-  return __fsqrt_rn(x);
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  float s = x * y;
+  return fmaf(fmaf(-s, s, x), 0.5f * y, s);
 #else
   return std::sqrt(x);
 #endif
 }
 
-// conserved (rho, m, E) -> per-cell quantities.  kernels.cu:54-71, 230-240.
+// conserved (rho, m, E) -> per-cell quantities.  kernels.cu:54-71, 230-240.  23 arithmetic instructions.
 template <typename T>
 T8B_HD Cell<T> to_cell(T rho, T mx, T my, T mz, T e) {
-  Cell<T> q;
-  const T km1 = T(1.4) - T(1);
-  q.rho = rho;
-  // p = (k-1)(e - |m|^2 / (2 rho)) ; one reciprocal serves 1/rho and 1/p
-  T m2  = mx * mx + my * my + mz * mz;
-  T pr  = km1 * (e * rho - T(0.5) * m2);  // = p * rho
-  T r   = fast_rcp(pr * rho);             // 1 / (p rho^2)
-  T sr  = r * pr;                         // 1 / rho = (p rho) / (p rho^2)
-  T sp  = r * rho * rho;                  // 1 / p   = rho^2 / (p rho^2)
-  q.vx  = sr * mx;
-  q.vy  = sr * my;
-  q.vz  = sr * mz;
-  q.p   = pr * sr;
-  q.B   = rho * sp;
-  q.w   = T(0.5) * q.B * (q.vx * q.vx + q.vy * q.vy + q.vz * q.vz);
-  return q;
+  Cell<T> c;
+  const T kappa = T(1.4), km1 = T(1.4) - T(1);
+  T hm2 = T(0.5) * (mx * mx + my * my + mz * mz);
+  T pr  = km1 * (e * rho - hm2);       // p * rho
+  T r   = fast_rcp(pr * rho);          // 1 / (p rho^2): one reciprocal serves 1/rho and 1/p
+  T hsr = (T(0.5) * r) * pr;           // 1 / (2 rho)
+  T t   = r * rho;                     // 1 / (p rho)
+  c.rho = rho;
+  c.hx  = hsr * mx;
+  c.hy  = hsr * my;
+  c.hz  = hsr * mz;
+  c.kp  = ((kappa + kappa) * pr) * hsr;  // kappa * p
+  c.b   = (T(0.5) * t) * (rho * rho);    // rho / (2p)
+  c.q   = (T(0.5) * hm2) * t;            // |m|^2 / (4 p rho) = b |v|^2 / 2
+  return c;
 }
 
-// mean = ln_mean(aL,aR) (kernels.cu:24-36), imean = 1/mean, lograt = log(aR/aL), given s = aL+aR, d = aR-aL and
-// is = 1/s.
+// Cold path of the logarithmic mean (kernels.cu:33-35): log(aR/aL), kept out of line so that the face loop stays
+// small and its live values stay in registers.
+#ifdef __CUDACC__
 template <typename T>
-T8B_HD void ln_mean3(T aL, T aR, T s, T d, T is, T& mean, T& imean, T& lograt) {
-  T f = d * is;
-  T u = f * f;
-  if (u < T(1.0e-4)) {
-    T x    = u * (T(1.0 / 3.0) + u * (T(1.0 / 5.0) + u * T(1.0 / 7.0)));
-    T y    = T(1) + x;
-    mean   = T(0.5) * s * (T(1) - x * (T(1) - x * (T(1) - x)));
-    imean  = (is + is) * y;
-    lograt = (f + f) * y;
-  } else {
-    lograt = log(aR / aL);
-    mean   = d / lograt;
-    imean  = lograt / d;
-  }
-}
+__host__ __device__ __noinline__ T log_ratio(T aL, T aR) { return log(aR / aL); }
+#else
+template <typename T>
+inline T log_ratio(T aL, T aR) { return std::log(aR / aL); }
+#endif
 
 // Numerical flux through a face with unit normal n (pointing L -> R), in xyz, NOT scaled by the area.
+// AXIS = 0,1,2: n = +e_AXIS (nx,ny,nz ignored);  AXIS = -1: general unit normal.
 // Returns the wave-speed estimate |uHat| + aHat (kernels.cu:222).
-template <typename T>
-T8B_HD T kepes_flux(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[5]) {
+template <typename T, int AXIS>
+T8B_HD T kepes_flux_n(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[5]) {
   const T kappa = T(1.4);
   const T km1   = kappa - T(1);
-  const T half  = T(0.5);
+  const T ikm1  = T(1) / km1;
+  const T c3 = T(1.0 / 3.0), c5 = T(1.0 / 5.0), c7 = T(1.0 / 7.0);
 
-  T sr = L.rho + R.rho, dr = R.rho - L.rho;
-  T sB = L.B + R.B, dB = R.B - L.B;
-  T rr  = fast_rcp(sr * sB);
-  T isr = rr * sB, isB = rr * sr;
+  const T sr = L.rho + R.rho, dr = R.rho - L.rho;
+  const T sb = L.b + R.b, db = R.b - L.b;
+  const T rr  = fast_rcp(sr * sb);
+  const T isr = rr * sb, isb = rr * sr;
+  const T hs  = T(0.5) * sr;
 
-  T rhoHat, irhoHat, dlogrho, BHat, iBHat, dlogB;
-  ln_mean3(L.rho, R.rho, sr, dr, isr, rhoHat, irhoHat, dlogrho);
-  ln_mean3(L.B, R.B, sB, dB, isB, BHat, iBHat, dlogB);
-  (void)BHat;
+  // logarithmic means (series branch), kernels.cu:24-36
+  const T fr = dr * isr, ur = fr * fr;
+  const T fb = db * isb, ub = fb * fb;
+  const T xr = ur * (c3 + ur * (c5 + ur * c7));
+  const T xb = ub * (c3 + ub * (c5 + ub * c7));
+  T rhoHat = hs * (T(1) - xr * (T(1) - xr * (T(1) - xr)));
+  T hir    = isr * xr + isr;   // 1 / (2 rhoHat)
+  T hlr    = fr * xr + fr;     // log(rhoR/rhoL) / 2
+  T hib    = isb * xb + isb;   // 1 / (2 betaHat)
+  T hlb    = fb * xb + fb;     // log(betaR/betaL) / 2
+  if (!(fmax_(ur, ub) < T(1.0e-4))) {  // strong jump: the reference's log branch
+    if (!(ur < T(1.0e-4))) {
+      const T lr = log_ratio(L.rho, R.rho);
+      rhoHat = dr * fast_rcp(lr);
+      hlr    = T(0.5) * lr;
+      hir    = hlr * fast_rcp(dr);
+    }
+    if (!(ub < T(1.0e-4))) {
+      const T lb = log_ratio(L.b, R.b);
+      hlb = T(0.5) * lb;
+      hib = hlb * fast_rcp(db);
+    }
+  }
 
-  T ax = half * (L.vx + R.vx), ay = half * (L.vy + R.vy), az = half * (L.vz + R.vz);  // averaged velocity
-  T uHat = ax * nx + ay * ny + az * nz;
-  T vv   = ax * ax + ay * ay + az * az;
-  T dLR  = half * (L.vx * R.vx + L.vy * R.vy + L.vz * R.vz);
-  T aHat = fast_sqrt((kappa * half) * (L.p + R.p) * irhoHat);
-  // 1/betaHat = 2/BHat ;  kappa/(2 (k-1) betaHat) = kappa/(k-1) * iBHat
-  T ibk   = iBHat / km1;            // 1 / (2 (k-1) betaHat)
-  T HHat  = kappa * ibk + dLR;      // kernels.cu:82
-  T p1Hat = sr * isB;               // (rhoMean/2) / betaMean, kernels.cu:83
+  const T ax = L.hx + R.hx, ay = L.hy + R.hy, az = L.hz + R.hz;  // averaged velocity
+  const T uHat = AXIS == 0 ? ax : AXIS == 1 ? ay : AXIS == 2 ? az : ax * nx + ay * ny + az * nz;
+  const T vv   = ax * ax + ay * ay + az * az;
+  const T hvv  = T(0.5) * vv;
+  const T dhh  = L.hx * R.hx + L.hy * R.hy + L.hz * R.hz;        // vL.vR / 4
+  const T aHat = fast_sqrt((L.kp + R.kp) * hir);                 // sqrt(kappa (pL+pR)/2 / rhoHat), kernels.cu:80
+  const T ibk  = hib * ikm1;                                     // 1 / (2 (k-1) betaHat)
+  const T tt   = T(2) * dhh + ibk;                               // 1/(2(k-1) betaHat) + vL.vR/2
+  const T HHat = tt + hib;                                       // kernels.cu:82
+  const T p1Hat = hs * isb;                                      // (rhoMean/2) / betaMean, kernels.cu:83
 
   // entropy-conservative part, kernels.cu:86-92
-  T F0  = rhoHat * uHat;
-  T Fs4 = F0 * (ibk + dLR) + uHat * p1Hat;
+  const T F0  = rhoHat * uHat;
+  const T Fs4 = F0 * tt + uHat * p1Hat;
 
-  // jump of the entropy variables, kernels.cu:227-266
-  T J0 = dlogrho + dlogB / km1 - (R.w - L.w);
-  T Jx = R.B * R.vx - L.B * L.vx, Jy = R.B * R.vy - L.B * L.vy, Jz = R.B * R.vz - L.B * L.vz;
-  T J4 = -dB;
+  // HALF the jump of the entropy variables, kernels.cu:227-266:  J0, 2*(jx,jy,jz), -db
+  const T J0 = hlr + ikm1 * hlb - (R.q - L.q);
+  const T jx = R.b * R.hx - L.b * L.hx, jy = R.b * R.hy - L.b * L.hy, jz = R.b * R.hz - L.b * L.hz;
+  const T aj = ax * jx + ay * jy + az * jz;
+  const T jn = AXIS == 0 ? jx : AXIS == 1 ? jy : AXIS == 2 ? jz : nx * jx + ny * jy + nz * jz;
+  const T g  = T(2) * jn - uHat * db;
 
-  T vJ = ax * Jx + ay * Jy + az * Jz;
-  T Jn = nx * Jx + ny * Jy + nz * Jz;
-  T g  = Jn + uHat * J4;
+  // R^T J scaled by D (kernels.cu:114-132, 267-270)
+  const T b  = T(2) * aj + J0;
+  const T c  = b - HHat * db;
+  const T e  = aHat * g;
+  const T a1 = b - hvv * db;
+  const T au = fabs_(uHat);
+  const T d0 = fabs_(uHat - aHat) * (rhoHat * (T(0.5) / kappa)) * (c - e);
+  const T d4 = fabs_(uHat + aHat) * (rhoHat * (T(0.5) / kappa)) * (c + e);
+  const T d1 = au * (rhoHat * (km1 / kappa)) * a1;
+  const T D2 = au * p1Hat;
 
-  // R^T J, scaled by D (kernels.cu:114-132, 267-270)
-  T b  = J0 + vJ;
-  T c  = b + HHat * J4;
-  T e  = aHat * g;
-  T a1 = b + half * vv * J4;
-  T rk = rhoHat * (half / kappa);
-  T d0 = fabs_(uHat - aHat) * rk * (c - e);
-  T d4 = fabs_(uHat + aHat) * rk * (c + e);
-  T au = fabs_(uHat);
-  T d1 = au * (T(2) * km1) * rk * a1;
-  T D2 = au * p1Hat;
-
-  // R (D R^T J), kernels.cu:272-275.  t = tangential part of (Jm + vbar J4).
-  T sum = d0 + d1 + d4;
-  T dif = aHat * (d4 - d0);
-  T ds4 = HHat * (d0 + d4) + uHat * dif + half * vv * d1 + D2 * (vJ + vv * J4 - uHat * g);
-  // momentum: Fs_m - 1/2 (sum vbar + dif n + D2 (Jm + vbar J4 - n g))  =  (F0 - sum/2 - D2 J4/2) vbar
-  //                                                                        + (p1Hat - dif/2 + D2 g/2) n - D2/2 Jm
-  T hD2 = half * D2;
-  T ca  = F0 - half * sum - hD2 * J4;
-  T cn  = p1Hat - half * dif + hD2 * g;
-
-  F[0] = F0 - half * sum;
-  F[1] = ca * ax + cn * nx - hD2 * Jx;
-  F[2] = ca * ay + cn * ny - hD2 * Jy;
-  F[3] = ca * az + cn * nz - hD2 * Jz;
-  F[4] = Fs4 - half * ds4;
+  // R (D R^T J), kernels.cu:272-275
+  const T s04 = d0 + d4;
+  const T sum = s04 + d1;
+  const T dif = aHat * (d4 - d0);
+  const T inr = (T(2) * aj - vv * db) - uHat * g;
+  F[0] = F0 - sum;
+  F[4] = (((Fs4 - HHat * s04) - uHat * dif) - hvv * d1) - D2 * inr;
+  // momentum: Fs_m - (sum vbar + dif n + D2 (Jm + vbar J4 - n g)) = (F0 - sum + D2 db) vbar + (p1Hat - dif + D2 g) n
+  //                                                                  - 2 D2 (jx,jy,jz)
+  const T ca = F[0] + D2 * db;
+  const T cn = (p1Hat - dif) + D2 * g;
+  const T D22 = D2 + D2;
+  if (AXIS == 0) {
+    F[1] = (ca * ax - D22 * jx) + cn; F[2] = ca * ay - D22 * jy; F[3] = ca * az - D22 * jz;
+  } else if (AXIS == 1) {
+    F[1] = ca * ax - D22 * jx; F[2] = (ca * ay - D22 * jy) + cn; F[3] = ca * az - D22 * jz;
+  } else if (AXIS == 2) {
+    F[1] = ca * ax - D22 * jx; F[2] = ca * ay - D22 * jy; F[3] = (ca * az - D22 * jz) + cn;
+  } else {
+    F[1] = (ca * ax - D22 * jx) + cn * nx; F[2] = (ca * ay - D22 * jy) + cn * ny; F[3] = (ca * az - D22 * jz) + cn * nz;
+  }
   return au + aHat;
+}
+
+// general-normal entry point used by the reference-shaped kernels
+template <typename T>
+T8B_HD T kepes_flux(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[5]) {
+  return kepes_flux_n<T, -1>(L, R, nx, ny, nz, F);
 }
 
 // wall boundary: right state = left state with the normal velocity mirrored (kernels.cu:371-375)
 template <typename T>
 T8B_HD Cell<T> mirror(const Cell<T>& L, T nx, T ny, T nz) {
   Cell<T> R  = L;
-  T       vn = L.vx * nx + L.vy * ny + L.vz * nz;
-  R.vx -= T(2) * vn * nx;
-  R.vy -= T(2) * vn * ny;
-  R.vz -= T(2) * vn * nz;
+  T       hn = L.hx * nx + L.hy * ny + L.hz * nz;
+  R.hx -= T(2) * hn * nx;
+  R.hy -= T(2) * hn * ny;
+  R.hz -= T(2) * hn * nz;
   return R;
 }
 

@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256) sg_inner_kernel(int64_t ne, const T* __re
   const int64_t g  = e * S + c;
   if (on) {
     Cell<T> q = to_cell(u.p[0][g], u.p[1][g], u.p[2][g], u.p[3][g], u.p[4][g]);
-    cq[0][tid] = q.rho; cq[1][tid] = q.vx; cq[2][tid] = q.vy; cq[3][tid] = q.vz; cq[4][tid] = q.p;
-    cq[5][tid] = q.B;   cq[6][tid] = q.w;
+    cq[0][tid] = q.rho; cq[1][tid] = q.hx; cq[2][tid] = q.hy; cq[3][tid] = q.hz; cq[4][tid] = q.kp;
+    cq[5][tid] = q.b;   cq[6][tid] = q.q;
   }
   __syncthreads();
   T surface = T(0);
@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256) sg_inner_kernel(int64_t ne, const T* __re
     if (on && ijk[ax] < 3) {
       Cell<T> L, R;
       int a = tid, b = tid + st[ax];
-      L.rho = cq[0][a]; L.vx = cq[1][a]; L.vy = cq[2][a]; L.vz = cq[3][a]; L.p = cq[4][a]; L.B = cq[5][a]; L.w = cq[6][a];
-      R.rho = cq[0][b]; R.vx = cq[1][b]; R.vy = cq[2][b]; R.vz = cq[3][b]; R.p = cq[4][b]; R.B = cq[5][b]; R.w = cq[6][b];
+      L.rho = cq[0][a]; L.hx = cq[1][a]; L.hy = cq[2][a]; L.hz = cq[3][a]; L.kp = cq[4][a]; L.b = cq[5][a]; L.q = cq[6][a];
+      R.rho = cq[0][b]; R.hx = cq[1][b]; R.hy = cq[2][b]; R.hz = cq[3][b]; R.kp = cq[4][b]; R.b = cq[5][b]; R.q = cq[6][b];
       T F[5];
       kepes_flux(L, R, ax == 0 ? T(1) : T(0), ax == 1 ? T(1) : T(0), ax == 2 ? T(1) : T(0), F);
 #pragma unroll
@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(256, MINB) sg_fused_kernel(const __grid_consta
     for (int v = 0; v < 5; v++) u[v] = A.in[v][g];
     Cell<T> q = to_cell(u[0], u[1], u[2], u[3], u[4]);
     int     s = el * PS + pslot(i + 1, j + 1, k + 1);
-    cq[0 * CS + s] = q.rho; cq[1 * CS + s] = q.vx; cq[2 * CS + s] = q.vy; cq[3 * CS + s] = q.vz;
-    cq[4 * CS + s] = q.p;   cq[5 * CS + s] = q.B;  cq[6 * CS + s] = q.w;
+    cq[0 * CS + s] = q.rho; cq[1 * CS + s] = q.hx; cq[2 * CS + s] = q.hy; cq[3 * CS + s] = q.hz;
+    cq[4 * CS + s] = q.kp;   cq[5 * CS + s] = q.b;  cq[6 * CS + s] = q.q;
     if (c == 0) {
       T edge  = cbrt(A.vol[e]) / T(4);   // kernels.inl:352-354
       ain[el] = edge * edge;
@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(256, MINB) sg_fused_kernel(const __grid_consta
       q = sg_load_remote(A, A.multi ? A.nrk[he * 6 + d] : 0, g);
     }
     int s = hel * PS + pslot_ax(ax, up ? 5 : 0, a, b);
-    cq[0 * CS + s] = q.rho; cq[1 * CS + s] = q.vx; cq[2 * CS + s] = q.vy; cq[3 * CS + s] = q.vz;
-    cq[4 * CS + s] = q.p;   cq[5 * CS + s] = q.B;  cq[6 * CS + s] = q.w;
+    cq[0 * CS + s] = q.rho; cq[1 * CS + s] = q.hx; cq[2 * CS + s] = q.hy; cq[3 * CS + s] = q.hz;
+    cq[4 * CS + s] = q.kp;   cq[5 * CS + s] = q.b;  cq[6 * CS + s] = q.q;
   }
   __syncthreads();
 
@@ -376,10 +376,10 @@ __global__ void __launch_bounds__(256, MINB) sg_fused_kernel(const __grid_consta
     if (kd != 3) {
       int sl = fel * PS + pslot_ax(ax, p, a, b), sr = fel * PS + pslot_ax(ax, p + 1, a, b);
       Cell<T> L, R;
-      L.rho = cq[0 * CS + sl]; L.vx = cq[1 * CS + sl]; L.vy = cq[2 * CS + sl]; L.vz = cq[3 * CS + sl];
-      L.p   = cq[4 * CS + sl]; L.B  = cq[5 * CS + sl]; L.w  = cq[6 * CS + sl];
-      R.rho = cq[0 * CS + sr]; R.vx = cq[1 * CS + sr]; R.vy = cq[2 * CS + sr]; R.vz = cq[3 * CS + sr];
-      R.p   = cq[4 * CS + sr]; R.B  = cq[5 * CS + sr]; R.w  = cq[6 * CS + sr];
+      L.rho = cq[0 * CS + sl]; L.hx = cq[1 * CS + sl]; L.hy = cq[2 * CS + sl]; L.hz = cq[3 * CS + sl];
+      L.kp   = cq[4 * CS + sl]; L.b  = cq[5 * CS + sl]; L.q  = cq[6 * CS + sl];
+      R.rho = cq[0 * CS + sr]; R.hx = cq[1 * CS + sr]; R.hy = cq[2 * CS + sr]; R.hz = cq[3 * CS + sr];
+      R.kp   = cq[4 * CS + sr]; R.b  = cq[5 * CS + sr]; R.q  = cq[6 * CS + sr];
       kepes_flux(L, R, nx, ny, nz, F);
       area = (p == 0 || p == 4) ? A.aout[fe * 6 + d] : ain[fel];
     } else {
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(256, MINB) sg_fused_kernel(const __grid_consta
       const int up = p == 4;
       int       so = fel * PS + pslot_ax(ax, up ? 4 : 1, a, b);
       Cell<T> O;
-      O.rho = cq[0 * CS + so]; O.vx = cq[1 * CS + so]; O.vy = cq[2 * CS + so]; O.vz = cq[3 * CS + so];
-      O.p   = cq[4 * CS + so]; O.B  = cq[5 * CS + so]; O.w  = cq[6 * CS + so];
+      O.rho = cq[0 * CS + so]; O.hx = cq[1 * CS + so]; O.hy = cq[2 * CS + so]; O.hz = cq[3 * CS + so];
+      O.kp   = cq[4 * CS + so]; O.b  = cq[5 * CS + so]; O.q  = cq[6 * CS + so];
       const int row = A.nid[fe * 6 + d], qq = (a >> 1) + 2 * (b >> 1);
       const int64_t nb0 = (int64_t)A.fine_id[row * 4 + qq] * 64;
       const int     rk  = A.multi ? A.fine_rk[row * 4 + qq] : 0;
