@@ -8,9 +8,10 @@
 //   and the thrust::reduce of solver.cu:213-217.
 //
 // Plan ("tile plan", built once per connectivity by t8b200_plan_create): per chunk of EC = 256 consecutive elements
-//   header   8 x int32: halo_off, face_off, nh | nfc << 16, e0 | e1 << 16, e2, ovf_off_base, ovf_ent_base, area
-//   halo     sorted unique elements outside the chunk that share a face with it (slot EC + h)
-//   faces    one 32-bit record slotL | slotR << 16 per face touching the chunk.
+//   header   8 x int32: -, -, nh | nfc << 16, e0 | e1 << 16, e2, ovf_off_base, ovf_ent_base, area
+//   halo     sorted unique elements outside the chunk that share a face with it (slot EC + h); fixed stride HS per
+//            chunk (padding = -1), so the indices can be requested without waiting for the header
+//   faces    one 32-bit record slotL | slotR << 16 per face touching the chunk, fixed stride FS per chunk.
 //            Cartesian forests ("cmp": every normal +-e_axis, <= 256 distinct areas): records are put in canonical
 //            orientation (normal = +e_axis, sides swapped where the stored normal was -e_axis) and grouped by axis,
 //            [0,e0) x, [e0,e1) y, [e1,e2) z, then wall faces [e2,nfc) with the outward normal coded in the slotR field;
@@ -20,7 +21,9 @@
 //            Elements with more than 8 faces (hanging faces on several sides) continue in a per-chunk overflow CSR.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/t8gpu_b200.h"
@@ -43,6 +46,7 @@ struct t8b200_plan {
   int     ms = 0, mf = 0;  // compile-time stride variant selected for the kernel
   int64_t dev_bytes = 0, n_records = 0, n_halo = 0;
   int     cmp = 0, n_areas = 0;
+  int     hs = 0, fs = 0;  // per-chunk strides of the halo and face arrays
   // device arrays
   int32_t*  hdr       = nullptr;  // 8 per chunk
   int32_t*  halo_elem = nullptr;  // index into the owner's arrays
@@ -66,6 +70,7 @@ struct FusedArgs {
   const T *       fnx, *fny, *fnz, *farea;
   const T*        area_tab;
   int             n_areas;
+  int             hs, fs;
   const uint4*    ell;
   const uint16_t* ovf_off;
   const uint16_t* ovf_ent;
@@ -103,6 +108,14 @@ __device__ __forceinline__ void gather_entry(const T* fl, unsigned en, T acc[5])
   for (int k = 0; k < 5; k++) acc[k] = fma(sg, fl[k * MF + j], acc[k]);
 }
 
+// bulk L2 prefetch of [p, p + bytes): 16-byte granules, address aligned down (a hint; used on the state rows inside
+// [0, n_local) and on plan arrays, which upload() pads)
+__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
+  const unsigned long long a = (unsigned long long)p & ~15ull;
+  bytes = (bytes + (unsigned)((unsigned long long)p & 15ull)) & ~15u;
+  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
+}
+
 // CTA = one chunk of EC consecutive elements.  MS / MF: compile-time strides of the shared-memory SoA arrays
 // (slots = EC own + halo; faces), so every shared access is base + index*sizeof(T) + immediate.
 //   phase 0: conserved -> per-cell quantities for the chunk's own elements (coalesced) and its halo (gather)
@@ -120,63 +133,83 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   const int64_t e   = (int64_t)c * EC + tid;
   const bool    own = e < A.n_local;
 
-  // ---- phase 0: issue every independent global load of the prologue first
+  // ---- phase 0: issue every independent global load of the prologue first.  The halo indices and the first face
+  // record sit at fixed strides, so nothing here waits for the chunk header.
   const int4 h0v = __ldg(A.hdr + 2 * c), h1v = __ldg(A.hdr + 2 * c + 1);
-  T u0 = T(1), u1 = T(0), u2 = T(0), u3 = T(0), u4 = T(1);
+  const int64_t hb = (int64_t)c * A.hs, fb = (int64_t)c * A.fs;
+  T   u0 = T(1), u1 = T(0), u2 = T(0), u3 = T(0), u4 = T(1);
+  int hidx = -1, hrk = 0;
+  if (tid < A.hs) {
+    hidx = A.halo_elem[hb + tid];
+    if (A.multi) hrk = A.halo_rank[hb + tid];
+  }
   if (own) {
     u0 = A.in[0][e]; u1 = A.in[1][e]; u2 = A.in[2][e]; u3 = A.in[3][e]; u4 = A.in[4][e];
   }
-  const int stage_ = A.stage;
-  (void)stage_;
-  const int h0 = h0v.x, f0 = h0v.y;
-  const int nh = h0v.z & 0xFFFF, nfc = (unsigned)h0v.z >> 16;
-  const int e0 = h0v.w & 0xFFFF, e1 = (unsigned)h0v.w >> 16, e2 = h1v.x;
-  const int area_idx = h1v.w;
   // first face record of this thread (consumed in phase 1; its latency hides behind phase 0)
   uint32_t lr_n = 0;
-  if (tid < nfc) lr_n = A.face_lr[f0 + tid];
+  if (tid < A.fs) lr_n = A.face_lr[fb + tid];
+  if (tid < 8) {  // phase-2 operands of this chunk -> L2 now, so that their loads before the barrier are L2 hits
+    const int64_t  b0 = (int64_t)c * EC;
+    const unsigned n0 = (unsigned)min((int64_t)EC, A.n_local - b0);
+    if (tid < 5) { if (A.stage != 1) prefetch_l2(A.prev[tid] + b0, n0 * sizeof(T)); }
+    else if (tid == 5) prefetch_l2(A.vol + b0, n0 * sizeof(T));
+    else if (tid == 6) prefetch_l2(A.ell + b0, n0 * sizeof(uint4));
+  }
   if (CMP && tid < A.n_areas) atab[tid] = A.area_tab[tid];
 
   if (own) store_cell<T, MS>(cq, tid, to_cell(u0, u1, u2, u3, u4));
-  for (int h = tid; h < nh; h += EC) {
-    const int idx = A.halo_elem[h0 + h];
-    T         a0, a1, a2, a3, a4;
-    if (A.multi) {
-      const int rk = A.halo_rank[h0 + h];
-      a0 = A.in_all[0][rk][idx]; a1 = A.in_all[1][rk][idx]; a2 = A.in_all[2][rk][idx];
-      a3 = A.in_all[3][rk][idx]; a4 = A.in_all[4][rk][idx];
-    } else {
-      a0 = A.in[0][idx]; a1 = A.in[1][idx]; a2 = A.in[2][idx]; a3 = A.in[3][idx]; a4 = A.in[4][idx];
+  for (int h = tid; h < A.hs; h += EC) {
+    if (h >= EC) {  // only plans with more than EC halo entries in some chunk (adaptive meshes)
+      hidx = A.halo_elem[hb + h];
+      if (A.multi) hrk = A.halo_rank[hb + h];
     }
-    store_cell<T, MS>(cq, EC + h, to_cell(a0, a1, a2, a3, a4));
+    if (hidx >= 0) {
+      T a0, a1, a2, a3, a4;
+      if (A.multi) {
+        a0 = A.in_all[0][hrk][hidx]; a1 = A.in_all[1][hrk][hidx]; a2 = A.in_all[2][hrk][hidx];
+        a3 = A.in_all[3][hrk][hidx]; a4 = A.in_all[4][hrk][hidx];
+      } else {
+        a0 = A.in[0][hidx]; a1 = A.in[1][hidx]; a2 = A.in[2][hidx]; a3 = A.in[3][hidx]; a4 = A.in[4][hidx];
+      }
+      store_cell<T, MS>(cq, EC + h, to_cell(a0, a1, a2, a3, a4));
+    }
   }
+  const int  nfc = (unsigned)h0v.z >> 16;
+  const int  e0 = h0v.w & 0xFFFF, e1 = (unsigned)h0v.w >> 16, e2 = h1v.x;
+  const int  area_idx  = h1v.w;
+  const bool want_smax = A.speed_max != nullptr;
   __syncthreads();
 
   // ---- phase 1: software-pipelined over this thread's faces (record j+EC is in flight while j is evaluated)
   T smax = T(0);
   if (CMP) {
-    const bool uniform = area_idx >= 0;
-    for (int j = tid; j < e2; j += EC) {
-      const uint32_t lr = lr_n;
-      if (j + EC < nfc) lr_n = A.face_lr[f0 + j + EC];
-      const Cell<T> L = load_cell<T, MS>(cq, lr & 0xFFFFu);
-      const Cell<T> R = load_cell<T, MS>(cq, lr >> 16);
-      T F[5], s;
-      if (j < e0) s = kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
-      else if (j < e1) s = kepes_flux_n<T, 1>(L, R, T(0), T(0), T(0), F);
-      else s = kepes_flux_n<T, 2>(L, R, T(0), T(0), T(0), F);
-      smax = fmax_(smax, s);
-      if (!uniform) {
-        const T ar = atab[A.face_ai[f0 + j]];
+    // SCALE = false: every face of the chunk has the same area, applied once per element in phase 2
+    auto interior = [&](auto scale_tag) {
+      constexpr bool SCALE = decltype(scale_tag)::value;
+      for (int j = tid; j < e2; j += EC) {
+        const uint32_t lr = lr_n;
+        if (j + EC < nfc) lr_n = A.face_lr[fb + j + EC];
+        const Cell<T> L = load_cell<T, MS>(cq, lr & 0xFFFFu);
+        const Cell<T> R = load_cell<T, MS>(cq, lr >> 16);
+        T F[5], s;
+        if (j < e0) s = kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
+        else if (j < e1) s = kepes_flux_n<T, 1>(L, R, T(0), T(0), T(0), F);
+        else s = kepes_flux_n<T, 2>(L, R, T(0), T(0), T(0), F);
+        if (want_smax) smax = fmax_(smax, s);
+        if (SCALE) {
+          const T ar = atab[A.face_ai[fb + j]];
 #pragma unroll
-        for (int k = 0; k < 5; k++) F[k] *= ar;
+          for (int k = 0; k < 5; k++) F[k] *= ar;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) fl[k * MF + j] = F[k];
       }
-#pragma unroll
-      for (int k = 0; k < 5; k++) fl[k * MF + j] = F[k];
-    }
+    };
+    if (area_idx >= 0) interior(std::false_type{}); else interior(std::true_type{});
     // wall faces: slotR field = 0xFFF8 | (axis << 1 | sign of the outward normal)
     for (int j = e2 + tid; j < nfc; j += EC) {
-      const uint32_t lr   = A.face_lr[f0 + j];
+      const uint32_t lr   = A.face_lr[fb + j];
       const int      code = (lr >> 16) & 7;
       const T        sg   = (code & 1) ? T(1) : T(-1);
       const int      ax   = code >> 1;
@@ -185,8 +218,8 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       const Cell<T> R = mirror(L, nx, ny, nz);
       T F[5];
       smax = fmax_(smax, kepes_flux_n<T, -1>(L, R, nx, ny, nz, F));
-      if (!uniform) {
-        const T ar = atab[A.face_ai[f0 + j]];
+      if (area_idx < 0) {
+        const T ar = atab[A.face_ai[fb + j]];
 #pragma unroll
         for (int k = 0; k < 5; k++) F[k] *= ar;
       }
@@ -195,12 +228,12 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     }
   } else {
     T nx_n = T(0), ny_n = T(0), nz_n = T(0), ar_n = T(0);
-    if (tid < nfc) { nx_n = A.fnx[f0 + tid]; ny_n = A.fny[f0 + tid]; nz_n = A.fnz[f0 + tid]; ar_n = A.farea[f0 + tid]; }
+    if (tid < nfc) { nx_n = A.fnx[fb + tid]; ny_n = A.fny[fb + tid]; nz_n = A.fnz[fb + tid]; ar_n = A.farea[fb + tid]; }
     for (int j = tid; j < nfc; j += EC) {
       const uint32_t lr = lr_n;
       const T        nx = nx_n, ny = ny_n, nz = nz_n, ar = ar_n;
       if (j + EC < nfc) {
-        const int g = f0 + j + EC;
+        const int64_t g = fb + j + EC;
         lr_n = A.face_lr[g]; nx_n = A.fnx[g]; ny_n = A.fny[g]; nz_n = A.fnz[g]; ar_n = A.farea[g];
       }
       const int     sr = lr >> 16;
@@ -213,19 +246,21 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     }
   }
 
-  // ---- phase 2 operands are requested BEFORE the barrier so their latency overlaps the wait.  The element's own
-  // conserved values are read again (L1/L2 hit) instead of being carried in 10 registers through the face loop.
+  // ---- phase 2: the element->face table, the volume and the old states are requested BEFORE the barrier so their
+  // latency overlaps the wait.  The element's own conserved values are read again (L1/L2 hit) instead of being
+  // carried in 10 registers through the face loop, and combined with U^n right away (5 live values, not 10).
   const int stage = A.stage;
   uint4     el = make_uint4(~0u, ~0u, ~0u, ~0u);
-  T         vol = T(1), uin[5], pv[5];
+  T         vol = T(1), base[5] = {T(0), T(0), T(0), T(0), T(0)};
   if (own) {
     el  = A.ell[e];
     vol = A.vol[e];
 #pragma unroll
-    for (int k = 0; k < 5; k++) uin[k] = A.in[k][e];
+    for (int k = 0; k < 5; k++) base[k] = A.in[k][e];
     if (stage != 1) {
+      const T cp = stage == 2 ? T(0.75) : T(0.33333333333333), ci = stage == 2 ? T(0.25) : T(0.66666666666666);
 #pragma unroll
-      for (int k = 0; k < 5; k++) pv[k] = A.prev[k][e];
+      for (int k = 0; k < 5; k++) base[k] = cp * A.prev[k][e] + ci * base[k];
     }
   }
   __syncthreads();
@@ -248,14 +283,8 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     if (stage == 2) sc *= T(0.25);
     if (stage == 3) sc *= T(0.66666666666666);
     if (CMP && area_idx >= 0) sc *= atab[area_idx];
-    if (stage == 1) {
 #pragma unroll
-      for (int k = 0; k < 5; k++) A.out[k][e] = uin[k] + sc * acc[k];
-    } else {
-      const T cp = stage == 2 ? T(0.75) : T(0.33333333333333), ci = stage == 2 ? T(0.25) : T(0.66666666666666);
-#pragma unroll
-      for (int k = 0; k < 5; k++) A.out[k][e] = cp * pv[k] + ci * uin[k] + sc * acc[k];
-    }
+    for (int k = 0; k < 5; k++) A.out[k][e] = base[k] + sc * acc[k];
   }
 
   if (A.speed_max) {
@@ -273,7 +302,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 template <typename T>
 static T* upload(const std::vector<T>& v, int64_t& bytes, cudaError_t& err) {
   T*     d = nullptr;
-  size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+  size_t n = std::max<size_t>(v.size(), 1) * sizeof(T) + 32;  // slack for 16-byte granular prefetch hints
   if (err != cudaSuccess) return nullptr;
   err = cudaMalloc(&d, n);
   if (err != cudaSuccess) return nullptr;
@@ -360,21 +389,24 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
     }
   }
 
-  std::vector<int32_t>  hdr((size_t)nchunks * 8, 0), halo_elem, halo_rank;
-  std::vector<uint32_t> face_lr(nrec);
-  std::vector<uint8_t>  face_ai(cmp ? nrec : 0);
-  std::vector<T>        fnx(cmp ? 0 : nrec), fny(cmp ? 0 : nrec), fnz(cmp ? 0 : nrec), far(cmp ? 0 : nrec);
+  int max_faces = 0;
+  for (int c = 0; c < nchunks; c++) max_faces = std::max(max_faces, cnt[c + 1]);
+  if (max_faces > 32767) return cudaErrorInvalidValue;
+  const int     FS   = (max_faces + 31) / 32 * 32;  // per-chunk stride of the face arrays
+  const int64_t nfix = (int64_t)nchunks * FS;
+  std::vector<int32_t>  hdr((size_t)nchunks * 8, 0), halo_elem, halo_rank, halo_cnt(nchunks, 0);
+  std::vector<uint32_t> face_lr(nfix, 0);
+  std::vector<uint8_t>  face_ai(cmp ? nfix : 0, 0);
+  std::vector<T>        fnx(cmp ? 0 : nfix), fny(cmp ? 0 : nfix), fnz(cmp ? 0 : nfix), far(cmp ? 0 : nfix);
   std::vector<uint16_t> ell((size_t)nchunks * EC * ELL, 0xFFFF), ovf_off, ovf_ent;
   std::vector<int32_t>  halo_tmp;
   std::vector<int64_t>  order;   // records of the chunk in kernel order
   std::vector<std::vector<uint16_t>> per_el(EC);
-  int max_halo = 0, max_faces = 0;
+  int max_halo = 0;
   for (int c = 0; c < nchunks; c++) {
     const int64_t e0 = (int64_t)c * EC, e1 = std::min<int64_t>(e0 + EC, n_local);
     const int64_t r0 = face_off[c], r1 = face_off[c + 1];
     const int     nfc = (int)(r1 - r0);
-    max_faces = std::max(max_faces, nfc);
-    if (nfc > 32767) return cudaErrorInvalidValue;
     // halo = endpoints outside the chunk, sorted + unique
     halo_tmp.clear();
     for (int64_t q = r0; q < r1; q++) {
@@ -389,8 +421,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
     if (EC + nh >= 0xFFF0) return cudaErrorInvalidValue;
     max_halo = std::max(max_halo, nh);
     int32_t* H = &hdr[(size_t)c * 8];
-    H[0] = (int32_t)halo_elem.size();
-    H[1] = (int32_t)r0;
+    halo_cnt[c] = nh;
     H[2] = nh | (nfc << 16);
     for (int h = 0; h < nh; h++) {
       int32_t id = halo_tmp[h];
@@ -428,7 +459,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
     int  area0 = -1;
     bool uniform = cmp;
     for (int j = 0; j < nfc; j++) {
-      const int64_t f = order[j], q = r0 + j;
+      const int64_t f = order[j], q = (int64_t)c * FS + j;
       int32_t       l, r;
       endpoints(f, l, r);
       const T* nrm;
@@ -472,10 +503,25 @@ static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t 
       ovf_off.push_back((uint16_t)n);
     }
   }
+  // halo lists at a fixed stride per chunk, padded with -1
+  const int HS = std::max(32, (max_halo + 31) / 32 * 32);
+  {
+    std::vector<int32_t> he((size_t)nchunks * HS, -1), hr(P->multi ? (size_t)nchunks * HS : 0, 0);
+    size_t src = 0;
+    for (int c = 0; c < nchunks; c++)
+      for (int h = 0; h < halo_cnt[c]; h++, src++) {
+        he[(size_t)c * HS + h] = halo_elem[src];
+        if (P->multi) hr[(size_t)c * HS + h] = halo_rank[src];
+      }
+    P->n_halo = (int64_t)halo_elem.size();
+    halo_elem.swap(he);
+    halo_rank.swap(hr);
+  }
+  P->hs = HS;
+  P->fs = FS;
   P->max_halo   = max_halo;
   P->max_faces  = max_faces;
   P->n_records  = nrec;
-  P->n_halo     = (int64_t)halo_elem.size();
   // stride variants compiled into the library (slots, faces)
   P->ms = EC + max_halo <= 512 ? 512 : 1280;
   P->mf = max_faces <= 1024 ? 1024 : 2560;
@@ -516,7 +562,7 @@ static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStrea
 template <typename T, bool CMP>
 static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
   // resident CTAs per SM are bounded by shared memory; tell ptxas so it can size the register budget
-  constexpr int B0 = sizeof(T) == 8 ? 3 : 6;
+  constexpr int B0 = sizeof(T) == 8 ? 3 : 5;
   if (P->ms == 512 && P->mf == 1024) return launch_variant<T, 512, 1024, B0, CMP>(P, A, st);
   if (P->ms == 512 && P->mf == 2560) return launch_variant<T, 512, 2560, 1, CMP>(P, A, st);
   if (P->ms == 1280 && P->mf == 1024) return launch_variant<T, 1280, 1024, 1, CMP>(P, A, st);
@@ -535,7 +581,7 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
   A.halo_elem = P->halo_elem; A.halo_rank = P->halo_rank;
   A.face_lr = P->face_lr; A.face_ai = P->face_ai;
   A.fnx = (const T*)P->fnx; A.fny = (const T*)P->fny; A.fnz = (const T*)P->fnz; A.farea = (const T*)P->farea;
-  A.area_tab = (const T*)P->area_tab; A.n_areas = P->n_areas;
+  A.area_tab = (const T*)P->area_tab; A.n_areas = P->n_areas; A.hs = P->hs; A.fs = P->fs;
   A.ell = P->ell; A.ovf_off = P->ovf_off; A.ovf_ent = P->ovf_ent;
   for (int k = 0; k < 5; k++) {
     A.in[k]     = in[k];

@@ -14,7 +14,7 @@ for l in out.splitlines():
     m = re.match(r'\s+/\*([0-9a-f]+)\*/\s+(.*?);', l)
     if m: ins.append((int(m.group(1), 16), m.group(2).strip()))
 def opc(s):
-    return re.match(r'(@!?U?P\d+\s+)?([A-Z0-9_]+)', s).group(2)
+    m = re.match(r'(@!?U?P[T\d]+\s+)?([A-Z0-9_]+)', s); return m.group(2) if m else s.split()[0]
 print('total', len(ins), dict(collections.Counter(opc(s) for _, s in ins).most_common(14)))
 idx = {a: i for i, (a, _) in enumerate(ins)}
 for i, (a, s) in enumerate(ins):
