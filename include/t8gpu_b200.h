@@ -139,22 +139,27 @@ int t8b200_fused_stage_f64(const t8b200_plan* plan, int stage, const double* con
                            const double* const* const* in_all, const double* const* prev, double* const* out,
                            const double* vol, double dt, double* speed_max_dev, void* stream);
 
-/* Fused Subgrid<4,4,4> stage (3-D): replaces compute_inner_fluxes + compute_boundary_fluxes + compute_outer_fluxes +
- * subgrid::SSP_3RK_step{1,2,3} of one stage (examples/subgrid/solver.inl:156-194) by ONE kernel without atomics.
- * The plan is built from the SubgridMeshConnectivityAccessor arrays (HOST pointers; normals with 3 components per
- * face, offsets 3 per face; x_*: optional faces whose ghost neighbour is owned by a lower rank, as in
- * t8b200_plan_create). */
+/* Fused Subgrid<4,4,4> (dim = 3) / Subgrid<4,4> (dim = 2) stage: replaces compute_inner_fluxes +
+ * compute_boundary_fluxes + compute_outer_fluxes + subgrid::SSP_3RK_step{1,2,3} of one stage
+ * (examples/subgrid/solver.inl:156-194) by ONE kernel without atomics: the subgrid mesh is handed to the tile-plan
+ * stage kernel at cell level (256 consecutive cells per chunk).
+ * The plan is built from the SubgridMeshConnectivityAccessor arrays (HOST pointers; normals with `dim` components per
+ * face, offsets `dim` per face, t8gpu/mesh/subgrid_mesh_manager.h:108-126) and the per-element volumes (host, n_local;
+ * they define the area of the faces between the cells of an element, kernels.inl:352-354, :542-544).
+ * x_*: optional faces whose ghost neighbour is owned by a lower rank, as in t8b200_plan_create. */
 typedef struct t8b200_subgrid_plan t8b200_subgrid_plan;
-int  t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
-                                int32_t nb, const int32_t* face_neighbors, const void* face_normals,
+int  t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local, int64_t n_ghost,
+                                int32_t nf, int32_t nb, const int32_t* face_neighbors, const void* face_normals,
                                 const void* face_surfaces, const int32_t* face_level_difference,
-                                const int32_t* face_neighbor_offset, const int32_t* ranks, const int32_t* indices,
-                                int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
-                                const void* x_face_surfaces, const int32_t* x_level_difference,
-                                const int32_t* x_neighbor_offset);
+                                const int32_t* face_neighbor_offset, const void* volumes, const int32_t* ranks,
+                                const int32_t* indices, int32_t n_xfaces, const int32_t* x_face_neighbors,
+                                const void* x_face_normals, const void* x_face_surfaces,
+                                const int32_t* x_level_difference, const int32_t* x_neighbor_offset);
 void t8b200_subgrid_plan_destroy(t8b200_subgrid_plan* plan);
+/* as t8b200_plan_info, counted in cells */
+int t8b200_subgrid_plan_info(const t8b200_subgrid_plan* plan, int64_t info[8]);
 /* in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's cell arrays; in_all: tables for ghost reads or NULL;
- * vol: device, per ELEMENT (cell volume = vol/64, ssp_runge_kutta.inl:116). */
+ * vol: device, per ELEMENT (cell volume = vol/64 resp. vol/16, ssp_runge_kutta.inl:116). */
 int t8b200_subgrid_fused_stage_f32(const t8b200_subgrid_plan* plan, int stage, const float* const* in,
                                    const float* const* const* in_all, const float* const* prev, float* const* out,
                                    const float* vol, float dt, void* stream);

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libt8gpu_b200.so")
+# T8GPU_B200_LIB: alternative build of the same ABI (A/B timing of kernel variants in one gpurun call)
+LIB_PATH = os.environ.get("T8GPU_B200_LIB") or os.path.join(_HERE, "libt8gpu_b200.so")
 _LIB = None
 
 NVAR = 5
@@ -217,7 +218,7 @@ class Plan:
 
 
 class SubgridPlan:
-    """Per-element neighbour tables for the fused Subgrid<4,4,4> stage kernel (3-D)."""
+    """Cell-level tile plan for the fused Subgrid<4,4,4> / Subgrid<4,4> stage kernel."""
 
     def __init__(self, conn, volumes, dtype):
         import numpy as np
@@ -225,8 +226,8 @@ class SubgridPlan:
         s, _ = _sfx(dtype)
         npdt = np.float64 if s == "f64" else np.float32
         self.dtype = dtype
-        if int(conn["dim"]) != 3:
-            raise ValueError("the fused subgrid kernel is 3-D (Subgrid<4,4,4>); use mode='unfused' for Subgrid<4,4>")
+        dim = int(conn["dim"])
+        vols = np.ascontiguousarray(volumes, dtype=npdt)
 
         def arr(k, dt):
             v = conn.get(k)
@@ -241,11 +242,15 @@ class SubgridPlan:
                 arr("x_face_areas", npdt), arr("x_level_diff", np.int32), arr("x_offsets", np.int32)]
         h = C.c_void_p()
         check(lib().t8b200_subgrid_plan_create(
-            C.byref(h), int(s == "f64"), C.c_int64(int(conn["n_local"])), C.c_int64(int(conn.get("n_ghost", 0))),
+            C.byref(h), int(s == "f64"), dim, C.c_int64(int(conn["n_local"])), C.c_int64(int(conn.get("n_ghost", 0))),
             int(conn["n_faces"]), int(conn["n_bfaces"]), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]), p(keep[4]),
-            p(keep[5]), p(keep[6]), int(conn.get("n_xfaces", 0)), p(keep[7]), p(keep[8]), p(keep[9]), p(keep[10]),
-            p(keep[11])), "subgrid_plan_create")
+            p(vols), p(keep[5]), p(keep[6]), int(conn.get("n_xfaces", 0)), p(keep[7]), p(keep[8]), p(keep[9]),
+            p(keep[10]), p(keep[11])), "subgrid_plan_create")
         self._h = h
+        info = (C.c_int64 * 8)()
+        check(lib().t8b200_subgrid_plan_info(self._h, info), "subgrid_plan_info")
+        self.info = dict(n_chunks=info[0], max_halo=info[1], max_faces=info[2], smem_bytes=info[3],
+                         device_bytes=info[4], face_records=info[5], halo_entries=info[6], chunk=info[7])
 
     def __del__(self):
         if getattr(self, "_h", None):

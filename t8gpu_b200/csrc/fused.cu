@@ -7,18 +7,7 @@
 //   reflective_boundary_condition (kernels.cu:311-469) + SSP_3RK_step{1,2,3} (ssp_runge_kutta.inl:30-99),
 //   and the thrust::reduce of solver.cu:213-217.
 //
-// Plan ("tile plan", built once per connectivity by t8b200_plan_create): per chunk of EC = 256 consecutive elements
-//   header   8 x int32: -, -, nh | nfc << 16, e0 | e1 << 16, e2, ovf_off_base, ovf_ent_base, area
-//   halo     sorted unique elements outside the chunk that share a face with it (slot EC + h); fixed stride HS per
-//            chunk (padding = -1), so the indices can be requested without waiting for the header
-//   faces    one 32-bit record slotL | slotR << 16 per face touching the chunk, fixed stride FS per chunk.
-//            Cartesian forests ("cmp": every normal +-e_axis, <= 256 distinct areas): records are put in canonical
-//            orientation (normal = +e_axis, sides swapped where the stored normal was -e_axis) and grouped by axis,
-//            [0,e0) x, [e0,e1) y, [e1,e2) z, then wall faces [e2,nfc) with the outward normal coded in the slotR field;
-//            a chunk whose faces all have the same area carries it in the header (applied once per element).
-//            General meshes: normals and areas as four T arrays, wall = slotR 0xFFFF.
-//   ell      per element 8 x uint16 entries (face_local << 1 | side), 0xFFFF = none; one 128-bit load per thread.
-//            Elements with more than 8 faces (hanging faces on several sides) continue in a per-chunk overflow CSR.
+// The plan (connectivity re-laid out per chunk) is described and built in tile_plan.cuh.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -29,36 +18,9 @@
 #include "../../include/t8gpu_b200.h"
 #include "common.cuh"
 #include "euler_flux.cuh"
+#include "tile_plan.cuh"
 
 using namespace t8b200;
-
-static constexpr int EC  = 256;  // elements per chunk == threads per CTA
-static constexpr int ELL = 8;    // face entries per element held in the fixed-width table
-
-struct t8b200_plan {
-  int     is_f64     = 0;
-  int64_t n_local    = 0;
-  int     n_chunks   = 0;
-  int     max_halo   = 0;
-  int     max_faces  = 0;
-  int     multi      = 0;  // has ghosts -> needs rank tables
-  size_t  smem_bytes = 0;
-  int     ms = 0, mf = 0;  // compile-time stride variant selected for the kernel
-  int64_t dev_bytes = 0, n_records = 0, n_halo = 0;
-  int     cmp = 0, n_areas = 0;
-  int     hs = 0, fs = 0;  // per-chunk strides of the halo and face arrays
-  // device arrays
-  int32_t*  hdr       = nullptr;  // 8 per chunk
-  int32_t*  halo_elem = nullptr;  // index into the owner's arrays
-  int32_t*  halo_rank = nullptr;  // owner rank (multi only)
-  uint32_t* face_lr   = nullptr;
-  uint8_t*  face_ai   = nullptr;  // cmp: area index per record (read only by chunks with mixed areas)
-  void *    fnx = nullptr, *fny = nullptr, *fnz = nullptr, *farea = nullptr;  // general geometry (cmp == 0)
-  void*     area_tab = nullptr;
-  uint4*    ell      = nullptr;  // n_chunks * EC
-  uint16_t* ovf_off  = nullptr;  // (EC + 1) per chunk that has overflow entries
-  uint16_t* ovf_ent  = nullptr;
-};
 
 template <typename T>
 struct FusedArgs {
@@ -79,6 +41,8 @@ struct FusedArgs {
   const T*        prev[5];
   T*              out[5];
   const T*        vol;
+  int             vol_shift;
+  T               vol_scale;
   T               dt;
   T*              speed_max;
   int64_t         n_local;
@@ -121,22 +85,26 @@ __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
 //   phase 0: conserved -> per-cell quantities for the chunk's own elements (coalesced) and its halo (gather)
 //   phase 1: every face touching the chunk: flux from the staged cells -> smem
 //   phase 2: per element: signed gather of its faces' fluxes (fixed order: deterministic), RK combination, store
-template <typename T, int MS, int MF, int MINB, bool CMP>
+template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
 __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_constant__ FusedArgs<T> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* cq = reinterpret_cast<T*>(smem_raw);  // [7][MS]
   T* fl = cq + NCELLQ * MS;                // [5][MF]
   __shared__ T atab[CMP ? 256 : 1];
   __shared__ T red[EC / 32];
-  const int     c   = blockIdx.x;
-  const int     tid = threadIdx.x;
-  const int64_t e   = (int64_t)c * EC + tid;
-  const bool    own = e < A.n_local;
+  const int c   = blockIdx.x;
+  const int tid = threadIdx.x;
 
   // ---- phase 0: issue every independent global load of the prologue first.  The halo indices and the first face
   // record sit at fixed strides, so nothing here waits for the chunk header.
   const int4 h0v = __ldg(A.hdr + 2 * c), h1v = __ldg(A.hdr + 2 * c + 1);
-  const int64_t hb = (int64_t)c * A.hs, fb = (int64_t)c * A.fs;
+  // chunk c covers elements [c * EC, ...) unless blocks were split (SPLIT: the header says, and only then do the
+  // loads of the own elements wait for it).  Element, halo and face indices fit 32 bits (checked by the plan).
+  const int e0c = SPLIT ? h0v.x : c * EC;
+  const int ecn = SPLIT ? h0v.y : min(EC, (int)A.n_local - c * EC);
+  const int  e   = e0c + tid;
+  const bool own = tid < ecn;
+  const int  hb = c * A.hs, fb = c * A.fs;
   T   u0 = T(1), u1 = T(0), u2 = T(0), u3 = T(0), u4 = T(1);
   int hidx = -1, hrk = 0;
   if (tid < A.hs) {
@@ -150,10 +118,10 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   uint32_t lr_n = 0;
   if (tid < A.fs) lr_n = A.face_lr[fb + tid];
   if (tid < 8) {  // phase-2 operands of this chunk -> L2 now, so that their loads before the barrier are L2 hits
-    const int64_t  b0 = (int64_t)c * EC;
-    const unsigned n0 = (unsigned)min((int64_t)EC, A.n_local - b0);
+    const int      b0 = e0c;
+    const unsigned n0 = (unsigned)ecn;
     if (tid < 5) { if (A.stage != 1) prefetch_l2(A.prev[tid] + b0, n0 * sizeof(T)); }
-    else if (tid == 5) prefetch_l2(A.vol + b0, n0 * sizeof(T));
+    else if (tid == 5) prefetch_l2(A.vol + (b0 >> A.vol_shift), ((n0 - 1) >> A.vol_shift) * sizeof(T) + sizeof(T));
     else if (tid == 6) prefetch_l2(A.ell + b0, n0 * sizeof(uint4));
   }
   if (CMP && tid < A.n_areas) atab[tid] = A.area_tab[tid];
@@ -233,7 +201,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       const uint32_t lr = lr_n;
       const T        nx = nx_n, ny = ny_n, nz = nz_n, ar = ar_n;
       if (j + EC < nfc) {
-        const int64_t g = fb + j + EC;
+        const int g = fb + j + EC;
         lr_n = A.face_lr[g]; nx_n = A.fnx[g]; ny_n = A.fny[g]; nz_n = A.fnz[g]; ar_n = A.farea[g];
       }
       const int     sr = lr >> 16;
@@ -254,7 +222,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   T         vol = T(1), base[5] = {T(0), T(0), T(0), T(0), T(0)};
   if (own) {
     el  = A.ell[e];
-    vol = A.vol[e];
+    vol = A.vol[e >> A.vol_shift] * A.vol_scale;
 #pragma unroll
     for (int k = 0; k < 5; k++) base[k] = A.in[k][e];
     if (stage != 1) {
@@ -299,261 +267,9 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   }
 }
 
-template <typename T>
-static T* upload(const std::vector<T>& v, int64_t& bytes, cudaError_t& err) {
-  T*     d = nullptr;
-  size_t n = std::max<size_t>(v.size(), 1) * sizeof(T) + 32;  // slack for 16-byte granular prefetch hints
-  if (err != cudaSuccess) return nullptr;
-  err = cudaMalloc(&d, n);
-  if (err != cudaSuccess) return nullptr;
-  if (!v.empty()) err = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-  bytes += (int64_t)n;
-  return d;
-}
-
-// axis-aligned unit normal -> axis * 2 + (1 if positive), else -1
-template <typename T>
-static int axis_code(const T* n) {
-  for (int d = 0; d < 3; d++) {
-    T o1 = n[(d + 1) % 3], o2 = n[(d + 2) % 3];
-    if (o1 == T(0) && o2 == T(0) && (n[d] == T(1) || n[d] == T(-1))) return 2 * d + (n[d] > T(0) ? 1 : 0);
-  }
-  return -1;
-}
-
-template <typename T>
-static int plan_build(t8b200_plan* P, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* nbr,
-                      const T* normals, const T* areas, const int32_t* ranks, const int32_t* indices, int32_t nx,
-                      const int32_t* xnbr, const T* xnormals, const T* xareas) {
-  const int nchunks = (int)((n_local + EC - 1) / EC);
-  P->n_local  = n_local;
-  P->n_chunks = nchunks;
-  P->multi    = n_ghost > 0;
-  if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
-
-  // global face ids: [0,nf) interior, [nf,nf+nb) boundary, then the extra partition-boundary faces
-  const int64_t ntot = (int64_t)nf + nb + nx;
-  auto endpoints = [&](int64_t f, int32_t& l, int32_t& r) {
-    if (f < nf) { l = nbr[2 * f]; r = nbr[2 * f + 1]; }
-    else if (f < (int64_t)nf + nb) { l = nbr[2 * (int64_t)nf + (f - nf)]; r = -1; }
-    else { int64_t g = f - nf - nb; l = xnbr[2 * g]; r = xnbr[2 * g + 1]; }
-  };
-  auto geometry = [&](int64_t f, const T*& nrm, T& a) {
-    if (f < (int64_t)nf + nb) { nrm = normals + 3 * f; a = areas[f]; }
-    else { int64_t g = f - nf - nb; nrm = xnormals + 3 * g; a = xareas[g]; }
-  };
-
-  // compressed geometry possible?  (every normal +-e_axis, <= 256 distinct areas)
-  bool                 cmp = true;
-  std::vector<T>       area_tab;
-  std::vector<uint8_t> area_of(ntot);
-  for (int64_t f = 0; f < ntot && cmp; f++) {
-    const T* nrm;
-    T        a;
-    geometry(f, nrm, a);
-    if (axis_code(nrm) < 0) { cmp = false; break; }
-    int ai = -1;
-    for (size_t t = area_tab.size(); t-- > 0;)
-      if (area_tab[t] == a) { ai = (int)t; break; }
-    if (ai < 0) {
-      if (area_tab.size() >= 256) { cmp = false; break; }
-      ai = (int)area_tab.size();
-      area_tab.push_back(a);
-    }
-    area_of[f] = (uint8_t)ai;
-  }
-
-  // bucket faces by chunk (a face between two chunks appears in both)
-  std::vector<int32_t> cnt(nchunks + 1, 0);
-  for (int64_t f = 0; f < ntot; f++) {
-    int32_t l, r;
-    endpoints(f, l, r);
-    int cl = l < n_local ? l / EC : -1, cr = (r >= 0 && r < n_local) ? r / EC : -1;
-    if (cl < 0 && cr < 0) return cudaErrorInvalidValue;
-    if (cl >= 0) cnt[cl + 1]++;
-    if (cr >= 0 && cr != cl) cnt[cr + 1]++;
-  }
-  std::vector<int64_t> face_off(nchunks + 1, 0);
-  for (int c = 0; c < nchunks; c++) face_off[c + 1] = face_off[c] + cnt[c + 1];
-  const int64_t nrec = face_off[nchunks];
-  if (nrec > 0x7FFFFFFF) return cudaErrorInvalidValue;
-  std::vector<int64_t> rec(nrec);
-  {
-    std::vector<int64_t> fill(face_off.begin(), face_off.end() - 1);
-    for (int64_t f = 0; f < ntot; f++) {
-      int32_t l, r;
-      endpoints(f, l, r);
-      int cl = l < n_local ? l / EC : -1, cr = (r >= 0 && r < n_local) ? r / EC : -1;
-      if (cl >= 0) rec[fill[cl]++] = f;
-      if (cr >= 0 && cr != cl) rec[fill[cr]++] = f;
-    }
-  }
-
-  int max_faces = 0;
-  for (int c = 0; c < nchunks; c++) max_faces = std::max(max_faces, cnt[c + 1]);
-  if (max_faces > 32767) return cudaErrorInvalidValue;
-  const int     FS   = (max_faces + 31) / 32 * 32;  // per-chunk stride of the face arrays
-  const int64_t nfix = (int64_t)nchunks * FS;
-  std::vector<int32_t>  hdr((size_t)nchunks * 8, 0), halo_elem, halo_rank, halo_cnt(nchunks, 0);
-  std::vector<uint32_t> face_lr(nfix, 0);
-  std::vector<uint8_t>  face_ai(cmp ? nfix : 0, 0);
-  std::vector<T>        fnx(cmp ? 0 : nfix), fny(cmp ? 0 : nfix), fnz(cmp ? 0 : nfix), far(cmp ? 0 : nfix);
-  std::vector<uint16_t> ell((size_t)nchunks * EC * ELL, 0xFFFF), ovf_off, ovf_ent;
-  std::vector<int32_t>  halo_tmp;
-  std::vector<int64_t>  order;   // records of the chunk in kernel order
-  std::vector<std::vector<uint16_t>> per_el(EC);
-  int max_halo = 0;
-  for (int c = 0; c < nchunks; c++) {
-    const int64_t e0 = (int64_t)c * EC, e1 = std::min<int64_t>(e0 + EC, n_local);
-    const int64_t r0 = face_off[c], r1 = face_off[c + 1];
-    const int     nfc = (int)(r1 - r0);
-    // halo = endpoints outside the chunk, sorted + unique
-    halo_tmp.clear();
-    for (int64_t q = r0; q < r1; q++) {
-      int32_t l, r;
-      endpoints(rec[q], l, r);
-      if (l < e0 || l >= e1) halo_tmp.push_back(l);
-      if (r >= 0 && (r < e0 || r >= e1)) halo_tmp.push_back(r);
-    }
-    std::sort(halo_tmp.begin(), halo_tmp.end());
-    halo_tmp.erase(std::unique(halo_tmp.begin(), halo_tmp.end()), halo_tmp.end());
-    const int nh = (int)halo_tmp.size();
-    if (EC + nh >= 0xFFF0) return cudaErrorInvalidValue;
-    max_halo = std::max(max_halo, nh);
-    int32_t* H = &hdr[(size_t)c * 8];
-    halo_cnt[c] = nh;
-    H[2] = nh | (nfc << 16);
-    for (int h = 0; h < nh; h++) {
-      int32_t id = halo_tmp[h];
-      if (id < n_local) {
-        halo_elem.push_back(id);
-        halo_rank.push_back(ranks ? ranks[id] : 0);
-      } else {
-        halo_elem.push_back(indices[id]);
-        halo_rank.push_back(ranks[id]);
-      }
-    }
-    auto slot_of = [&](int32_t id) -> int {
-      if (id >= e0 && id < e1) return (int)(id - e0);
-      return EC + (int)(std::lower_bound(halo_tmp.begin(), halo_tmp.end(), id) - halo_tmp.begin());
-    };
-    // kernel order of the records: cmp -> x, y, z interior faces, then walls; general -> as enumerated
-    order.assign(rec.begin() + r0, rec.begin() + r1);
-    int seg[4] = {0, 0, 0, 0};
-    if (cmp) {
-      auto key = [&](int64_t f) -> int {
-        int32_t l, r;
-        endpoints(f, l, r);
-        if (r < 0) return 3;
-        const T* nrm;
-        T        a;
-        geometry(f, nrm, a);
-        return axis_code(nrm) >> 1;
-      };
-      std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key(a) < key(b); });
-      for (int64_t f : order) seg[key(f)]++;
-    }
-    H[3] = seg[0] | ((seg[0] + seg[1]) << 16);
-    H[4] = seg[0] + seg[1] + seg[2];
-    for (auto& v : per_el) v.clear();
-    int  area0 = -1;
-    bool uniform = cmp;
-    for (int j = 0; j < nfc; j++) {
-      const int64_t f = order[j], q = (int64_t)c * FS + j;
-      int32_t       l, r;
-      endpoints(f, l, r);
-      const T* nrm;
-      T        a;
-      geometry(f, nrm, a);
-      int sl = slot_of(l), sr = r < 0 ? 0xFFFF : slot_of(r);
-      if (cmp) {
-        const int code = axis_code(nrm);
-        if (r < 0) sr = 0xFFF8 | code;                  // wall: outward normal coded in the slotR field
-        else if (!(code & 1)) std::swap(sl, sr);        // canonical orientation: normal = +e_axis
-        face_ai[q] = area_of[f];
-        if (area0 < 0) area0 = area_of[f];
-        if (area_of[f] != area0) uniform = false;
-      } else {
-        fnx[q] = nrm[0]; fny[q] = nrm[1]; fnz[q] = nrm[2]; far[q] = a;
-      }
-      face_lr[q] = (uint32_t)sl | ((uint32_t)sr << 16);
-      if (sl < EC) per_el[sl].push_back((uint16_t)(j << 1));
-      if (sr < EC) per_el[sr].push_back((uint16_t)((j << 1) | 1));
-    }
-    H[7] = (uniform && area0 >= 0) ? area0 : -1;
-    // fixed-width table + overflow CSR
-    bool overflow = false;
-    for (int i = 0; i < EC; i++) {
-      const auto& v = per_el[i];
-      for (size_t s = 0; s < v.size() && s < (size_t)ELL; s++) ell[((size_t)c * EC + i) * ELL + s] = v[s];
-      if (v.size() > (size_t)ELL) overflow = true;
-    }
-    H[5] = -1;
-    H[6] = 0;
-    if (overflow) {
-      if (ovf_off.size() + EC + 1 > 0x7FFFFFFF || ovf_ent.size() > 0x7FFFFFFF) return cudaErrorInvalidValue;
-      H[5] = (int32_t)ovf_off.size();
-      H[6] = (int32_t)ovf_ent.size();
-      size_t n = 0;
-      for (int i = 0; i < EC; i++) {
-        ovf_off.push_back((uint16_t)n);
-        for (size_t s = ELL; s < per_el[i].size(); s++) { ovf_ent.push_back(per_el[i][s]); n++; }
-      }
-      if (n > 65535) return cudaErrorInvalidValue;
-      ovf_off.push_back((uint16_t)n);
-    }
-  }
-  // halo lists at a fixed stride per chunk, padded with -1
-  const int HS = std::max(32, (max_halo + 31) / 32 * 32);
-  {
-    std::vector<int32_t> he((size_t)nchunks * HS, -1), hr(P->multi ? (size_t)nchunks * HS : 0, 0);
-    size_t src = 0;
-    for (int c = 0; c < nchunks; c++)
-      for (int h = 0; h < halo_cnt[c]; h++, src++) {
-        he[(size_t)c * HS + h] = halo_elem[src];
-        if (P->multi) hr[(size_t)c * HS + h] = halo_rank[src];
-      }
-    P->n_halo = (int64_t)halo_elem.size();
-    halo_elem.swap(he);
-    halo_rank.swap(hr);
-  }
-  P->hs = HS;
-  P->fs = FS;
-  P->max_halo   = max_halo;
-  P->max_faces  = max_faces;
-  P->n_records  = nrec;
-  // stride variants compiled into the library (slots, faces)
-  P->ms = EC + max_halo <= 512 ? 512 : 1280;
-  P->mf = max_faces <= 1024 ? 1024 : 2560;
-  if (EC + max_halo > P->ms || max_faces > P->mf) return cudaErrorInvalidValue;  // chunk too irregular for one CTA
-  P->smem_bytes = sizeof(T) * ((size_t)NCELLQ * P->ms + 5 * (size_t)P->mf);
-  if (P->smem_bytes > 220 * 1024) return cudaErrorInvalidValue;
-
-  cudaError_t err = cudaSuccess;
-  P->hdr       = upload(hdr, P->dev_bytes, err);
-  P->halo_elem = upload(halo_elem, P->dev_bytes, err);
-  if (P->multi) P->halo_rank = upload(halo_rank, P->dev_bytes, err);
-  P->face_lr = upload(face_lr, P->dev_bytes, err);
-  P->cmp     = cmp ? 1 : 0;
-  if (cmp) {
-    P->face_ai  = upload(face_ai, P->dev_bytes, err);
-    P->area_tab = upload(area_tab, P->dev_bytes, err);
-    P->n_areas  = (int)area_tab.size();
-  } else {
-    P->fnx   = upload(fnx, P->dev_bytes, err);
-    P->fny   = upload(fny, P->dev_bytes, err);
-    P->fnz   = upload(fnz, P->dev_bytes, err);
-    P->farea = upload(far, P->dev_bytes, err);
-  }
-  P->ell     = reinterpret_cast<uint4*>(upload(ell, P->dev_bytes, err));
-  P->ovf_off = upload(ovf_off, P->dev_bytes, err);
-  P->ovf_ent = upload(ovf_ent, P->dev_bytes, err);
-  return err;
-}
-
-template <typename T, int MS, int MF, int MINB, bool CMP>
+template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
 static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
-  auto k = fused_stage_kernel<T, MS, MF, MINB, CMP>;
+  auto k = fused_stage_kernel<T, MS, MF, MINB, CMP, SPLIT>;
   T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
   k<<<P->n_chunks, EC, P->smem_bytes, st>>>(A);
   return cudaGetLastError();
@@ -561,12 +277,11 @@ static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStrea
 
 template <typename T, bool CMP>
 static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
-  // resident CTAs per SM are bounded by shared memory; tell ptxas so it can size the register budget
+  // resident CTAs per SM are bounded by shared memory (68 KB fp64 / 34 KB fp32 per CTA); tell ptxas so it can size
+  // the register budget (fp32: 5 CTAs of 48 registers measured faster than 6 of 40)
   constexpr int B0 = sizeof(T) == 8 ? 3 : 5;
-  if (P->ms == 512 && P->mf == 1024) return launch_variant<T, 512, 1024, B0, CMP>(P, A, st);
-  if (P->ms == 512 && P->mf == 2560) return launch_variant<T, 512, 2560, 1, CMP>(P, A, st);
-  if (P->ms == 1280 && P->mf == 1024) return launch_variant<T, 1280, 1024, 1, CMP>(P, A, st);
-  return launch_variant<T, 1280, 2560, 1, CMP>(P, A, st);
+  return P->split ? launch_variant<T, MS, MF, B0, CMP, true>(P, A, st)
+                  : launch_variant<T, MS, MF, B0, CMP, false>(P, A, st);
 }
 
 template <typename T>
@@ -589,12 +304,48 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
     A.prev[k]   = stage > 1 ? prev[k] : in[k];
     A.out[k]    = out[k];
   }
-  A.vol = vol; A.dt = dt; A.speed_max = speed_max; A.n_local = P->n_local;
+  A.vol = vol; A.vol_shift = P->vol_shift; A.vol_scale = (T)P->vol_scale; A.dt = dt; A.speed_max = speed_max; A.n_local = P->n_local;
   A.stage = stage; A.multi = P->multi;
   cudaStream_t st = (cudaStream_t)stream;
   if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), st));
   return P->cmp ? launch_fused<T, true>(P, A, st) : launch_fused<T, false>(P, A, st);
 }
+
+// Face source over the arrays behind MeshConnectivityAccessor<float_type,3> (t8gpu/mesh/mesh_manager.h:159-166):
+// global face ids [0,nf) interior, [nf,nf+nb) boundary, then the extra partition-boundary faces.
+template <typename T>
+struct MeshFaces {
+  int32_t        nf, nb, nx;
+  const int32_t* nbr;
+  const T *      normals, *areas;
+  const int32_t *ranks, *indices, *xnbr;
+  const T *      xnormals, *xareas;
+  int64_t num_faces() const { return (int64_t)nf + nb + nx; }
+  void endpoints(int64_t f, int32_t& l, int32_t& r) const {
+    if (f < nf) { l = nbr[2 * f]; r = nbr[2 * f + 1]; }
+    else if (f < (int64_t)nf + nb) { l = nbr[2 * (int64_t)nf + (f - nf)]; r = -1; }
+    else { int64_t g = f - nf - nb; l = xnbr[2 * g]; r = xnbr[2 * g + 1]; }
+  }
+  void geometry(int64_t f, T nrm[3], T& a) const {
+    const T* n;
+    if (f < (int64_t)nf + nb) { n = normals + 3 * f; a = areas[f]; }
+    else { int64_t g = f - nf - nb; n = xnormals + 3 * g; a = xareas[g]; }
+    nrm[0] = n[0]; nrm[1] = n[1]; nrm[2] = n[2];
+  }
+  void owner(int32_t id, int32_t& rk, int32_t& ix) const { rk = ranks[id]; ix = indices[id]; }
+};
+
+template <typename T>
+int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
+                        const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream) {
+  return fused_stage_impl<T>(P, stage, in, in_all, prev, out, vol, dt, speed_max, stream);
+}
+template int t8b_fused_stage_run<float>(const t8b200_plan*, int, const float* const*, const float* const* const*,
+                                        const float* const*, float* const*, const float*, float, float*, void*);
+template int t8b_fused_stage_run<double>(const t8b200_plan*, int, const double* const*, const double* const* const*,
+                                         const double* const*, double* const*, const double*, double, double*, void*);
+
+void t8b_plan_free(t8b200_plan* P) { t8b200_plan_destroy(P); }
 
 // ============================================================================================================
 // C ABI
@@ -608,12 +359,19 @@ int t8b200_plan_create(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n
   if (!out || n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0) return cudaErrorInvalidValue;
   if ((nf + nb > 0) && (!nbr || !normals || !areas)) return cudaErrorInvalidValue;
   if (nx > 0 && (!xnbr || !xnormals || !xareas)) return cudaErrorInvalidValue;
+  if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
   t8b200_plan* P = new t8b200_plan();
   P->is_f64      = is_f64 ? 1 : 0;
-  int rc = is_f64 ? plan_build<double>(P, n_local, n_ghost, nf, nb, nbr, (const double*)normals, (const double*)areas,
-                                       ranks, indices, nx, xnbr, (const double*)xnormals, (const double*)xareas)
-                  : plan_build<float>(P, n_local, n_ghost, nf, nb, nbr, (const float*)normals, (const float*)areas,
-                                      ranks, indices, nx, xnbr, (const float*)xnormals, (const float*)xareas);
+  int rc;
+  if (is_f64) {
+    MeshFaces<double> src{nf, nb, nx, nbr, (const double*)normals, (const double*)areas, ranks, indices, xnbr,
+                          (const double*)xnormals, (const double*)xareas};
+    rc = plan_build<double>(P, n_local, n_ghost > 0, src);
+  } else {
+    MeshFaces<float> src{nf, nb, nx, nbr, (const float*)normals, (const float*)areas, ranks, indices, xnbr,
+                         (const float*)xnormals, (const float*)xareas};
+    rc = plan_build<float>(P, n_local, n_ghost > 0, src);
+  }
   if (rc != 0) {
     t8b200_plan_destroy(P);
     return rc;

@@ -7,11 +7,14 @@
 //   examples/subgrid/solver.inl:152-266    iterate() schedule
 // Cell (e,i,j,k) of a variable lives at  base[e*S + i + 4j + 16k]  (t8gpu/memory/subgrid_memory_manager.h:35-135).
 #include <algorithm>
+#include <cmath>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/t8gpu_b200.h"
 #include "common.cuh"
 #include "euler_flux.cuh"
+#include "tile_plan.cuh"
 
 using namespace t8b200;
 
@@ -70,7 +73,9 @@ __global__ void __launch_bounds__(256) sg_inner_kernel(int64_t ne, const T* __re
       L.rho = cq[0][a]; L.hx = cq[1][a]; L.hy = cq[2][a]; L.hz = cq[3][a]; L.kp = cq[4][a]; L.b = cq[5][a]; L.q = cq[6][a];
       R.rho = cq[0][b]; R.hx = cq[1][b]; R.hy = cq[2][b]; R.hz = cq[3][b]; R.kp = cq[4][b]; R.b = cq[5][b]; R.q = cq[6][b];
       T F[5];
-      kepes_flux(L, R, ax == 0 ? T(1) : T(0), ax == 1 ? T(1) : T(0), ax == 2 ? T(1) : T(0), F);
+      if (ax == 0) kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
+      else if (ax == 1) kepes_flux_n<T, 1>(L, R, T(0), T(0), T(0), F);
+      else kepes_flux_n<T, 2>(L, R, T(0), T(0), T(0), F);
 #pragma unroll
       for (int v = 0; v < 5; v++) fx[ax][v][tid] = F[v] * surface;
     }
@@ -237,365 +242,206 @@ int t8b200_subgrid_boundary_flux_f64(int dim, int32_t nf, int32_t nb, const int3
 }
 
 // ============================================================================================================
-// 2. fused Subgrid<4,4,4> stage: owner-computes, no atomics, fluxes never reach HBM
+// 2. fused Subgrid<4,4,4> / Subgrid<4,4> stage: owner-computes, no atomics, fluxes never reach HBM
 // ============================================================================================================
 //
-// CTA = 4 consecutive elements (256 cells, one thread per cell).  Each element's cells plus a one-cell halo layer on
-// its 6 faces are staged as a padded 6x6x6 block of per-cell quantities in shared memory.  The halo of a face comes
-// from the same-level neighbour's boundary layer, from the coarser neighbour's cells by injection (exactly the
-// reference's r = anchor + (i*stride)/2 rule, kernels.inl:756-758), or from the mirrored own cell at a wall.  Every
-// face of the 5 planes per axis is then evaluated ONCE per element with the canonical orientation (lower cell = left,
-// normal = +axis): the two elements sharing a face evaluate bit-identical fluxes from the same two cells, so the
-// scheme stays exactly conservative without atomics and is deterministic.  Where the neighbour is FINER (2:1 hanging
-// face seen from the coarse side) the face flux of a coarse boundary cell is the sum of its four fine sub-faces.
-// Replaces inner + boundary + outer + SSP_3RK_step (examples/subgrid/solver.inl:156-194).
+// The subgrid mesh is handed to the tile-plan stage kernel (fused.cu) at CELL level: every cell is an "element" of the
+// plan, a chunk of 256 consecutive cells is 4 hexahedral (16 quadrilateral) elements -- for same-level siblings an
+// 8x8x4 (16x16) box of cells, the same tile shape as on an unstructured Morton-ordered hex (quad) forest.  The face
+// source below enumerates
+//   * the faces between the cells of one element (compute_inner_fluxes, kernels.inl:335-662): normal +e_axis, area
+//     (cbrt(vol)/4)^2 in 3-D (kernels.inl:352-354), sqrt(vol)/4 in 2-D (:542-544);
+//   * 16 (4) cell faces per element face (compute_outer_fluxes, kernels.inl:664-911): left cell from the face normal,
+//     right cell r = anchor + (i * stride) / 2 (kernels.inl:756-758, stride 2 for equal levels, 1 towards a coarser
+//     neighbour: a coarse cell receives its four fine sub-faces as four faces), area face_surface/16 (/4);
+//   * 16 (4) wall faces per boundary face (compute_boundary_fluxes, kernels.inl:913-1107).
+// Both owners of a face evaluate it in the same canonical orientation from the same two cells, so the scheme stays
+// exactly conservative without atomics and is deterministic.  Cell volume = vol[element] / 64 (/16)
+// (ssp_runge_kutta.inl:116).  Replaces inner + boundary + outer + SSP_3RK_step (examples/subgrid/solver.inl:156-194).
 
 struct t8b200_subgrid_plan {
-  int      is_f64 = 0, multi = 0;
-  int64_t  ne = 0, dev_bytes = 0;
-  uint8_t* kind = nullptr;   // ne*6 : 0 wall, 1 same level, 2 coarser, 3 finer
-  uint8_t* quad = nullptr;   // ne*6 : kind 2: quarter of the coarse face (a | b << 1)
-  int32_t* nid  = nullptr;   // ne*6 : neighbour element (index in its owner's arrays) or row of fine_id
-  int32_t* nrk  = nullptr;   // ne*6 : owner rank (multi)
-  void*    aout = nullptr;   // ne*6 : cell-face area of that side ( = face_surface / 16 )
-  int32_t* fine_id = nullptr;  // 4 per hanging coarse face
-  int32_t* fine_rk = nullptr;
-};
-
-template <typename T>
-struct SgFusedArgs {
-  const uint8_t* kind;
-  const uint8_t* quad;
-  const int32_t* nid;
-  const int32_t* nrk;
-  const T*       aout;
-  const int32_t* fine_id;
-  const int32_t* fine_rk;
-  const T*        in[5];
-  const T* const* in_all[5];
-  const T*        prev[5];
-  T*              out[5];
-  const T*        vol;
-  T               dt;
-  int64_t         ne;
-  int             stage, multi;
+  t8b200_plan* plan = nullptr;
+  int          dim  = 3;
 };
 
 namespace {
-constexpr int G   = 4;      // elements per CTA
-constexpr int PS  = 216;    // padded 6^3 slots per element
-constexpr int NFA = 80;     // faces per axis per element (5 planes x 16)
-
-__device__ __forceinline__ int pslot(int i, int j, int k) { return i + 6 * j + 36 * k; }  // padded coords 0..5
-
-// (axis, plane-normal coordinate x, tangential a, b) -> padded coords
-__device__ __forceinline__ int pslot_ax(int ax, int x, int a, int b) {
-  return ax == 0 ? pslot(x, a + 1, b + 1) : (ax == 1 ? pslot(a + 1, x, b + 1) : pslot(a + 1, b + 1, x));
-}
-// cell index inside an element from (axis, x along axis, tangential a, b), unpadded 0..3
-__device__ __forceinline__ int cell_ax(int ax, int x, int a, int b) {
+// cell index inside an element from (axis, x along the axis, tangential a, b)
+inline int cell_ax(int dim, int ax, int x, int a, int b) {
+  if (dim == 2) return ax == 0 ? x + 4 * a : a + 4 * x;
   return ax == 0 ? x + 4 * a + 16 * b : (ax == 1 ? a + 4 * x + 16 * b : a + 4 * b + 16 * x);
 }
+
+template <typename T>
+struct SubgridFaces {
+  int            dim;
+  int64_t        n_local;  // elements
+  int32_t        nf, nb, nx;
+  const int32_t* nbr;
+  const T *      normals, *areas;   // normals: dim components per face
+  const int32_t *ld, *off;          // off: dim components per face
+  const T*       vol;
+  const int32_t *ranks, *indices, *xnbr;
+  const T *      xnormals, *xareas;
+  const int32_t *xld, *xoff;
+  int     S() const { return dim == 3 ? 64 : 16; }
+  int     TPF() const { return dim == 3 ? 16 : 4; }
+  int     IPE() const { return dim * 3 * TPF(); }   // inner faces per element: dim axes x 3 planes x TPF
+  int64_t n_inner() const { return n_local * IPE(); }
+  int64_t num_faces() const { return n_inner() + ((int64_t)nf + nb + nx) * TPF(); }
+
+  // element face F (0..nf+nb+nx), sub-face s -> left / right cell inside their elements
+  void sub_cells(const T* n, const int32_t* o, int dstride, int s, int& lc, int& rc) const {
+    const int i = s & 3, j = s >> 2;
+    int al[3] = {0, 0, 0}, si[3] = {0, 0, 0}, sj[3] = {0, 0, 0};
+    if (n[0] == T(1)) { al[0] = 3; si[1] = 1; sj[2] = 1; }
+    if (n[0] == T(-1)) { si[1] = 1; sj[2] = 1; }
+    if (n[1] == T(1)) { al[1] = 3; si[0] = 1; sj[2] = 1; }
+    if (n[1] == T(-1)) { si[0] = 1; sj[2] = 1; }
+    if (dim == 3) {
+      if (n[2] == T(1)) { al[2] = 3; si[0] = 1; sj[1] = 1; }
+      if (n[2] == T(-1)) { si[0] = 1; sj[1] = 1; }
+    }
+    int l[3], r[3];
+    for (int d = 0; d < 3; d++) {
+      l[d] = al[d] + i * si[d] + j * sj[d];
+      r[d] = (o && d < dim ? o[d] : 0) + dstride * (i * si[d] + j * sj[d]) / 2;
+    }
+    lc = l[0] + 4 * l[1] + 16 * l[2];
+    rc = r[0] + 4 * r[1] + 16 * r[2];
+  }
+  void outer(int64_t g, int64_t& F, int& s, const int32_t*& pn, const T*& n, const T*& ar, const int32_t*& l_d,
+             const int32_t*& o, bool& wall) const {
+    F = g / TPF();
+    s = (int)(g % TPF());
+    wall = false;
+    if (F < nf) { pn = nbr + 2 * F; n = normals + dim * F; ar = areas + F; l_d = ld + F; o = off + dim * F; }
+    else if (F < (int64_t)nf + nb) {
+      wall = true;
+      pn = nbr + 2 * (int64_t)nf + (F - nf); n = normals + dim * F; ar = areas + F; l_d = nullptr; o = nullptr;
+    } else {
+      const int64_t x = F - nf - nb;
+      pn = xnbr + 2 * x; n = xnormals + dim * x; ar = xareas + x; l_d = xld + x; o = xoff + dim * x;
+    }
+  }
+  void endpoints(int64_t f, int32_t& l, int32_t& r) const {
+    if (f < n_inner()) {
+      const int64_t e = f / IPE();
+      const int     q = (int)(f % IPE()), ax = q / (3 * TPF()), t = q % (3 * TPF()), p = t / TPF(), s = t % TPF();
+      l = (int32_t)(e * S() + cell_ax(dim, ax, p, s & 3, s >> 2));
+      r = (int32_t)(e * S() + cell_ax(dim, ax, p + 1, s & 3, s >> 2));
+      return;
+    }
+    int64_t        F;
+    int            s, lc, rc;
+    const int32_t *pn, *l_d, *o;
+    const T *      n, *ar;
+    bool           wall;
+    outer(f - n_inner(), F, s, pn, n, ar, l_d, o, wall);
+    sub_cells(n, o, (l_d && *l_d != 0) ? 1 : 2, s, lc, rc);
+    l = (int32_t)((int64_t)pn[0] * S() + lc);
+    r = wall ? -1 : (int32_t)((int64_t)pn[1] * S() + rc);
+  }
+  void geometry(int64_t f, T nrm[3], T& a) const {
+    nrm[0] = nrm[1] = nrm[2] = T(0);
+    if (f < n_inner()) {
+      const int64_t e  = f / IPE();
+      const int     ax = (int)(f % IPE()) / (3 * TPF());
+      nrm[ax] = T(1);
+      if (dim == 3) {
+        // libm's cbrt is off by an ulp on exact cubes (dyadic Cartesian volumes): take the exact root when there is
+        // one, so that the faces inside an element and between elements get the same area entry
+        T c = std::cbrt(vol[e]);
+        for (T t : {std::nextafter(c, T(0)), std::nextafter(c, T(2) * c)})
+          if (t * t * t == vol[e]) c = t;
+        const T edge = c / T(4);
+        a = edge * edge;
+      } else {
+        a = std::sqrt(vol[e]) / T(4);
+      }
+      return;
+    }
+    int64_t        F;
+    int            s;
+    const int32_t *pn, *l_d, *o;
+    const T *      n, *ar;
+    bool           wall;
+    outer(f - n_inner(), F, s, pn, n, ar, l_d, o, wall);
+    for (int d = 0; d < dim; d++) nrm[d] = n[d];
+    a = *ar / T(TPF());
+  }
+  void owner(int32_t id, int32_t& rk, int32_t& ix) const {
+    const int32_t e = id / S(), c = id % S();
+    rk = ranks[e];
+    ix = indices[e] * S() + c;
+  }
+};
 }  // namespace
 
 template <typename T>
-__device__ __forceinline__ Cell<T> sg_load_remote(const SgFusedArgs<T>& A, int rk, int64_t g) {
-  if (A.multi)
-    return to_cell(A.in_all[0][rk][g], A.in_all[1][rk][g], A.in_all[2][rk][g], A.in_all[3][rk][g], A.in_all[4][rk][g]);
-  return to_cell(A.in[0][g], A.in[1][g], A.in[2][g], A.in[3][g], A.in[4][g]);
-}
-
-template <typename T, int MINB>
-__global__ void __launch_bounds__(256, MINB) sg_fused_kernel(const __grid_constant__ SgFusedArgs<T> A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* cq = reinterpret_cast<T*>(smem_raw);   // [7][G*PS]
-  T* fl = cq + NCELLQ * G * PS;             // [3][5][G*NFA]
-  __shared__ T ain[G];
-  constexpr int CS = G * PS, FS = G * NFA;
-  const int     tid = threadIdx.x;
-  const int64_t e0  = (int64_t)blockIdx.x * G;
-  const int     el  = tid >> 6, c = tid & 63;
-  const int     i = c & 3, j = (c >> 2) & 3, k = c >> 4;
-  const int64_t e   = e0 + el;
-  const bool    on  = e < A.ne;
-
-  // ---- phase 0: own cells (coalesced) ...
-  T u[5] = {T(1), T(0), T(0), T(0), T(1)};
-  if (on) {
-    const int64_t g = e * 64 + c;
-#pragma unroll
-    for (int v = 0; v < 5; v++) u[v] = A.in[v][g];
-    Cell<T> q = to_cell(u[0], u[1], u[2], u[3], u[4]);
-    int     s = el * PS + pslot(i + 1, j + 1, k + 1);
-    cq[0 * CS + s] = q.rho; cq[1 * CS + s] = q.hx; cq[2 * CS + s] = q.hy; cq[3 * CS + s] = q.hz;
-    cq[4 * CS + s] = q.kp;   cq[5 * CS + s] = q.b;  cq[6 * CS + s] = q.q;
-    if (c == 0) {
-      T edge  = cbrt(A.vol[e]) / T(4);   // kernels.inl:352-354
-      ain[el] = edge * edge;
-    }
-  }
-  // ... and the halo layers: 6 sides x 16 cells per element
-  for (int it = tid; it < G * 96; it += 256) {
-    const int     hel = it / 96, r = it % 96, d = r >> 4, a = r & 3, b = (r >> 2) & 3;
-    const int64_t he  = e0 + hel;
-    if (he >= A.ne) continue;
-    const int ax = d >> 1, up = d & 1;
-    const int kd = A.kind[he * 6 + d];
-    if (kd == 3) continue;
-    Cell<T> q;
-    if (kd == 0) {   // wall: mirrored own boundary cell (kernels.inl:169-176)
-      int64_t g = he * 64 + cell_ax(ax, up ? 3 : 0, a, b);
-      q = to_cell(A.in[0][g], A.in[1][g], A.in[2][g], A.in[3][g], A.in[4][g]);
-      q = mirror(q, ax == 0 ? T(1) : T(0), ax == 1 ? T(1) : T(0), ax == 2 ? T(1) : T(0));
-    } else {
-      int na = a, nb = b;
-      if (kd == 2) {
-        int qd = A.quad[he * 6 + d];
-        na = 2 * (qd & 1) + (a >> 1);
-        nb = 2 * (qd >> 1) + (b >> 1);
-      }
-      int64_t g = (int64_t)A.nid[he * 6 + d] * 64 + cell_ax(ax, up ? 0 : 3, na, nb);
-      q = sg_load_remote(A, A.multi ? A.nrk[he * 6 + d] : 0, g);
-    }
-    int s = hel * PS + pslot_ax(ax, up ? 5 : 0, a, b);
-    cq[0 * CS + s] = q.rho; cq[1 * CS + s] = q.hx; cq[2 * CS + s] = q.hy; cq[3 * CS + s] = q.hz;
-    cq[4 * CS + s] = q.kp;   cq[5 * CS + s] = q.b;  cq[6 * CS + s] = q.q;
-  }
-  __syncthreads();
-
-  // ---- phase 1: 3 axes x 5 planes x 16 faces per element, canonical orientation
-  for (int it = tid; it < G * 240; it += 256) {
-    const int     fel = it / 240, r = it % 240, ax = r / 80, p = (r % 80) >> 4, a = r & 3, b = (r >> 2) & 3;
-    const int64_t fe  = e0 + fel;
-    if (fe >= A.ne) continue;
-    const T nx = ax == 0 ? T(1) : T(0), ny = ax == 1 ? T(1) : T(0), nz = ax == 2 ? T(1) : T(0);
-    T F[5];
-    T area;
-    const int d  = p == 0 ? 2 * ax : 2 * ax + 1;
-    const int kd = (p == 0 || p == 4) ? A.kind[fe * 6 + d] : 1;
-    if (kd != 3) {
-      int sl = fel * PS + pslot_ax(ax, p, a, b), sr = fel * PS + pslot_ax(ax, p + 1, a, b);
-      Cell<T> L, R;
-      L.rho = cq[0 * CS + sl]; L.hx = cq[1 * CS + sl]; L.hy = cq[2 * CS + sl]; L.hz = cq[3 * CS + sl];
-      L.kp   = cq[4 * CS + sl]; L.b  = cq[5 * CS + sl]; L.q  = cq[6 * CS + sl];
-      R.rho = cq[0 * CS + sr]; R.hx = cq[1 * CS + sr]; R.hy = cq[2 * CS + sr]; R.hz = cq[3 * CS + sr];
-      R.kp   = cq[4 * CS + sr]; R.b  = cq[5 * CS + sr]; R.q  = cq[6 * CS + sr];
-      kepes_flux(L, R, nx, ny, nz, F);
-      area = (p == 0 || p == 4) ? A.aout[fe * 6 + d] : ain[fel];
-    } else {
-      // finer neighbours: this coarse boundary cell faces 2x2 fine cells of neighbour quarter (a/2, b/2)
-      const int up = p == 4;
-      int       so = fel * PS + pslot_ax(ax, up ? 4 : 1, a, b);
-      Cell<T> O;
-      O.rho = cq[0 * CS + so]; O.hx = cq[1 * CS + so]; O.hy = cq[2 * CS + so]; O.hz = cq[3 * CS + so];
-      O.kp   = cq[4 * CS + so]; O.b  = cq[5 * CS + so]; O.q  = cq[6 * CS + so];
-      const int row = A.nid[fe * 6 + d], qq = (a >> 1) + 2 * (b >> 1);
-      const int64_t nb0 = (int64_t)A.fine_id[row * 4 + qq] * 64;
-      const int     rk  = A.multi ? A.fine_rk[row * 4 + qq] : 0;
-#pragma unroll
-      for (int v = 0; v < 5; v++) F[v] = T(0);
-#pragma unroll
-      for (int sb = 0; sb < 2; sb++)
-#pragma unroll
-        for (int sa = 0; sa < 2; sa++) {
-          Cell<T> N = sg_load_remote(A, rk, nb0 + cell_ax(ax, up ? 0 : 3, 2 * (a & 1) + sa, 2 * (b & 1) + sb));
-          T       Fs[5];
-          if (up) kepes_flux(O, N, nx, ny, nz, Fs); else kepes_flux(N, O, nx, ny, nz, Fs);
-#pragma unroll
-          for (int v = 0; v < 5; v++) F[v] += Fs[v];
-        }
-      area = A.aout[fe * 6 + d];
-    }
-    const int fs = fel * NFA + p * 16 + a + 4 * b;
-#pragma unroll
-    for (int v = 0; v < 5; v++) fl[(ax * 5 + v) * FS + fs] = F[v] * area;
-  }
-
-  // phase-2 operands requested before the barrier
-  const int stage = A.stage;
-  T pv[5] = {u[0], u[1], u[2], u[3], u[4]};
-  T vol   = T(1);
-  if (on) {
-    vol = A.vol[e] / T(64);   // ssp_runge_kutta.inl:116
-    if (stage != 1) {
-      const int64_t g = e * 64 + c;
-#pragma unroll
-      for (int v = 0; v < 5; v++) pv[v] = A.prev[v][g];
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2: each cell gathers its 6 faces (+lower, -upper), RK combination, store
-  if (on) {
-    const int64_t g  = e * 64 + c;
-    const int     bx = el * NFA + j + 4 * k, by = el * NFA + i + 4 * k, bz = el * NFA + i + 4 * j;
-    T             sc = rk_scale<T>(stage, A.dt, vol);
-#pragma unroll
-    for (int v = 0; v < 5; v++) {
-      T acc = fl[(0 * 5 + v) * FS + bx + 16 * i] - fl[(0 * 5 + v) * FS + bx + 16 * (i + 1)];
-      acc += fl[(1 * 5 + v) * FS + by + 16 * j] - fl[(1 * 5 + v) * FS + by + 16 * (j + 1)];
-      acc += fl[(2 * 5 + v) * FS + bz + 16 * k] - fl[(2 * 5 + v) * FS + bz + 16 * (k + 1)];
-      A.out[v][g] = rk_apply<T>(stage, pv[v], u[v], acc, sc);
-    }
-  }
-}
-
-template <typename T>
-static T* sg_upload(const std::vector<T>& v, int64_t& bytes, cudaError_t& err) {
-  T*     d = nullptr;
-  size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
-  if (err != cudaSuccess) return nullptr;
-  err = cudaMalloc(&d, n);
-  if (err != cudaSuccess) return nullptr;
-  if (!v.empty()) err = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-  bytes += (int64_t)n;
-  return d;
-}
-
-template <typename T>
-static int sg_plan_build(t8b200_subgrid_plan* P, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
+static int sg_plan_build(t8b200_subgrid_plan* SP, int dim, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
                          const int32_t* nbr, const T* normals, const T* areas, const int32_t* level_diff,
-                         const int32_t* offsets, const int32_t* ranks, const int32_t* indices, int32_t nx,
+                         const int32_t* offsets, const T* vol, const int32_t* ranks, const int32_t* indices, int32_t nx,
                          const int32_t* xnbr, const T* xnormals, const T* xareas, const int32_t* xld,
                          const int32_t* xoff) {
-  P->ne    = n_local;
-  P->multi = n_ghost > 0;
-  if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
-  std::vector<uint8_t> kind(n_local * 6, 255), quad(n_local * 6, 0);
-  std::vector<int32_t> nid(n_local * 6, 0), nrk(n_local * 6, 0), fine_id, fine_rk;
-  std::vector<T>       aout(n_local * 6, T(0));
-  auto owner = [&](int32_t id, int32_t& rk, int32_t& ix) {
-    if (id < n_local || !ranks) { rk = ranks ? ranks[id] : 0; ix = ranks ? indices[id] : id; }
-    else { rk = ranks[id]; ix = indices[id]; }
-  };
-  auto face = [&](int32_t l, int32_t r, const T* n, T area, int ld, const int32_t* off) -> int {
-    int ax = -1, sg = 0;
-    for (int d = 0; d < 3; d++)
-      if (n[d] == T(1) || n[d] == T(-1)) { ax = d; sg = n[d] > T(0) ? 1 : 0; }
-    if (ax < 0) return cudaErrorInvalidValue;   // the subgrid path is Cartesian-only
-    const int dl = 2 * ax + sg, dr = dl ^ 1;
-    const int t0 = ax == 0 ? 1 : 0, t1 = ax == 2 ? 1 : 2;   // tangential axes in increasing order
-    const T   ca = area / T(16);
-    int32_t   rk, ix;
-    if (ld == 0) {
-      if (l < n_local) { owner(r, rk, ix); kind[l * 6 + dl] = 1; nid[l * 6 + dl] = ix; nrk[l * 6 + dl] = rk; aout[l * 6 + dl] = ca; }
-      if (r < n_local) { owner(l, rk, ix); kind[r * 6 + dr] = 1; nid[r * 6 + dr] = ix; nrk[r * 6 + dr] = rk; aout[r * 6 + dr] = ca; }
-    } else {   // r is one level coarser than l
-      const int qa = off[t0] / 2, qb = off[t1] / 2;
-      if (l < n_local) {
-        owner(r, rk, ix);
-        kind[l * 6 + dl] = 2; nid[l * 6 + dl] = ix; nrk[l * 6 + dl] = rk; aout[l * 6 + dl] = ca;
-        quad[l * 6 + dl] = (uint8_t)(qa | (qb << 1));
-      }
-      if (r < n_local) {
-        if (kind[r * 6 + dr] != 3) {
-          kind[r * 6 + dr] = 3;
-          nid[r * 6 + dr]  = (int32_t)(fine_id.size() / 4);
-          fine_id.resize(fine_id.size() + 4, 0);
-          fine_rk.resize(fine_rk.size() + 4, 0);
-          aout[r * 6 + dr] = ca;
-        }
-        owner(l, rk, ix);
-        fine_id[(size_t)nid[r * 6 + dr] * 4 + qa + 2 * qb] = ix;
-        fine_rk[(size_t)nid[r * 6 + dr] * 4 + qa + 2 * qb] = rk;
-      }
-    }
-    return 0;
-  };
-  for (int32_t f = 0; f < nf; f++) {
-    int rc = face(nbr[2 * f], nbr[2 * f + 1], normals + 3 * f, areas[f], level_diff[f], offsets + 3 * f);
-    if (rc) return rc;
-  }
-  for (int32_t f = 0; f < nx; f++) {
-    int rc = face(xnbr[2 * f], xnbr[2 * f + 1], xnormals + 3 * f, xareas[f], xld[f], xoff + 3 * f);
-    if (rc) return rc;
-  }
-  for (int32_t b = 0; b < nb; b++) {
-    int32_t  e = nbr[2 * (int64_t)nf + b];
-    const T* n = normals + 3 * ((int64_t)nf + b);
-    int      ax = -1, sg = 0;
-    for (int d = 0; d < 3; d++)
-      if (n[d] == T(1) || n[d] == T(-1)) { ax = d; sg = n[d] > T(0) ? 1 : 0; }
-    if (ax < 0 || e >= n_local) return cudaErrorInvalidValue;
-    kind[e * 6 + 2 * ax + sg] = 0;
-    aout[e * 6 + 2 * ax + sg] = areas[nf + b] / T(16);
-  }
-  for (auto kd : kind)
-    if (kd == 255) return cudaErrorInvalidValue;   // an element side without a face record: inconsistent connectivity
-  cudaError_t err = cudaSuccess;
-  P->kind = sg_upload(kind, P->dev_bytes, err);
-  P->quad = sg_upload(quad, P->dev_bytes, err);
-  P->nid  = sg_upload(nid, P->dev_bytes, err);
-  if (P->multi) P->nrk = sg_upload(nrk, P->dev_bytes, err);
-  P->aout    = sg_upload(aout, P->dev_bytes, err);
-  P->fine_id = sg_upload(fine_id, P->dev_bytes, err);
-  if (P->multi) P->fine_rk = sg_upload(fine_rk, P->dev_bytes, err);
-  return err;
-}
-
-template <typename T>
-static int sg_fused_impl(const t8b200_subgrid_plan* P, int stage, const T* const* in, const T* const* const* in_all,
-                         const T* const* prev, T* const* out, const T* vol, T dt, void* stream) {
-  if (!P || stage < 1 || stage > 3 || !in || !out || !vol || (stage > 1 && !prev)) return cudaErrorInvalidValue;
-  if (P->is_f64 != (sizeof(T) == 8) || (P->multi && !in_all)) return cudaErrorInvalidValue;
-  if (P->ne == 0) return 0;
-  SgFusedArgs<T> A{};
-  A.kind = P->kind; A.quad = P->quad; A.nid = P->nid; A.nrk = P->nrk; A.aout = (const T*)P->aout;
-  A.fine_id = P->fine_id; A.fine_rk = P->fine_rk;
-  for (int k = 0; k < 5; k++) {
-    A.in[k] = in[k]; A.in_all[k] = in_all ? in_all[k] : nullptr; A.prev[k] = stage > 1 ? prev[k] : in[k];
-    A.out[k] = out[k];
-  }
-  A.vol = vol; A.dt = dt; A.ne = P->ne; A.stage = stage; A.multi = P->multi;
-  constexpr int MINB = sizeof(T) == 8 ? 2 : 4;
-  size_t   smem   = sizeof(T) * ((size_t)NCELLQ * G * PS + 15 * (size_t)G * NFA);
-  auto     kfn    = sg_fused_kernel<T, MINB>;
-  T8B_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unsigned blocks = (unsigned)((P->ne + G - 1) / G);
-  kfn<<<blocks, 256, smem, (cudaStream_t)stream>>>(A);
-  return cudaGetLastError();
+  SubgridFaces<T> src{dim, n_local, nf, nb, nx, nbr, normals, areas, level_diff, offsets, vol, ranks, indices, xnbr,
+                      xnormals, xareas, xld, xoff};
+  if ((n_local + n_ghost) * src.S() > 0x7FFFFFF0LL) return cudaErrorInvalidValue;
+  t8b200_plan* P = new t8b200_plan();
+  SP->plan       = P;
+  P->is_f64      = sizeof(T) == 8;
+  P->vol_shift   = dim == 3 ? 6 : 4;
+  P->vol_scale   = dim == 3 ? 1.0 / 64.0 : 1.0 / 16.0;
+  return plan_build<T>(P, n_local * src.S(), n_ghost > 0, src);
 }
 
 extern "C" {
 
-int t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
-                               int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
-                               const int32_t* level_diff, const int32_t* offsets, const int32_t* ranks,
-                               const int32_t* indices, int32_t nx, const int32_t* xnbr, const void* xnormals,
-                               const void* xareas, const int32_t* xld, const int32_t* xoff) {
-  if (!out || n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0) return cudaErrorInvalidValue;
+int t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local, int64_t n_ghost,
+                               int32_t nf, int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
+                               const int32_t* level_diff, const int32_t* offsets, const void* volumes,
+                               const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                               const void* xnormals, const void* xareas, const int32_t* xld, const int32_t* xoff) {
+  if (!out || (dim != 2 && dim != 3) || n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0)
+    return cudaErrorInvalidValue;
   if (nf + nb > 0 && (!nbr || !normals || !areas)) return cudaErrorInvalidValue;
   if (nf > 0 && (!level_diff || !offsets)) return cudaErrorInvalidValue;
   if (nx > 0 && (!xnbr || !xnormals || !xareas || !xld || !xoff)) return cudaErrorInvalidValue;
-  auto* P   = new t8b200_subgrid_plan();
-  P->is_f64 = is_f64 ? 1 : 0;
-  int rc = is_f64 ? sg_plan_build<double>(P, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
-                                          (const double*)areas, level_diff, offsets, ranks, indices, nx, xnbr,
-                                          (const double*)xnormals, (const double*)xareas, xld, xoff)
-                  : sg_plan_build<float>(P, n_local, n_ghost, nf, nb, nbr, (const float*)normals, (const float*)areas,
-                                         level_diff, offsets, ranks, indices, nx, xnbr, (const float*)xnormals,
-                                         (const float*)xareas, xld, xoff);
+  if (n_local > 0 && !volumes) return cudaErrorInvalidValue;
+  if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
+  auto* SP = new t8b200_subgrid_plan();
+  SP->dim  = dim;
+  int rc = is_f64 ? sg_plan_build<double>(SP, dim, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
+                                          (const double*)areas, level_diff, offsets, (const double*)volumes, ranks,
+                                          indices, nx, xnbr, (const double*)xnormals, (const double*)xareas, xld, xoff)
+                  : sg_plan_build<float>(SP, dim, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
+                                         (const float*)areas, level_diff, offsets, (const float*)volumes, ranks,
+                                         indices, nx, xnbr, (const float*)xnormals, (const float*)xareas, xld, xoff);
   if (rc) {
-    t8b200_subgrid_plan_destroy(P);
+    t8b200_subgrid_plan_destroy(SP);
     return rc;
   }
-  *out = P;
+  *out = SP;
   return 0;
 }
-void t8b200_subgrid_plan_destroy(t8b200_subgrid_plan* P) {
-  if (!P) return;
-  cudaFree(P->kind); cudaFree(P->quad); cudaFree(P->nid); cudaFree(P->nrk); cudaFree(P->aout);
-  cudaFree(P->fine_id); cudaFree(P->fine_rk);
-  delete P;
+void t8b200_subgrid_plan_destroy(t8b200_subgrid_plan* SP) {
+  if (!SP) return;
+  t8b_plan_free(SP->plan);
+  delete SP;
 }
-int t8b200_subgrid_fused_stage_f32(const t8b200_subgrid_plan* plan, int stage, const float* const* in,
+int t8b200_subgrid_plan_info(const t8b200_subgrid_plan* SP, int64_t info[8]) {
+  if (!SP) return cudaErrorInvalidValue;
+  return t8b200_plan_info(SP->plan, info);
+}
+int t8b200_subgrid_fused_stage_f32(const t8b200_subgrid_plan* SP, int stage, const float* const* in,
                                    const float* const* const* in_all, const float* const* prev, float* const* out,
                                    const float* vol, float dt, void* stream) {
-  return sg_fused_impl<float>(plan, stage, in, in_all, prev, out, vol, dt, stream);
+  if (!SP) return cudaErrorInvalidValue;
+  return t8b_fused_stage_run<float>(SP->plan, stage, in, in_all, prev, out, vol, dt, nullptr, stream);
 }
-int t8b200_subgrid_fused_stage_f64(const t8b200_subgrid_plan* plan, int stage, const double* const* in,
+int t8b200_subgrid_fused_stage_f64(const t8b200_subgrid_plan* SP, int stage, const double* const* in,
                                    const double* const* const* in_all, const double* const* prev, double* const* out,
                                    const double* vol, double dt, void* stream) {
-  return sg_fused_impl<double>(plan, stage, in, in_all, prev, out, vol, dt, stream);
+  if (!SP) return cudaErrorInvalidValue;
+  return t8b_fused_stage_run<double>(SP->plan, stage, in, in_all, prev, out, vol, dt, nullptr, stream);
 }
 }

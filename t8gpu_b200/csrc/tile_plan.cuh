@@ -1,0 +1,364 @@
+// Tile plan shared by the unstructured (fused.cu) and the subgrid (subgrid.cu) fused stage: the connectivity of one
+// rank re-laid out per chunk of EC = 256 consecutive elements (cells), built on the host from any face source.
+//
+// Plan layout (device), per chunk:
+//   header   8 x int32: first element, elements, nh | nfc << 16, e0 | e1 << 16, e2, ovf_off_base, ovf_ent_base, area
+//   halo     sorted unique elements outside the chunk that share a face with it (slot EC + h); fixed stride HS per
+//            chunk (padding = -1), so the indices can be requested without waiting for the header
+//   faces    one 32-bit record slotL | slotR << 16 per face touching the chunk, fixed stride FS per chunk.
+//            Cartesian forests ("cmp": every normal +-e_axis, <= 256 distinct areas): records are put in canonical
+//            orientation (normal = +e_axis, sides swapped where the stored normal was -e_axis) and grouped by axis,
+//            [0,e0) x, [e0,e1) y, [e1,e2) z, then wall faces [e2,nfc) with the outward normal coded in the slotR field;
+//            a chunk whose faces all have the same area carries it in the header (applied once per element).
+//            General meshes: normals and areas as four T arrays, wall = slotR 0xFFFF.
+//   ell      per element 8 x uint16 entries (face_local << 1 | side), 0xFFFF = none; one 128-bit load per thread.
+//            Elements with more than 8 faces (hanging faces on several sides) continue in a per-chunk overflow CSR.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/t8gpu_b200.h"
+#include "euler_flux.cuh"
+
+static constexpr int EC  = 256;  // elements per chunk == threads per CTA
+static constexpr int ELL = 8;    // face entries per element held in the fixed-width table
+
+struct t8b200_plan {
+  int     is_f64     = 0;
+  int64_t n_local    = 0;
+  int     n_chunks   = 0;
+  int     max_halo   = 0;
+  int     max_faces  = 0;
+  int     multi      = 0;  // has ghosts -> needs rank tables
+  int     split      = 0;  // some blocks of EC elements were split: chunk c no longer starts at element c * EC
+  size_t  smem_bytes = 0;
+  int     ms = 0, mf = 0;  // compile-time stride variant selected for the kernel
+  int64_t dev_bytes = 0, n_records = 0, n_halo = 0;
+  int     cmp = 0, n_areas = 0;
+  int     hs = 0, fs = 0;  // per-chunk strides of the halo and face arrays
+  // device arrays
+  int32_t*  hdr       = nullptr;  // 8 per chunk
+  int32_t*  halo_elem = nullptr;  // index into the owner's arrays
+  int32_t*  halo_rank = nullptr;  // owner rank (multi only)
+  uint32_t* face_lr   = nullptr;
+  uint8_t*  face_ai   = nullptr;  // cmp: area index per record (read only by chunks with mixed areas)
+  void *    fnx = nullptr, *fny = nullptr, *fnz = nullptr, *farea = nullptr;  // general geometry (cmp == 0)
+  void*     area_tab = nullptr;
+  uint4*    ell      = nullptr;  // n_chunks * EC
+  uint16_t* ovf_off  = nullptr;  // (EC + 1) per chunk that has overflow entries
+  uint16_t* ovf_ent  = nullptr;
+  // volume lookup of the stage kernel: volume of element e = vol[e >> vol_shift] * vol_scale (subgrid cells share
+  // their element's volume: shift 6 / 4, scale 1/64 / 1/16, ssp_runge_kutta.inl:116)
+  int    vol_shift = 0;
+  double vol_scale = 1.0;
+};
+
+
+template <typename T>
+static T* upload(const std::vector<T>& v, int64_t& bytes, cudaError_t& err) {
+  T*     d = nullptr;
+  size_t n = std::max<size_t>(v.size(), 1) * sizeof(T) + 32;  // slack for 16-byte granular prefetch hints
+  if (err != cudaSuccess) return nullptr;
+  err = cudaMalloc(&d, n);
+  if (err != cudaSuccess) return nullptr;
+  if (!v.empty()) err = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  bytes += (int64_t)n;
+  return d;
+}
+
+// axis-aligned unit normal -> axis * 2 + (1 if positive), else -1
+template <typename T>
+static int axis_code(const T* n) {
+  for (int d = 0; d < 3; d++) {
+    T o1 = n[(d + 1) % 3], o2 = n[(d + 2) % 3];
+    if (o1 == T(0) && o2 == T(0) && (n[d] == T(1) || n[d] == T(-1))) return 2 * d + (n[d] > T(0) ? 1 : 0);
+  }
+  return -1;
+}
+
+// Shared-memory geometry of the stage kernel: a chunk holds at most EC own elements, MS - EC halo elements and
+// MF - 1 faces.  Chunks are EC consecutive elements; a block of EC elements whose halo or face count exceeds these
+// limits (2:1 hanging faces, unstructured meshes with many small neighbours) is split recursively into smaller
+// chunks, so ONE kernel variant serves every mesh.
+static constexpr int MS = 512, MF = 1024;
+
+// Builds the plan from any face source `src`:
+//   int64_t num_faces();                                  faces of this rank, every face of a local element exactly once
+//   void endpoints(int64_t f, int32_t& l, int32_t& r);    element ids; r = -1: wall; ids >= n_local: ghosts
+//   void geometry(int64_t f, T nrm[3], T& area);          unit normal pointing l -> r (outward at a wall), face area
+//   void owner(int32_t id, int32_t& rank, int32_t& idx);  owner rank and index in the owner's arrays (multi only)
+template <typename T, typename Src>
+static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
+  const int nblocks = (int)((n_local + EC - 1) / EC);
+  P->n_local = n_local;
+  P->multi   = multi ? 1 : 0;
+  const int64_t ntot = src.num_faces();
+  auto endpoints = [&](int64_t f, int32_t& l, int32_t& r) { src.endpoints(f, l, r); };
+  int max_halo_allowed = MS - EC, max_faces_allowed = MF - 1;
+  if (const char* t = getenv("T8B200_TEST_MAX_HALO")) max_halo_allowed = std::min(max_halo_allowed, std::max(8, atoi(t)));
+
+  // compressed geometry possible?  (every normal +-e_axis, <= 256 distinct areas)
+  bool                 cmp = true;
+  std::vector<T>       area_tab;
+  std::vector<uint8_t> area_of(ntot);
+  for (int64_t f = 0; f < ntot && cmp; f++) {
+    T nrm[3], a;
+    src.geometry(f, nrm, a);
+    if (axis_code(nrm) < 0) { cmp = false; break; }
+    int ai = -1;
+    for (size_t t = area_tab.size(); t-- > 0;)
+      if (area_tab[t] == a) { ai = (int)t; break; }
+    if (ai < 0) {
+      if (area_tab.size() >= 256) { cmp = false; break; }
+      ai = (int)area_tab.size();
+      area_tab.push_back(a);
+    }
+    area_of[f] = (uint8_t)ai;
+  }
+
+  // bucket faces by block of EC elements (a face between two blocks appears in both)
+  std::vector<int64_t> face_off(nblocks + 1, 0);
+  for (int64_t f = 0; f < ntot; f++) {
+    int32_t l, r;
+    endpoints(f, l, r);
+    int cl = l < n_local ? l / EC : -1, cr = (r >= 0 && r < n_local) ? r / EC : -1;
+    if (cl < 0 && cr < 0) return cudaErrorInvalidValue;
+    if (cl >= 0) face_off[cl + 1]++;
+    if (cr >= 0 && cr != cl) face_off[cr + 1]++;
+  }
+  for (int c = 0; c < nblocks; c++) face_off[c + 1] += face_off[c];
+  std::vector<int64_t> rec(face_off[nblocks]);
+  {
+    std::vector<int64_t> fill(face_off.begin(), face_off.end() - 1);
+    for (int64_t f = 0; f < ntot; f++) {
+      int32_t l, r;
+      endpoints(f, l, r);
+      int cl = l < n_local ? l / EC : -1, cr = (r >= 0 && r < n_local) ? r / EC : -1;
+      if (cl >= 0) rec[fill[cl]++] = f;
+      if (cr >= 0 && cr != cl) rec[fill[cr]++] = f;
+    }
+  }
+
+  // per-chunk data, flat (re-laid out at fixed strides once the maxima are known)
+  std::vector<int32_t>  hdr, halo_elem, halo_rank;
+  std::vector<int64_t>  halo_off{0}, rec_off{0};
+  std::vector<uint32_t> face_lr;
+  std::vector<uint8_t>  face_ai;
+  std::vector<T>        fnx, fny, fnz, far;
+  std::vector<uint16_t> ell((size_t)std::max<int64_t>(n_local, 1) * ELL, 0xFFFF), ovf_off, ovf_ent;
+  std::vector<int32_t>  halo_tmp;
+  std::vector<int64_t>  cand, sub;
+  std::vector<std::vector<uint16_t>> per_el(EC);
+  int  max_halo = 0, max_faces = 0;
+  bool split = false;
+
+  // emits the chunk [b0, b1) whose faces are `faces`; false if it does not fit the kernel's shared memory
+  auto emit = [&](int64_t b0, int64_t b1, const std::vector<int64_t>& faces, bool dry) -> int {
+    const int nfc = (int)faces.size();
+    halo_tmp.clear();
+    for (int64_t f : faces) {
+      int32_t l, r;
+      endpoints(f, l, r);
+      if (l < b0 || l >= b1) halo_tmp.push_back(l);
+      if (r >= 0 && (r < b0 || r >= b1)) halo_tmp.push_back(r);
+    }
+    std::sort(halo_tmp.begin(), halo_tmp.end());
+    halo_tmp.erase(std::unique(halo_tmp.begin(), halo_tmp.end()), halo_tmp.end());
+    const int nh = (int)halo_tmp.size();
+    if (nh > max_halo_allowed || nfc > max_faces_allowed) return 1;
+    if (dry) return 0;
+    max_halo  = std::max(max_halo, nh);
+    max_faces = std::max(max_faces, nfc);
+    hdr.resize(hdr.size() + 8, 0);
+    int32_t* H = &hdr[hdr.size() - 8];
+    H[0] = (int32_t)b0;
+    H[1] = (int32_t)(b1 - b0);
+    H[2] = nh | (nfc << 16);
+    for (int h = 0; h < nh; h++) {
+      int32_t id = halo_tmp[h], rk = 0, ix = id;
+      if (multi) src.owner(id, rk, ix);
+      else if (id >= n_local) return cudaErrorInvalidValue;
+      halo_elem.push_back(ix);
+      halo_rank.push_back(rk);
+    }
+    halo_off.push_back((int64_t)halo_elem.size());
+    auto slot_of = [&](int32_t id) -> int {
+      if (id >= b0 && id < b1) return (int)(id - b0);
+      return EC + (int)(std::lower_bound(halo_tmp.begin(), halo_tmp.end(), id) - halo_tmp.begin());
+    };
+    // kernel order of the records: cmp -> x, y, z interior faces, then walls; inside a group by left slot, so that
+    // the threads of a warp read neighbouring slots of the cell array (few bank conflicts whatever the face numbering)
+    struct Rec { int grp, sl, sr; int64_t f; };
+    std::vector<Rec> recs(nfc);
+    int seg[4] = {0, 0, 0, 0};
+    for (int j = 0; j < nfc; j++) {
+      const int64_t f = faces[j];
+      int32_t       l, r;
+      endpoints(f, l, r);
+      int sl = slot_of(l), sr = r < 0 ? 0xFFFF : slot_of(r), grp = 0;
+      if (cmp) {
+        T nrm[3], a;
+        src.geometry(f, nrm, a);
+        const int code = axis_code(nrm);
+        grp = r < 0 ? 3 : code >> 1;
+        if (r < 0) sr = 0xFFF8 | code;                  // wall: outward normal coded in the slotR field
+        else if (!(code & 1)) std::swap(sl, sr);        // canonical orientation: normal = +e_axis
+        seg[grp]++;
+      }
+      recs[j] = Rec{grp, sl, sr, f};
+    }
+    static const bool by_id = getenv("T8B200_TEST_NOSORT") != nullptr;   // experiment: group order = face id order
+    std::sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) {
+      if (x.grp != y.grp) return x.grp < y.grp;
+      if (by_id) return x.f < y.f;
+      if (x.sl != y.sl) return x.sl < y.sl;
+      if (x.sr != y.sr) return x.sr < y.sr;
+      return x.f < y.f;
+    });
+    H[3] = seg[0] | ((seg[0] + seg[1]) << 16);
+    H[4] = seg[0] + seg[1] + seg[2];
+    for (auto& v : per_el) v.clear();
+    int  area0 = -1;
+    bool uniform = cmp;
+    for (int j = 0; j < nfc; j++) {
+      const int64_t f  = recs[j].f;
+      const int     sl = recs[j].sl, sr = recs[j].sr;
+      if (cmp) {
+        face_ai.push_back(area_of[f]);
+        if (area0 < 0) area0 = area_of[f];
+        if (area_of[f] != area0) uniform = false;
+      } else {
+        T nrm[3], a;
+        src.geometry(f, nrm, a);
+        fnx.push_back(nrm[0]); fny.push_back(nrm[1]); fnz.push_back(nrm[2]); far.push_back(a);
+      }
+      face_lr.push_back((uint32_t)sl | ((uint32_t)sr << 16));
+      if (sl < EC) per_el[sl].push_back((uint16_t)(j << 1));
+      if (sr < EC) per_el[sr].push_back((uint16_t)((j << 1) | 1));
+    }
+    rec_off.push_back((int64_t)face_lr.size());
+    H[7] = (uniform && area0 >= 0) ? area0 : -1;
+    // fixed-width table + overflow CSR
+    bool overflow = false;
+    for (int i = 0; i < (int)(b1 - b0); i++) {
+      const auto& v = per_el[i];
+      for (size_t t = 0; t < v.size() && t < (size_t)ELL; t++) ell[((size_t)b0 + i) * ELL + t] = v[t];
+      if (v.size() > (size_t)ELL) overflow = true;
+    }
+    H[5] = -1;
+    H[6] = 0;
+    if (overflow) {
+      if (ovf_off.size() + EC + 1 > 0x7FFFFFFF || ovf_ent.size() > 0x7FFFFFFF) return cudaErrorInvalidValue;
+      H[5] = (int32_t)ovf_off.size();
+      H[6] = (int32_t)ovf_ent.size();
+      size_t n = 0;
+      for (int i = 0; i < EC; i++) {
+        ovf_off.push_back((uint16_t)n);
+        for (size_t t = ELL; t < per_el[i].size(); t++) { ovf_ent.push_back(per_el[i][t]); n++; }
+      }
+      if (n > 65535) return cudaErrorInvalidValue;
+      ovf_off.push_back((uint16_t)n);
+    }
+    return 0;
+  };
+  // chunk [b0,b1) from the candidate faces of its block; halves it while it does not fit
+  struct Range { int64_t b0, b1; };
+  std::vector<Range> todo;
+  for (int blk = 0; blk < nblocks; blk++) {
+    cand.assign(rec.begin() + face_off[blk], rec.begin() + face_off[blk + 1]);
+    todo.clear();
+    todo.push_back({(int64_t)blk * EC, std::min<int64_t>((int64_t)blk * EC + EC, n_local)});
+    while (!todo.empty()) {
+      const Range rg = todo.back();
+      todo.pop_back();
+      const std::vector<int64_t>* fs = &cand;
+      if (rg.b1 - rg.b0 < std::min<int64_t>(EC, n_local - (int64_t)blk * EC)) {   // part of a split block
+        sub.clear();
+        for (int64_t f : cand) {
+          int32_t l, r;
+          endpoints(f, l, r);
+          if ((l >= rg.b0 && l < rg.b1) || (r >= rg.b0 && r < rg.b1)) sub.push_back(f);
+        }
+        fs = &sub;
+      }
+      int rc = emit(rg.b0, rg.b1, *fs, true);
+      if (rc == 1) {
+        if (rg.b1 - rg.b0 <= 1) return cudaErrorInvalidValue;   // one element with more faces than a CTA can hold
+        const int64_t mid = (rg.b0 + rg.b1) / 2;
+        todo.push_back({mid, rg.b1});   // LIFO: the lower half is emitted first, chunks stay in element order
+        todo.push_back({rg.b0, mid});
+        split = true;
+        continue;
+      }
+      rc = emit(rg.b0, rg.b1, *fs, false);
+      if (rc) return rc;
+    }
+  }
+  const int nchunks = (int)(hdr.size() / 8);
+  if (n_local > 0x7FFFFF00LL || (int64_t)nchunks * MF > 0x7FFFFF00LL) return cudaErrorInvalidValue;  // 32-bit indices
+  P->n_chunks = nchunks;
+  P->split    = split ? 1 : 0;
+
+  // fixed strides per chunk: halo lists padded with -1, face arrays with 0
+  const int HS = std::max(32, (max_halo + 31) / 32 * 32), FS = std::max(32, (max_faces + 31) / 32 * 32);
+  {
+    std::vector<int32_t> he((size_t)nchunks * HS, -1), hr(multi ? (size_t)nchunks * HS : 0, 0);
+    for (int c = 0; c < nchunks; c++)
+      for (int64_t q = halo_off[c]; q < halo_off[c + 1]; q++) {
+        he[(size_t)c * HS + (q - halo_off[c])] = halo_elem[q];
+        if (multi) hr[(size_t)c * HS + (q - halo_off[c])] = halo_rank[q];
+      }
+    P->n_halo = (int64_t)halo_elem.size();
+    halo_elem.swap(he);
+    halo_rank.swap(hr);
+  }
+  auto restride = [&](auto& v) {
+    typename std::remove_reference<decltype(v)>::type out((size_t)nchunks * FS);
+    for (int c = 0; c < nchunks; c++)
+      std::copy(v.begin() + rec_off[c], v.begin() + rec_off[c + 1], out.begin() + (size_t)c * FS);
+    v.swap(out);
+  };
+  P->n_records = (int64_t)face_lr.size();
+  restride(face_lr);
+  if (cmp) restride(face_ai);
+  else { restride(fnx); restride(fny); restride(fnz); restride(far); }
+  P->hs = HS;
+  P->fs = FS;
+  P->max_halo   = max_halo;
+  P->max_faces  = max_faces;
+  P->ms = MS;
+  P->mf = MF;
+  P->smem_bytes = sizeof(T) * ((size_t)t8b200::NCELLQ * MS + 5 * (size_t)MF);
+
+  cudaError_t err = cudaSuccess;
+  P->hdr       = upload(hdr, P->dev_bytes, err);
+  P->halo_elem = upload(halo_elem, P->dev_bytes, err);
+  if (P->multi) P->halo_rank = upload(halo_rank, P->dev_bytes, err);
+  P->face_lr = upload(face_lr, P->dev_bytes, err);
+  P->cmp     = cmp ? 1 : 0;
+  if (cmp) {
+    P->face_ai  = upload(face_ai, P->dev_bytes, err);
+    P->area_tab = upload(area_tab, P->dev_bytes, err);
+    P->n_areas  = (int)area_tab.size();
+  } else {
+    P->fnx   = upload(fnx, P->dev_bytes, err);
+    P->fny   = upload(fny, P->dev_bytes, err);
+    P->fnz   = upload(fnz, P->dev_bytes, err);
+    P->farea = upload(far, P->dev_bytes, err);
+  }
+  P->ell     = reinterpret_cast<uint4*>(upload(ell, P->dev_bytes, err));
+  P->ovf_off = upload(ovf_off, P->dev_bytes, err);
+  P->ovf_ent = upload(ovf_ent, P->dev_bytes, err);
+  return err;
+}
+
+// defined in fused.cu (explicitly instantiated for float and double)
+template <typename T>
+int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
+                        const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream);
+void t8b_plan_free(t8b200_plan* P);

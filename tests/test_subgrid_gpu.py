@@ -51,7 +51,7 @@ def sg_state(forest, dtype, seed):
 
 
 def modes_for(dim):
-    return ["unfused", "fused"] if dim == 3 else ["unfused"]
+    return ["unfused", "fused"]
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

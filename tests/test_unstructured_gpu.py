@@ -264,3 +264,32 @@ def test_brick_partitions_agree_with_single_rank(cuda, brick, P):
                 plans[r].stage(stage, v(sin), v(prv), v(sout), bufs[r][NVAR * NB_STEPS], dt, in_all=tabs[sin])
         got = np.concatenate([bufs[r][nxt * NVAR:(nxt + 1) * NVAR].cpu().numpy() for r in range(P)], axis=1)
         assert rel_linf(got, one.state().cpu().numpy()) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,general", [("hex4", False), ("hex_amr", False), ("hex_amr", True), ("quad_amr_walls", False)])
+def test_split_chunks(cuda, kind, general, dtype, monkeypatch):
+    """Blocks of 256 elements whose halo does not fit the kernel's shared memory are split into smaller chunks
+    (forced here by lowering the limit): same results, more chunks."""
+    import t8gpu_b200
+    forest, lvl = make_forest(kind)
+    conn = forest.connectivity(dtype=dtype)
+    if general:
+        conn = rotated(conn)
+    u0, vol = perturbed_kh(forest, dtype, seed=5)
+    dt = 0.05 * 2.0 ** -lvl
+    whole = t8gpu_b200.EulerSolver(conn, vol, DT[dtype], device=cuda, mode="fused")
+    limit = 40 if forest.dim == 3 else 12
+    monkeypatch.setenv("T8B200_TEST_MAX_HALO", str(limit))
+    sol = t8gpu_b200.EulerSolver(conn, vol, DT[dtype], device=cuda, mode="fused")
+    monkeypatch.delenv("T8B200_TEST_MAX_HALO")
+    assert sol.plan.info["n_chunks"] > whole.plan.info["n_chunks"]
+    assert sol.plan.info["max_halo"] <= limit
+    sol.set_state(u0)
+    u = u0
+    for it in range(3):
+        u, _, _ = oracle.iterate(conn, vol, u, dt)
+        sol.iterate(dt)
+        err = rel_linf(sol.state().cpu().numpy(), u)
+        assert err <= (it + 1) * TOL[np.dtype(dtype)], (kind, it, err)
+    assert float(sol.max_wave_speed().item()) > 0
