@@ -206,6 +206,40 @@ int t8b200_shared_open(const unsigned char handle[64], void** dev_ptr);
 int t8b200_shared_close(void* dev_ptr);
 int t8b200_shared_free(void* dev_ptr);
 
+/* -------------------------------------------------------------------------------------------------------------
+ * 5. Device-side remap of variables and volumes after t8code adapt / partition (which stay on the host).
+ *    Every value is written straight into the new arrays (no temporary + set_variable round trip).
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Replaces adapt_variables_and_volume (t8gpu/mesh/mesh_manager.inl:164-193) when subgrid_dim = 0, and
+ * adapt_variables + adapt_volume of the subgrid manager (t8gpu/mesh/subgrid_mesh_manager.inl:245-425) when
+ * subgrid_dim = 3 (Subgrid<4,4,4>) or 2 (Subgrid<4,4>).
+ * adapt_data: DEVICE, n_new + 1 entries, adapt_data[i] = first old element behind new element i
+ *   (mesh_manager.inl:258-281).  Refined: every child copies its parent (subgrid: injection of the parent's octant),
+ *   coarsened: mean of the family (subgrid: mean of 2^dim fine cells), else copy.  Volumes: x 1/8, 8 (elements and 3-D
+ *   subgrids; the reference hard-codes the 3-D factors for MeshManager) or 1/4, 4 (2-D subgrids).
+ * vars_old / vars_new: HOST arrays of nvar (<= 8) DEVICE pointers; vol_*: device, per element. */
+int t8b200_adapt_remap_f32(int subgrid_dim, int nvar, int64_t n_new, const int32_t* adapt_data,
+                           const float* const* vars_old, float* const* vars_new, const float* vol_old, float* vol_new,
+                           void* stream);
+int t8b200_adapt_remap_f64(int subgrid_dim, int nvar, int64_t n_new, const int32_t* adapt_data,
+                           const double* const* vars_old, double* const* vars_new, const double* vol_old,
+                           double* vol_new, void* stream);
+
+/* Replaces partition_data (t8gpu/mesh/mesh_manager.inl:625-643; cells_per_element = 1) and
+ * partition_variable_data + partition_volume_data (t8gpu/mesh/subgrid_mesh_manager.inl:1216-1283; cells_per_element
+ * = 64 / 16): new element e <- old element indices[e] of rank ranks[e], read through the [var][rank] tables
+ * (MemoryAccessorAll / get_all_volume; peer pointers over NVLink when the ranks are GPUs).
+ * ranks / indices: DEVICE, n_new entries (what t8_forest_partition_data delivers); vars_new: HOST array of nvar DEVICE
+ * pointers; vars_old_all: HOST array of nvar DEVICE tables; vol_new may be NULL (then vol_old_all is ignored). */
+int t8b200_partition_remap_f32(int nvar, int64_t n_new, int cells_per_element, const int32_t* ranks,
+                               const int32_t* indices, float* const* vars_new, const float* const* const* vars_old_all,
+                               float* vol_new, const float* const* vol_old_all, void* stream);
+int t8b200_partition_remap_f64(int nvar, int64_t n_new, int cells_per_element, const int32_t* ranks,
+                               const int32_t* indices, double* const* vars_new,
+                               const double* const* const* vars_old_all, double* vol_new,
+                               const double* const* vol_old_all, void* stream);
+
 /* Cartesian Kelvin-Helmholtz initial state (examples/subgrid/solver.inl:36-56 / :82-103) sampled at n points
  * (device, 3 per point, float_type).  u: HOST array of 5 device pointers. */
 int t8b200_init_kelvin_helmholtz_f32(int dim, int64_t n, const float* centers, float* const* u, void* stream);

@@ -256,3 +256,89 @@ def subgrid_flux(conn, vol, u, flux, elem_index=None):
     getattr(L, "orc_subgrid_outer_" + s)(dim, int(conn["n_faces"]), _p(conn["face_neighbors"]), _p(nrm), _p(ar),
                                          _p(conn["level_diff"]), _p(conn["offsets"]), _p(elem_index), _p(u), _p(flux),
                                          stride)
+
+
+# ---------------------------------------------------------------------------------------------- adapt / partition remap
+
+def adapt_remap(adapt_data, u_old, vol_old, subgrid_dim=0):
+    """Restatement of adapt_variables_and_volume (t8gpu/mesh/mesh_manager.inl:164-193; subgrid_dim = 0) and of the
+    subgrid manager's adapt_volume + adapt_variables (t8gpu/mesh/subgrid_mesh_manager.inl:245-425; subgrid_dim = 3 or 2).
+    adapt_data: n_new + 1 ints (mesh_manager.inl:258-281); u_old: (nvar, n_old [* cells]); returns (u_new, vol_new) in
+    u_old's dtype, with the reference's summation order."""
+    ad = np.asarray(adapt_data, dtype=np.int64)
+    dt = u_old.dtype
+    n_new = len(ad) - 1
+    diff = ad[1:] - ad[:-1]
+    prev_same = np.zeros(n_new, bool)
+    prev_same[1:] = ad[1:-1] == ad[:-2]
+    if subgrid_dim == 2:
+        fr, fc = dt.type(0.25), dt.type(4.0)
+    else:
+        fr, fc = dt.type(0.125), dt.type(8.0)     # also for MeshManager on 2-D meshes (SURVEY D-8)
+    vol_new = vol_old[ad[:-1]] * np.where(diff == 0, fr, np.where(diff == 1, dt.type(1.0), fc)).astype(dt)
+    vol_new[prev_same] = vol_old[ad[:-1]][prev_same] * fr
+    vol_new = vol_new.astype(dt)
+    nvar = u_old.shape[0]
+    if subgrid_dim == 0:
+        u_new = np.zeros((nvar, n_new), dt)
+        for i in range(n_new):
+            ns = max(1, int(diff[i]))
+            for k in range(nvar):
+                s = dt.type(0.0)
+                for j in range(ns):
+                    s = dt.type(s + dt.type(u_old[k, ad[i] + j] / dt.type(ns)))
+                u_new[k, i] = s
+        return u_new, vol_new
+    dim = subgrid_dim
+    S = 64 if dim == 3 else 16
+    uo = u_old.reshape(nvar, -1, *([4] * dim)[::-1])          # [var][elem][(k)][j][i]
+    un = np.zeros((nvar, n_new) + (4,) * dim, dt)
+    for e in range(n_new):
+        a = int(ad[e])
+        if diff[e] == 0 or prev_same[e]:
+            ri = 0
+            while e - ri >= 0 and ad[e - ri] == a:
+                ri += 1
+            I, J, K = (ri - 1) & 1, ((ri - 1) >> 1) & 1, ((ri - 1) >> 2) & 1
+            idx = np.arange(4) // 2
+            if dim == 3:
+                un[:, e] = uo[:, a][:, (K * 2 + idx)[:, None, None], (J * 2 + idx)[None, :, None], (I * 2 + idx)[None, None, :]]
+            else:
+                un[:, e] = uo[:, a][:, (J * 2 + idx)[:, None], (I * 2 + idx)[None, :]]
+        elif diff[e] > 1:
+            for c in range(S):
+                i, j, k = c & 3, (c >> 2) & 3, (c >> 4) if dim == 3 else 0
+                z = (i >> 1) | ((j >> 1) << 1) | ((k >> 1) << 2)
+                for l in range(nvar):
+                    s = dt.type(0.0)
+                    for ii in range(2):
+                        for jj in range(2):
+                            for kk in range(2 if dim == 3 else 1):
+                                if dim == 3:
+                                    s = dt.type(s + uo[l, a + z, 2 * (k & 1) + kk, 2 * (j & 1) + jj, 2 * (i & 1) + ii])
+                                else:
+                                    s = dt.type(s + uo[l, a + z, 2 * (j & 1) + jj, 2 * (i & 1) + ii])
+                    v = dt.type(s / dt.type(1 << dim))
+                    if dim == 3:
+                        un[l, e, k, j, i] = v
+                    else:
+                        un[l, e, j, i] = v
+        else:
+            un[:, e] = uo[:, a]
+    return un.reshape(nvar, n_new * S), vol_new
+
+
+def partition_remap(ranks, indices, u_old_by_rank, vol_old_by_rank, cells_per_element=1):
+    """Restatement of partition_data (mesh_manager.inl:625-643) / partition_variable_data + partition_volume_data
+    (subgrid_mesh_manager.inl:1216-1283): new element e <- old element indices[e] of rank ranks[e]."""
+    S = cells_per_element
+    nvar = u_old_by_rank[0].shape[0]
+    n = len(ranks)
+    dt = u_old_by_rank[0].dtype
+    u = np.zeros((nvar, n * S), dt)
+    vol = np.zeros(n, dt)
+    for e in range(n):
+        r, i = int(ranks[e]), int(indices[e])
+        u[:, e * S:(e + 1) * S] = u_old_by_rank[r][:, i * S:(i + 1) * S]
+        vol[e] = vol_old_by_rank[r][i]
+    return u, vol

@@ -314,6 +314,28 @@ def cartesian_uniform_connectivity(dim, level, dtype, nranks=1, rank=0, device=N
     return out
 
 
+def adapt_remap(adapt_data, vars_old, vars_new, vol_old, vol_new, subgrid_dim=0, stream=None):
+    """adapt_variables_and_volume (subgrid_dim = 0) / subgrid adapt_variables + adapt_volume (3 or 2): device-side remap
+    after t8code adapt.  adapt_data: device int32 tensor (n_new + 1); vars_*: lists of per-variable device tensors."""
+    s, _ = _sfx(vol_old.dtype)
+    check(getattr(lib(), "t8b200_adapt_remap_" + s)(
+        int(subgrid_dim), len(vars_old), C.c_int64(adapt_data.numel() - 1), C.c_void_p(adapt_data.data_ptr()),
+        ptrs(vars_old), ptrs(vars_new), C.c_void_p(vol_old.data_ptr()), C.c_void_p(vol_new.data_ptr()),
+        stream_ptr(stream)), "adapt_remap")
+
+
+def partition_remap(ranks, indices, vars_new, vars_old_all, vol_new, vol_old_all, cells_per_element=1, stream=None):
+    """partition_data / partition_variable_data + partition_volume_data.  ranks / indices: device int32 tensors;
+    vars_old_all: RankTables / PointerTables; vol_old_all: device int64 tensor of per-rank volume pointers or None."""
+    s, _ = _sfx(vars_new[0].dtype)
+    check(getattr(lib(), "t8b200_partition_remap_" + s)(
+        len(vars_new), C.c_int64(ranks.numel()), int(cells_per_element), C.c_void_p(ranks.data_ptr()),
+        C.c_void_p(indices.data_ptr()), ptrs(vars_new), vars_old_all.host,
+        C.c_void_p(vol_new.data_ptr() if vol_new is not None else None),
+        C.c_void_p(vol_old_all.data_ptr() if vol_old_all is not None else None), stream_ptr(stream)),
+        "partition_remap")
+
+
 class SharedBuffer:
     """A device allocation that other processes on this node can map (cudaIpc handle exchange is up to the caller).
     `.tensor(shape, dtype)` views it as a torch tensor; `.handle` is the 64-byte IPC handle."""

@@ -1,0 +1,175 @@
+// Device-side remap of the variables and volumes after t8code adapt / partition (which stay on the host), for sm_100a.
+// C ABI in include/t8gpu_b200.h (section 5).  Pure bandwidth kernels: one thread per NEW element / cell, every value
+// written straight into the new allocation (the reference stages through a temporary buffer and five device-to-device
+// set_variable copies, mesh_manager.inl:290-324, subgrid_mesh_manager.inl:520-552).
+//
+// Reference behaviour replaced (not translated):
+//   t8gpu/mesh/mesh_manager.inl:164-193           adapt_variables_and_volume
+//   t8gpu/mesh/mesh_manager.inl:625-643           partition_data
+//   t8gpu/mesh/subgrid_mesh_manager.inl:245-425   adapt_volume, adapt_variables (3-D and 2-D)
+//   t8gpu/mesh/subgrid_mesh_manager.inl:1216-1283 partition_variable_data, partition_volume_data
+#include "../../include/t8gpu_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXV = 8;
+template <typename T>
+struct Ptrs { T* p[MAXV]; };
+template <typename T>
+struct PtrsC { const T* p[MAXV]; };
+template <typename T>
+struct TablesC { const T* const* p[MAXV]; };
+
+// adapt_data[i] = first old element behind new element i (n_new + 1 entries, mesh_manager.inl:258-281):
+//   diff = adapt_data[i+1] - adapt_data[i] : 0 -> i is a child of a refined element (not the last one),
+//   1 -> copy OR the last child of a refined element (then adapt_data[i-1] == adapt_data[i]), > 1 -> coarsened family.
+template <typename T>
+__global__ void __launch_bounds__(256)
+adapt_elements_kernel(int nvar, int64_t n_new, const int32_t* __restrict__ ad, PtrsC<T> uo, Ptrs<T> un,
+                      const T* __restrict__ vo, T* __restrict__ vn) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_new) return;
+  const int a = ad[i], diff = ad[i + 1] - a;
+  const int nsum = diff > 1 ? diff : 1;
+  // volume factors are the reference's 3-D constants whatever the mesh dimension (mesh_manager.inl:180-183)
+  T v = vo[a] * (diff == 0 ? T(0.125) : (diff == 1 ? T(1.0) : T(8.0)));
+  if (i > 0 && ad[i - 1] == a) v = vo[a] * T(0.125);
+  vn[i] = v;
+#pragma unroll
+  for (int k = 0; k < MAXV; k++) {
+    if (k < nvar) {
+      T s = T(0);
+      for (int j = 0; j < nsum; j++) s += uo.p[k][a + j] / T(nsum);   // same order and rounding as the reference
+      un.p[k][i] = s;
+    }
+  }
+}
+
+// Subgrid: one thread per new cell; DIM = 3: Subgrid<4,4,4>, DIM = 2: Subgrid<4,4>.
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+adapt_cells_kernel(int nvar, int64_t n_new, const int32_t* __restrict__ ad, PtrsC<T> uo, Ptrs<T> un,
+                   const T* __restrict__ vo, T* __restrict__ vn) {
+  constexpr int S = DIM == 3 ? 64 : 16, NC = 1 << DIM;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = g / S;
+  if (e >= n_new) return;
+  const int c = (int)(g % S), i = c & 3, j = (c >> 2) & 3, k = DIM == 3 ? c >> 4 : 0;
+  const int a = ad[e], diff = ad[e + 1] - a;
+  const bool child = diff == 0 || (e > 0 && ad[e - 1] == a);
+  if (c == 0) {   // adapt_volume, subgrid_mesh_manager.inl:245-290
+    const T fr = DIM == 3 ? T(0.125) : T(0.25), fc = DIM == 3 ? T(8.0) : T(4.0);
+    T v = vo[a] * (diff == 0 ? fr : (diff == 1 ? T(1.0) : fc));
+    if (e > 0 && ad[e - 1] == a) v = vo[a] * fr;
+    vn[e] = v;
+  }
+  if (child) {   // injection from the parent's cell (i/2, j/2, k/2) of octant (I,J,K), :310-330
+    int ri = 0;
+    while (e - ri >= 0 && ad[e - ri] == a) ri++;
+    const int I = (ri - 1) & 1, J = ((ri - 1) >> 1) & 1, K = ((ri - 1) >> 2) & 1;
+    const int64_t src = (int64_t)a * S + (I * 2 + i / 2) + 4 * (J * 2 + j / 2) + (DIM == 3 ? 16 * (K * 2 + k / 2) : 0);
+#pragma unroll
+    for (int l = 0; l < MAXV; l++)
+      if (l < nvar) un.p[l][g] = uo.p[l][src];
+  } else if (diff > 1) {   // mean of the 2^DIM fine cells, summed in the reference's order (ii, jj, kk), :332-352
+    const int I = i >> 1, J = j >> 1, K = k >> 1, z = I | (J << 1) | (K << 2);
+    const int64_t b = (int64_t)(a + z) * S;
+#pragma unroll
+    for (int l = 0; l < MAXV; l++) {
+      if (l < nvar) {
+        T s = T(0);
+        for (int ii = 0; ii < 2; ii++)
+          for (int jj = 0; jj < 2; jj++)
+            for (int kk = 0; kk < (DIM == 3 ? 2 : 1); kk++)
+              s += uo.p[l][b + (2 * (i & 1) + ii) + 4 * (2 * (j & 1) + jj) + (DIM == 3 ? 16 * (2 * (k & 1) + kk) : 0)];
+        un.p[l][g] = s / T(NC);
+      }
+    }
+  } else {
+    const int64_t src = (int64_t)a * S + c;
+#pragma unroll
+    for (int l = 0; l < MAXV; l++)
+      if (l < nvar) un.p[l][g] = uo.p[l][src];
+  }
+}
+
+// new element / cell i <- old (ranks[e], indices[e]) through the [var][rank] pointer tables (possibly peer GPUs)
+template <typename T>
+__global__ void __launch_bounds__(256)
+partition_kernel(int nvar, int64_t n_new_cells, int cpe, const int32_t* __restrict__ ranks,
+                 const int32_t* __restrict__ indices, Ptrs<T> un, TablesC<T> uo, T* __restrict__ vn,
+                 const T* const* __restrict__ vo) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_new_cells) return;
+  const int64_t e = g / cpe;
+  const int     c = (int)(g % cpe), rk = ranks[e];
+  const int64_t src = (int64_t)indices[e] * cpe + c;
+#pragma unroll
+  for (int l = 0; l < MAXV; l++)
+    if (l < nvar) un.p[l][g] = uo.p[l][rk][src];
+  if (c == 0 && vn) vn[e] = vo[rk][indices[e]];
+}
+
+template <typename T>
+int adapt_impl(int dim_subgrid, int nvar, int64_t n_new, const int32_t* ad, const T* const* uo, T* const* un,
+               const T* vo, T* vn, void* stream) {
+  if (nvar < 1 || nvar > MAXV || n_new < 0 || (dim_subgrid != 0 && dim_subgrid != 2 && dim_subgrid != 3))
+    return cudaErrorInvalidValue;
+  if (n_new == 0) return 0;
+  if (!ad || !uo || !un || !vo || !vn) return cudaErrorInvalidValue;
+  PtrsC<T> o{};
+  Ptrs<T>  n{};
+  for (int k = 0; k < nvar; k++) { o.p[k] = uo[k]; n.p[k] = un[k]; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dim_subgrid == 0) {
+    adapt_elements_kernel<T><<<(unsigned)((n_new + 255) / 256), 256, 0, st>>>(nvar, n_new, ad, o, n, vo, vn);
+  } else if (dim_subgrid == 3) {
+    adapt_cells_kernel<T, 3><<<(unsigned)((n_new * 64 + 255) / 256), 256, 0, st>>>(nvar, n_new, ad, o, n, vo, vn);
+  } else {
+    adapt_cells_kernel<T, 2><<<(unsigned)((n_new * 16 + 255) / 256), 256, 0, st>>>(nvar, n_new, ad, o, n, vo, vn);
+  }
+  return cudaGetLastError();
+}
+
+template <typename T>
+int partition_impl(int nvar, int64_t n_new, int cpe, const int32_t* ranks, const int32_t* indices, T* const* un,
+                   const T* const* const* uo_all, T* vn, const T* const* vo_all, void* stream) {
+  if (nvar < 1 || nvar > MAXV || n_new < 0 || cpe < 1) return cudaErrorInvalidValue;
+  if (n_new == 0) return 0;
+  if (!ranks || !indices || !un || !uo_all || (vn && !vo_all)) return cudaErrorInvalidValue;
+  Ptrs<T>    n{};
+  TablesC<T> o{};
+  for (int k = 0; k < nvar; k++) { n.p[k] = un[k]; o.p[k] = uo_all[k]; }
+  const int64_t cells = n_new * cpe;
+  partition_kernel<T><<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nvar, cells, cpe, ranks,
+                                                                                         indices, n, o, vn, vo_all);
+  return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" {
+int t8b200_adapt_remap_f32(int subgrid_dim, int nvar, int64_t n_new, const int32_t* adapt_data,
+                           const float* const* vars_old, float* const* vars_new, const float* vol_old, float* vol_new,
+                           void* stream) {
+  return adapt_impl<float>(subgrid_dim, nvar, n_new, adapt_data, vars_old, vars_new, vol_old, vol_new, stream);
+}
+int t8b200_adapt_remap_f64(int subgrid_dim, int nvar, int64_t n_new, const int32_t* adapt_data,
+                           const double* const* vars_old, double* const* vars_new, const double* vol_old,
+                           double* vol_new, void* stream) {
+  return adapt_impl<double>(subgrid_dim, nvar, n_new, adapt_data, vars_old, vars_new, vol_old, vol_new, stream);
+}
+int t8b200_partition_remap_f32(int nvar, int64_t n_new, int cells_per_element, const int32_t* ranks,
+                               const int32_t* indices, float* const* vars_new, const float* const* const* vars_old_all,
+                               float* vol_new, const float* const* vol_old_all, void* stream) {
+  return partition_impl<float>(nvar, n_new, cells_per_element, ranks, indices, vars_new, vars_old_all, vol_new,
+                               vol_old_all, stream);
+}
+int t8b200_partition_remap_f64(int nvar, int64_t n_new, int cells_per_element, const int32_t* ranks,
+                               const int32_t* indices, double* const* vars_new,
+                               const double* const* const* vars_old_all, double* vol_new,
+                               const double* const* vol_old_all, void* stream) {
+  return partition_impl<double>(nvar, n_new, cells_per_element, ranks, indices, vars_new, vars_old_all, vol_new,
+                                vol_old_all, stream);
+}
+}
