@@ -240,6 +240,29 @@ int t8b200_partition_remap_f64(int nvar, int64_t n_new, int cells_per_element, c
                                const double* const* const* vars_old_all, double* vol_new,
                                const double* const* vol_old_all, void* stream);
 
+/* -------------------------------------------------------------------------------------------------------------
+ * 6. Refinement indicators (the step before t8code adapt)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Replaces estimate_gradient<<<>>> + compute_refinement_criteria<<<>>> + the cudaMemset of the flux array
+ * (examples/compressible_euler/kernels.cu:471-501, solver.cu:231-263):
+ *   criteria[e] = sum over the interior faces of e of |rho_R - rho_L|, divided by cbrt(volume[e]).
+ * Uses the tile plan (every rank sums all faces of its own elements: no remote atomics, fixed order, the flux array is
+ * not touched).  rho: device, this rank's density; rho_all: device table of one pointer per rank (NULL without
+ * ghosts); vol, criteria: device, per element. */
+int t8b200_gradient_criteria_f32(const t8b200_plan* plan, const float* rho, const float* const* rho_all,
+                                 const float* vol, float* criteria, void* stream);
+int t8b200_gradient_criteria_f64(const t8b200_plan* plan, const double* rho, const double* const* rho_all,
+                                 const double* vol, double* criteria, void* stream);
+
+/* Replaces compute_refinement_criteria<SubgridType><<<>>> (examples/subgrid/kernels.inl:1109-1168, launched at
+ * solver.inl:331-337): H1 seminorm of the density over the cells of each element / volume, summed in the reference's
+ * loop order.  dim = 3: Subgrid<4,4,4>, dim = 2: Subgrid<4,4>.  rho: device, n_elements * 64 (16) cells. */
+int t8b200_subgrid_criteria_f32(int dim, int64_t n_elements, const float* rho, const float* vol, float* criteria,
+                                void* stream);
+int t8b200_subgrid_criteria_f64(int dim, int64_t n_elements, const double* rho, const double* vol, double* criteria,
+                                void* stream);
+
 /* Cartesian Kelvin-Helmholtz initial state (examples/subgrid/solver.inl:36-56 / :82-103) sampled at n points
  * (device, 3 per point, float_type).  u: HOST array of 5 device pointers. */
 int t8b200_init_kelvin_helmholtz_f32(int dim, int64_t n, const float* centers, float* const* u, void* stream);

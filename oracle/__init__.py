@@ -342,3 +342,49 @@ def partition_remap(ranks, indices, u_old_by_rank, vol_old_by_rank, cells_per_el
         u[:, e * S:(e + 1) * S] = u_old_by_rank[r][:, i * S:(i + 1) * S]
         vol[e] = vol_old_by_rank[r][i]
     return u, vol
+
+
+# ---------------------------------------------------------------------------------------------- refinement criteria
+
+def gradient_criteria(conn, rho, vol):
+    """Restatement of estimate_gradient + compute_refinement_criteria of the unstructured example
+    (examples/compressible_euler/kernels.cu:471-501, solver.cu:231-245), single rank: every INTERIOR face adds
+    |rho_R - rho_L| to both of its elements; criteria = sum / cbrt(volume).  (The reference accumulates with atomics, so
+    its summation order is not defined; this one adds in face order.)"""
+    dt = rho.dtype
+    nf = int(conn["n_faces"])
+    nbr = conn["face_neighbors"][:2 * nf].reshape(-1, 2)
+    g = np.abs(rho[nbr[:, 1]] - rho[nbr[:, 0]]).astype(dt)
+    acc = np.zeros(len(rho), dt)
+    np.add.at(acc, nbr[:, 0], g)
+    np.add.at(acc, nbr[:, 1], g)
+    return (acc / np.cbrt(vol.astype(dt))).astype(dt)
+
+
+def subgrid_criteria(dim, rho, vol):
+    """Restatement of compute_refinement_criteria<Subgrid> (examples/subgrid/kernels.inl:1109-1168): H1 seminorm of
+    the density over the cells of each element, summed in the reference's loop order, divided by the volume."""
+    dt = rho.dtype
+    n = len(vol)
+    d = rho.reshape((n,) + (4,) * dim)          # [e][(r)][q][p], p fastest
+    at = (lambda p, q, r: d[:, r, q, p]) if dim == 3 else (lambda p, q, r: d[:, q, p])
+    h = (np.cbrt(vol) if dim == 3 else np.sqrt(vol)).astype(dt) / dt.type(4)
+    s = np.zeros(n, dt)
+    R = range(4) if dim == 3 else range(1)
+    for p in range(3):
+        for q in range(4):
+            for r in R:
+                x = at(p + 1, q, r) - at(p, q, r)
+                s = (s + x * x * h).astype(dt)
+    for p in range(4):
+        for q in range(3):
+            for r in R:
+                x = at(p, q + 1, r) - at(p, q, r)
+                s = (s + x * x * h).astype(dt)
+    if dim == 3:
+        for p in range(4):
+            for q in range(4):
+                for r in range(3):
+                    x = at(p, q, r + 1) - at(p, q, r)
+                    s = (s + x * x * h).astype(dt)
+    return (s / vol.astype(dt)).astype(dt)

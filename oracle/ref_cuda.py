@@ -116,6 +116,14 @@ class RefSolver:
         err = self.L.ref_last_cuda_error()
         assert err == 0, "CUDA error %d in the reference" % err
 
+    def criteria(self):
+        """The refinement criteria the reference's own adapt() would compute from the current state."""
+        out = np.zeros(self.counts()["n_local"], self.dtype)
+        self.L.ref_criteria(self.h, _p(out))
+        err = self.L.ref_last_cuda_error()
+        assert err == 0, "CUDA error %d in the reference" % err
+        return out
+
     def compute_timestep(self):
         return self.L.ref_compute_timestep(self.h)
 

@@ -18,6 +18,7 @@
 #define private public
 #define protected public
 #include "solver.h"
+#include "kernels.h"
 #undef private
 #undef protected
 
@@ -104,6 +105,20 @@ static void mesh_adapt(S* s, const T* crit) {
   cudaDeviceSynchronize();
 }
 
+// the reference's own compute_refinement_criteria kernel, launched as SubgridCompressibleEulerSolver::adapt does
+// (solver.inl:331-339)
+template <typename S>
+static void criteria(S* s, T* out) {
+  using SubgridType = typename S::subgrid_type;
+  int n = s->m_mesh_manager.get_num_local_elements();
+  thrust::device_vector<T> c(n);
+  compute_refinement_criteria<SubgridType><<<(n + 255) / 256, 256>>>(
+      s->m_mesh_manager.get_own_variable(s->next, Rho), thrust::raw_pointer_cast(c.data()),
+      s->m_mesh_manager.get_own_volume(), n);
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, thrust::raw_pointer_cast(c.data()), sizeof(T) * n, cudaMemcpyDeviceToHost);
+}
+
 extern "C" {
 int ref_float_size() { return (int)sizeof(T); }
 
@@ -138,5 +153,6 @@ void ref_iterate(void* h, double dt, int nsteps) {
 void   ref_adapt(void* h) { DISPATCH(h, s->adapt()); cudaDeviceSynchronize(); }
 double ref_time_steps(void* h, double dt, int warmup, int steps) { return DISPATCH(h, time_steps(s, dt, warmup, steps)); }
 void   ref_mesh_adapt(void* h, const T* crit) { DISPATCH(h, mesh_adapt(s, crit)); }
+void   ref_criteria(void* h, T* out) { DISPATCH(h, criteria(s, out)); }
 int    ref_last_cuda_error() { return (int)cudaGetLastError(); }
 }

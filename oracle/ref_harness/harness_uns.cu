@@ -21,6 +21,7 @@
 #define private public
 #define protected public
 #include "solver.h"
+#include "kernels.h"
 #undef private
 #undef protected
 
@@ -32,6 +33,12 @@ static void d2h(V const& dv, void* out) {
   if (dv.size())
     cudaMemcpy(out, thrust::raw_pointer_cast(dv.data()), dv.size() * sizeof(typename V::value_type),
                cudaMemcpyDeviceToHost);
+}
+
+__global__ static void crit_div(T const* fluxes_rho, T const* volume, T* criteria, int n) {
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  criteria[i] = fluxes_rho[i] / cbrt(volume[i]);   // solver.cu:243
 }
 
 extern "C" {
@@ -119,6 +126,23 @@ void ref_mesh_adapt(void* h, const T* crit) {
   s->m_device_face_speed_estimate.resize(s->m_mesh_manager.get_num_local_faces() +
                                          s->m_mesh_manager.get_num_local_boundary_faces());
   cudaDeviceSynchronize();
+}
+// Refinement criteria exactly as CompressibleEulerSolver::adapt computes them (solver.cu:246-271): the reference's own
+// estimate_gradient kernel, then fluxes_rho / cbrt(volume) (compute_refinement_criteria is file-static in solver.cu, so
+// its one line is restated in crit_div below), then the flux array is cleared again.
+void ref_criteria(void* h, T* out) {
+  auto* s = static_cast<CompressibleEulerSolver*>(h);
+  auto& m = s->m_mesh_manager;
+  int   n = m.get_num_local_elements(), nf = m.get_num_local_faces();
+  if (nf > 0)
+    t8gpu::estimate_gradient<<<(nf + 255) / 256, 256>>>(m.get_connectivity_information(), m.get_all_variables(s->next),
+                                                       m.get_all_variables(Fluxes));
+  cudaDeviceSynchronize();
+  thrust::device_vector<T> c(n);
+  crit_div<<<(n + 255) / 256, 256>>>(m.get_own_variable(Fluxes, Rho), m.get_own_volume(),
+                                     thrust::raw_pointer_cast(c.data()), n);
+  cudaMemcpy(out, thrust::raw_pointer_cast(c.data()), sizeof(T) * n, cudaMemcpyDeviceToHost);
+  cudaMemset(m.get_own_variable(Fluxes, Rho), 0, sizeof(T) * n);
 }
 int ref_last_cuda_error() { return (int)cudaGetLastError(); }
 }

@@ -336,6 +336,31 @@ def partition_remap(ranks, indices, vars_new, vars_old_all, vol_new, vol_old_all
         "partition_remap")
 
 
+def gradient_criteria(plan, rho, vol, rho_all=None, out=None, stream=None):
+    """estimate_gradient + compute_refinement_criteria of the unstructured example on the tile plan `plan` (Plan).
+    rho, vol: device tensors; rho_all: device int64 tensor of per-rank density pointers (multi-rank)."""
+    torch = _torch()
+    s, _ = _sfx(rho.dtype)
+    if out is None:
+        out = torch.empty(rho.numel(), dtype=rho.dtype, device=rho.device)
+    check(getattr(lib(), "t8b200_gradient_criteria_" + s)(
+        plan._h, C.c_void_p(rho.data_ptr()), C.c_void_p(rho_all.data_ptr() if rho_all is not None else None),
+        C.c_void_p(vol.data_ptr()), C.c_void_p(out.data_ptr()), stream_ptr(stream)), "gradient_criteria")
+    return out
+
+
+def subgrid_criteria(dim, rho, vol, out=None, stream=None):
+    """compute_refinement_criteria<Subgrid>: H1 seminorm of the density per element / volume."""
+    torch = _torch()
+    s, _ = _sfx(rho.dtype)
+    if out is None:
+        out = torch.empty(vol.numel(), dtype=rho.dtype, device=rho.device)
+    check(getattr(lib(), "t8b200_subgrid_criteria_" + s)(
+        int(dim), C.c_int64(vol.numel()), C.c_void_p(rho.data_ptr()), C.c_void_p(vol.data_ptr()),
+        C.c_void_p(out.data_ptr()), stream_ptr(stream)), "subgrid_criteria")
+    return out
+
+
 class SharedBuffer:
     """A device allocation that other processes on this node can map (cudaIpc handle exchange is up to the caller).
     `.tensor(shape, dtype)` views it as a torch tensor; `.handle` is the 64-byte IPC handle."""
