@@ -97,6 +97,10 @@ namespace t8gpu {
         return {get(static_cast<variable_index_type>(is))...};
       }
 
+      /// Host-side view of the pointer array, as the C ABI (t8gpu_b200.h) takes it.  The reference keeps the array
+      /// private so that the implementation may change (memory_manager.h:172-185); this is the one addition.
+      [[nodiscard]] __host__ Ptr const* data() const { return m_pointers.data(); }
+
      protected:
       std::array<Ptr, nb_variables> m_pointers;
       template<typename Container>
@@ -160,7 +164,11 @@ namespace t8gpu {
     static constexpr size_t nb_steps     = step_traits<StepType>::nb_steps;
 
     MemoryManager(size_t nb_elements = 0, sc_MPI_Comm comm = sc_MPI_COMM_WORLD) : m_device_buffer(nb_elements, comm) {}
-    ~MemoryManager() = default;
+    ~MemoryManager()                               = default;
+    MemoryManager(MemoryManager&&)                 = default;   // move-only, like the storage it owns
+    MemoryManager& operator=(MemoryManager&&)      = default;
+    MemoryManager(MemoryManager const&)            = delete;
+    MemoryManager& operator=(MemoryManager const&) = delete;
 
     void set_variable(step_index_type step, variable_index_type variable,
                       thrust::device_vector<float_type> const& buffer) {

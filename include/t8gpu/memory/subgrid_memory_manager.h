@@ -129,6 +129,12 @@ namespace t8gpu {
 
    private:
     std::array<float_type*, nb_variables> m_pointers;
+
+   public:
+    /// host-side view of the pointer array, as the C ABI (t8gpu_b200.h) takes it
+    [[nodiscard]] __host__ float_type* const* data() const { return m_pointers.data(); }
+
+   private:
     template<typename Container>
     SubgridMemoryAccessorOwn(Container&& array) : m_pointers(std::forward<Container>(array)) {}
   };
@@ -183,6 +189,12 @@ namespace t8gpu {
 
    private:
     std::array<float_type* const*, nb_variables> m_pointers;
+
+   public:
+    /// host-side view of the table array, as the C ABI (t8gpu_b200.h) takes it
+    [[nodiscard]] __host__ float_type* const* const* data() const { return m_pointers.data(); }
+
+   private:
     template<typename Container>
     SubgridMemoryAccessorAll(Container&& array) : m_pointers(std::forward<Container>(array)) {}
   };
