@@ -103,7 +103,8 @@ namespace t8gpu {
 
      protected:
       std::array<Ptr, nb_variables> m_pointers;
-      template<typename Container>
+      // (constrained so that it never competes with the copy constructor for a non-const accessor)
+      template<typename Container, typename = std::enable_if_t<!std::is_base_of_v<AccessorBase, std::decay_t<Container>>>>
       AccessorBase(Container&& array) : m_pointers(std::forward<Container>(array)) {}
     };
   }  // namespace detail
@@ -127,7 +128,8 @@ namespace t8gpu {
     MemoryAccessorOwn& operator=(MemoryAccessorOwn const&) = default;
 
    private:
-    template<typename Container>
+    template<typename Container,
+             typename = std::enable_if_t<!std::is_same_v<std::decay_t<Container>, MemoryAccessorOwn>>>
     MemoryAccessorOwn(Container&& array) : Base(std::forward<Container>(array)) {}
   };
 
@@ -148,7 +150,8 @@ namespace t8gpu {
     MemoryAccessorAll& operator=(MemoryAccessorAll const&) = default;
 
    private:
-    template<typename Container>
+    template<typename Container,
+             typename = std::enable_if_t<!std::is_same_v<std::decay_t<Container>, MemoryAccessorAll>>>
     MemoryAccessorAll(Container&& array) : Base(std::forward<Container>(array)) {}
   };
 

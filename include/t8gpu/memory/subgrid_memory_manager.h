@@ -135,7 +135,9 @@ namespace t8gpu {
     [[nodiscard]] __host__ float_type* const* data() const { return m_pointers.data(); }
 
    private:
-    template<typename Container>
+    // (constrained so that it never competes with the copy constructor for a non-const accessor)
+    template<typename Container,
+             typename = std::enable_if_t<!std::is_same_v<std::decay_t<Container>, SubgridMemoryAccessorOwn>>>
     SubgridMemoryAccessorOwn(Container&& array) : m_pointers(std::forward<Container>(array)) {}
   };
 
@@ -195,7 +197,8 @@ namespace t8gpu {
     [[nodiscard]] __host__ float_type* const* const* data() const { return m_pointers.data(); }
 
    private:
-    template<typename Container>
+    template<typename Container,
+             typename = std::enable_if_t<!std::is_same_v<std::decay_t<Container>, SubgridMemoryAccessorAll>>>
     SubgridMemoryAccessorAll(Container&& array) : m_pointers(std::forward<Container>(array)) {}
   };
 
@@ -213,7 +216,11 @@ namespace t8gpu {
 
     SubgridMemoryManager(size_t nb_elements = 0, sc_MPI_Comm comm = sc_MPI_COMM_WORLD)
         : m_device_buffer(nb_elements * SubgridType::size, comm), m_device_volume(nb_elements, comm) {}
-    ~SubgridMemoryManager() = default;
+    ~SubgridMemoryManager()                                      = default;
+    SubgridMemoryManager(SubgridMemoryManager&&)                 = default;   // move-only, like its storage
+    SubgridMemoryManager& operator=(SubgridMemoryManager&&)      = default;
+    SubgridMemoryManager(SubgridMemoryManager const&)            = delete;
+    SubgridMemoryManager& operator=(SubgridMemoryManager const&) = delete;
 
     void set_variable(step_index_type step, variable_index_type variable,
                       thrust::device_vector<float_type> const& buffer) {

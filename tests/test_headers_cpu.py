@@ -18,8 +18,9 @@ def test_user_translation_unit_compiles():
 
 
 @pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
-def test_mesh_manager_translation_unit_compiles():
+@pytest.mark.parametrize("src", ["mesh_harness.cu", "subgrid_harness.cu"])
+def test_mesh_manager_translation_unit_compiles(src):
     inc = ["-I", os.path.join(HERE, "..", "include"), "-I", os.path.join(HERE, "..", "oracle", "ref_shim")]
     subprocess.check_call(["nvcc", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
                            "--expt-relaxed-constexpr", "-w"] + inc +
-                          ["-c", os.path.join(HERE, "_headers", "mesh_harness.cu"), "-o", os.devnull])
+                          ["-c", os.path.join(HERE, "_headers", src), "-o", os.devnull])
