@@ -33,6 +33,7 @@ struct FusedArgs {
   const T*        area_tab;
   int             n_areas;
   int             hs, fs;
+  int             wave;  // CTAs resident on the device at once = distance of the next-wave prefetch (0: off)
   const uint4*    ell;
   const uint16_t* ovf_off;
   const uint16_t* ovf_ent;
@@ -117,12 +118,24 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   // first face record of this thread (consumed in phase 1; its latency hides behind phase 0)
   uint32_t lr_n = 0;
   if (tid < A.fs) lr_n = A.face_lr[fb + tid];
-  if (tid < 8) {  // phase-2 operands of this chunk -> L2 now, so that their loads before the barrier are L2 hits
-    const int      b0 = e0c;
-    const unsigned n0 = (unsigned)ecn;
-    if (tid < 5) { if (A.stage != 1) prefetch_l2(A.prev[tid] + b0, n0 * sizeof(T)); }
-    else if (tid == 5) prefetch_l2(A.vol + (b0 >> A.vol_shift), ((n0 - 1) >> A.vol_shift) * sizeof(T) + sizeof(T));
-    else if (tid == 6) prefetch_l2(A.ell + b0, n0 * sizeof(uint4));
+  if ((tid & 31) == 0) {
+    // L2 prefetch hints, one or two per warp (a bulk prefetch is a warp-uniform instruction: spreading them avoids a
+    // serial loop in one warp).  Items 0-6: the phase-2 operands of this chunk, so that their loads before the barrier
+    // are L2 hits.  Items 8-15 (SPLIT == false only: addresses computable without a header): the streams of the chunk
+    // that takes over a CTA slot about one wave later (CTAs are dispatched in index order).
+    const int w = tid >> 5;   // 0..7
+    if (w < 5) { if (A.stage != 1) prefetch_l2(A.prev[w] + e0c, (unsigned)ecn * sizeof(T)); }
+    else if (w == 5) prefetch_l2(A.vol + (e0c >> A.vol_shift), ((unsigned)(ecn - 1) >> A.vol_shift) * sizeof(T) + sizeof(T));
+    else if (w == 6) prefetch_l2(A.ell + e0c, (unsigned)ecn * sizeof(uint4));
+    const int cw = c + A.wave;
+    if (!SPLIT && A.wave > 0 && cw < (int)gridDim.x) {
+      const int      b1 = cw * EC;
+      const unsigned n1 = (unsigned)min(EC, (int)A.n_local - b1);
+      if (w < 5) prefetch_l2(A.in[w] + b1, n1 * sizeof(T));
+      else if (w == 5) prefetch_l2(A.halo_elem + (int64_t)cw * A.hs, A.hs * 4u);
+      else if (w == 6) prefetch_l2(A.face_lr + (int64_t)cw * A.fs, A.fs * 4u);
+      else prefetch_l2(A.hdr + 2 * cw, 32u);
+    }
   }
   if (CMP && tid < A.n_areas) atab[tid] = A.area_tab[tid];
 
@@ -270,8 +283,19 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
 static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
   auto k = fused_stage_kernel<T, MS, MF, MINB, CMP, SPLIT>;
-  T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
-  k<<<P->n_chunks, EC, P->smem_bytes, st>>>(A);
+  static int resident = -1;   // CTAs of this variant the device holds at once
+  if (resident < 0) {
+    T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
+    int dev = 0, sms = 0, per_sm = 0;
+    T8B_TRY(cudaGetDevice(&dev));
+    T8B_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    T8B_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, EC, P->smem_bytes));
+    resident = std::max(1, sms * per_sm);
+  }
+  FusedArgs<T> B = A;
+  static const int wave_knob = getenv("T8B200_WAVE") ? atoi(getenv("T8B200_WAVE")) : -1;   // tuning knob
+  B.wave = wave_knob >= 0 ? wave_knob : resident;
+  k<<<P->n_chunks, EC, P->smem_bytes, st>>>(B);
   return cudaGetLastError();
 }
 
