@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
         objs.append(obj)
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread"])
     return LIB
 
 

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -87,7 +88,23 @@ static int axis_code(const T* n) {
 // chunks, so ONE kernel variant serves every mesh.
 static constexpr int MS = 512, MF = 1024;
 
-// Builds the plan from any face source `src`:
+// Host threads used to build a plan (per-block work is independent; results are merged in block order, so the plan
+// does not depend on the thread count).
+static inline int plan_threads() {
+  if (const char* t = getenv("T8B200_PLAN_THREADS")) return std::max(1, atoi(t));
+  unsigned hc = std::thread::hardware_concurrency();
+  return (int)std::min(32u, std::max(1u, hc));
+}
+template <typename Fn>
+static void parallel_ranges(int64_t n, int nthreads, Fn&& fn) {   // fn(thread, begin, end)
+  nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, n));
+  if (nthreads == 1) { fn(0, (int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) th.emplace_back([&, t] { fn(t, n * t / nthreads, n * (t + 1) / nthreads); });
+  for (auto& x : th) x.join();
+}
+
+// Builds the plan from any face source `src` (its member functions are called concurrently, they must be const-safe):
 //   int64_t num_faces();                                  faces of this rank, every face of a local element exactly once
 //   void endpoints(int64_t f, int32_t& l, int32_t& r);    element ids; r = -1: wall; ids >= n_local: ghosts
 //   void geometry(int64_t f, T nrm[3], T& area);          unit normal pointing l -> r (outward at a wall), face area
@@ -95,238 +112,319 @@ static constexpr int MS = 512, MF = 1024;
 template <typename T, typename Src>
 static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   const int nblocks = (int)((n_local + EC - 1) / EC);
+  const int NT      = plan_threads();
   P->n_local = n_local;
   P->multi   = multi ? 1 : 0;
   const int64_t ntot = src.num_faces();
-  auto endpoints = [&](int64_t f, int32_t& l, int32_t& r) { src.endpoints(f, l, r); };
-  int max_halo_allowed = MS - EC, max_faces_allowed = MF - 1;
+  int max_halo_allowed = MS - EC;
+  const int max_faces_allowed = MF - 1;
   if (const char* t = getenv("T8B200_TEST_MAX_HALO")) max_halo_allowed = std::min(max_halo_allowed, std::max(8, atoi(t)));
+  static const bool by_id = getenv("T8B200_TEST_NOSORT") != nullptr;   // experiment: group order = face id order
 
-  // compressed geometry possible?  (every normal +-e_axis, <= 256 distinct areas)
-  bool                 cmp = true;
-  std::vector<T>       area_tab;
-  std::vector<uint8_t> area_of(ntot);
-  for (int64_t f = 0; f < ntot && cmp; f++) {
-    T nrm[3], a;
-    src.geometry(f, nrm, a);
-    if (axis_code(nrm) < 0) { cmp = false; break; }
-    int ai = -1;
-    for (size_t t = area_tab.size(); t-- > 0;)
-      if (area_tab[t] == a) { ai = (int)t; break; }
-    if (ai < 0) {
-      if (area_tab.size() >= 256) { cmp = false; break; }
-      ai = (int)area_tab.size();
-      area_tab.push_back(a);
+  // ---- compressed geometry possible?  (every normal +-e_axis, <= 256 distinct areas): per-thread area sets, merged in
+  // thread order, then one parallel pass assigns the table index of every face
+  std::vector<std::vector<T>> local_areas(NT);
+  std::vector<int>            not_axis(NT, 0);
+  parallel_ranges(ntot, NT, [&](int t, int64_t f0, int64_t f1) {
+    auto& la = local_areas[t];
+    for (int64_t f = f0; f < f1; f++) {
+      T nrm[3], a;
+      src.geometry(f, nrm, a);
+      if (axis_code(nrm) < 0) { not_axis[t] = 1; return; }
+      if (!la.empty() && la.back() == a) continue;
+      if (std::find(la.begin(), la.end(), a) == la.end()) {
+        if (la.size() > 256) { not_axis[t] = 1; return; }
+        la.push_back(a);
+      }
     }
-    area_of[f] = (uint8_t)ai;
+  });
+  bool           cmp = true;
+  std::vector<T> area_tab;
+  for (int t = 0; t < NT && cmp; t++) {
+    if (not_axis[t]) cmp = false;
+    for (T a : local_areas[t])
+      if (std::find(area_tab.begin(), area_tab.end(), a) == area_tab.end()) area_tab.push_back(a);
   }
-
-  // bucket faces by block of EC elements (a face between two blocks appears in both)
-  std::vector<int64_t> face_off(nblocks + 1, 0);
-  for (int64_t f = 0; f < ntot; f++) {
-    int32_t l, r;
-    endpoints(f, l, r);
-    int cl = l < n_local ? l / EC : -1, cr = (r >= 0 && r < n_local) ? r / EC : -1;
-    if (cl < 0 && cr < 0) return cudaErrorInvalidValue;
-    if (cl >= 0) face_off[cl + 1]++;
-    if (cr >= 0 && cr != cl) face_off[cr + 1]++;
-  }
-  for (int c = 0; c < nblocks; c++) face_off[c + 1] += face_off[c];
-  std::vector<int64_t> rec(face_off[nblocks]);
-  {
-    std::vector<int64_t> fill(face_off.begin(), face_off.end() - 1);
-    for (int64_t f = 0; f < ntot; f++) {
-      int32_t l, r;
-      endpoints(f, l, r);
-      int cl = l < n_local ? l / EC : -1, cr = (r >= 0 && r < n_local) ? r / EC : -1;
-      if (cl >= 0) rec[fill[cl]++] = f;
-      if (cr >= 0 && cr != cl) rec[fill[cr]++] = f;
-    }
-  }
-
-  // per-chunk data, flat (re-laid out at fixed strides once the maxima are known)
-  std::vector<int32_t>  hdr, halo_elem, halo_rank;
-  std::vector<int64_t>  halo_off{0}, rec_off{0};
-  std::vector<uint32_t> face_lr;
-  std::vector<uint8_t>  face_ai;
-  std::vector<T>        fnx, fny, fnz, far;
-  std::vector<uint16_t> ell((size_t)std::max<int64_t>(n_local, 1) * ELL, 0xFFFF), ovf_off, ovf_ent;
-  std::vector<int32_t>  halo_tmp;
-  std::vector<int64_t>  cand, sub;
-  std::vector<std::vector<uint16_t>> per_el(EC);
-  int  max_halo = 0, max_faces = 0;
-  bool split = false;
-
-  // emits the chunk [b0, b1) whose faces are `faces`; false if it does not fit the kernel's shared memory
-  auto emit = [&](int64_t b0, int64_t b1, const std::vector<int64_t>& faces, bool dry) -> int {
-    const int nfc = (int)faces.size();
-    halo_tmp.clear();
-    for (int64_t f : faces) {
-      int32_t l, r;
-      endpoints(f, l, r);
-      if (l < b0 || l >= b1) halo_tmp.push_back(l);
-      if (r >= 0 && (r < b0 || r >= b1)) halo_tmp.push_back(r);
-    }
-    std::sort(halo_tmp.begin(), halo_tmp.end());
-    halo_tmp.erase(std::unique(halo_tmp.begin(), halo_tmp.end()), halo_tmp.end());
-    const int nh = (int)halo_tmp.size();
-    if (nh > max_halo_allowed || nfc > max_faces_allowed) return 1;
-    if (dry) return 0;
-    max_halo  = std::max(max_halo, nh);
-    max_faces = std::max(max_faces, nfc);
-    hdr.resize(hdr.size() + 8, 0);
-    int32_t* H = &hdr[hdr.size() - 8];
-    H[0] = (int32_t)b0;
-    H[1] = (int32_t)(b1 - b0);
-    H[2] = nh | (nfc << 16);
-    for (int h = 0; h < nh; h++) {
-      int32_t id = halo_tmp[h], rk = 0, ix = id;
-      if (multi) src.owner(id, rk, ix);
-      else if (id >= n_local) return cudaErrorInvalidValue;
-      halo_elem.push_back(ix);
-      halo_rank.push_back(rk);
-    }
-    halo_off.push_back((int64_t)halo_elem.size());
-    auto slot_of = [&](int32_t id) -> int {
-      if (id >= b0 && id < b1) return (int)(id - b0);
-      return EC + (int)(std::lower_bound(halo_tmp.begin(), halo_tmp.end(), id) - halo_tmp.begin());
-    };
-    // kernel order of the records: cmp -> x, y, z interior faces, then walls; inside a group by left slot, so that
-    // the threads of a warp read neighbouring slots of the cell array (few bank conflicts whatever the face numbering)
-    struct Rec { int grp, sl, sr; int64_t f; };
-    std::vector<Rec> recs(nfc);
-    int seg[4] = {0, 0, 0, 0};
-    for (int j = 0; j < nfc; j++) {
-      const int64_t f = faces[j];
-      int32_t       l, r;
-      endpoints(f, l, r);
-      int sl = slot_of(l), sr = r < 0 ? 0xFFFF : slot_of(r), grp = 0;
-      if (cmp) {
+  if (area_tab.size() > 256) cmp = false;
+  std::sort(area_tab.begin(), area_tab.end());   // table order independent of the thread count
+  std::vector<uint8_t> area_of(cmp ? ntot : 0);
+  if (cmp)
+    parallel_ranges(ntot, NT, [&](int, int64_t f0, int64_t f1) {
+      int last = 0;
+      for (int64_t f = f0; f < f1; f++) {
         T nrm[3], a;
         src.geometry(f, nrm, a);
-        const int code = axis_code(nrm);
-        grp = r < 0 ? 3 : code >> 1;
-        if (r < 0) sr = 0xFFF8 | code;                  // wall: outward normal coded in the slotR field
-        else if (!(code & 1)) std::swap(sl, sr);        // canonical orientation: normal = +e_axis
-        seg[grp]++;
+        if (area_tab[last] != a) last = (int)(std::find(area_tab.begin(), area_tab.end(), a) - area_tab.begin());
+        area_of[f] = (uint8_t)last;
       }
-      recs[j] = Rec{grp, sl, sr, f};
-    }
-    static const bool by_id = getenv("T8B200_TEST_NOSORT") != nullptr;   // experiment: group order = face id order
-    std::sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) {
-      if (x.grp != y.grp) return x.grp < y.grp;
-      if (by_id) return x.f < y.f;
-      if (x.sl != y.sl) return x.sl < y.sl;
-      if (x.sr != y.sr) return x.sr < y.sr;
-      return x.f < y.f;
     });
-    H[3] = seg[0] | ((seg[0] + seg[1]) << 16);
-    H[4] = seg[0] + seg[1] + seg[2];
-    for (auto& v : per_el) v.clear();
-    int  area0 = -1;
-    bool uniform = cmp;
-    for (int j = 0; j < nfc; j++) {
-      const int64_t f  = recs[j].f;
-      const int     sl = recs[j].sl, sr = recs[j].sr;
-      if (cmp) {
-        face_ai.push_back(area_of[f]);
-        if (area0 < 0) area0 = area_of[f];
-        if (area_of[f] != area0) uniform = false;
-      } else {
-        T nrm[3], a;
-        src.geometry(f, nrm, a);
-        fnx.push_back(nrm[0]); fny.push_back(nrm[1]); fnz.push_back(nrm[2]); far.push_back(a);
-      }
-      face_lr.push_back((uint32_t)sl | ((uint32_t)sr << 16));
-      if (sl < EC) per_el[sl].push_back((uint16_t)(j << 1));
-      if (sr < EC) per_el[sr].push_back((uint16_t)((j << 1) | 1));
+
+  // ---- bucket faces by block of EC elements (a face between two blocks appears in both): per-thread counts
+  std::vector<std::vector<int32_t>> cnt(NT, std::vector<int32_t>(nblocks, 0));
+  std::vector<int>                  bad(NT, 0);
+  parallel_ranges(ntot, NT, [&](int t, int64_t f0, int64_t f1) {
+    auto& c = cnt[t];
+    for (int64_t f = f0; f < f1; f++) {
+      int32_t l, r;
+      src.endpoints(f, l, r);
+      int cl = l < n_local ? l / EC : -1, cr = (r >= 0 && r < n_local) ? r / EC : -1;
+      if (cl < 0 && cr < 0) { bad[t] = 1; return; }
+      if (cl >= 0) c[cl]++;
+      if (cr >= 0 && cr != cl) c[cr]++;
     }
-    rec_off.push_back((int64_t)face_lr.size());
-    H[7] = (uniform && area0 >= 0) ? area0 : -1;
-    // fixed-width table + overflow CSR
-    bool overflow = false;
-    for (int i = 0; i < (int)(b1 - b0); i++) {
-      const auto& v = per_el[i];
-      for (size_t t = 0; t < v.size() && t < (size_t)ELL; t++) ell[((size_t)b0 + i) * ELL + t] = v[t];
-      if (v.size() > (size_t)ELL) overflow = true;
-    }
-    H[5] = -1;
-    H[6] = 0;
-    if (overflow) {
-      if (ovf_off.size() + EC + 1 > 0x7FFFFFFF || ovf_ent.size() > 0x7FFFFFFF) return cudaErrorInvalidValue;
-      H[5] = (int32_t)ovf_off.size();
-      H[6] = (int32_t)ovf_ent.size();
-      size_t n = 0;
-      for (int i = 0; i < EC; i++) {
-        ovf_off.push_back((uint16_t)n);
-        for (size_t t = ELL; t < per_el[i].size(); t++) { ovf_ent.push_back(per_el[i][t]); n++; }
-      }
-      if (n > 65535) return cudaErrorInvalidValue;
-      ovf_off.push_back((uint16_t)n);
-    }
-    return 0;
-  };
-  // chunk [b0,b1) from the candidate faces of its block; halves it while it does not fit
-  struct Range { int64_t b0, b1; };
-  std::vector<Range> todo;
-  for (int blk = 0; blk < nblocks; blk++) {
-    cand.assign(rec.begin() + face_off[blk], rec.begin() + face_off[blk + 1]);
-    todo.clear();
-    todo.push_back({(int64_t)blk * EC, std::min<int64_t>((int64_t)blk * EC + EC, n_local)});
-    while (!todo.empty()) {
-      const Range rg = todo.back();
-      todo.pop_back();
-      const std::vector<int64_t>* fs = &cand;
-      if (rg.b1 - rg.b0 < std::min<int64_t>(EC, n_local - (int64_t)blk * EC)) {   // part of a split block
-        sub.clear();
-        for (int64_t f : cand) {
-          int32_t l, r;
-          endpoints(f, l, r);
-          if ((l >= rg.b0 && l < rg.b1) || (r >= rg.b0 && r < rg.b1)) sub.push_back(f);
-        }
-        fs = &sub;
-      }
-      int rc = emit(rg.b0, rg.b1, *fs, true);
-      if (rc == 1) {
-        if (rg.b1 - rg.b0 <= 1) return cudaErrorInvalidValue;   // one element with more faces than a CTA can hold
-        const int64_t mid = (rg.b0 + rg.b1) / 2;
-        todo.push_back({mid, rg.b1});   // LIFO: the lower half is emitted first, chunks stay in element order
-        todo.push_back({rg.b0, mid});
-        split = true;
-        continue;
-      }
-      rc = emit(rg.b0, rg.b1, *fs, false);
-      if (rc) return rc;
-    }
+  });
+  for (int t = 0; t < NT; t++)
+    if (bad[t]) return cudaErrorInvalidValue;
+  std::vector<int64_t> face_off(nblocks + 1, 0);
+  for (int b = 0; b < nblocks; b++) {
+    int64_t sum = 0;
+    for (int t = 0; t < NT; t++) { int32_t v = cnt[t][b]; cnt[t][b] = (int32_t)sum; sum += v; }   // thread offset in block
+    face_off[b + 1] = face_off[b] + sum;
   }
-  const int nchunks = (int)(hdr.size() / 8);
-  if (n_local > 0x7FFFFF00LL || (int64_t)nchunks * MF > 0x7FFFFF00LL) return cudaErrorInvalidValue;  // 32-bit indices
+  std::vector<int64_t> rec(face_off[nblocks]);
+  parallel_ranges(ntot, NT, [&](int t, int64_t f0, int64_t f1) {
+    auto& c = cnt[t];
+    for (int64_t f = f0; f < f1; f++) {
+      int32_t l, r;
+      src.endpoints(f, l, r);
+      int cl = l < n_local ? l / EC : -1, cr = (r >= 0 && r < n_local) ? r / EC : -1;
+      if (cl >= 0) rec[face_off[cl] + c[cl]++] = f;
+      if (cr >= 0 && cr != cl) rec[face_off[cr] + c[cr]++] = f;
+    }
+  });
+  cnt.clear();
+
+  // ---- per-block chunk emission, one builder per thread over a contiguous range of blocks
+  std::vector<uint16_t> ell((size_t)std::max<int64_t>(n_local, 1) * ELL, 0xFFFF);
+  struct Builder {
+    std::vector<int32_t>  hdr, halo_elem, halo_rank;
+    std::vector<int64_t>  halo_off{0}, rec_off{0};
+    std::vector<uint32_t> face_lr;
+    std::vector<uint8_t>  face_ai;
+    std::vector<T>        fnx, fny, fnz, far;
+    std::vector<uint16_t> ovf_off, ovf_ent;
+    int  max_halo = 0, max_faces = 0, rc = 0;
+    bool split = false;
+  };
+  std::vector<Builder> builders(NT);
+  parallel_ranges(nblocks, NT, [&](int t, int64_t blk0, int64_t blk1) {
+    Builder& B = builders[t];
+    std::vector<int32_t> halo_tmp;
+    std::vector<int64_t> cand, sub;
+    std::vector<std::vector<uint16_t>> per_el(EC);
+    struct Rec { int grp, sl, sr; int64_t f; };
+    std::vector<Rec> recs;
+
+    // emits the chunk [b0, b1) whose faces are `faces`; 1 if it does not fit the kernel's shared memory
+    auto emit = [&](int64_t b0, int64_t b1, const std::vector<int64_t>& faces, bool dry) -> int {
+      const int nfc = (int)faces.size();
+      halo_tmp.clear();
+      for (int64_t f : faces) {
+        int32_t l, r;
+        src.endpoints(f, l, r);
+        if (l < b0 || l >= b1) halo_tmp.push_back(l);
+        if (r >= 0 && (r < b0 || r >= b1)) halo_tmp.push_back(r);
+      }
+      std::sort(halo_tmp.begin(), halo_tmp.end());
+      halo_tmp.erase(std::unique(halo_tmp.begin(), halo_tmp.end()), halo_tmp.end());
+      const int nh = (int)halo_tmp.size();
+      if (nh > max_halo_allowed || nfc > max_faces_allowed) return 1;
+      if (dry) return 0;
+      B.max_halo  = std::max(B.max_halo, nh);
+      B.max_faces = std::max(B.max_faces, nfc);
+      B.hdr.resize(B.hdr.size() + 8, 0);
+      int32_t* H = &B.hdr[B.hdr.size() - 8];
+      H[0] = (int32_t)b0;
+      H[1] = (int32_t)(b1 - b0);
+      H[2] = nh | (nfc << 16);
+      for (int h = 0; h < nh; h++) {
+        int32_t id = halo_tmp[h], rk = 0, ix = id;
+        if (multi) src.owner(id, rk, ix);
+        else if (id >= n_local) return cudaErrorInvalidValue;
+        B.halo_elem.push_back(ix);
+        B.halo_rank.push_back(rk);
+      }
+      B.halo_off.push_back((int64_t)B.halo_elem.size());
+      auto slot_of = [&](int32_t id) -> int {
+        if (id >= b0 && id < b1) return (int)(id - b0);
+        return EC + (int)(std::lower_bound(halo_tmp.begin(), halo_tmp.end(), id) - halo_tmp.begin());
+      };
+      // kernel order of the records: cmp -> x, y, z interior faces, then walls; inside a group by left slot, so that
+      // the threads of a warp read neighbouring slots of the cell array (few bank conflicts whatever the numbering)
+      recs.resize(nfc);
+      int seg[4] = {0, 0, 0, 0};
+      for (int j = 0; j < nfc; j++) {
+        const int64_t f = faces[j];
+        int32_t       l, r;
+        src.endpoints(f, l, r);
+        int sl = slot_of(l), sr = r < 0 ? 0xFFFF : slot_of(r), grp = 0;
+        if (cmp) {
+          T nrm[3], a;
+          src.geometry(f, nrm, a);
+          const int code = axis_code(nrm);
+          grp = r < 0 ? 3 : code >> 1;
+          if (r < 0) sr = 0xFFF8 | code;                  // wall: outward normal coded in the slotR field
+          else if (!(code & 1)) std::swap(sl, sr);        // canonical orientation: normal = +e_axis
+          seg[grp]++;
+        }
+        recs[j] = Rec{grp, sl, sr, f};
+      }
+      std::sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) {
+        if (x.grp != y.grp) return x.grp < y.grp;
+        if (by_id) return x.f < y.f;
+        if (x.sl != y.sl) return x.sl < y.sl;
+        if (x.sr != y.sr) return x.sr < y.sr;
+        return x.f < y.f;
+      });
+      H[3] = seg[0] | ((seg[0] + seg[1]) << 16);
+      H[4] = seg[0] + seg[1] + seg[2];
+      for (auto& v : per_el) v.clear();
+      int  area0 = -1;
+      bool uniform = cmp;
+      for (int j = 0; j < nfc; j++) {
+        const int64_t f  = recs[j].f;
+        const int     sl = recs[j].sl, sr = recs[j].sr;
+        if (cmp) {
+          B.face_ai.push_back(area_of[f]);
+          if (area0 < 0) area0 = area_of[f];
+          if (area_of[f] != area0) uniform = false;
+        } else {
+          T nrm[3], a;
+          src.geometry(f, nrm, a);
+          B.fnx.push_back(nrm[0]); B.fny.push_back(nrm[1]); B.fnz.push_back(nrm[2]); B.far.push_back(a);
+        }
+        B.face_lr.push_back((uint32_t)sl | ((uint32_t)sr << 16));
+        if (sl < EC) per_el[sl].push_back((uint16_t)(j << 1));
+        if (sr < EC) per_el[sr].push_back((uint16_t)((j << 1) | 1));
+      }
+      B.rec_off.push_back((int64_t)B.face_lr.size());
+      H[7] = (uniform && area0 >= 0) ? area0 : -1;
+      // fixed-width table (disjoint element ranges: written in place) + overflow CSR (bases relative to this builder)
+      bool overflow = false;
+      for (int i = 0; i < (int)(b1 - b0); i++) {
+        const auto& v = per_el[i];
+        for (size_t q = 0; q < v.size() && q < (size_t)ELL; q++) ell[((size_t)b0 + i) * ELL + q] = v[q];
+        if (v.size() > (size_t)ELL) overflow = true;
+      }
+      H[5] = -1;
+      H[6] = 0;
+      if (overflow) {
+        H[5] = (int32_t)B.ovf_off.size();
+        H[6] = (int32_t)B.ovf_ent.size();
+        size_t n = 0;
+        for (int i = 0; i < EC; i++) {
+          B.ovf_off.push_back((uint16_t)n);
+          for (size_t q = ELL; q < per_el[i].size(); q++) { B.ovf_ent.push_back(per_el[i][q]); n++; }
+        }
+        if (n > 65535) return cudaErrorInvalidValue;
+        B.ovf_off.push_back((uint16_t)n);
+      }
+      return 0;
+    };
+    // chunk [b0,b1) from the candidate faces of its block; halves it while it does not fit
+    struct Range { int64_t b0, b1; };
+    std::vector<Range> todo;
+    for (int64_t blk = blk0; blk < blk1 && !B.rc; blk++) {
+      cand.assign(rec.begin() + face_off[blk], rec.begin() + face_off[blk + 1]);
+      const int64_t blk_b0 = blk * EC, blk_b1 = std::min<int64_t>(blk * EC + EC, n_local);
+      todo.clear();
+      todo.push_back({blk_b0, blk_b1});
+      while (!todo.empty()) {
+        const Range rg = todo.back();
+        todo.pop_back();
+        const std::vector<int64_t>* fs = &cand;
+        if (rg.b1 - rg.b0 < blk_b1 - blk_b0) {   // part of a split block
+          sub.clear();
+          for (int64_t f : cand) {
+            int32_t l, r;
+            src.endpoints(f, l, r);
+            if ((l >= rg.b0 && l < rg.b1) || (r >= rg.b0 && r < rg.b1)) sub.push_back(f);
+          }
+          fs = &sub;
+        }
+        int rc = emit(rg.b0, rg.b1, *fs, true);
+        if (rc == 1) {
+          if (rg.b1 - rg.b0 <= 1) { B.rc = cudaErrorInvalidValue; break; }   // one element exceeds a CTA
+          const int64_t mid = (rg.b0 + rg.b1) / 2;
+          todo.push_back({mid, rg.b1});   // LIFO: the lower half is emitted first, chunks stay in element order
+          todo.push_back({rg.b0, mid});
+          B.split = true;
+          continue;
+        }
+        rc = emit(rg.b0, rg.b1, *fs, false);
+        if (rc) { B.rc = rc; break; }
+      }
+    }
+  });
+  rec.clear();
+  rec.shrink_to_fit();
+
+  // ---- merge the builders in block order, at fixed strides per chunk (halo padded with -1, faces with 0)
+  int     nchunks = 0, max_halo = 0, max_faces = 0;
+  bool    split = false;
+  int64_t n_halo = 0, n_rec = 0;
+  size_t  n_ovf_off = 0, n_ovf_ent = 0;
+  for (auto& B : builders) {
+    if (B.rc) return B.rc;
+    nchunks += (int)(B.hdr.size() / 8);
+    max_halo  = std::max(max_halo, B.max_halo);
+    max_faces = std::max(max_faces, B.max_faces);
+    split |= B.split;
+    n_halo += (int64_t)B.halo_elem.size();
+    n_rec += (int64_t)B.face_lr.size();
+    n_ovf_off += B.ovf_off.size();
+    n_ovf_ent += B.ovf_ent.size();
+  }
+  if (n_local > 0x7FFFFF00LL || (int64_t)nchunks * MF > 0x7FFFFF00LL || n_ovf_off > 0x7FFFFF00ULL ||
+      n_ovf_ent > 0x7FFFFF00ULL)
+    return cudaErrorInvalidValue;   // 32-bit indices in the kernel
   P->n_chunks = nchunks;
   P->split    = split ? 1 : 0;
-
-  // fixed strides per chunk: halo lists padded with -1, face arrays with 0
   const int HS = std::max(32, (max_halo + 31) / 32 * 32), FS = std::max(32, (max_faces + 31) / 32 * 32);
+  std::vector<int32_t>  hdr((size_t)nchunks * 8), halo_elem((size_t)nchunks * HS, -1),
+      halo_rank(multi ? (size_t)nchunks * HS : 0, 0);
+  std::vector<uint32_t> face_lr((size_t)nchunks * FS, 0);
+  std::vector<uint8_t>  face_ai(cmp ? (size_t)nchunks * FS : 0, 0);
+  std::vector<T>        fnx(cmp ? 0 : (size_t)nchunks * FS), fny(fnx.size()), fnz(fnx.size()), far(fnx.size());
+  std::vector<uint16_t> ovf_off(n_ovf_off), ovf_ent(n_ovf_ent);
   {
-    std::vector<int32_t> he((size_t)nchunks * HS, -1), hr(multi ? (size_t)nchunks * HS : 0, 0);
-    for (int c = 0; c < nchunks; c++)
-      for (int64_t q = halo_off[c]; q < halo_off[c + 1]; q++) {
-        he[(size_t)c * HS + (q - halo_off[c])] = halo_elem[q];
-        if (multi) hr[(size_t)c * HS + (q - halo_off[c])] = halo_rank[q];
+    std::vector<int>    chunk_base(NT + 1, 0);
+    std::vector<size_t> oo_base(NT + 1, 0), oe_base(NT + 1, 0);
+    for (int t = 0; t < NT; t++) {
+      chunk_base[t + 1] = chunk_base[t] + (int)(builders[t].hdr.size() / 8);
+      oo_base[t + 1]    = oo_base[t] + builders[t].ovf_off.size();
+      oe_base[t + 1]    = oe_base[t] + builders[t].ovf_ent.size();
+    }
+    parallel_ranges(NT, NT, [&](int, int64_t t0, int64_t t1) {
+      for (int64_t t = t0; t < t1; t++) {
+        Builder& B  = builders[t];
+        const int nc = (int)(B.hdr.size() / 8);
+        for (int i = 0; i < nc; i++) {
+          const size_t c = (size_t)chunk_base[t] + i;
+          int32_t*     H = &hdr[c * 8];
+          std::copy(B.hdr.begin() + (size_t)i * 8, B.hdr.begin() + (size_t)i * 8 + 8, H);
+          if (H[5] >= 0) { H[5] += (int32_t)oo_base[t]; H[6] += (int32_t)oe_base[t]; }
+          std::copy(B.halo_elem.begin() + B.halo_off[i], B.halo_elem.begin() + B.halo_off[i + 1], halo_elem.begin() + c * HS);
+          if (multi)
+            std::copy(B.halo_rank.begin() + B.halo_off[i], B.halo_rank.begin() + B.halo_off[i + 1], halo_rank.begin() + c * HS);
+          const int64_t r0 = B.rec_off[i], r1 = B.rec_off[i + 1];
+          std::copy(B.face_lr.begin() + r0, B.face_lr.begin() + r1, face_lr.begin() + c * FS);
+          if (cmp) std::copy(B.face_ai.begin() + r0, B.face_ai.begin() + r1, face_ai.begin() + c * FS);
+          else {
+            std::copy(B.fnx.begin() + r0, B.fnx.begin() + r1, fnx.begin() + c * FS);
+            std::copy(B.fny.begin() + r0, B.fny.begin() + r1, fny.begin() + c * FS);
+            std::copy(B.fnz.begin() + r0, B.fnz.begin() + r1, fnz.begin() + c * FS);
+            std::copy(B.far.begin() + r0, B.far.begin() + r1, far.begin() + c * FS);
+          }
+        }
+        std::copy(B.ovf_off.begin(), B.ovf_off.end(), ovf_off.begin() + oo_base[t]);
+        std::copy(B.ovf_ent.begin(), B.ovf_ent.end(), ovf_ent.begin() + oe_base[t]);
+        B = Builder();
       }
-    P->n_halo = (int64_t)halo_elem.size();
-    halo_elem.swap(he);
-    halo_rank.swap(hr);
+    });
   }
-  auto restride = [&](auto& v) {
-    typename std::remove_reference<decltype(v)>::type out((size_t)nchunks * FS);
-    for (int c = 0; c < nchunks; c++)
-      std::copy(v.begin() + rec_off[c], v.begin() + rec_off[c + 1], out.begin() + (size_t)c * FS);
-    v.swap(out);
-  };
-  P->n_records = (int64_t)face_lr.size();
-  restride(face_lr);
-  if (cmp) restride(face_ai);
-  else { restride(fnx); restride(fny); restride(fnz); restride(far); }
+  P->n_halo     = n_halo;
+  P->n_records  = n_rec;
   P->hs = HS;
   P->fs = FS;
   P->max_halo   = max_halo;
