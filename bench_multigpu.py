@@ -12,7 +12,7 @@ import time
 import torch
 import torch.distributed as dist
 
-BRICK = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+from t8gpu_b200.multi import BRICK, exchange_wires, global_max_wave_speed, row_pointers, stage_barrier, timestep
 
 
 class MultiGpuEuler:
@@ -31,20 +31,12 @@ class MultiGpuEuler:
         self.shared = tb.SharedBuffer(nrows * self.cap * esz, device)
         self.buffer = self.shared.tensor((nrows, self.cap), dtype)
         self.buffer[NVAR * NB_STEPS, :self.n] = conn["volumes"]
-        # exchange (handle, capacity) with every rank
-        mine = torch.tensor(list(self.shared.handle) + list(int(self.cap).to_bytes(8, "little")), dtype=torch.uint8,
-                            device=device)
-        allh = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allh, mine)
-        bases, caps = [], []
-        for r in range(world):
-            raw = bytes(allh[r].cpu().tolist())
-            caps.append(int.from_bytes(raw[64:72], "little"))
-            bases.append(self.shared.ptr if r == rank else self.shared.open_peer(raw[:64]))
-        self.tables = {}
-        for s in range(NB_STEPS):
-            self.tables[s] = tb.PointerTables([[bases[r] + (s * NVAR + k) * caps[r] * esz for r in range(world)]
-                                               for k in range(NVAR)], device)
+        # exchange (handle, capacity) with every rank, map the peers, fill the [var][rank] tables
+        wires = exchange_wires(dist, self.shared.handle, self.cap, world, device)
+        caps = [c for _, c in wires]
+        bases = [self.shared.ptr if r == rank else self.shared.open_peer(wires[r][0]) for r in range(world)]
+        rows = row_pointers(bases, caps, NVAR, NB_STEPS, esz)
+        self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
         self.plan = tb.Plan(tb.conn_to_host(conn), dtype)
         tb.init_kelvin_helmholtz(3, conn["centroids"], self.variables(0))
         self.next, self.prev = 0, 3
@@ -66,11 +58,11 @@ class MultiGpuEuler:
         prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
         vol, T = self.volume(), self.tables
         self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev])
-        dist.all_reduce(self.token, op=dist.ReduceOp.MAX)          # device-side stage barrier
+        stage_barrier(dist, self.token)                            # device-side, on the compute stream
         self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1])
-        dist.all_reduce(self.token, op=dist.ReduceOp.MAX)
+        stage_barrier(dist, self.token)
         self.plan.stage(3, s2, prev, nxt, vol, dt, in_all=T[2], speed_max=self.speed_max)
-        dist.all_reduce(self.speed_max, op=dist.ReduceOp.MAX)      # barrier + global CFL reduction
+        global_max_wave_speed(dist, self.speed_max)                # barrier + global CFL reduction
         return 3
 
     def close(self):
@@ -133,7 +125,7 @@ def run_multi(args, rank, world, device):
         sol.iterate(cur_dt)
         vmax_host.copy_(sol.speed_max, non_blocking=True)
         stream.synchronize()
-        cur_dt = min(dt, 0.7 * 0.5 ** args.level / float(vmax_host[0]))
+        cur_dt = timestep(float(vmax_host[0]), 0.7, args.level, dt_cap=dt)
     out_host.copy_(sol.buffer[sol.next * 5:(sol.next + 1) * 5, :n], non_blocking=True)
     e1.record(stream)
     torch.cuda.synchronize()
