@@ -67,3 +67,45 @@ class MultiRankEuler:
                 for r in range(self.P):
                     t8gpu_b200.rk3_stage(stage, self.vars(r, self.prev), self.vars(r, sin) if stage > 1 else None,
                                          self.vars(r, sout), self.vars(r, FLUXES), self.vol(r), dt)
+
+
+class MultiRankSubgrid:
+    """P ranks of the fused subgrid solver on ONE device: SubgridMemoryManager-layout buffers per rank, ghost cells read
+    through [var][rank] pointer tables, stage s of every rank launched before stage s+1 of any."""
+
+    def __init__(self, forest, P, dtype, device):
+        self.P, self.dtype, self.device = P, dtype, device
+        npdt = np.float64 if dtype == torch.float64 else np.float32
+        self.S = 64 if forest.dim == 3 else 16
+        self.off = forest.partition_offsets(P)
+        lv, cent, vol, _ = forest.elements()
+        self.conn = [forest.connectivity(P, r, subgrid=True, dtype=npdt) for r in range(P)]
+        self.n = [int(c["n_local"]) for c in self.conn]
+        self.buf, self.vol = [], []
+        for r in range(P):
+            self.buf.append(torch.zeros((NVAR * NB_STEPS, max(32, self.n[r] * self.S)), dtype=dtype, device=device))
+            self.vol.append(torch.as_tensor(vol[self.off[r]:self.off[r + 1]].astype(npdt)).to(device))
+        self.tables = {s: t8gpu_b200.RankTables([self.vars(r, s) for r in range(P)], device) for s in range(NB_STEPS)}
+        self.plans = [t8gpu_b200.SubgridPlan(self.conn[r], vol[self.off[r]:self.off[r + 1]].astype(npdt), dtype)
+                      for r in range(P)]
+        self.next, self.prev = STEP0, STEP3
+
+    def vars(self, r, step):
+        return [self.buf[r][step * NVAR + k, :self.n[r] * self.S] for k in range(NVAR)]
+
+    def set_global_state(self, u):
+        S = self.S
+        for r in range(self.P):
+            t = torch.as_tensor(np.ascontiguousarray(u[:, self.off[r] * S:self.off[r + 1] * S])).to(self.dtype)
+            self.buf[r][self.next * NVAR:(self.next + 1) * NVAR, :self.n[r] * S] = t.to(self.device)
+
+    def global_state(self):
+        return np.concatenate([self.buf[r][self.next * NVAR:(self.next + 1) * NVAR, :self.n[r] * self.S].cpu().numpy()
+                               for r in range(self.P)], axis=1)
+
+    def iterate(self, dt):
+        self.next, self.prev = self.prev, self.next
+        for stage, sin, sout in [(1, self.prev, STEP1), (2, STEP1, STEP2), (3, STEP2, self.next)]:
+            for r in range(self.P):
+                self.plans[r].stage(stage, self.vars(r, sin), self.vars(r, self.prev), self.vars(r, sout), self.vol[r],
+                                    dt, in_all=self.tables[sin])

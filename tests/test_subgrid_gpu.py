@@ -123,3 +123,23 @@ def test_subgrid_product_vs_reference_live(cuda, dim, level, dtype):
             sol.iterate(dt)
             err = rel_linf(sol.state().cpu().numpy(), s.get_state())
             assert err <= (it + 1) * TOL[np.dtype(dtype)], (mode, it, err)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,P", [("hex2", 2), ("hex_amr", 3), ("quad_amr_walls", 2)])
+def test_subgrid_multi_rank_on_one_gpu(cuda, kind, P, dtype):
+    """P ranks of the fused subgrid stage emulated on one device: ghost cells through the (rank, index) tables,
+    partition-boundary faces evaluated by both owners (x-faces), 2:1 hanging faces across ranks."""
+    from multirank import MultiRankSubgrid
+    forest, lvl = sg_forest(kind)
+    conn1 = forest.connectivity(subgrid=True, dtype=dtype)
+    u0, vol = sg_state(forest, dtype, seed=17)
+    dt = 0.1 * 2.0 ** -(lvl + 2)
+    mr = MultiRankSubgrid(forest, P, DT[dtype], cuda)
+    mr.set_global_state(u0)
+    u = u0
+    for it in range(4):
+        u, _, _ = oracle.subgrid_iterate(conn1, vol, u, dt)
+        mr.iterate(dt)
+        err = rel_linf(mr.global_state(), u)
+        assert err <= (it + 1) * TOL[np.dtype(dtype)], (it, err)
