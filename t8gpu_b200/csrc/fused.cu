@@ -34,6 +34,8 @@ struct FusedArgs {
   int             n_areas;
   int             hs, fs;
   int             wave;  // CTAs resident on the device at once = distance of the next-wave prefetch (0: off)
+  const char*     pf_ptr[16];   // L2 prefetch table: base pointer (null: skip) and bytes per index
+  unsigned        pf_unit[16];
   const uint4*    ell;
   const uint16_t* ovf_off;
   const uint16_t* ovf_ent;
@@ -119,41 +121,38 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   uint32_t lr_n = 0;
   if (tid < A.fs) lr_n = A.face_lr[fb + tid];
   if ((tid & 31) == 0) {
-    // L2 prefetch hints, one or two per warp (a bulk prefetch is a warp-uniform instruction: spreading them avoids a
-    // serial loop in one warp).  Items 0-6: the phase-2 operands of this chunk, so that their loads before the barrier
-    // are L2 hits.  Items 8-15 (SPLIT == false only: addresses computable without a header): the streams of the chunk
-    // that takes over a CTA slot about one wave later (CTAs are dispatched in index order).
-    const int w = tid >> 5;   // 0..7
-    if (w < 5) { if (A.stage != 1) prefetch_l2(A.prev[w] + e0c, (unsigned)ecn * sizeof(T)); }
-    else if (w == 5) prefetch_l2(A.vol + (e0c >> A.vol_shift), ((unsigned)(ecn - 1) >> A.vol_shift) * sizeof(T) + sizeof(T));
-    else if (w == 6) prefetch_l2(A.ell + e0c, (unsigned)ecn * sizeof(uint4));
+    // L2 prefetch hints, two per warp (a bulk prefetch is a warp-uniform instruction: spreading them avoids a serial
+    // loop in one warp), table-driven (A.pf_*, filled by the host).  Items 0-7: the phase-2 operands of this chunk, so
+    // that their loads before the barrier are L2 hits.  Items 8-15 (SPLIT == false only: addresses computable
+    // without a header): the streams of the chunk that takes over a CTA slot about one wave later (CTAs are
+    // dispatched in index order): 8-12 state rows, 13-15 halo indices, face records, header.
+    const int w  = tid >> 5;   // 0..7
     const int cw = c + A.wave;
-    if (!SPLIT && A.wave > 0 && cw < (int)gridDim.x) {
-      const int      b1 = cw * EC;
-      const unsigned n1 = (unsigned)min(EC, (int)A.n_local - b1);
-      if (w < 5) prefetch_l2(A.in[w] + b1, n1 * sizeof(T));
-      else if (w == 5) prefetch_l2(A.halo_elem + (int64_t)cw * A.hs, A.hs * 4u);
-      else if (w == 6) prefetch_l2(A.face_lr + (int64_t)cw * A.fs, A.fs * 4u);
-      else prefetch_l2(A.hdr + 2 * cw, 32u);
+    if (A.pf_ptr[w]) prefetch_l2(A.pf_ptr[w] + (size_t)e0c * A.pf_unit[w], (unsigned)ecn * A.pf_unit[w]);
+    if (!SPLIT && A.pf_ptr[w + 8] && cw < (int)gridDim.x) {
+      const unsigned idx = w < 5 ? (unsigned)cw * EC : (unsigned)cw;
+      const unsigned cnt = w < 5 ? (unsigned)min(EC, (int)A.n_local - cw * EC) : 1u;
+      prefetch_l2(A.pf_ptr[w + 8] + (size_t)idx * A.pf_unit[w + 8], cnt * A.pf_unit[w + 8]);
     }
   }
   if (CMP && tid < A.n_areas) atab[tid] = A.area_tab[tid];
 
   if (own) store_cell<T, MS>(cq, tid, to_cell(u0, u1, u2, u3, u4));
-  for (int h = tid; h < A.hs; h += EC) {
-    if (h >= EC) {  // only plans with more than EC halo entries in some chunk (adaptive meshes)
-      hidx = A.halo_elem[hb + h];
-      if (A.multi) hrk = A.halo_rank[hb + h];
+  auto convert_halo = [&](int h, int idx, int rk) {
+    T a0, a1, a2, a3, a4;
+    if (A.multi) {
+      a0 = A.in_all[0][rk][idx]; a1 = A.in_all[1][rk][idx]; a2 = A.in_all[2][rk][idx];
+      a3 = A.in_all[3][rk][idx]; a4 = A.in_all[4][rk][idx];
+    } else {
+      a0 = A.in[0][idx]; a1 = A.in[1][idx]; a2 = A.in[2][idx]; a3 = A.in[3][idx]; a4 = A.in[4][idx];
     }
-    if (hidx >= 0) {
-      T a0, a1, a2, a3, a4;
-      if (A.multi) {
-        a0 = A.in_all[0][hrk][hidx]; a1 = A.in_all[1][hrk][hidx]; a2 = A.in_all[2][hrk][hidx];
-        a3 = A.in_all[3][hrk][hidx]; a4 = A.in_all[4][hrk][hidx];
-      } else {
-        a0 = A.in[0][hidx]; a1 = A.in[1][hidx]; a2 = A.in[2][hidx]; a3 = A.in[3][hidx]; a4 = A.in[4][hidx];
-      }
-      store_cell<T, MS>(cq, EC + h, to_cell(a0, a1, a2, a3, a4));
+    store_cell<T, MS>(cq, EC + h, to_cell(a0, a1, a2, a3, a4));
+  };
+  if (hidx >= 0) convert_halo(tid, hidx, hrk);
+  if (A.hs > EC) {   // only plans with more than EC halo entries in some chunk (adaptive meshes)
+    for (int h = tid + EC; h < A.hs; h += EC) {
+      const int idx = A.halo_elem[hb + h];
+      if (idx >= 0) convert_halo(h, idx, A.multi ? A.halo_rank[hb + h] : 0);
     }
   }
   const int  nfc = (unsigned)h0v.z >> 16;
@@ -295,6 +294,18 @@ static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStrea
   FusedArgs<T> B = A;
   static const int wave_knob = getenv("T8B200_WAVE") ? atoi(getenv("T8B200_WAVE")) : -1;   // tuning knob
   B.wave = wave_knob >= 0 ? wave_knob : resident;
+  for (int k = 0; k < 16; k++) { B.pf_ptr[k] = nullptr; B.pf_unit[k] = 0; }
+  for (int k = 0; k < 5; k++) {
+    if (B.stage != 1) { B.pf_ptr[k] = (const char*)B.prev[k]; B.pf_unit[k] = sizeof(T); }
+    if (B.wave > 0) { B.pf_ptr[8 + k] = (const char*)B.in[k]; B.pf_unit[8 + k] = sizeof(T); }
+  }
+  if (B.vol_shift == 0) { B.pf_ptr[5] = (const char*)B.vol; B.pf_unit[5] = sizeof(T); }
+  B.pf_ptr[6] = (const char*)B.ell; B.pf_unit[6] = sizeof(uint4);
+  if (B.wave > 0) {
+    B.pf_ptr[13] = (const char*)B.halo_elem; B.pf_unit[13] = (unsigned)B.hs * 4u;
+    B.pf_ptr[14] = (const char*)B.face_lr;   B.pf_unit[14] = (unsigned)B.fs * 4u;
+    B.pf_ptr[15] = (const char*)B.hdr;       B.pf_unit[15] = 32u;
+  }
   k<<<P->n_chunks, EC, P->smem_bytes, st>>>(B);
   return cudaGetLastError();
 }
