@@ -293,3 +293,32 @@ def test_split_chunks(cuda, kind, general, dtype, monkeypatch):
         err = rel_linf(sol.state().cpu().numpy(), u)
         assert err <= (it + 1) * TOL[np.dtype(dtype)], (kind, it, err)
     assert float(sol.max_wave_speed().item()) > 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("mode", ["fused", "unfused"])
+@pytest.mark.parametrize("periodic,shuffle", [(True, False), (False, False), (True, True)])
+def test_hybrid_tet_prism_hex_mesh(cuda, periodic, shuffle, mode, dtype):
+    """Mixed element types (BASELINE config 5 at kernel level): hexahedra (8 faces after splitting their horizontal
+    quads), prisms (5) and tetrahedra (4) with general normals, optionally in a scrambled element order (no spatial
+    locality at all: large halos, blocks get split)."""
+    import t8gpu_b200
+    from util import hybrid_mesh, smooth_state
+    conn, vol, cent = hybrid_mesh(6, periodic, dtype, shuffle=shuffle)
+    u0 = smooth_state(cent, dtype, seed=31)
+    dt = 0.02 / 6
+    sol = t8gpu_b200.EulerSolver(conn, vol, DT[dtype], device=cuda, mode=mode)
+    if mode == "fused" and shuffle:
+        assert sol.plan.info["n_chunks"] > (conn["n_local"] + 255) // 256
+    sol.set_state(u0)
+    u = u0
+    for it in range(4):
+        u, _, _ = oracle.iterate(conn, vol, u, dt)
+        sol.iterate(dt)
+        err = rel_linf(sol.state().cpu().numpy(), u)
+        assert err <= (it + 1) * TOL[np.dtype(dtype)], (it, err)
+    # conservation: sum(vol * u) is preserved on the periodic mesh (fluxes cancel pairwise)
+    if periodic and dtype == np.float64:
+        tot0 = (u0.astype(np.float64) * vol).sum(1)
+        tot1 = (sol.state().cpu().numpy() * vol).sum(1)
+        assert np.abs(tot1 - tot0).max() <= 1e-12 * np.abs(tot0).max()
