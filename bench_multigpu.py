@@ -37,6 +37,13 @@ class MultiGpuEuler:
         bases = [self.shared.ptr if r == rank else self.shared.open_peer(wires[r][0]) for r in range(world)]
         rows = row_pointers(bases, caps, NVAR, NB_STEPS, esz)
         self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
+        # stage barrier + CFL max over peer memory (T8B200_SYNC=nccl: 1-element NCCL all-reduces instead)
+        self.mail = None
+        if os.environ.get("T8B200_SYNC", "peer") == "peer":
+            self.mail = tb.PeerMailboxes(rank, world, device)
+            mw = exchange_wires(dist, self.mail.handle, 0, world, device)
+            self.mail.exchange([h for h, _ in mw])
+            self.speed_loc = torch.zeros(1, dtype=dtype, device=device)
         self.plan = tb.Plan(tb.conn_to_host(conn), dtype)
         tb.init_kelvin_helmholtz(3, conn["centroids"], self.variables(0))
         self.next, self.prev = 0, 3
@@ -57,6 +64,14 @@ class MultiGpuEuler:
         self.next, self.prev = self.prev, self.next
         prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
         vol, T = self.volume(), self.tables
+        if self.mail is not None:   # barriers and the CFL reduction through the peers' mailboxes (NVLink stores)
+            self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev])
+            self.mail.barrier()
+            self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1])
+            self.mail.barrier()
+            self.plan.stage(3, s2, prev, nxt, vol, dt, in_all=T[2], speed_max=self.speed_loc)
+            self.mail.barrier(self.speed_loc, self.speed_max)
+            return 3
         self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev])
         stage_barrier(dist, self.token)                            # device-side, on the compute stream
         self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1])
@@ -69,6 +84,8 @@ class MultiGpuEuler:
         torch.cuda.synchronize()
         dist.barrier()
         self.plan = None
+        if self.mail is not None:
+            self.mail.close()
         self.shared.close()
 
 
@@ -155,8 +172,11 @@ def run_multi(args, rank, world, device):
                            "elements_per_gpu": n, "faces_per_gpu": nfaces, "ghosts_per_gpu": nghost,
                            "partition": "one tree (one t8code SFC partition) per GPU; ghosts read from peer GPUs "
                                         "over NVLink (cudaIpc-mapped state arrays), owner-computes boundary faces",
-                           "sync": "1 NCCL all-reduce (1 element) per RK stage on the compute stream; stage 3 "
-                                   "carries the max wave speed", "l2": "inputs larger than L2",
+                           "sync": ("peer-memory mailbox barrier per RK stage on the compute stream (NVLink stores + "
+                                    "acquire spin); stage 3 carries the max wave speed" if os.environ.get(
+                                        "T8B200_SYNC", "peer") == "peer" else
+                                    "1 NCCL all-reduce (1 element) per RK stage on the compute stream; stage 3 "
+                                    "carries the max wave speed"), "l2": "inputs larger than L2",
                            "host_setup_s": round(t_setup, 2), "host_cores": os.cpu_count(), "plan": info},
                 "clocks": clocks,
                 "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",

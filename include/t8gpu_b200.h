@@ -206,6 +206,17 @@ int t8b200_shared_open(const unsigned char handle[64], void** dev_ptr);
 int t8b200_shared_close(void* dev_ptr);
 int t8b200_shared_free(void* dev_ptr);
 
+/* Stage barrier + max-reduction between the GPUs of one node over peer memory; stays on the stream.  Replaces the
+ * cudaDeviceSynchronize() + MPI_Barrier pairs of iterate() (examples/compressible_euler/solver.cu:98-99, ...) and the
+ * MPI_Allreduce(MAX) of compute_timestep (solver.cu:219-223).
+ * mailboxes_dev: DEVICE array of nranks pointers; entry p is rank p's mailbox (nranks slots of 16 bytes, zero-initialised,
+ *   allocated with t8b200_shared_alloc and mapped here with t8b200_shared_open).  Every rank stores (value, epoch) into
+ *   its slot of every mailbox, then waits until all slots of its own mailbox carry `epoch` (strictly increasing, > 0,
+ *   the same on all ranks).  value_dev: device scalar (float or double per value_is_f64) or NULL (pure barrier);
+ *   out_max_dev: receives the maximum over the ranks, or NULL.  nranks <= 32. */
+int t8b200_peer_barrier(int nranks, int rank, long long epoch, void* const* mailboxes_dev, const void* value_dev,
+                        int value_is_f64, void* out_max_dev, void* stream);
+
 /* -------------------------------------------------------------------------------------------------------------
  * 5. Device-side remap of variables and volumes after t8code adapt / partition (which stay on the host).
  *    Every value is written straight into the new arrays (no temporary + set_variable round trip).

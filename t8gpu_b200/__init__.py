@@ -404,6 +404,44 @@ class SharedBuffer:
             self.ptr = None
 
 
+class PeerMailboxes:
+    """Mailboxes of t8b200_peer_barrier: one SharedBuffer of nranks 16-byte slots per rank, mapped on every rank.
+    `exchange(handles)`: handles = list over ranks of the 64-byte IPC handles (this rank's own entry is ignored)."""
+
+    def __init__(self, rank, nranks, device):
+        torch = _torch()
+        self.rank, self.nranks, self.device = rank, nranks, device
+        # a whole 2 MiB granule of its own, so that the IPC handle maps exactly this buffer
+        self.buf = SharedBuffer(max(16 * nranks, 2 << 20), device)
+        self.epoch = 0
+        self.table = None
+
+    @property
+    def handle(self):
+        return self.buf.handle
+
+    def exchange(self, handles):
+        torch = _torch()
+        ptrs_ = [self.buf.ptr if r == self.rank else self.buf.open_peer(handles[r]) for r in range(self.nranks)]
+        self.table = torch.tensor(ptrs_, dtype=torch.int64).to(self.device)
+
+    def barrier(self, value=None, out=None, stream=None):
+        """Stage barrier on `stream`; with value / out (device scalars) also the maximum over the ranks."""
+        self.epoch += 1
+        is64 = 1
+        if value is not None:
+            s, _ = _sfx(value.dtype)
+            is64 = int(s == "f64")
+        check(lib().t8b200_peer_barrier(self.nranks, self.rank, C.c_longlong(self.epoch),
+                                        C.c_void_p(self.table.data_ptr()),
+                                        C.c_void_p(value.data_ptr() if value is not None else None), is64,
+                                        C.c_void_p(out.data_ptr() if out is not None else None), stream_ptr(stream)),
+              "peer_barrier")
+
+    def close(self):
+        self.buf.close()
+
+
 class PointerTables:
     """`[var][rank] -> pointer` device tables built from raw integer pointers (peer-mapped or own)."""
 

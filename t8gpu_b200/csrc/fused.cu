@@ -51,6 +51,7 @@ struct FusedArgs {
   int64_t         n_local;
   int             stage;
   int             multi;
+  int             my_rank;
 };
 
 template <typename T, int MS>
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   if (own) store_cell<T, MS>(cq, tid, to_cell(u0, u1, u2, u3, u4));
   auto convert_halo = [&](int h, int idx, int rk) {
     T a0, a1, a2, a3, a4;
-    if (A.multi) {
+    if (A.multi && rk != A.my_rank) {   // ghost: through the [var][rank] tables (a peer GPU's array over NVLink)
       a0 = A.in_all[0][rk][idx]; a1 = A.in_all[1][rk][idx]; a2 = A.in_all[2][rk][idx];
       a3 = A.in_all[3][rk][idx]; a4 = A.in_all[4][rk][idx];
     } else {
@@ -340,7 +341,7 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
     A.out[k]    = out[k];
   }
   A.vol = vol; A.vol_shift = P->vol_shift; A.vol_scale = (T)P->vol_scale; A.dt = dt; A.speed_max = speed_max; A.n_local = P->n_local;
-  A.stage = stage; A.multi = P->multi;
+  A.stage = stage; A.multi = P->multi; A.my_rank = P->my_rank;
   cudaStream_t st = (cudaStream_t)stream;
   if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), st));
   return P->cmp ? launch_fused<T, true>(P, A, st) : launch_fused<T, false>(P, A, st);

@@ -18,6 +18,8 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <thread>
 #include <type_traits>
@@ -36,6 +38,7 @@ struct t8b200_plan {
   int     max_halo   = 0;
   int     max_faces  = 0;
   int     multi      = 0;  // has ghosts -> needs rank tables
+  int     my_rank    = 0;  // owner rank of the local elements (halo entries of this rank skip the pointer tables)
   int     split      = 0;  // some blocks of EC elements were split: chunk c no longer starts at element c * EC
   size_t  smem_bytes = 0;
   int     ms = 0, mf = 0;  // compile-time stride variant selected for the kernel
@@ -113,8 +116,21 @@ template <typename T, typename Src>
 static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   const int nblocks = (int)((n_local + EC - 1) / EC);
   const int NT      = plan_threads();
+  static const bool timing = getenv("T8B200_PLAN_TIMING") != nullptr;
+  auto              t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[t8b200 plan] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
   P->n_local = n_local;
   P->multi   = multi ? 1 : 0;
+  if (multi && n_local > 0) {
+    int32_t rk = 0, ix = 0;
+    src.owner(0, rk, ix);
+    P->my_rank = rk;
+  }
   const int64_t ntot = src.num_faces();
   int max_halo_allowed = MS - EC;
   const int max_faces_allowed = MF - 1;
@@ -159,6 +175,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
       }
     });
 
+  lap("geometry classes");
   // ---- bucket faces by block of EC elements (a face between two blocks appears in both): per-thread counts
   std::vector<std::vector<int32_t>> cnt(NT, std::vector<int32_t>(nblocks, 0));
   std::vector<int>                  bad(NT, 0);
@@ -194,6 +211,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   });
   cnt.clear();
 
+  lap("bucket faces by block");
   // ---- per-block chunk emission, one builder per thread over a contiguous range of blocks
   std::vector<uint16_t> ell((size_t)std::max<int64_t>(n_local, 1) * ELL, 0xFFFF);
   struct Builder {
@@ -359,6 +377,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   rec.clear();
   rec.shrink_to_fit();
 
+  lap("chunk emission");
   // ---- merge the builders in block order, at fixed strides per chunk (halo padded with -1, faces with 0)
   int     nchunks = 0, max_halo = 0, max_faces = 0;
   bool    split = false;
@@ -433,6 +452,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   P->mf = MF;
   P->smem_bytes = sizeof(T) * ((size_t)t8b200::NCELLQ * MS + 5 * (size_t)MF);
 
+  lap("merge");
   cudaError_t err = cudaSuccess;
   P->hdr       = upload(hdr, P->dev_bytes, err);
   P->halo_elem = upload(halo_elem, P->dev_bytes, err);
@@ -452,6 +472,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   P->ell     = reinterpret_cast<uint4*>(upload(ell, P->dev_bytes, err));
   P->ovf_off = upload(ovf_off, P->dev_bytes, err);
   P->ovf_ent = upload(ovf_ent, P->dev_bytes, err);
+  lap("upload");
   return err;
 }
 

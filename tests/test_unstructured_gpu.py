@@ -322,3 +322,24 @@ def test_hybrid_tet_prism_hex_mesh(cuda, periodic, shuffle, mode, dtype):
         tot0 = (u0.astype(np.float64) * vol).sum(1)
         tot1 = (sol.state().cpu().numpy() * vol).sum(1)
         assert np.abs(tot1 - tot0).max() <= 1e-12 * np.abs(tot0).max()
+
+
+def test_peer_barrier_single_rank(cuda):
+    """One rank: the mailbox barrier passes the value through and accepts increasing epochs (the multi-GPU semantics are
+    exercised by bench.py under torchrun: kernels of different ranks must run on different GPUs)."""
+    import ctypes as C
+    import t8gpu_b200 as tb
+    mb = tb.PeerMailboxes(0, 1, cuda)
+    mb.exchange([mb.handle])
+    for dt in (torch.float64, torch.float32):
+        v = torch.tensor([3.25], dtype=dt, device=cuda)
+        out = torch.zeros(1, dtype=dt, device=cuda)
+        mb.barrier(v, out)
+        mb.barrier()
+        torch.cuda.synchronize()
+        assert float(out[0]) == 3.25
+    L = tb.lib()
+    assert L.t8b200_peer_barrier(0, 0, C.c_longlong(1), None, None, 1, None, None) != 0
+    assert L.t8b200_peer_barrier(2, 2, C.c_longlong(1), C.c_void_p(mb.table.data_ptr()), None, 1, None, None) != 0
+    assert L.t8b200_peer_barrier(1, 0, C.c_longlong(0), C.c_void_p(mb.table.data_ptr()), None, 1, None, None) != 0
+    mb.close()
