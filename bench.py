@@ -80,7 +80,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_problem(level, dtype_name, rank, nranks, device, rotate=False):
+def build_problem(level, dtype_name, rank, nranks, device, rotate=False, mode="fused"):
     """Device connectivity + KH state for this rank's partition; returns (solver, info)."""
     import torch
     import t8gpu_b200 as tb
@@ -99,13 +99,13 @@ def build_problem(level, dtype_name, rank, nranks, device, rotate=False):
         q, _ = np.linalg.qr(np.random.default_rng(7).normal(size=(3, 3)))
         nrm = host["face_normals"].reshape(-1, 3).astype(np.float64) @ q.T
         host["face_normals"] = np.ascontiguousarray(nrm.reshape(-1).astype(host["face_normals"].dtype))
-    sol = tb.EulerSolver(host, host["volumes"], dtype, device=device, mode="fused")
+    sol = tb.EulerSolver(host, host["volumes"], dtype, device=device, mode=mode)
     torch.cuda.synchronize()
     t_plan = time.time() - t0
     tb.init_kelvin_helmholtz(3, conn["centroids"], sol.variables(sol.next))
     torch.cuda.synchronize()
     info = dict(n=n, faces=int(conn["n_faces"]), t_connectivity_s=round(t_conn, 3), t_plan_s=round(t_plan, 3),
-                plan=sol.plan.info)
+                plan=sol.plan.info if sol.plan is not None else None)
     del conn
     return sol, info
 
@@ -129,7 +129,7 @@ def run_ours(args):
 
     dtype_name = args.dtype
     dt = 0.1 * 2.0 ** -args.level
-    sol, info = build_problem(args.level, dtype_name, 0, 1, device, rotate=args.rotate)
+    sol, info = build_problem(args.level, dtype_name, 0, 1, device, rotate=args.rotate, mode=args.mode)
     n = info["n"]
     stream = torch.cuda.current_stream()
 
@@ -198,7 +198,8 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "fused_stage_kernel",
+                "traffic": traffic if args.mode == "fused" and not args.rotate else None, "peak_source": peak_src,
+                "kernel": "fused_stage_kernel" if args.mode == "fused" else "flux_faces_kernel + rk3_stage_kernel",
                 "alg_bytes_per_launch": alg * n / 3.0, "avg_launch_ms": ms_per_step / 3.0}
 
     line = {"metric": "cell-updates/s per RK3 step", "value": value, "unit": "cell-updates/s", "n_gpus": 1,
@@ -208,7 +209,8 @@ def run_ours(args):
                                    "fixed dt, no adaptation" % (args.level, n, dtype_name),
                        "elements_per_gpu": n, "faces_per_gpu": info["faces"], "l2": "inputs larger than L2 "
                        "(%.0f MB of state per stage)" % (2 * state_bytes / 1e6),
-                       "mode": "fused tile plan" + (", general normals (mesh rotated)" if args.rotate else ""),
+                       "mode": ("fused tile plan" if args.mode == "fused" else "reference-shaped kernels, reference schedule") +
+                               (", general normals (mesh rotated)" if args.rotate else ""),
                        "host_setup_s": {"connectivity_device": info["t_connectivity_s"],
                                         "tile_plan_host": info["t_plan_s"], "host_cores": os.cpu_count()}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
@@ -258,6 +260,8 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rotate", action="store_true", help="rotate the mesh in space: general-normal path of the plan")
+    ap.add_argument("--mode", default="fused", choices=["fused", "unfused"],
+                    help="unfused = the reference's schedule through the reference-shaped drop-in kernels")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -54,27 +54,71 @@ struct FusedArgs {
   int             my_rank;
 };
 
-template <typename T, int MS>
-__device__ __forceinline__ void store_cell(T* cq, int s, const Cell<T>& q) {
-  cq[0 * MS + s] = q.rho; cq[1 * MS + s] = q.hx; cq[2 * MS + s] = q.hy; cq[3 * MS + s] = q.hz;
-  cq[4 * MS + s] = q.kp;  cq[5 * MS + s] = q.b;  cq[6 * MS + s] = q.q;
-}
-template <typename T, int MS>
-__device__ __forceinline__ Cell<T> load_cell(const T* cq, int s) {
-  Cell<T> q;
-  q.rho = cq[0 * MS + s]; q.hx = cq[1 * MS + s]; q.hy = cq[2 * MS + s]; q.hz = cq[3 * MS + s];
-  q.kp  = cq[4 * MS + s]; q.b  = cq[5 * MS + s]; q.q  = cq[6 * MS + s];
-  return q;
-}
-
-// one entry of the element -> face table: acc += (side ? +1 : -1) * flux[face]
-template <typename T, int MF>
-__device__ __forceinline__ void gather_entry(const T* fl, unsigned en, T acc[5]) {
-  const int j  = en >> 1;
-  const T   sg = (en & 1u) ? T(1) : T(-1);
+// Shared-memory layout of the staged data.
+//   fp64: struct of arrays, cells [7][MS], fluxes [5][MF] (64-bit accesses, conflict-free for neighbouring slots).
+//   fp32: the kernel is issue-bound, so the cells are two float4 records per slot (rho,hx,hy,hz | kp,b,q,-) and the
+//         fluxes one float4 + one float per face: 2 instead of 7 loads per cell, 2 instead of 5 per flux.
+template <typename T, int MS, int MF>
+struct Smem;
+template <int MS, int MF>
+struct Smem<double, MS, MF> {
+  static constexpr size_t bytes = sizeof(double) * ((size_t)NCELLQ * MS + 5 * (size_t)MF);
+  double* cq;
+  double* fl;
+  __device__ explicit Smem(unsigned char* raw) : cq(reinterpret_cast<double*>(raw)), fl(cq + NCELLQ * MS) {}
+  __device__ __forceinline__ void store_cell(int s, const Cell<double>& q) const {
+    cq[0 * MS + s] = q.rho; cq[1 * MS + s] = q.hx; cq[2 * MS + s] = q.hy; cq[3 * MS + s] = q.hz;
+    cq[4 * MS + s] = q.kp;  cq[5 * MS + s] = q.b;  cq[6 * MS + s] = q.q;
+  }
+  __device__ __forceinline__ Cell<double> load_cell(int s) const {
+    Cell<double> q;
+    q.rho = cq[0 * MS + s]; q.hx = cq[1 * MS + s]; q.hy = cq[2 * MS + s]; q.hz = cq[3 * MS + s];
+    q.kp  = cq[4 * MS + s]; q.b  = cq[5 * MS + s]; q.q  = cq[6 * MS + s];
+    return q;
+  }
+  __device__ __forceinline__ void store_flux(int j, const double F[5]) const {
 #pragma unroll
-  for (int k = 0; k < 5; k++) acc[k] = fma(sg, fl[k * MF + j], acc[k]);
-}
+    for (int k = 0; k < 5; k++) fl[k * MF + j] = F[k];
+  }
+  // one entry of the element -> face table: acc += (side ? +1 : -1) * flux[face]
+  __device__ __forceinline__ void gather(unsigned en, double acc[5]) const {
+    const int    j  = en >> 1;
+    const double sg = (en & 1u) ? 1.0 : -1.0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) acc[k] = fma(sg, fl[k * MF + j], acc[k]);
+  }
+};
+template <int MS, int MF>
+struct Smem<float, MS, MF> {
+  static constexpr size_t bytes = sizeof(float4) * 2 * (size_t)MS + sizeof(float4) * (size_t)MF + sizeof(float) * (size_t)MF;
+  float4* ca;   // [MS] rho, hx, hy, hz
+  float4* cb;   // [MS] kp, b, q, -
+  float4* f4;   // [MF] F0..F3
+  float*  f1;   // [MF] F4
+  __device__ explicit Smem(unsigned char* raw)
+      : ca(reinterpret_cast<float4*>(raw)), cb(ca + MS), f4(cb + MS), f1(reinterpret_cast<float*>(f4 + MF)) {}
+  __device__ __forceinline__ void store_cell(int s, const Cell<float>& q) const {
+    ca[s] = make_float4(q.rho, q.hx, q.hy, q.hz);
+    cb[s] = make_float4(q.kp, q.b, q.q, 0.f);
+  }
+  __device__ __forceinline__ Cell<float> load_cell(int s) const {
+    const float4 a = ca[s], b = cb[s];
+    Cell<float>  q;
+    q.rho = a.x; q.hx = a.y; q.hy = a.z; q.hz = a.w; q.kp = b.x; q.b = b.y; q.q = b.z;
+    return q;
+  }
+  __device__ __forceinline__ void store_flux(int j, const float F[5]) const {
+    f4[j] = make_float4(F[0], F[1], F[2], F[3]);
+    f1[j] = F[4];
+  }
+  __device__ __forceinline__ void gather(unsigned en, float acc[5]) const {
+    const int    j  = en >> 1;
+    const float  sg = (en & 1u) ? 1.f : -1.f;
+    const float4 a  = f4[j];
+    acc[0] = fmaf(sg, a.x, acc[0]); acc[1] = fmaf(sg, a.y, acc[1]); acc[2] = fmaf(sg, a.z, acc[2]);
+    acc[3] = fmaf(sg, a.w, acc[3]); acc[4] = fmaf(sg, f1[j], acc[4]);
+  }
+};
 
 // bulk L2 prefetch of [p, p + bytes): 16-byte granules, address aligned down (a hint; used on the state rows inside
 // [0, n_local) and on plan arrays, which upload() pads)
@@ -92,8 +136,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
 template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
 __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_constant__ FusedArgs<T> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* cq = reinterpret_cast<T*>(smem_raw);  // [7][MS]
-  T* fl = cq + NCELLQ * MS;                // [5][MF]
+  const Smem<T, MS, MF> sm(smem_raw);
   __shared__ T atab[CMP ? 256 : 1];
   __shared__ T red[EC / 32];
   const int c   = blockIdx.x;
@@ -138,7 +181,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   }
   if (CMP && tid < A.n_areas) atab[tid] = A.area_tab[tid];
 
-  if (own) store_cell<T, MS>(cq, tid, to_cell(u0, u1, u2, u3, u4));
+  if (own) sm.store_cell(tid, to_cell(u0, u1, u2, u3, u4));
   auto convert_halo = [&](int h, int idx, int rk) {
     T a0, a1, a2, a3, a4;
     if (A.multi && rk != A.my_rank) {   // ghost: through the [var][rank] tables (a peer GPU's array over NVLink)
@@ -147,7 +190,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     } else {
       a0 = A.in[0][idx]; a1 = A.in[1][idx]; a2 = A.in[2][idx]; a3 = A.in[3][idx]; a4 = A.in[4][idx];
     }
-    store_cell<T, MS>(cq, EC + h, to_cell(a0, a1, a2, a3, a4));
+    sm.store_cell(EC + h, to_cell(a0, a1, a2, a3, a4));
   };
   if (hidx >= 0) convert_halo(tid, hidx, hrk);
   if (A.hs > EC) {   // only plans with more than EC halo entries in some chunk (adaptive meshes)
@@ -171,8 +214,8 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       for (int j = tid; j < e2; j += EC) {
         const uint32_t lr = lr_n;
         if (j + EC < nfc) lr_n = A.face_lr[fb + j + EC];
-        const Cell<T> L = load_cell<T, MS>(cq, lr & 0xFFFFu);
-        const Cell<T> R = load_cell<T, MS>(cq, lr >> 16);
+        const Cell<T> L = sm.load_cell(lr & 0xFFFFu);
+        const Cell<T> R = sm.load_cell(lr >> 16);
         T F[5], s;
         if (j < e0) s = kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
         else if (j < e1) s = kepes_flux_n<T, 1>(L, R, T(0), T(0), T(0), F);
@@ -183,8 +226,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 #pragma unroll
           for (int k = 0; k < 5; k++) F[k] *= ar;
         }
-#pragma unroll
-        for (int k = 0; k < 5; k++) fl[k * MF + j] = F[k];
+        sm.store_flux(j, F);
       }
     };
     if (area_idx >= 0) interior(std::false_type{}); else interior(std::true_type{});
@@ -195,7 +237,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       const T        sg   = (code & 1) ? T(1) : T(-1);
       const int      ax   = code >> 1;
       const T nx = ax == 0 ? sg : T(0), ny = ax == 1 ? sg : T(0), nz = ax == 2 ? sg : T(0);
-      const Cell<T> L = load_cell<T, MS>(cq, lr & 0xFFFFu);
+      const Cell<T> L = sm.load_cell(lr & 0xFFFFu);
       const Cell<T> R = mirror(L, nx, ny, nz);
       T F[5];
       smax = fmax_(smax, kepes_flux_n<T, -1>(L, R, nx, ny, nz, F));
@@ -204,8 +246,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 #pragma unroll
         for (int k = 0; k < 5; k++) F[k] *= ar;
       }
-#pragma unroll
-      for (int k = 0; k < 5; k++) fl[k * MF + j] = F[k];
+      sm.store_flux(j, F);
     }
   } else {
     T nx_n = T(0), ny_n = T(0), nz_n = T(0), ar_n = T(0);
@@ -218,12 +259,13 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
         lr_n = A.face_lr[g]; nx_n = A.fnx[g]; ny_n = A.fny[g]; nz_n = A.fnz[g]; ar_n = A.farea[g];
       }
       const int     sr = lr >> 16;
-      const Cell<T> L  = load_cell<T, MS>(cq, lr & 0xFFFFu);
-      const Cell<T> R  = sr == 0xFFFF ? mirror(L, nx, ny, nz) : load_cell<T, MS>(cq, sr);
+      const Cell<T> L  = sm.load_cell(lr & 0xFFFFu);
+      const Cell<T> R  = sr == 0xFFFF ? mirror(L, nx, ny, nz) : sm.load_cell(sr);
       T F[5];
       smax = fmax_(smax, kepes_flux_n<T, -1>(L, R, nx, ny, nz, F));
 #pragma unroll
-      for (int k = 0; k < 5; k++) fl[k * MF + j] = ar * F[k];
+      for (int k = 0; k < 5; k++) F[k] *= ar;
+      sm.store_flux(j, F);
     }
   }
 
@@ -252,13 +294,13 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 #pragma unroll
     for (int s = 0; s < ELL; s++) {
       const unsigned en = (s & 1) ? w[s >> 1] >> 16 : w[s >> 1] & 0xFFFFu;
-      if (en != 0xFFFFu) gather_entry<T, MF>(fl, en, acc);
+      if (en != 0xFFFFu) sm.gather(en, acc);
     }
     if (h1v.y >= 0) {  // rare: elements of this chunk with more than ELL faces
       const uint16_t* off = A.ovf_off + h1v.y;
       const uint16_t* ent = A.ovf_ent + h1v.z;
 #pragma unroll 1
-      for (int q = off[tid], q1 = off[tid + 1]; q < q1; q++) gather_entry<T, MF>(fl, ent[q], acc);
+      for (int q = off[tid], q1 = off[tid + 1]; q < q1; q++) sm.gather(ent[q], acc);
     }
     T sc = fast_rcp(vol) * A.dt;
     if (stage == 2) sc *= T(0.25);
@@ -283,13 +325,14 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
 static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
   auto k = fused_stage_kernel<T, MS, MF, MINB, CMP, SPLIT>;
+  constexpr size_t smem = Smem<T, MS, MF>::bytes;
   static int resident = -1;   // CTAs of this variant the device holds at once
   if (resident < 0) {
-    T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bytes));
+    T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 0;
     T8B_TRY(cudaGetDevice(&dev));
     T8B_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    T8B_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, EC, P->smem_bytes));
+    T8B_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, EC, smem));
     resident = std::max(1, sms * per_sm);
   }
   FusedArgs<T> B = A;
@@ -307,14 +350,14 @@ static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStrea
     B.pf_ptr[14] = (const char*)B.face_lr;   B.pf_unit[14] = (unsigned)B.fs * 4u;
     B.pf_ptr[15] = (const char*)B.hdr;       B.pf_unit[15] = 32u;
   }
-  k<<<P->n_chunks, EC, P->smem_bytes, st>>>(B);
+  k<<<P->n_chunks, EC, smem, st>>>(B);
   return cudaGetLastError();
 }
 
 template <typename T, bool CMP>
 static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
-  // resident CTAs per SM are bounded by shared memory (68 KB fp64 / 34 KB fp32 per CTA); tell ptxas so it can size
-  // the register budget (fp32: 5 CTAs of 48 registers measured faster than 6 of 40)
+  // resident CTAs per SM are bounded by shared memory (68 KB fp64 / 36 KB fp32 per CTA); tell ptxas so it can size
+  // the register budget (fp32: 5 CTAs of 48 registers measured faster than 6 of 40 and than 4 of 64)
   constexpr int B0 = sizeof(T) == 8 ? 3 : 5;
   return P->split ? launch_variant<T, MS, MF, B0, CMP, true>(P, A, st)
                   : launch_variant<T, MS, MF, B0, CMP, false>(P, A, st);

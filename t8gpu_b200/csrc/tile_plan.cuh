@@ -450,7 +450,8 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   P->max_faces  = max_faces;
   P->ms = MS;
   P->mf = MF;
-  P->smem_bytes = sizeof(T) * ((size_t)t8b200::NCELLQ * MS + 5 * (size_t)MF);
+  // fp64: [7][MS] + [5][MF] doubles; fp32: two float4 per slot + float4 + float per face (fused.cu: Smem)
+  P->smem_bytes = sizeof(T) == 8 ? 8 * ((size_t)t8b200::NCELLQ * MS + 5 * (size_t)MF) : 32 * (size_t)MS + 20 * (size_t)MF;
 
   lap("merge");
   cudaError_t err = cudaSuccess;
