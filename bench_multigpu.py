@@ -71,7 +71,7 @@ class MultiGpuEuler:
             self.mail.barrier()
             self.plan.stage(3, s2, prev, nxt, vol, dt, in_all=T[2], speed_max=self.speed_loc)
             self.mail.barrier(self.speed_loc, self.speed_max)
-            return 3
+            return 6                                               # 3 stage kernels + 3 barrier kernels
         self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev])
         stage_barrier(dist, self.token)                            # device-side, on the compute stream
         self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1])
