@@ -123,6 +123,12 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    if args.workload == "subgrid":
+        from bench_subgrid import run_subgrid
+        run_subgrid(args, rank, world, device)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if world > 1:
         from bench_multigpu import run_multi
         return run_multi(args, rank, world, device)
@@ -256,7 +262,10 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--level", type=int, default=8, help="uniform refinement level per GPU (8 = 16.8M hexes)")
+    ap.add_argument("--workload", default="unstructured", choices=["unstructured", "subgrid"],
+                    help="unstructured = BASELINE configs[1] (the headline); subgrid = configs[3], Subgrid<4,4,4>")
+    ap.add_argument("--level", type=int, default=None,
+                    help="uniform refinement level per GPU (default 8 = 16.8M hexes; subgrid: 6 = 16.8M cells)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rotate", action="store_true", help="rotate the mesh in space: general-normal path of the plan")
@@ -265,6 +274,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.level is None:
+        args.level = 6 if args.workload == "subgrid" else 8
     if args.impl == "reference":
         return run_reference(args)
     import t8gpu_b200

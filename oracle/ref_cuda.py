@@ -140,6 +140,8 @@ def bench(args):
     import oracle
     dtype = np.float64 if args.dtype == "f64" else np.float32
     level = args.level
+    if getattr(args, "workload", "unstructured") == "subgrid":
+        return bench_subgrid(args, dtype, level)
     t0 = time.time()
     s = RefSolver("uns", dtype, 3, level, True)   # host-side: t8mini forest + the reference's connectivity loop
     t_mesh = time.time() - t0
@@ -164,6 +166,37 @@ def bench(args):
                                          (" with float_type=double" if args.dtype == "f64" else ""),
                        "host_mesh_s": round(t_mesh, 3), "host_mesh": "t8mini (t8code absent), reference's own "
                        "compute_connectivity_information loop, 1 thread", "host_cores": os.cpu_count()},
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 0, "kind": "reference",
+                             "sample": "full workload on the GPU: the reference has no CPU implementation of this "
+                                       "path; this is its own CUDA build on the same B200"},
+            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def bench_subgrid(args, dtype, level):
+    """--workload subgrid: SubgridCompressibleEulerSolver<Subgrid<4,4,4>>::iterate of the reference, one rank."""
+    import oracle
+    t0 = time.time()
+    s = RefSolver("sg", dtype, 3, level, True)
+    t_mesh = time.time() - t0
+    f = oracle.Forest(3, level)
+    lv, cent, vol, _ = f.elements()
+    s.set_state(oracle.subgrid_init_kh(3, cent.astype(dtype), lv, dtype))
+    n = s.num_cells()
+    dt = 0.1 * 2.0 ** -(level + 2)
+    ms = s.time_steps(dt, args.warmup, args.steps)
+    assert np.isfinite(s.get_state()).all()
+    value = n * args.steps / (ms * 1e-3)
+    line = {"impl": "reference", "metric": "cell-updates/s per RK3 step", "value": value, "unit": "cell-updates/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": "kelvin_helmholtz 3D Subgrid<4,4,4> on a uniform periodic hex forest level %d (%d "
+                                   "cells) %s, fixed dt, no adaptation" % (level, n, args.dtype),
+                       "implementation": "reference CUDA kernels (examples/subgrid) compiled unmodified for sm_100a%s, "
+                                         "reference iterate() schedule, 1 rank" %
+                                         (" with float_type=double" if args.dtype == "f64" else ""),
+                       "host_mesh_s": round(t_mesh, 3), "host_cores": os.cpu_count()},
             "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 0, "kind": "reference",
                              "sample": "full workload on the GPU: the reference has no CPU implementation of this "
                                        "path; this is its own CUDA build on the same B200"},

@@ -143,3 +143,56 @@ def test_subgrid_multi_rank_on_one_gpu(cuda, kind, P, dtype):
         mr.iterate(dt)
         err = rel_linf(mr.global_state(), u)
         assert err <= (it + 1) * TOL[np.dtype(dtype)], (it, err)
+
+
+def test_bench_subgrid_connectivity_and_cells(cuda):
+    """bench.py --workload subgrid builds its mesh without the oracle: the arrays must be the ones the reference's
+    SubgridMeshManager produces for the same forest (bit-exact), and the cell centres those of the reference's IC."""
+    import oracle
+    import t8gpu_b200 as tb
+    from bench_subgrid import cell_centers, subgrid_connectivity
+    L = 3
+    f = oracle.Forest(3, L)
+    ref = f.connectivity(subgrid=True, dtype=np.float64)
+    got = tb.conn_to_host(subgrid_connectivity(L, torch.float64, 0, 1, cuda, (1, 1, 1)))
+    for key in ("face_neighbors", "face_normals", "face_areas", "level_diff", "offsets"):
+        assert np.array_equal(got[key], ref[key]), key
+    lv, cent, vol, _ = f.elements()
+    assert np.array_equal(got["volumes"], vol)
+    u = [torch.zeros(f.num_elements * 64, dtype=torch.float64, device=cuda) for _ in range(5)]
+    tb.init_kelvin_helmholtz(3, cell_centers(torch.as_tensor(cent).to(cuda), L, torch.float64), u)
+    want = oracle.subgrid_init_kh(3, cent, lv, np.float64)
+    assert rel_linf(torch.stack(u).cpu().numpy(), want) <= 1e-14
+
+
+def test_bench_subgrid_brick_ranks_agree_with_one_rank(cuda):
+    """The weak-scaling subgrid mesh: 2 ranks (one tree each, emulated on one device) vs the same brick on one rank."""
+    import t8gpu_b200 as tb
+    from bench_subgrid import cell_centers, subgrid_connectivity
+    L, P, brick, dt = 2, 2, (2, 1, 1), 0.1 * 2.0 ** -4
+    c1 = subgrid_connectivity(L, torch.float64, 0, 1, cuda, brick)
+    one = tb.SubgridEulerSolver(dict(tb.conn_to_host(c1), dim=3), c1["volumes"].cpu().numpy(), torch.float64,
+                                device=cuda, mode="fused")
+    tb.init_kelvin_helmholtz(3, cell_centers(c1["centroids"], L, torch.float64), one.variables(one.next))
+    rng = np.random.default_rng(4)
+    u0 = one.state().cpu().numpy() * (1 + 0.02 * rng.uniform(-1, 1, (5, one.nc)))
+    one.set_state(u0)
+    conns = [subgrid_connectivity(L, torch.float64, r, P, cuda, brick) for r in range(P)]
+    nc = [int(c["n_local"]) * 64 for c in conns]
+    off = np.concatenate([[0], np.cumsum(nc)])
+    assert off[-1] == one.nc and all(int(c["n_xfaces"]) + int(c["n_ghost"]) > 0 for c in conns)
+    bufs = [torch.zeros((25, nc[r]), dtype=torch.float64, device=cuda) for r in range(P)]
+    for r in range(P):
+        bufs[r][0:5] = torch.as_tensor(u0[:, off[r]:off[r + 1]]).to(cuda)
+    tabs = {s: tb.RankTables([[bufs[r][s * 5 + k] for k in range(5)] for r in range(P)], cuda) for s in range(5)}
+    plans = [tb.SubgridPlan(tb.conn_to_host(c), c["volumes"].cpu().numpy(), torch.float64) for c in conns]
+    nxt, prv = 0, 3
+    for it in range(3):
+        one.iterate(dt)
+        nxt, prv = prv, nxt
+        for stage, sin, sout in ((1, prv, 1), (2, 1, 2), (3, 2, nxt)):
+            for r in range(P):
+                v = lambda s: [bufs[r][s * 5 + k] for k in range(5)]  # noqa: E731
+                plans[r].stage(stage, v(sin), v(prv), v(sout), conns[r]["volumes"], dt, in_all=tabs[sin])
+        got = np.concatenate([bufs[r][nxt * 5:(nxt + 1) * 5].cpu().numpy() for r in range(P)], axis=1)
+        assert rel_linf(got, one.state().cpu().numpy()) <= 1e-12
