@@ -80,9 +80,14 @@ struct Smem<double, MS, MF> {
 #pragma unroll
     for (int k = 0; k < 5; k++) fl[k * MF + j] = F[k];
   }
-  // one entry of the element -> face table: acc += (side ? +1 : -1) * flux[face]
+  __device__ __forceinline__ void zero_flux(int j) const {
+#pragma unroll
+    for (int k = 0; k < 5; k++) fl[k * MF + j] = 0.0;
+  }
+  // one entry of the element -> face table: acc += (side ? +1 : -1) * flux[face]; an empty entry (0xFFFF) reads the
+  // zero column MF - 1 (the plan never uses it), so the entries need no branches and their loads overlap
   __device__ __forceinline__ void gather(unsigned en, double acc[5]) const {
-    const int    j  = en >> 1;
+    const int    j  = min((int)(en >> 1), MF - 1);
     const double sg = (en & 1u) ? 1.0 : -1.0;
 #pragma unroll
     for (int k = 0; k < 5; k++) acc[k] = fma(sg, fl[k * MF + j], acc[k]);
@@ -111,8 +116,12 @@ struct Smem<float, MS, MF> {
     f4[j] = make_float4(F[0], F[1], F[2], F[3]);
     f1[j] = F[4];
   }
+  __device__ __forceinline__ void zero_flux(int j) const {
+    f4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    f1[j] = 0.f;
+  }
   __device__ __forceinline__ void gather(unsigned en, float acc[5]) const {
-    const int    j  = en >> 1;
+    const int    j  = min((int)(en >> 1), MF - 1);
     const float  sg = (en & 1u) ? 1.f : -1.f;
     const float4 a  = f4[j];
     acc[0] = fmaf(sg, a.x, acc[0]); acc[1] = fmaf(sg, a.y, acc[1]); acc[2] = fmaf(sg, a.z, acc[2]);
@@ -128,6 +137,24 @@ __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
   if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
 }
 
+#ifdef T8B_PHASE_CLOCKS   // tools/build_variant.py: per-phase CTA timing (sum of clock64 deltas of warp 0 and warp 7)
+__device__ unsigned long long t8b_phase_clk[16];
+__device__ long long t8b_cta_log[4 * 65536];   // per CTA (index < 65536): smid, clock at start, at phase 1, at end
+extern "C" int t8b200_debug_cta_log(long long* out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, t8b_cta_log, sizeof(t8b_cta_log));
+}
+#define T8B_CLK(i) do { if ((tid & 31) == 0 && (tid == 0 || tid == 224)) clk[i] = clock64(); } while (0)
+extern "C" int t8b200_debug_phase_clocks(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, t8b_phase_clk, sizeof(t8b_phase_clk));
+  if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(t8b_phase_clk, z, sizeof(z)); }
+  return 0;
+}
+#else
+#define T8B_CLK(i)
+#endif
+
 // CTA = one chunk of EC consecutive elements.  MS / MF: compile-time strides of the shared-memory SoA arrays
 // (slots = EC own + halo; faces), so every shared access is base + index*sizeof(T) + immediate.
 //   phase 0: conserved -> per-cell quantities for the chunk's own elements (coalesced) and its halo (gather)
@@ -141,6 +168,10 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   __shared__ T red[EC / 32];
   const int c   = blockIdx.x;
   const int tid = threadIdx.x;
+#ifdef T8B_PHASE_CLOCKS
+  long long clk[6] = {0, 0, 0, 0, 0, 0};
+#endif
+  T8B_CLK(0);
 
   // ---- phase 0: issue every independent global load of the prologue first.  The halo indices and the first face
   // record sit at fixed strides, so nothing here waits for the chunk header.
@@ -158,9 +189,13 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     hidx = A.halo_elem[hb + tid];
     if (A.multi) hrk = A.halo_rank[hb + tid];
   }
+#ifdef T8B_ABLATE_MEM   // timing experiment only (compute floor: no state traffic), results are wrong
+  u0 = T(1) + T(1e-3) * T(tid); u1 = T(0.1); u2 = T(0.2); u3 = T(0.3); u4 = T(3) + T(1e-3) * T(tid & 7);
+#else
   if (own) {
     u0 = A.in[0][e]; u1 = A.in[1][e]; u2 = A.in[2][e]; u3 = A.in[3][e]; u4 = A.in[4][e];
   }
+#endif
   // first face record of this thread (consumed in phase 1; its latency hides behind phase 0)
   uint32_t lr_n = 0;
   if (tid < A.fs) lr_n = A.face_lr[fb + tid];
@@ -180,19 +215,30 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     }
   }
   if (CMP && tid < A.n_areas) atab[tid] = A.area_tab[tid];
+  if (tid == EC - 1) sm.zero_flux(MF - 1);
 
-  if (own) sm.store_cell(tid, to_cell(u0, u1, u2, u3, u4));
-  auto convert_halo = [&](int h, int idx, int rk) {
-    T a0, a1, a2, a3, a4;
+  auto load_halo = [&](int idx, int rk, T& a0, T& a1, T& a2, T& a3, T& a4) {
     if (A.multi && rk != A.my_rank) {   // ghost: through the [var][rank] tables (a peer GPU's array over NVLink)
       a0 = A.in_all[0][rk][idx]; a1 = A.in_all[1][rk][idx]; a2 = A.in_all[2][rk][idx];
       a3 = A.in_all[3][rk][idx]; a4 = A.in_all[4][rk][idx];
     } else {
+#ifdef T8B_ABLATE_MEM
+      a0 = T(1) + T(1e-3) * T(idx & 255); a1 = T(0.1); a2 = T(0.2); a3 = T(0.3); a4 = T(3) + T(1e-3) * T(idx & 7);
+#else
       a0 = A.in[0][idx]; a1 = A.in[1][idx]; a2 = A.in[2][idx]; a3 = A.in[3][idx]; a4 = A.in[4][idx];
+#endif
     }
+  };
+  auto convert_halo = [&](int h, int idx, int rk) {
+    T a0, a1, a2, a3, a4;
+    load_halo(idx, rk, a0, a1, a2, a3, a4);
     sm.store_cell(EC + h, to_cell(a0, a1, a2, a3, a4));
   };
-  if (hidx >= 0) convert_halo(tid, hidx, hrk);
+  // the gathers of the halo states are issued before the own elements are converted: the two latencies overlap
+  T g0 = T(1), g1 = T(0), g2 = T(0), g3 = T(0), g4 = T(1);
+  if (hidx >= 0) load_halo(hidx, hrk, g0, g1, g2, g3, g4);
+  if (own) sm.store_cell(tid, to_cell(u0, u1, u2, u3, u4));
+  if (hidx >= 0) sm.store_cell(EC + tid, to_cell(g0, g1, g2, g3, g4));
   if (A.hs > EC) {   // only plans with more than EC halo entries in some chunk (adaptive meshes)
     for (int h = tid + EC; h < A.hs; h += EC) {
       const int idx = A.halo_elem[hb + h];
@@ -203,7 +249,9 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   const int  e0 = h0v.w & 0xFFFF, e1 = (unsigned)h0v.w >> 16, e2 = h1v.x;
   const int  area_idx  = h1v.w;
   const bool want_smax = A.speed_max != nullptr;
+  T8B_CLK(1);
   __syncthreads();
+  T8B_CLK(2);
 
   // ---- phase 1: software-pipelined over this thread's faces (record j+EC is in flight while j is evaluated)
   T smax = T(0);
@@ -217,9 +265,14 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
         const Cell<T> L = sm.load_cell(lr & 0xFFFFu);
         const Cell<T> R = sm.load_cell(lr >> 16);
         T F[5], s;
+#ifdef T8B_ABLATE_FLUX   // tools/build_variant.py: timing experiment only (memory + indexing floor), results are wrong
+        F[0] = L.rho - R.rho; F[1] = L.hx - R.hx; F[2] = L.hy - R.hy; F[3] = L.hz - R.hz; F[4] = L.kp - R.kp + L.b - R.b + L.q - R.q;
+        s = F[0];
+#else
         if (j < e0) s = kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
         else if (j < e1) s = kepes_flux_n<T, 1>(L, R, T(0), T(0), T(0), F);
         else s = kepes_flux_n<T, 2>(L, R, T(0), T(0), T(0), F);
+#endif
         if (want_smax) smax = fmax_(smax, s);
         if (SCALE) {
           const T ar = atab[A.face_ai[fb + j]];
@@ -277,6 +330,11 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   T         vol = T(1), base[5] = {T(0), T(0), T(0), T(0), T(0)};
   if (own) {
     el  = A.ell[e];
+#ifdef T8B_ABLATE_MEM
+    vol = A.vol_scale;
+#pragma unroll
+    for (int k = 0; k < 5; k++) base[k] = T(k + tid);
+#else
     vol = A.vol[e >> A.vol_shift] * A.vol_scale;
 #pragma unroll
     for (int k = 0; k < 5; k++) base[k] = A.in[k][e];
@@ -285,8 +343,14 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 #pragma unroll
       for (int k = 0; k < 5; k++) base[k] = cp * A.prev[k][e] + ci * base[k];
     }
+#endif
   }
+  T sc = fast_rcp(vol) * A.dt;   // before the barrier: the reciprocal chain hides in the wait
+  if (stage == 2) sc *= T(0.25);
+  if (stage == 3) sc *= T(0.66666666666666);
+  T8B_CLK(3);
   __syncthreads();
+  T8B_CLK(4);
 
   if (own) {
     T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
@@ -294,7 +358,9 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 #pragma unroll
     for (int s = 0; s < ELL; s++) {
       const unsigned en = (s & 1) ? w[s >> 1] >> 16 : w[s >> 1] & 0xFFFFu;
-      if (en != 0xFFFFu) sm.gather(en, acc);
+      // fp32: the first six entries without a branch (empty ones read the zero column), so their loads overlap:
+      // -4 % per step; fp64: the 60 registers the overlapped loads would need are not there, branches measured faster
+      if (s < (sizeof(T) == 4 ? 6 : 0) || en != 0xFFFFu) sm.gather(en, acc);
     }
     if (h1v.y >= 0) {  // rare: elements of this chunk with more than ELL faces
       const uint16_t* off = A.ovf_off + h1v.y;
@@ -302,14 +368,27 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 #pragma unroll 1
       for (int q = off[tid], q1 = off[tid + 1]; q < q1; q++) sm.gather(ent[q], acc);
     }
-    T sc = fast_rcp(vol) * A.dt;
-    if (stage == 2) sc *= T(0.25);
-    if (stage == 3) sc *= T(0.66666666666666);
     if (CMP && area_idx >= 0) sc *= atab[area_idx];
+#ifdef T8B_ABLATE_MEM
+    if (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] == T(123.456))
+#endif
 #pragma unroll
     for (int k = 0; k < 5; k++) A.out[k][e] = base[k] + sc * acc[k];
   }
 
+#ifdef T8B_PHASE_CLOCKS
+  T8B_CLK(5);
+  if (tid == 0 || tid == 224) {
+    const int o = tid == 0 ? 0 : 8;
+    for (int i = 0; i < 5; i++) atomicAdd(&t8b_phase_clk[o + i], (unsigned long long)(clk[i + 1] - clk[i]));
+    atomicAdd(&t8b_phase_clk[o + 5], 1ull);
+    if (tid == 0 && c < 65536) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      t8b_cta_log[4 * c] = smid; t8b_cta_log[4 * c + 1] = clk[0]; t8b_cta_log[4 * c + 2] = clk[2]; t8b_cta_log[4 * c + 3] = clk[5];
+    }
+  }
+#endif
   if (A.speed_max) {
     smax = warp_max(smax);
     if ((tid & 31) == 0) red[tid >> 5] = smax;
