@@ -404,7 +404,11 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
 static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
   auto k = fused_stage_kernel<T, MS, MF, MINB, CMP, SPLIT>;
+#ifdef T8B_PHASE_CLOCKS   // analysis builds: T8B200_SMEM_PAD lowers the occupancy (e.g. 140000: one CTA per SM)
+  static const size_t smem = Smem<T, MS, MF>::bytes + (getenv("T8B200_SMEM_PAD") ? atoi(getenv("T8B200_SMEM_PAD")) : 0);
+#else
   constexpr size_t smem = Smem<T, MS, MF>::bytes;
+#endif
   static int resident = -1;   // CTAs of this variant the device holds at once
   if (resident < 0) {
     T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
