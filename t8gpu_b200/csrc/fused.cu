@@ -80,6 +80,19 @@ struct Smem<double, MS, MF> {
 #pragma unroll
     for (int k = 0; k < 5; k++) fl[k * MF + j] = F[k];
   }
+  // Axis-permuted access for faces with normal +e_a: (p0,p1,p2) = (a, a+1, a+2) mod 3 is a cyclic permutation of the
+  // axes, i.e. a rotation, under which the flux is invariant; reading the velocity rows / writing the momentum-flux
+  // rows in that order lets ONE copy of the x-normal flux serve all three axes (the rows are only addresses here).
+  __device__ __forceinline__ Cell<double> load_cell_axis(int s, int p0, int p1, int p2) const {
+    Cell<double> q;
+    q.rho = cq[0 * MS + s]; q.hx = cq[(1 + p0) * MS + s]; q.hy = cq[(1 + p1) * MS + s]; q.hz = cq[(1 + p2) * MS + s];
+    q.kp  = cq[4 * MS + s]; q.b  = cq[5 * MS + s]; q.q  = cq[6 * MS + s];
+    return q;
+  }
+  __device__ __forceinline__ void store_flux_axis(int j, const double F[5], int p0, int p1, int p2) const {
+    fl[j] = F[0]; fl[(1 + p0) * MF + j] = F[1]; fl[(1 + p1) * MF + j] = F[2]; fl[(1 + p2) * MF + j] = F[3];
+    fl[4 * MF + j] = F[4];
+  }
   __device__ __forceinline__ void zero_flux(int j) const {
 #pragma unroll
     for (int k = 0; k < 5; k++) fl[k * MF + j] = 0.0;
@@ -114,6 +127,20 @@ struct Smem<float, MS, MF> {
   }
   __device__ __forceinline__ void store_flux(int j, const float F[5]) const {
     f4[j] = make_float4(F[0], F[1], F[2], F[3]);
+    f1[j] = F[4];
+  }
+  // records are vectors here, so the permutation is done in registers
+  __device__ __forceinline__ Cell<float> load_cell_axis(int s, int p0, int, int) const {
+    const Cell<float> c = load_cell(s);
+    Cell<float>       q = c;
+    q.hx = p0 == 0 ? c.hx : p0 == 1 ? c.hy : c.hz;
+    q.hy = p0 == 0 ? c.hy : p0 == 1 ? c.hz : c.hx;
+    q.hz = p0 == 0 ? c.hz : p0 == 1 ? c.hx : c.hy;
+    return q;
+  }
+  __device__ __forceinline__ void store_flux_axis(int j, const float F[5], int p0, int, int) const {
+    f4[j] = make_float4(F[0], p0 == 0 ? F[1] : p0 == 1 ? F[3] : F[2], p0 == 0 ? F[2] : p0 == 1 ? F[1] : F[3],
+                        p0 == 0 ? F[3] : p0 == 1 ? F[2] : F[1]);
     f1[j] = F[4];
   }
   __device__ __forceinline__ void zero_flux(int j) const {
@@ -169,7 +196,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   const int c   = blockIdx.x;
   const int tid = threadIdx.x;
 #ifdef T8B_PHASE_CLOCKS
-  long long clk[6] = {0, 0, 0, 0, 0, 0};
+  long long clk[7] = {0, 0, 0, 0, 0, 0, 0};
 #endif
   T8B_CLK(0);
 
@@ -255,6 +282,10 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 
   // ---- phase 1: software-pipelined over this thread's faces (record j+EC is in flight while j is evaluated)
   T smax = T(0);
+#ifndef T8B_AXPERM
+#define T8B_AXPERM (sizeof(T) == 8)
+#endif
+  constexpr bool AXPERM = T8B_AXPERM;
   if (CMP) {
     // SCALE = false: every face of the chunk has the same area, applied once per element in phase 2
     auto interior = [&](auto scale_tag) {
@@ -262,9 +293,23 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       for (int j = tid; j < e2; j += EC) {
         const uint32_t lr = lr_n;
         if (j + EC < nfc) lr_n = A.face_lr[fb + j + EC];
+        T F[5], s;
+        if (AXPERM) {   // one copy of the x-normal flux, the axis enters through the row addresses
+          const int p0 = (j >= e0) + (j >= e1), p1 = p0 == 2 ? 0 : p0 + 1, p2 = p0 == 0 ? 2 : p0 - 1;
+          const Cell<T> L = sm.load_cell_axis(lr & 0xFFFFu, p0, p1, p2);
+          const Cell<T> R = sm.load_cell_axis(lr >> 16, p0, p1, p2);
+          s = kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
+          if (want_smax) smax = fmax_(smax, s);
+          if (SCALE) {
+            const T ar = atab[A.face_ai[fb + j]];
+#pragma unroll
+            for (int k = 0; k < 5; k++) F[k] *= ar;
+          }
+          sm.store_flux_axis(j, F, p0, p1, p2);
+          continue;
+        }
         const Cell<T> L = sm.load_cell(lr & 0xFFFFu);
         const Cell<T> R = sm.load_cell(lr >> 16);
-        T F[5], s;
 #ifdef T8B_ABLATE_FLUX   // tools/build_variant.py: timing experiment only (memory + indexing floor), results are wrong
         F[0] = L.rho - R.rho; F[1] = L.hx - R.hx; F[2] = L.hy - R.hy; F[3] = L.hz - R.hz; F[4] = L.kp - R.kp + L.b - R.b + L.q - R.q;
         s = F[0];
@@ -322,6 +367,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     }
   }
 
+  T8B_CLK(6);
   // ---- phase 2: the element->face table, the volume and the old states are requested BEFORE the barrier so their
   // latency overlaps the wait.  The element's own conserved values are read again (L1/L2 hit) instead of being
   // carried in 10 registers through the face loop, and combined with U^n right away (5 live values, not 10).
@@ -382,6 +428,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     const int o = tid == 0 ? 0 : 8;
     for (int i = 0; i < 5; i++) atomicAdd(&t8b_phase_clk[o + i], (unsigned long long)(clk[i + 1] - clk[i]));
     atomicAdd(&t8b_phase_clk[o + 5], 1ull);
+    atomicAdd(&t8b_phase_clk[o + 6], (unsigned long long)(clk[6] - clk[2]));   // the face loops alone
     if (tid == 0 && c < 65536) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));

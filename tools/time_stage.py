@@ -44,7 +44,7 @@ if hasattr(L, "t8b200_debug_phase_clocks"):
     for o, w in ((0, "warp0"), (8, "warp7")):
         n = max(1, out[o + 5])
         print("  %s cycles/CTA:" % w, ", ".join("%s %.0f" % (nm, out[o + i] / n) for i, nm in enumerate(names)),
-              "| total %.0f" % (sum(out[o:o + 5]) / n))
+              "| total %.0f | face loops alone %.0f" % (sum(out[o:o + 5]) / n, out[o + 6] / n))
 if hasattr(L, "t8b200_debug_cta_log"):
     import numpy as np
     log = np.zeros(4 * 65536, np.int64)
