@@ -34,7 +34,6 @@ struct FusedArgs {
   int             n_areas;
   int             hs, fs;
   int             wave;  // CTAs resident on the device at once = distance of the next-wave prefetch (0: off)
-  int             n_chunks;
   const char*     pf_ptr[16];   // L2 prefetch table: base pointer (null: skip) and bytes per index
   unsigned        pf_unit[16];
   const uint4*    ell;
@@ -449,250 +448,6 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Warp-specialised persistent variant (compressed-geometry plans without split chunks): one CTA per SM, three teams of
-// EC threads.  Teams 0 and 1 ("element teams") alternate over the CTA's chunks and do phase 0 and phase 2; team 2
-// ("face team") does nothing but phase 1, chunk after chunk, so the FP64 pipe always has face work while the element
-// teams wait on HBM.  Three chunk buffers (cells + fluxes) rotate; the hand-over points are named barriers:
-//   FULL[b]  element team -> face team   cells of the chunk in buffer b are staged
-//   DONE[b]  face team -> element team   its fluxes are complete
-//   EMPTY[b] element team -> the other element team   phase 2 has consumed the fluxes, buffer b may be refilled
-// An element team runs software-pipelined: phase 0 of chunk n, then phase 2 of chunk n-2, so it never idles on the
-// face team, and nothing is carried in registers from one chunk to the next.
-constexpr int WS_TEAMS = 3, WS_BUFS = 3;
-enum { WS_BAR_FULL = 1, WS_BAR_DONE = 4, WS_BAR_EMPTY = 7, WS_BAR_FACE_TEAM = 10 };
-__device__ __forceinline__ void nb_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void nb_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-template <typename T, int MS, int MF>
-__global__ void __launch_bounds__(WS_TEAMS* EC, 1) fused_stage_ws_kernel(const __grid_constant__ FusedArgs<T> A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ T atab[256];
-  __shared__ T red[EC / 32];
-  constexpr size_t BUF = Smem<T, MS, MF>::bytes;
-  const int team = threadIdx.x / EC, tid = threadIdx.x % EC;
-  const int grid = gridDim.x;
-  const int n_my = ((int)A.n_chunks - (int)blockIdx.x + grid - 1) / grid;   // chunks of this CTA: blockIdx + n * grid
-  if (threadIdx.x < A.n_areas) atab[threadIdx.x] = A.area_tab[threadIdx.x];
-  __syncthreads();
-  const int stage = A.stage;
-#ifdef T8B_PHASE_CLOCKS
-#define WS_T(v) long long v = clock64()
-#define WS_ACC(slot, a, b) do { if (tid == 0) atomicAdd(&t8b_phase_clk[slot], (unsigned long long)((b) - (a))); } while (0)
-#else
-#define WS_T(v)
-#define WS_ACC(slot, a, b)
-#endif
-
-  if (team == 2) {
-    // ------------------------------------------------------------------------------------------- face team
-    const bool want_smax = A.speed_max != nullptr;
-    T          smax      = T(0);
-    for (int n = 0; n < n_my; n++) {
-      const int             c = blockIdx.x + n * grid, b = n % WS_BUFS;
-      const Smem<T, MS, MF> sm(smem_raw + b * BUF);
-      const int4 h0v = __ldg(A.hdr + 2 * c), h1v = __ldg(A.hdr + 2 * c + 1);
-      const int  fb = c * A.fs;
-      const int  nfc = (unsigned)h0v.z >> 16;
-      const int  e0 = h0v.w & 0xFFFF, e1 = (unsigned)h0v.w >> 16, e2 = h1v.x;
-      const int  area_idx = h1v.w;
-      // alternate which half of the team takes the extra round of faces
-      const int  t0 = (tid + (n & 1) * (EC / 2)) % EC;
-      uint32_t   lr_n = t0 < nfc ? A.face_lr[fb + t0] : 0u;
-      WS_T(ta);
-      nb_sync(WS_BAR_FULL + b, 2 * EC);
-      WS_T(tb);
-      auto interior = [&](auto scale_tag) {
-        constexpr bool SCALE = decltype(scale_tag)::value;
-        for (int j = t0; j < e2; j += EC) {
-          const uint32_t lr = lr_n;
-          if (j + EC < nfc) lr_n = A.face_lr[fb + j + EC];
-          const int p0 = (j >= e0) + (j >= e1), p1 = p0 == 2 ? 0 : p0 + 1, p2 = p0 == 0 ? 2 : p0 - 1;
-          const Cell<T> L = sm.load_cell_axis(lr & 0xFFFFu, p0, p1, p2);
-          const Cell<T> R = sm.load_cell_axis(lr >> 16, p0, p1, p2);
-          T F[5];
-          const T s = kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
-          if (want_smax) smax = fmax_(smax, s);
-          if (SCALE) {
-            const T ar = atab[A.face_ai[fb + j]];
-#pragma unroll
-            for (int k = 0; k < 5; k++) F[k] *= ar;
-          }
-          sm.store_flux_axis(j, F, p0, p1, p2);
-        }
-      };
-      if (area_idx >= 0) interior(std::false_type{}); else interior(std::true_type{});
-      for (int j = e2 + t0; j < nfc; j += EC) {   // wall faces
-        const uint32_t lr   = A.face_lr[fb + j];
-        const int      code = (lr >> 16) & 7;
-        const T        sg   = (code & 1) ? T(1) : T(-1);
-        const int      ax   = code >> 1;
-        const T nx = ax == 0 ? sg : T(0), ny = ax == 1 ? sg : T(0), nz = ax == 2 ? sg : T(0);
-        const Cell<T> L = sm.load_cell(lr & 0xFFFFu);
-        const Cell<T> R = mirror(L, nx, ny, nz);
-        T F[5];
-        smax = fmax_(smax, kepes_flux_n<T, -1>(L, R, nx, ny, nz, F));
-        if (area_idx < 0) {
-          const T ar = atab[A.face_ai[fb + j]];
-#pragma unroll
-          for (int k = 0; k < 5; k++) F[k] *= ar;
-        }
-        sm.store_flux(j, F);
-      }
-      WS_T(tc);
-      WS_ACC(0, ta, tb); WS_ACC(1, tb, tc); WS_ACC(8, 0, 1);
-      nb_arrive(WS_BAR_DONE + b, 2 * EC);
-    }
-    if (want_smax) {
-      smax = warp_max(smax);
-      if ((tid & 31) == 0) red[tid >> 5] = smax;
-      nb_sync(WS_BAR_FACE_TEAM, EC);
-      if (tid == 0) {
-        T m = red[0];
-        for (int w = 1; w < EC / 32; w++) m = fmax_(m, red[w]);
-        atomic_max_nonneg(A.speed_max, m);
-      }
-    }
-    return;
-  }
-
-  // --------------------------------------------------------------------------------------------- element teams
-  auto load_halo = [&](int idx, int rk, T& a0, T& a1, T& a2, T& a3, T& a4) {
-    if (A.multi && rk != A.my_rank) {
-      a0 = A.in_all[0][rk][idx]; a1 = A.in_all[1][rk][idx]; a2 = A.in_all[2][rk][idx];
-      a3 = A.in_all[3][rk][idx]; a4 = A.in_all[4][rk][idx];
-    } else {
-      a0 = A.in[0][idx]; a1 = A.in[1][idx]; a2 = A.in[2][idx]; a3 = A.in[3][idx]; a4 = A.in[4][idx];
-    }
-  };
-  for (int n = team; n < n_my + 2; n += 2) {
-    if (n < n_my) {   // ---- phase 0 of chunk n
-      const int             c = blockIdx.x + n * grid, b = n % WS_BUFS;
-      const Smem<T, MS, MF> sm(smem_raw + b * BUF);
-      const int ecn = min(EC, (int)A.n_local - c * EC);
-      const int e = c * EC + tid, hb = c * A.hs;
-      const bool own = tid < ecn;
-      WS_T(t0c);
-      int hidx = -1, hrk = 0;
-      if (tid < A.hs) {
-        hidx = A.halo_elem[hb + tid];
-        if (A.multi) hrk = A.halo_rank[hb + tid];
-      }
-      T u0 = T(1), u1 = T(0), u2 = T(0), u3 = T(0), u4 = T(1);
-      if (own) { u0 = A.in[0][e]; u1 = A.in[1][e]; u2 = A.in[2][e]; u3 = A.in[3][e]; u4 = A.in[4][e]; }
-      if ((tid & 31) == 0) {   // L2 prefetch hints as in fused_stage_kernel; "later" = A.wave chunks further on
-        const int w  = tid >> 5;
-        const int cw = c + A.wave;
-        if (A.pf_ptr[w]) prefetch_l2(A.pf_ptr[w] + (size_t)c * EC * A.pf_unit[w], (unsigned)ecn * A.pf_unit[w]);
-        if (A.pf_ptr[w + 8] && cw < A.n_chunks) {
-          const unsigned idx = w < 5 ? (unsigned)cw * EC : (unsigned)cw;
-          const unsigned cnt = w < 5 ? (unsigned)min(EC, (int)A.n_local - cw * EC) : 1u;
-          prefetch_l2(A.pf_ptr[w + 8] + (size_t)idx * A.pf_unit[w + 8], cnt * A.pf_unit[w + 8]);
-        }
-      }
-      T g0 = T(1), g1 = T(0), g2 = T(0), g3 = T(0), g4 = T(1);
-      if (hidx >= 0) load_halo(hidx, hrk, g0, g1, g2, g3, g4);
-      WS_T(t1c);
-      if (n >= WS_BUFS) nb_sync(WS_BAR_EMPTY + b, 2 * EC);   // phase 2 of chunk n-3 (the other team) is through
-      WS_T(t2c);
-      if (own) sm.store_cell(tid, to_cell(u0, u1, u2, u3, u4));
-      if (hidx >= 0) sm.store_cell(EC + tid, to_cell(g0, g1, g2, g3, g4));
-      for (int h = tid + EC; h < A.hs; h += EC) {
-        const int idx = A.halo_elem[hb + h];
-        if (idx >= 0) {
-          T a0, a1, a2, a3, a4;
-          load_halo(idx, A.multi ? A.halo_rank[hb + h] : 0, a0, a1, a2, a3, a4);
-          sm.store_cell(EC + h, to_cell(a0, a1, a2, a3, a4));
-        }
-      }
-      WS_T(t3c);
-      WS_ACC(2, t0c, t1c); WS_ACC(3, t1c, t2c); WS_ACC(4, t2c, t3c); WS_ACC(9, 0, 1);
-      nb_arrive(WS_BAR_FULL + b, 2 * EC);
-    }
-    const int m = n - 2;
-    if (m >= 0 && m < n_my) {   // ---- phase 2 of chunk n-2
-      const int             c = blockIdx.x + m * grid, b = m % WS_BUFS;
-      const Smem<T, MS, MF> sm(smem_raw + b * BUF);
-      const int4 h1v = __ldg(A.hdr + 2 * c + 1);
-      const int  ecn = min(EC, (int)A.n_local - c * EC);
-      const int  e = c * EC + tid;
-      const bool own = tid < ecn;
-      WS_T(t4c);
-      uint4 el = make_uint4(~0u, ~0u, ~0u, ~0u);
-      T     vol = T(1), base[5] = {T(0), T(0), T(0), T(0), T(0)};
-      if (own) {
-        el  = A.ell[e];
-        vol = A.vol[e >> A.vol_shift] * A.vol_scale;
-#pragma unroll
-        for (int k = 0; k < 5; k++) base[k] = A.in[k][e];
-        if (stage != 1) {
-          const T cp = stage == 2 ? T(0.75) : T(0.33333333333333), ci = stage == 2 ? T(0.25) : T(0.66666666666666);
-#pragma unroll
-          for (int k = 0; k < 5; k++) base[k] = cp * A.prev[k][e] + ci * base[k];
-        }
-      }
-      T sc = fast_rcp(vol) * A.dt;
-      if (stage == 2) sc *= T(0.25);
-      if (stage == 3) sc *= T(0.66666666666666);
-      if (h1v.w >= 0) sc *= atab[h1v.w];
-      WS_T(t5c);
-      nb_sync(WS_BAR_DONE + b, 2 * EC);
-      WS_T(t6c);
-      if (own) {
-        T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
-        const unsigned w[4] = {el.x, el.y, el.z, el.w};
-#pragma unroll
-        for (int s = 0; s < ELL; s++) {
-          const unsigned en = (s & 1) ? w[s >> 1] >> 16 : w[s >> 1] & 0xFFFFu;
-          if (en != 0xFFFFu) sm.gather(en, acc);
-        }
-        if (h1v.y >= 0) {
-          const uint16_t* off = A.ovf_off + h1v.y;
-          const uint16_t* ent = A.ovf_ent + h1v.z;
-#pragma unroll 1
-          for (int q = off[tid], q1 = off[tid + 1]; q < q1; q++) sm.gather(ent[q], acc);
-        }
-#pragma unroll
-        for (int k = 0; k < 5; k++) A.out[k][e] = base[k] + sc * acc[k];
-      }
-      WS_T(t7c);
-      WS_ACC(5, t4c, t5c); WS_ACC(6, t5c, t6c); WS_ACC(7, t6c, t7c);
-      if (m + WS_BUFS < n_my) nb_arrive(WS_BAR_EMPTY + b, 2 * EC);
-    }
-  }
-}
-
-template <typename T>
-static int launch_ws(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
-  auto k = fused_stage_ws_kernel<T, MS, MF>;
-  constexpr size_t smem = WS_BUFS * Smem<T, MS, MF>::bytes;
-  static int sms = 0;
-  if (!sms) {
-    T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    T8B_TRY(cudaGetDevice(&dev));
-    T8B_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  FusedArgs<T> B = A;
-  B.n_chunks = P->n_chunks;
-  static const int ahead = getenv("T8B200_WS_AHEAD") ? atoi(getenv("T8B200_WS_AHEAD")) : 2;
-  B.wave = ahead * sms;
-  for (int i = 0; i < 16; i++) { B.pf_ptr[i] = nullptr; B.pf_unit[i] = 0; }
-  for (int i = 0; i < 5; i++) {
-    if (B.stage != 1) { B.pf_ptr[i] = (const char*)B.prev[i]; B.pf_unit[i] = sizeof(T); }
-    if (B.wave > 0) { B.pf_ptr[8 + i] = (const char*)B.in[i]; B.pf_unit[8 + i] = sizeof(T); }
-  }
-  if (B.vol_shift == 0) { B.pf_ptr[5] = (const char*)B.vol; B.pf_unit[5] = sizeof(T); }
-  B.pf_ptr[6] = (const char*)B.ell; B.pf_unit[6] = sizeof(uint4);
-  if (B.wave > 0) {
-    B.pf_ptr[13] = (const char*)B.halo_elem; B.pf_unit[13] = (unsigned)B.hs * 4u;
-    B.pf_ptr[14] = (const char*)B.face_lr;   B.pf_unit[14] = (unsigned)B.fs * 4u;
-    B.pf_ptr[15] = (const char*)B.hdr;       B.pf_unit[15] = 32u;
-  }
-  k<<<std::min(sms, (int)P->n_chunks), WS_TEAMS * EC, smem, st>>>(B);
-  return cudaGetLastError();
-}
-
 template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
 static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
   auto k = fused_stage_kernel<T, MS, MF, MINB, CMP, SPLIT>;
@@ -762,8 +517,6 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
   A.stage = stage; A.multi = P->multi; A.my_rank = P->my_rank;
   cudaStream_t st = (cudaStream_t)stream;
   if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), st));
-  static const int ws_knob = getenv("T8B200_WS") ? atoi(getenv("T8B200_WS")) : 0;
-  if (ws_knob && sizeof(T) == 8 && P->cmp && !P->split) return launch_ws<T>(P, A, st);
   return P->cmp ? launch_fused<T, true>(P, A, st) : launch_fused<T, false>(P, A, st);
 }
 

@@ -40,14 +40,21 @@ if hasattr(L, "t8b200_debug_phase_clocks"):
     L.t8b200_debug_phase_clocks(out, 1)
     sol.iterate(dt)
     L.t8b200_debug_phase_clocks(out, 0)
-    if os.environ.get("T8B200_WS"):
-        nf, ne = max(1, out[8]), max(1, out[9])
-        print("  face team cycles/chunk: wait FULL %.0f, faces %.0f" % (out[0] / nf, out[1] / nf))
-        print("  element team cycles/chunk: phase-0 loads %.0f, wait EMPTY %.0f, convert %.0f | phase-2 loads %.0f, "
-              "wait DONE %.0f, gather+store %.0f" % tuple(out[i] / ne for i in range(2, 8)))
-    else:
-        names = ["phase0", "barrier1", "phase1", "barrier2", "phase2"]
-        for o, w in ((0, "warp0"), (8, "warp7")):
-            n = max(1, out[o + 5])
-            print("  %s cycles/CTA:" % w, ", ".join("%s %.0f" % (nm, out[o + i] / n) for i, nm in enumerate(names)),
-                  "| total %.0f | face loops alone %.0f" % (sum(out[o:o + 5]) / n, out[o + 6] / n))
+    names = ["phase0", "barrier1", "phase1", "barrier2", "phase2"]
+    for o, w in ((0, "warp0"), (8, "warp7")):
+        n = max(1, out[o + 5])
+        print("  %s cycles/CTA:" % w, ", ".join("%s %.0f" % (nm, out[o + i] / n) for i, nm in enumerate(names)),
+              "| total %.0f | face loops alone %.0f" % (sum(out[o:o + 5]) / n, out[o + 6] / n))
+if hasattr(L, "t8b200_debug_cta_log"):
+    import numpy as np
+    log = np.zeros(4 * 65536, np.int64)
+    L.t8b200_debug_cta_log(log.ctypes.data_as(C.c_void_p))
+    log = log.reshape(-1, 4)
+    for sm in (0, 57, 147):
+        rows = log[log[:, 0] == sm]
+        rows = rows[np.argsort(rows[:, 1])]
+        t0 = rows[0, 1]
+        print("  SM %d: %d CTAs; start / phase-1 start / end (cycles since first start):" % (sm, len(rows)))
+        print("   ", " ".join("%d/%d/%d" % (r[1] - t0, r[2] - t0, r[3] - t0) for r in rows[:9]))
+        mid = len(rows) // 2
+        print("    mid-launch:", " ".join("%d/%d/%d" % (r[1] - t0, r[2] - t0, r[3] - t0) for r in rows[mid:mid + 9]))
