@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(EC) gradient_criteria_kernel(const __grid_cons
     const unsigned sr = lr >> 16;
     // boundary faces do not contribute (the reference loops over the interior faces only, kernels.cu:476-477)
     const bool wall = A.cmp ? j >= e2 : sr == 0xFFFFu;
-    jump[j] = wall ? T(0) : t8b200::fabs_(rho_s[sr] - rho_s[lr & 0xFFFFu]);
+    jump[j] = wall ? T(0) : t8b200::fabs_(rho_s[sr] - rho_s[lr & 0x3FFFu]);
   }
   __syncthreads();
   if (!own) return;

@@ -187,7 +187,7 @@ extern "C" int t8b200_debug_phase_clocks(unsigned long long* out, int reset) {
 //   phase 0: conserved -> per-cell quantities for the chunk's own elements (coalesced) and its halo (gather)
 //   phase 1: every face touching the chunk: flux from the staged cells -> smem
 //   phase 2: per element: signed gather of its faces' fluxes (fixed order: deterministic), RK combination, store
-template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
+template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT, bool SMAX>
 __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_constant__ FusedArgs<T> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Smem<T, MS, MF> sm(smem_raw);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   const int  nfc = (unsigned)h0v.z >> 16;
   const int  e0 = h0v.w & 0xFFFF, e1 = (unsigned)h0v.w >> 16, e2 = h1v.x;
   const int  area_idx  = h1v.w;
-  const bool want_smax = A.speed_max != nullptr;
+  constexpr bool want_smax = SMAX;   // stage 3 with a CFL reduction; a template parameter frees its registers elsewhere
   T8B_CLK(1);
   __syncthreads();
   T8B_CLK(2);
@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
         if (j + EC < nfc) lr_n = A.face_lr[fb + j + EC];
         T F[5], s;
         if (AXPERM) {   // one copy of the x-normal flux, the axis enters through the row addresses
-          const int p0 = (j >= e0) + (j >= e1), p1 = p0 == 2 ? 0 : p0 + 1, p2 = p0 == 0 ? 2 : p0 - 1;
-          const Cell<T> L = sm.load_cell_axis(lr & 0xFFFFu, p0, p1, p2);
+          const int p0 = (lr >> 14) & 3, p1 = p0 == 2 ? 0 : p0 + 1, p2 = p0 == 0 ? 2 : p0 - 1;   // axis from the record
+          const Cell<T> L = sm.load_cell_axis(lr & 0x3FFFu, p0, p1, p2);
           const Cell<T> R = sm.load_cell_axis(lr >> 16, p0, p1, p2);
           s = kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
           if (want_smax) smax = fmax_(smax, s);
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
           sm.store_flux_axis(j, F, p0, p1, p2);
           continue;
         }
-        const Cell<T> L = sm.load_cell(lr & 0xFFFFu);
+        const Cell<T> L = sm.load_cell(lr & 0x3FFFu);
         const Cell<T> R = sm.load_cell(lr >> 16);
 #ifdef T8B_ABLATE_FLUX   // tools/build_variant.py: timing experiment only (memory + indexing floor), results are wrong
         F[0] = L.rho - R.rho; F[1] = L.hx - R.hx; F[2] = L.hy - R.hy; F[3] = L.hz - R.hz; F[4] = L.kp - R.kp + L.b - R.b + L.q - R.q;
@@ -335,10 +335,11 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       const T        sg   = (code & 1) ? T(1) : T(-1);
       const int      ax   = code >> 1;
       const T nx = ax == 0 ? sg : T(0), ny = ax == 1 ? sg : T(0), nz = ax == 2 ? sg : T(0);
-      const Cell<T> L = sm.load_cell(lr & 0xFFFFu);
+      const Cell<T> L = sm.load_cell(lr & 0x3FFFu);
       const Cell<T> R = mirror(L, nx, ny, nz);
       T F[5];
-      smax = fmax_(smax, kepes_flux_n<T, -1>(L, R, nx, ny, nz, F));
+      const T s = kepes_flux_n<T, -1>(L, R, nx, ny, nz, F);
+      if (want_smax) smax = fmax_(smax, s);
       if (area_idx < 0) {
         const T ar = atab[A.face_ai[fb + j]];
 #pragma unroll
@@ -357,10 +358,11 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
         lr_n = A.face_lr[g]; nx_n = A.fnx[g]; ny_n = A.fny[g]; nz_n = A.fnz[g]; ar_n = A.farea[g];
       }
       const int     sr = lr >> 16;
-      const Cell<T> L  = sm.load_cell(lr & 0xFFFFu);
+      const Cell<T> L  = sm.load_cell(lr & 0x3FFFu);
       const Cell<T> R  = sr == 0xFFFF ? mirror(L, nx, ny, nz) : sm.load_cell(sr);
       T F[5];
-      smax = fmax_(smax, kepes_flux_n<T, -1>(L, R, nx, ny, nz, F));
+      const T s = kepes_flux_n<T, -1>(L, R, nx, ny, nz, F);
+      if (want_smax) smax = fmax_(smax, s);
 #pragma unroll
       for (int k = 0; k < 5; k++) F[k] *= ar;
       sm.store_flux(j, F);
@@ -391,6 +393,13 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     }
 #endif
   }
+  // the overflow-table words of the header are read again here rather than kept in registers through the face loops
+  // (fp32, 48 registers: frees two and removes its spills, -2.6 % per step; fp64 measured 0.5 % faster without)
+  int2 ovf = make_int2(h1v.y, h1v.z);
+  if (sizeof(T) == 4) {
+    const int4 h1b = __ldg(A.hdr + 2 * c + 1);
+    ovf = make_int2(h1b.y, h1b.z);
+  }
   T sc = fast_rcp(vol) * A.dt;   // before the barrier: the reciprocal chain hides in the wait
   if (stage == 2) sc *= T(0.25);
   if (stage == 3) sc *= T(0.66666666666666);
@@ -408,9 +417,9 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       // -4 % per step; fp64: the 60 registers the overlapped loads would need are not there, branches measured faster
       if (s < (sizeof(T) == 4 ? 6 : 0) || en != 0xFFFFu) sm.gather(en, acc);
     }
-    if (h1v.y >= 0) {  // rare: elements of this chunk with more than ELL faces
-      const uint16_t* off = A.ovf_off + h1v.y;
-      const uint16_t* ent = A.ovf_ent + h1v.z;
+    if (ovf.x >= 0) {  // rare: elements of this chunk with more than ELL faces
+      const uint16_t* off = A.ovf_off + ovf.x;
+      const uint16_t* ent = A.ovf_ent + ovf.y;
 #pragma unroll 1
       for (int q = off[tid], q1 = off[tid + 1]; q < q1; q++) sm.gather(ent[q], acc);
     }
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     }
   }
 #endif
-  if (A.speed_max) {
+  if (SMAX) {
     smax = warp_max(smax);
     if ((tid & 31) == 0) red[tid >> 5] = smax;
     __syncthreads();
@@ -448,9 +457,9 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   }
 }
 
-template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT>
+template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT, bool SMAX>
 static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
-  auto k = fused_stage_kernel<T, MS, MF, MINB, CMP, SPLIT>;
+  auto k = fused_stage_kernel<T, MS, MF, MINB, CMP, SPLIT, SMAX>;
 #ifdef T8B_PHASE_CLOCKS   // analysis builds: T8B200_SMEM_PAD lowers the occupancy (e.g. 140000: one CTA per SM)
   static const size_t smem = Smem<T, MS, MF>::bytes + (getenv("T8B200_SMEM_PAD") ? atoi(getenv("T8B200_SMEM_PAD")) : 0);
 #else
@@ -488,9 +497,15 @@ template <typename T, bool CMP>
 static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_t st) {
   // resident CTAs per SM are bounded by shared memory (68 KB fp64 / 36 KB fp32 per CTA); tell ptxas so it can size
   // the register budget (fp32: 5 CTAs of 48 registers measured faster than 6 of 40 and than 4 of 64)
-  constexpr int B0 = sizeof(T) == 8 ? 3 : 5;
-  return P->split ? launch_variant<T, MS, MF, B0, CMP, true>(P, A, st)
-                  : launch_variant<T, MS, MF, B0, CMP, false>(P, A, st);
+#ifndef T8B_MINB64
+#define T8B_MINB64 3
+#endif
+  constexpr int B0 = sizeof(T) == 8 ? T8B_MINB64 : 5;
+  if (A.speed_max)
+    return P->split ? launch_variant<T, MS, MF, B0, CMP, true, true>(P, A, st)
+                    : launch_variant<T, MS, MF, B0, CMP, false, true>(P, A, st);
+  return P->split ? launch_variant<T, MS, MF, B0, CMP, true, false>(P, A, st)
+                  : launch_variant<T, MS, MF, B0, CMP, false, false>(P, A, st);
 }
 
 template <typename T>

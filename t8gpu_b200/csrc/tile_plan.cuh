@@ -311,7 +311,10 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
           src.geometry(f, nrm, a);
           B.fnx.push_back(nrm[0]); B.fny.push_back(nrm[1]); B.fnz.push_back(nrm[2]); B.far.push_back(a);
         }
-        B.face_lr.push_back((uint32_t)sl | ((uint32_t)sr << 16));
+        // record: left slot (bits 0-13), axis of the normal (bits 14-15; compressed interior faces, else 0), right
+        // slot or wall code (bits 16-31)
+        const uint32_t axis_bits = (cmp && recs[j].grp < 3) ? (uint32_t)recs[j].grp << 14 : 0u;
+        B.face_lr.push_back((uint32_t)sl | axis_bits | ((uint32_t)sr << 16));
         if (sl < EC) per_el[sl].push_back((uint16_t)(j << 1));
         if (sr < EC) per_el[sr].push_back((uint16_t)((j << 1) | 1));
       }
