@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   // first face record of this thread (consumed in phase 1; its latency hides behind phase 0)
   uint32_t lr_n = 0;
   if (tid < A.fs) lr_n = A.face_lr[fb + tid];
-  if ((tid & 31) == 0) {
+  if ((tid & 31) == 0 && tid < 256) {
     // L2 prefetch hints, two per warp (a bulk prefetch is a warp-uniform instruction: spreading them avoids a serial
     // loop in one warp), table-driven (A.pf_*, filled by the host).  Items 0-7: the phase-2 operands of this chunk, so
     // that their loads before the barrier are L2 hits.  Items 8-15 (SPLIT == false only: addresses computable

@@ -28,7 +28,10 @@
 #include "../../include/t8gpu_b200.h"
 #include "euler_flux.cuh"
 
-static constexpr int EC  = 256;  // elements per chunk == threads per CTA
+#ifndef T8B_EC
+#define T8B_EC 256
+#endif
+static constexpr int EC  = T8B_EC;  // elements per chunk == threads per CTA
 static constexpr int ELL = 8;    // face entries per element held in the fixed-width table
 
 struct t8b200_plan {
@@ -89,7 +92,11 @@ static int axis_code(const T* n) {
 // MF - 1 faces.  Chunks are EC consecutive elements; a block of EC elements whose halo or face count exceeds these
 // limits (2:1 hanging faces, unstructured meshes with many small neighbours) is split recursively into smaller
 // chunks, so ONE kernel variant serves every mesh.
-static constexpr int MS = 512, MF = 1024;
+#ifndef T8B_MS
+#define T8B_MS 512
+#define T8B_MF 1024
+#endif
+static constexpr int MS = T8B_MS, MF = T8B_MF;
 
 // Host threads used to build a plan (per-block work is independent; results are merged in block order, so the plan
 // does not depend on the thread count).
