@@ -205,4 +205,28 @@ def run_subgrid(args, rank, world, device):
                              "frac": achieved / peak, "traffic": None, "peak_source": src,
                              "kernel": "fused_stage_kernel (cell-level tile plan)", "note": "per GPU",
                              "alg_bytes_per_launch": alg * n / 3.0, "avg_launch_ms": ms_per_step / 3.0}}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.dtype)
         print(json.dumps(line))
+
+
+def cpu_baseline(dtype_name, budget_s=10.0, level=3):
+    """The CPU oracle (kind "port": the reference has no CPU implementation of this path) on a bounded sample of the
+    same workload: Subgrid<4,4,4> on the uniform periodic hex forest of level 3 (32 768 cells), single thread."""
+    import numpy as np
+    import oracle
+    npdt = np.float64 if dtype_name == "f64" else np.float32
+    f = oracle.Forest(3, level)
+    conn = f.connectivity(subgrid=True, dtype=npdt)
+    lv, cent, vol, _ = f.elements()
+    u = oracle.subgrid_init_kh(3, cent.astype(npdt), lv, npdt)
+    vol = vol.astype(npdt)
+    dt = 0.1 * 2.0 ** -(level + 2)
+    steps, t0 = 0, time.time()
+    while steps < 2 or time.time() - t0 < budget_s:
+        u, _, _ = oracle.subgrid_iterate(conn, vol, u, dt)
+        steps += 1
+    el = time.time() - t0
+    return {"value": u.shape[1] * steps / el, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "sample": "Subgrid<4,4,4>, uniform periodic hex level %d (%d cells), %d RK3 steps, %.1f s, %s" %
+                      (level, u.shape[1], steps, el, dtype_name)}
