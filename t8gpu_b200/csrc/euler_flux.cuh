@@ -141,6 +141,7 @@ T8B_HD T kepes_flux_n(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[
 
   const T sr = L.rho + R.rho, dr = R.rho - L.rho;
   const T sb = L.b + R.b, db = R.b - L.b;
+  const T kps = L.kp + R.kp, dq = R.q - L.q;   // kp and q enter only as a sum / a difference
   const T rr  = fast_rcp(sr * sb);
   const T isr = rr * sb, isb = rr * sr;
   const T hs  = T(0.5) * sr;
@@ -174,7 +175,7 @@ T8B_HD T kepes_flux_n(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[
   const T vv   = ax * ax + ay * ay + az * az;
   const T hvv  = T(0.5) * vv;
   const T dhh  = L.hx * R.hx + L.hy * R.hy + L.hz * R.hz;        // vL.vR / 4
-  const T aHat = fast_sqrt((L.kp + R.kp) * hir);                 // sqrt(kappa (pL+pR)/2 / rhoHat), kernels.cu:80
+  const T aHat = fast_sqrt(kps * hir);                           // sqrt(kappa (pL+pR)/2 / rhoHat), kernels.cu:80
   const T ibk  = hib * ikm1;                                     // 1 / (2 (k-1) betaHat)
   const T tt   = T(2) * dhh + ibk;                               // 1/(2(k-1) betaHat) + vL.vR/2
   const T HHat = tt + hib;                                       // kernels.cu:82
@@ -185,7 +186,7 @@ T8B_HD T kepes_flux_n(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[
   const T Fs4 = F0 * tt + uHat * p1Hat;
 
   // HALF the jump of the entropy variables, kernels.cu:227-266:  J0, 2*(jx,jy,jz), -db
-  const T J0 = hlr + ikm1 * hlb - (R.q - L.q);
+  const T J0 = hlr + ikm1 * hlb - dq;
   const T jx = R.b * R.hx - L.b * L.hx, jy = R.b * R.hy - L.b * L.hy, jz = R.b * R.hz - L.b * L.hz;
   const T aj = ax * jx + ay * jy + az * jz;
   const T jn = AXIS == 0 ? jx : AXIS == 1 ? jy : AXIS == 2 ? jz : nx * jx + ny * jy + nz * jz;
