@@ -56,11 +56,11 @@ T8B_HD double fast_rcp(double x) {
 #ifdef __CUDA_ARCH__
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r        = fma(r, e, r);
-  e        = fma(-x, r, 1.0);
-  r        = fma(r, e, r);
-  return r;
+  // two Newton steps in three dependent levels: the residual after the first step is e^2, known without r1
+  const double e  = fma(-x, r, 1.0);
+  const double r1 = fma(r, e, r);
+  const double e1 = e * e;
+  return fma(r1, e1, r1);
 #else
   return 1.0 / x;
 #endif
@@ -78,12 +78,13 @@ T8B_HD double fast_sqrt(double x) {
 #ifdef __CUDA_ARCH__
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double xh = 0.5 * x;
-  double t  = fma(-xh * y, y, 0.5);
-  y         = fma(y, t, y);
-  t         = fma(-xh * y, y, 0.5);
-  y         = fma(y, t, y);
-  return x * y;
+  // coupled iteration on g ~ sqrt(x), h ~ 1/(2 sqrt(x)): five dependent levels after the seed, g is the result
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g        = fma(g, r, g);
+  h        = fma(h, r, h);
+  r        = fma(-g, h, 0.5);
+  return fma(g, r, g);
 #else
   return std::sqrt(x);
 #endif
@@ -149,9 +150,19 @@ T8B_HD T kepes_flux_n(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[
   // logarithmic means (series branch), kernels.cu:24-36
   const T fr = dr * isr, ur = fr * fr;
   const T fb = db * isb, ub = fb * fb;
-  const T xr = ur * (c3 + ur * (c5 + ur * c7));
-  const T xb = ub * (c3 + ub * (c5 + ub * c7));
-  T rhoHat = hs * (T(1) - xr * (T(1) - xr * (T(1) - xr)));
+  // fp64 is bound by the dependent chain through these values (the square root of this face hangs off them): Estrin
+  // / factored forms, one dependent level less each; fp32 is issue-bound: Horner, one instruction less each
+  T xr, xb, rhoHat;
+  if (sizeof(T) == 8) {
+    xr = (ur * c3) + (ur * ur) * (c5 + ur * c7);
+    xb = (ub * c3) + (ub * ub) * (c5 + ub * c7);
+    const T omx = T(1) - xr;
+    rhoHat = hs * (omx + (xr * xr) * omx);   // (1 - x)(1 + x^2) = 1 - x + x^2 - x^3
+  } else {
+    xr = ur * (c3 + ur * (c5 + ur * c7));
+    xb = ub * (c3 + ub * (c5 + ub * c7));
+    rhoHat = hs * (T(1) - xr * (T(1) - xr * (T(1) - xr)));
+  }
   T hir    = isr * xr + isr;   // 1 / (2 rhoHat)
   T hlr    = fr * xr + fr;     // log(rhoR/rhoL) / 2
   T hib    = isb * xb + isb;   // 1 / (2 betaHat)
