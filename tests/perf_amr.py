@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--cycles", type=int, default=4)
     ap.add_argument("--every", type=int, default=10)
     ap.add_argument("--dtype", default="f64")
+    ap.add_argument("--subgrid", action="store_true",
+                    help="config 4: Subgrid<4,4,4>, the subgrid criterion (threshold 0.02), cell-level remap")
     args = ap.parse_args()
     import torch
     import oracle
@@ -36,11 +38,23 @@ def main():
     dev = torch.device("cuda", 0)
     f = oracle.Forest(3, args.level)
     lv, cent, vol, _ = f.elements()
-    u0 = oracle.init_kh_points(3, cent.astype(npdt), npdt)
-    conn = f.connectivity(dtype=npdt)
-    sol = tb.EulerSolver(conn, vol.astype(npdt), tdt, device=dev, mode="fused", max_level=args.max_level)
+    S = 64 if args.subgrid else 1
+
+    def make_solver(forest, volumes):
+        if args.subgrid:
+            return tb.SubgridEulerSolver(forest.connectivity(subgrid=True, dtype=npdt), volumes.astype(npdt), tdt,
+                                         device=dev, mode="fused")
+        return tb.EulerSolver(forest.connectivity(dtype=npdt), volumes.astype(npdt), tdt, device=dev, mode="fused",
+                              max_level=args.max_level)
+
+    def volume_of(solver):
+        return solver.vol if args.subgrid else solver.volume()
+
+    u0 = (oracle.subgrid_init_kh(3, cent.astype(npdt), lv, npdt) if args.subgrid
+          else oracle.init_kh_points(3, cent.astype(npdt), npdt))
+    sol = make_solver(f, vol)
     sol.set_state(u0)
-    dt = 0.1 * 2.0 ** -args.max_level
+    dt = 0.1 * 2.0 ** -(args.max_level + (2 if args.subgrid else 0))
     for _ in range(3):
         sol.iterate(dt)
     torch.cuda.synchronize()
@@ -49,7 +63,7 @@ def main():
     hist = []
     wall0 = time.time()
     for cyc in range(args.cycles):
-        n = sol.n
+        n = sol.nc if args.subgrid else sol.n
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.every):
@@ -60,35 +74,44 @@ def main():
         updates += n * args.every
         # criteria on the device (threshold of the example: refine where the scaled density jump is large)
         t = time.time()
-        crit = tb.gradient_criteria(sol.plan, sol.state()[0], sol.volume())
-        # the example's threshold (10) is tuned for its shell mesh; scale so that the shear layers refine
-        crit_h = (crit * (10.0 / 0.5)).cpu().numpy()
+        if args.subgrid:
+            crit_h = tb.subgrid_criteria(3, sol.state()[0], sol.vol).cpu().numpy()
+            threshold = 0.02    # examples/subgrid: refine above, coarsen below (subgrid_mesh_manager.inl adapt callback)
+        else:
+            crit = tb.gradient_criteria(sol.plan, sol.state()[0], sol.volume())
+            # the example's threshold (10) is tuned for its shell mesh; scale so that the shear layers refine
+            crit_h = (crit * (10.0 / 0.5)).cpu().numpy()
+            threshold = 10.0
         torch.cuda.synchronize()
         t_crit += time.time() - t
         t = time.time()
-        f2 = f.adapt(crit_h, 10.0, 1, args.max_level)
+        f2 = f.adapt(crit_h, threshold, 1, args.max_level)
         amap = f.adapt_map(f2)
         t_forest += time.time() - t
         t = time.time()
         lv2, cent2, vol2, _ = f2.elements()
-        conn2 = f2.connectivity(dtype=npdt)
+        conn2 = f2.connectivity(subgrid=args.subgrid, dtype=npdt)
         t_conn += time.time() - t
         t = time.time()
-        new = tb.EulerSolver(conn2, vol2.astype(npdt), tdt, device=dev, mode="fused", max_level=args.max_level)
+        if args.subgrid:
+            new = tb.SubgridEulerSolver(conn2, vol2.astype(npdt), tdt, device=dev, mode="fused")
+        else:
+            new = tb.EulerSolver(conn2, vol2.astype(npdt), tdt, device=dev, mode="fused", max_level=args.max_level)
         torch.cuda.synchronize()
         t_plan += time.time() - t
         t = time.time()
-        tb.adapt_remap(torch.as_tensor(amap).to(dev), sol.variables(sol.next), new.variables(new.next), sol.volume(),
-                       new.volume(), 0)
+        tb.adapt_remap(torch.as_tensor(amap).to(dev), sol.variables(sol.next), new.variables(new.next), volume_of(sol),
+                       volume_of(new), 3 if args.subgrid else 0)
         torch.cuda.synchronize()
         t_remap += time.time() - t
-        hist.append(dict(cycle=cyc, elements=int(n), new_elements=int(new.n), chunks=int(new.plan.info["n_chunks"]),
+        hist.append(dict(cycle=cyc, cells=int(n), new_cells=int(new.nc if args.subgrid else new.n),
+                         chunks=int(new.plan.info["n_chunks"]),
                          max_halo=int(new.plan.info["max_halo"]), max_faces=int(new.plan.info["max_faces"])))
         sol, f = new, f2
         assert torch.isfinite(sol.state()).all()
     wall = time.time() - wall0
     print(json.dumps({
-        "dtype": args.dtype, "every": args.every, "cycles": args.cycles, "history": hist,
+        "dtype": args.dtype, "subgrid": args.subgrid, "every": args.every, "cycles": args.cycles, "history": hist,
         "stepping_cell_updates_per_s": updates / t_step, "end_to_end_cell_updates_per_s": updates / wall,
         "seconds": {"stepping": t_step, "criteria_gpu+d2h": t_crit, "forest_adapt_host(mini-forest)": t_forest,
                     "connectivity_host(mini-forest)": t_conn, "plan_build+alloc": t_plan, "remap_gpu": t_remap,
