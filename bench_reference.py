@@ -20,15 +20,21 @@ def run_reference_arm(args):
             return ref_cuda.bench(args)
     except ImportError:
         pass
-    from bench import cpu_baseline
     t0 = time.time()
+    subgrid = getattr(args, "workload", "unstructured") == "subgrid"
+    if subgrid:
+        from bench_subgrid import cpu_baseline
+        n = 32768
+    else:
+        from bench import cpu_baseline
+        n = 262144
     cb = cpu_baseline(args.dtype, budget_s=20.0)
-    n = 262144
     line = {"impl": "reference", "metric": "cell-updates/s per RK3 step", "value": cb["value"],
             "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * n / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "kelvin_helmholtz 3D uniform periodic hex mesh, bounded sample: " + cb["sample"]},
+            "config": {"workload": ("kelvin_helmholtz 3D Subgrid<4,4,4>, bounded sample: " if subgrid else
+                                    "kelvin_helmholtz 3D uniform periodic hex mesh, bounded sample: ") + cb["sample"]},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
