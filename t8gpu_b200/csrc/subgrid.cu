@@ -283,6 +283,7 @@ struct SubgridFaces {
   const int32_t *ranks, *indices, *xnbr;
   const T *      xnormals, *xareas;
   const int32_t *xld, *xoff;
+  std::vector<T> inner_area;   // per element: area of the faces between its cells (prepare())
   int     S() const { return dim == 3 ? 64 : 16; }
   int     TPF() const { return dim == 3 ? 16 : 4; }
   int     IPE() const { return dim * 3 * TPF(); }   // inner faces per element: dim axes x 3 planes x TPF
@@ -347,17 +348,7 @@ struct SubgridFaces {
       const int64_t e  = f / IPE();
       const int     ax = (int)(f % IPE()) / (3 * TPF());
       nrm[ax] = T(1);
-      if (dim == 3) {
-        // libm's cbrt is off by an ulp on exact cubes (dyadic Cartesian volumes): take the exact root when there is
-        // one, so that the faces inside an element and between elements get the same area entry
-        T c = std::cbrt(vol[e]);
-        for (T t : {std::nextafter(c, T(0)), std::nextafter(c, T(2) * c)})
-          if (t * t * t == vol[e]) c = t;
-        const T edge = c / T(4);
-        a = edge * edge;
-      } else {
-        a = std::sqrt(vol[e]) / T(4);
-      }
+      a = inner_area[e];
       return;
     }
     int64_t        F;
@@ -368,6 +359,26 @@ struct SubgridFaces {
     outer(f - n_inner(), F, s, pn, n, ar, l_d, o, wall);
     for (int d = 0; d < dim; d++) nrm[d] = n[d];
     a = *ar / T(TPF());
+  }
+  // surface = (cbrt(vol)/4)^2 (kernels.inl:352-354) resp. sqrt(vol)/4 (2-D, :542-544), once per element (the plan
+  // asks for the geometry of every cell face several times)
+  void prepare() {
+    inner_area.resize((size_t)n_local);
+    parallel_ranges(n_local, plan_threads(), [&](int, int64_t e0, int64_t e1) {
+      for (int64_t e = e0; e < e1; e++) {
+        if (dim == 3) {
+          // libm's cbrt is off by an ulp on exact cubes (dyadic Cartesian volumes): take the exact root when there is
+          // one, so that the faces inside an element and between elements get the same area entry
+          T c = std::cbrt(vol[e]);
+          for (T t : {std::nextafter(c, T(0)), std::nextafter(c, T(2) * c)})
+            if (t * t * t == vol[e]) c = t;
+          const T edge = c / T(4);
+          inner_area[e] = edge * edge;
+        } else {
+          inner_area[e] = std::sqrt(vol[e]) / T(4);
+        }
+      }
+    });
   }
   void owner(int32_t id, int32_t& rk, int32_t& ix) const {
     const int32_t e = id / S(), c = id % S();
@@ -384,7 +395,8 @@ static int sg_plan_build(t8b200_subgrid_plan* SP, int dim, int64_t n_local, int6
                          const int32_t* xnbr, const T* xnormals, const T* xareas, const int32_t* xld,
                          const int32_t* xoff) {
   SubgridFaces<T> src{dim, n_local, nf, nb, nx, nbr, normals, areas, level_diff, offsets, vol, ranks, indices, xnbr,
-                      xnormals, xareas, xld, xoff};
+                      xnormals, xareas, xld, xoff, {}};
+  src.prepare();
   if ((n_local + n_ghost) * src.S() > 0x7FFFFFF0LL) return cudaErrorInvalidValue;
   t8b200_plan* P = new t8b200_plan();
   SP->plan       = P;

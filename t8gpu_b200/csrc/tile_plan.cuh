@@ -170,7 +170,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   }
   if (area_tab.size() > 256) cmp = false;
   std::sort(area_tab.begin(), area_tab.end());   // table order independent of the thread count
-  std::vector<uint8_t> area_of(cmp ? ntot : 0);
+  std::vector<uint8_t> area_of(cmp ? ntot : 0), code_of(cmp ? ntot : 0);   // per face: area index, axis_code of the normal
   if (cmp)
     parallel_ranges(ntot, NT, [&](int, int64_t f0, int64_t f1) {
       int last = 0;
@@ -179,6 +179,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
         src.geometry(f, nrm, a);
         if (area_tab[last] != a) last = (int)(std::find(area_tab.begin(), area_tab.end(), a) - area_tab.begin());
         area_of[f] = (uint8_t)last;
+        code_of[f] = (uint8_t)axis_code(nrm);
       }
     });
 
@@ -238,15 +239,19 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     std::vector<int64_t> cand, sub;
     std::vector<std::vector<uint16_t>> per_el(EC);
     struct Rec { int grp, sl, sr; int64_t f; };
-    std::vector<Rec> recs;
+    std::vector<Rec>      recs, recs_sorted;
+    std::vector<uint64_t> keys;
+    std::vector<int32_t>  ends;   // endpoints of the faces of the block being emitted (face sources compute them)
 
     // emits the chunk [b0, b1) whose faces are `faces`; 1 if it does not fit the kernel's shared memory
     auto emit = [&](int64_t b0, int64_t b1, const std::vector<int64_t>& faces, bool dry) -> int {
       const int nfc = (int)faces.size();
       halo_tmp.clear();
-      for (int64_t f : faces) {
+      ends.resize(2 * (size_t)nfc);
+      for (int j = 0; j < nfc; j++) {
         int32_t l, r;
-        src.endpoints(f, l, r);
+        src.endpoints(faces[j], l, r);
+        ends[2 * j] = l; ends[2 * j + 1] = r;
         if (l < b0 || l >= b1) halo_tmp.push_back(l);
         if (r >= 0 && (r < b0 || r >= b1)) halo_tmp.push_back(r);
       }
@@ -280,13 +285,10 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
       int seg[4] = {0, 0, 0, 0};
       for (int j = 0; j < nfc; j++) {
         const int64_t f = faces[j];
-        int32_t       l, r;
-        src.endpoints(f, l, r);
+        const int32_t l = ends[2 * j], r = ends[2 * j + 1];
         int sl = slot_of(l), sr = r < 0 ? 0xFFFF : slot_of(r), grp = 0;
         if (cmp) {
-          T nrm[3], a;
-          src.geometry(f, nrm, a);
-          const int code = axis_code(nrm);
+          const int code = code_of[f];
           grp = r < 0 ? 3 : code >> 1;
           if (r < 0) sr = 0xFFF8 | code;                  // wall: outward normal coded in the slotR field
           else if (!(code & 1)) std::swap(sl, sr);        // canonical orientation: normal = +e_axis
@@ -294,13 +296,23 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
         }
         recs[j] = Rec{grp, sl, sr, f};
       }
-      std::sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) {
-        if (x.grp != y.grp) return x.grp < y.grp;
-        if (by_id) return x.f < y.f;
-        if (x.sl != y.sl) return x.sl < y.sl;
-        if (x.sr != y.sr) return x.sr < y.sr;
-        return x.f < y.f;
-      });
+      if (by_id) {
+        std::sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) {
+          if (x.grp != y.grp) return x.grp < y.grp;
+          return x.f < y.f;
+        });
+      } else {
+        // (group, left slot, right slot, face id) packed into one integer; the face id enters through the position in
+        // `faces`, which is ascending in the id
+        keys.resize(nfc);
+        for (int j = 0; j < nfc; j++)
+          keys[j] = ((uint64_t)recs[j].grp << 44) | ((uint64_t)recs[j].sl << 28) | ((uint64_t)recs[j].sr << 12) | (uint64_t)j;
+        std::sort(keys.begin(), keys.end());
+        std::vector<Rec>& sorted = recs_sorted;
+        sorted.resize(nfc);
+        for (int j = 0; j < nfc; j++) sorted[j] = recs[keys[j] & 0xFFFu];
+        recs.swap(sorted);
+      }
       H[3] = seg[0] | ((seg[0] + seg[1]) << 16);
       H[4] = seg[0] + seg[1] + seg[2];
       for (auto& v : per_el) v.clear();
