@@ -270,7 +270,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
       for (int h = 0; h < nh; h++) {
         int32_t id = halo_tmp[h], rk = 0, ix = id;
         if (multi) src.owner(id, rk, ix);
-        else if (id >= n_local) return cudaErrorInvalidValue;
+        else if (id >= n_local) return -1;   // a ghost without owner tables: invalid input (not "does not fit")
         B.halo_elem.push_back(ix);
         B.halo_rank.push_back(rk);
       }
@@ -382,7 +382,8 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
           }
           fs = &sub;
         }
-        int rc = emit(rg.b0, rg.b1, *fs, true);
+        // emit() checks the fit before it writes anything: no dry run needed
+        int rc = emit(rg.b0, rg.b1, *fs, false);
         if (rc == 1) {
           if (rg.b1 - rg.b0 <= 1) { B.rc = cudaErrorInvalidValue; break; }   // one element exceeds a CTA
           const int64_t mid = (rg.b0 + rg.b1) / 2;
@@ -391,8 +392,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
           B.split = true;
           continue;
         }
-        rc = emit(rg.b0, rg.b1, *fs, false);
-        if (rc) { B.rc = rc; break; }
+        if (rc) { B.rc = rc < 0 ? (int)cudaErrorInvalidValue : rc; break; }
       }
     }
   });
