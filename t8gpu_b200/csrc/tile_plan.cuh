@@ -66,8 +66,19 @@ struct t8b200_plan {
 };
 
 
+// std::vector that does not value-initialise on resize: the large per-chunk arrays of the merge are written in full by
+// the parallel copy (payload + padding), a serial zero fill of hundreds of MB first would only add page-fault time
 template <typename T>
-static T* upload(const std::vector<T>& v, int64_t& bytes, cudaError_t& err) {
+struct default_init_allocator : std::allocator<T> {
+  template <typename U> struct rebind { using other = default_init_allocator<U>; };
+  template <typename U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <typename U, typename... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <typename T>
+using raw_vector = std::vector<T, default_init_allocator<T>>;
+
+template <typename T, typename Alloc>
+static T* upload(const std::vector<T, Alloc>& v, int64_t& bytes, cudaError_t& err) {
   T*     d = nullptr;
   size_t n = std::max<size_t>(v.size(), 1) * sizeof(T) + 32;  // slack for 16-byte granular prefetch hints
   if (err != cudaSuccess) return nullptr;
@@ -221,7 +232,8 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
 
   lap("bucket faces by block");
   // ---- per-block chunk emission, one builder per thread over a contiguous range of blocks
-  std::vector<uint16_t> ell((size_t)std::max<int64_t>(n_local, 1) * ELL, 0xFFFF);
+  raw_vector<uint16_t> ell((size_t)std::max<int64_t>(n_local, 1) * ELL);   // 0xFFFF-filled per chunk by emit()
+  if (n_local == 0) std::fill(ell.begin(), ell.end(), (uint16_t)0xFFFF);
   struct Builder {
     std::vector<int32_t>  hdr, halo_elem, halo_rank;
     std::vector<int64_t>  halo_off{0}, rec_off{0};
@@ -340,6 +352,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
       B.rec_off.push_back((int64_t)B.face_lr.size());
       H[7] = (uniform && area0 >= 0) ? area0 : -1;
       // fixed-width table (disjoint element ranges: written in place) + overflow CSR (bases relative to this builder)
+      std::fill(ell.begin() + (size_t)b0 * ELL, ell.begin() + (size_t)b1 * ELL, (uint16_t)0xFFFF);
       bool overflow = false;
       for (int i = 0; i < (int)(b1 - b0); i++) {
         const auto& v = per_el[i];
@@ -422,11 +435,11 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   P->n_chunks = nchunks;
   P->split    = split ? 1 : 0;
   const int HS = std::max(32, (max_halo + 31) / 32 * 32), FS = std::max(32, (max_faces + 31) / 32 * 32);
-  std::vector<int32_t>  hdr((size_t)nchunks * 8), halo_elem((size_t)nchunks * HS, -1),
-      halo_rank(multi ? (size_t)nchunks * HS : 0, 0);
-  std::vector<uint32_t> face_lr((size_t)nchunks * FS, 0);
-  std::vector<uint8_t>  face_ai(cmp ? (size_t)nchunks * FS : 0, 0);
-  std::vector<T>        fnx(cmp ? 0 : (size_t)nchunks * FS), fny(fnx.size()), fnz(fnx.size()), far(fnx.size());
+  raw_vector<int32_t>  hdr((size_t)nchunks * 8), halo_elem((size_t)nchunks * HS),
+      halo_rank(multi ? (size_t)nchunks * HS : 0);
+  raw_vector<uint32_t> face_lr((size_t)nchunks * FS);
+  raw_vector<uint8_t>  face_ai(cmp ? (size_t)nchunks * FS : 0);
+  raw_vector<T>        fnx(cmp ? 0 : (size_t)nchunks * FS), fny(fnx.size()), fnz(fnx.size()), far(fnx.size());
   std::vector<uint16_t> ovf_off(n_ovf_off), ovf_ent(n_ovf_ent);
   {
     std::vector<int>    chunk_base(NT + 1, 0);
@@ -445,17 +458,21 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
           int32_t*     H = &hdr[c * 8];
           std::copy(B.hdr.begin() + (size_t)i * 8, B.hdr.begin() + (size_t)i * 8 + 8, H);
           if (H[5] >= 0) { H[5] += (int32_t)oo_base[t]; H[6] += (int32_t)oe_base[t]; }
-          std::copy(B.halo_elem.begin() + B.halo_off[i], B.halo_elem.begin() + B.halo_off[i + 1], halo_elem.begin() + c * HS);
-          if (multi)
-            std::copy(B.halo_rank.begin() + B.halo_off[i], B.halo_rank.begin() + B.halo_off[i + 1], halo_rank.begin() + c * HS);
+          // payload, then the padding up to the fixed stride (halo -1, everything else 0)
+          auto place = [](auto& dst, size_t at, size_t stride, const auto& from, int64_t q0, int64_t q1, auto pad) {
+            std::copy(from.begin() + q0, from.begin() + q1, dst.begin() + at);
+            std::fill(dst.begin() + at + (size_t)(q1 - q0), dst.begin() + at + stride, pad);
+          };
+          place(halo_elem, c * HS, HS, B.halo_elem, B.halo_off[i], B.halo_off[i + 1], (int32_t)-1);
+          if (multi) place(halo_rank, c * HS, HS, B.halo_rank, B.halo_off[i], B.halo_off[i + 1], (int32_t)0);
           const int64_t r0 = B.rec_off[i], r1 = B.rec_off[i + 1];
-          std::copy(B.face_lr.begin() + r0, B.face_lr.begin() + r1, face_lr.begin() + c * FS);
-          if (cmp) std::copy(B.face_ai.begin() + r0, B.face_ai.begin() + r1, face_ai.begin() + c * FS);
+          place(face_lr, c * FS, FS, B.face_lr, r0, r1, (uint32_t)0);
+          if (cmp) place(face_ai, c * FS, FS, B.face_ai, r0, r1, (uint8_t)0);
           else {
-            std::copy(B.fnx.begin() + r0, B.fnx.begin() + r1, fnx.begin() + c * FS);
-            std::copy(B.fny.begin() + r0, B.fny.begin() + r1, fny.begin() + c * FS);
-            std::copy(B.fnz.begin() + r0, B.fnz.begin() + r1, fnz.begin() + c * FS);
-            std::copy(B.far.begin() + r0, B.far.begin() + r1, far.begin() + c * FS);
+            place(fnx, c * FS, FS, B.fnx, r0, r1, T(0));
+            place(fny, c * FS, FS, B.fny, r0, r1, T(0));
+            place(fnz, c * FS, FS, B.fnz, r0, r1, T(0));
+            place(far, c * FS, FS, B.far, r0, r1, T(0));
           }
         }
         std::copy(B.ovf_off.begin(), B.ovf_off.end(), ovf_off.begin() + oo_base[t]);
