@@ -181,7 +181,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   }
   if (area_tab.size() > 256) cmp = false;
   std::sort(area_tab.begin(), area_tab.end());   // table order independent of the thread count
-  std::vector<uint8_t> area_of(cmp ? ntot : 0), code_of(cmp ? ntot : 0);   // per face: area index, axis_code of the normal
+  raw_vector<uint8_t> area_of(cmp ? ntot : 0), code_of(cmp ? ntot : 0);   // per face: area index, axis_code of the normal
   if (cmp)
     parallel_ranges(ntot, NT, [&](int, int64_t f0, int64_t f1) {
       int last = 0;
@@ -217,7 +217,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     for (int t = 0; t < NT; t++) { int32_t v = cnt[t][b]; cnt[t][b] = (int32_t)sum; sum += v; }   // thread offset in block
     face_off[b + 1] = face_off[b] + sum;
   }
-  std::vector<int64_t> rec(face_off[nblocks]);
+  raw_vector<int64_t> rec(face_off[nblocks]);   // written in full by the pass below
   parallel_ranges(ntot, NT, [&](int t, int64_t f0, int64_t f1) {
     auto& c = cnt[t];
     for (int64_t f = f0; f < f1; f++) {
@@ -249,10 +249,11 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     Builder& B = builders[t];
     std::vector<int32_t> halo_tmp;
     std::vector<int64_t> cand, sub;
-    std::vector<std::vector<uint16_t>> per_el(EC);
+    uint16_t              el_cnt[EC];
+    std::vector<uint32_t> ovf_pairs;
     struct Rec { int grp, sl, sr; int64_t f; };
     std::vector<Rec>      recs, recs_sorted;
-    std::vector<uint64_t> keys;
+    std::vector<int>      bucket;
     std::vector<int32_t>  ends;   // endpoints of the faces of the block being emitted (face sources compute them)
 
     // emits the chunk [b0, b1) whose faces are `faces`; 1 if it does not fit the kernel's shared memory
@@ -316,18 +317,39 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
       } else {
         // (group, left slot, right slot, face id) packed into one integer; the face id enters through the position in
         // `faces`, which is ascending in the id
-        keys.resize(nfc);
-        for (int j = 0; j < nfc; j++)
-          keys[j] = ((uint64_t)recs[j].grp << 44) | ((uint64_t)recs[j].sl << 28) | ((uint64_t)recs[j].sr << 12) | (uint64_t)j;
-        std::sort(keys.begin(), keys.end());
+        // counting sort on (group, left slot) -- stable, so the face id order survives -- then the few records that
+        // share a left slot are ordered by right slot
+        constexpr int NB = 4 * MS;
+        bucket.assign(NB + 1, 0);
+        for (int j = 0; j < nfc; j++) bucket[recs[j].grp * MS + std::min(recs[j].sl, MS - 1) + 1]++;
+        for (int b = 0; b < NB; b++) bucket[b + 1] += bucket[b];
         std::vector<Rec>& sorted = recs_sorted;
         sorted.resize(nfc);
-        for (int j = 0; j < nfc; j++) sorted[j] = recs[keys[j] & 0xFFFu];
+        for (int j = 0; j < nfc; j++) sorted[bucket[recs[j].grp * MS + std::min(recs[j].sl, MS - 1)]++] = recs[j];
+        for (int j = 1; j < nfc; j++) {   // insertion sort inside runs of equal (group, left slot): (right slot, id)
+          const Rec x = sorted[j];
+          int       k = j;
+          while (k > 0 && sorted[k - 1].grp == x.grp && sorted[k - 1].sl == x.sl &&
+                 (sorted[k - 1].sr > x.sr || (sorted[k - 1].sr == x.sr && sorted[k - 1].f > x.f))) {
+            sorted[k] = sorted[k - 1];
+            k--;
+          }
+          sorted[k] = x;
+        }
         recs.swap(sorted);
       }
       H[3] = seg[0] | ((seg[0] + seg[1]) << 16);
       H[4] = seg[0] + seg[1] + seg[2];
-      for (auto& v : per_el) v.clear();
+      // element -> face table written in place while the records are emitted (disjoint element ranges per chunk):
+      // the first ELL entries of an element go to the fixed-width table, the rest to (slot, entry) pairs
+      std::fill(ell.begin() + (size_t)b0 * ELL, ell.begin() + (size_t)b1 * ELL, (uint16_t)0xFFFF);
+      std::fill(el_cnt, el_cnt + EC, (uint16_t)0);
+      ovf_pairs.clear();
+      auto add_entry = [&](int slot, uint16_t en) {
+        const int k = el_cnt[slot]++;
+        if (k < ELL) ell[((size_t)b0 + slot) * ELL + k] = en;
+        else ovf_pairs.push_back(((uint32_t)slot << 16) | en);
+      };
       int  area0 = -1;
       bool uniform = cmp;
       for (int j = 0; j < nfc; j++) {
@@ -346,31 +368,25 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
         // slot or wall code (bits 16-31)
         const uint32_t axis_bits = (cmp && recs[j].grp < 3) ? (uint32_t)recs[j].grp << 14 : 0u;
         B.face_lr.push_back((uint32_t)sl | axis_bits | ((uint32_t)sr << 16));
-        if (sl < EC) per_el[sl].push_back((uint16_t)(j << 1));
-        if (sr < EC) per_el[sr].push_back((uint16_t)((j << 1) | 1));
+        if (sl < EC) add_entry(sl, (uint16_t)(j << 1));
+        if (sr < EC) add_entry(sr, (uint16_t)((j << 1) | 1));
       }
       B.rec_off.push_back((int64_t)B.face_lr.size());
       H[7] = (uniform && area0 >= 0) ? area0 : -1;
-      // fixed-width table (disjoint element ranges: written in place) + overflow CSR (bases relative to this builder)
-      std::fill(ell.begin() + (size_t)b0 * ELL, ell.begin() + (size_t)b1 * ELL, (uint16_t)0xFFFF);
-      bool overflow = false;
-      for (int i = 0; i < (int)(b1 - b0); i++) {
-        const auto& v = per_el[i];
-        for (size_t q = 0; q < v.size() && q < (size_t)ELL; q++) ell[((size_t)b0 + i) * ELL + q] = v[q];
-        if (v.size() > (size_t)ELL) overflow = true;
-      }
+      // overflow CSR (bases relative to this builder): entries per element in emission order
       H[5] = -1;
       H[6] = 0;
-      if (overflow) {
+      if (!ovf_pairs.empty()) {
+        if (ovf_pairs.size() > 65535) return -1;
         H[5] = (int32_t)B.ovf_off.size();
         H[6] = (int32_t)B.ovf_ent.size();
-        size_t n = 0;
+        std::stable_sort(ovf_pairs.begin(), ovf_pairs.end(), [](uint32_t x, uint32_t y) { return (x >> 16) < (y >> 16); });
+        size_t q = 0;
         for (int i = 0; i < EC; i++) {
-          B.ovf_off.push_back((uint16_t)n);
-          for (size_t q = ELL; q < per_el[i].size(); q++) { B.ovf_ent.push_back(per_el[i][q]); n++; }
+          B.ovf_off.push_back((uint16_t)q);
+          while (q < ovf_pairs.size() && (int)(ovf_pairs[q] >> 16) == i) B.ovf_ent.push_back((uint16_t)(ovf_pairs[q++] & 0xFFFFu));
         }
-        if (n > 65535) return cudaErrorInvalidValue;
-        B.ovf_off.push_back((uint16_t)n);
+        B.ovf_off.push_back((uint16_t)q);
       }
       return 0;
     };
