@@ -204,7 +204,7 @@ class Plan:
                          device_bytes=info[4], face_records=info[5], halo_entries=info[6], chunk=info[7])
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:   # `lib` is gone when the interpreter shuts down
             lib().t8b200_plan_destroy(self._h)
             self._h = None
 
@@ -253,7 +253,7 @@ class SubgridPlan:
                          device_bytes=info[4], face_records=info[5], halo_entries=info[6], chunk=info[7])
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().t8b200_subgrid_plan_destroy(self._h)
             self._h = None
 
