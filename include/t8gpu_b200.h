@@ -127,6 +127,19 @@ void t8b200_plan_destroy(t8b200_plan* plan);
  * [4]=device bytes held by the plan, [5]=face records (faces counted once per chunk they touch),
  * [6]=total halo entries, [7]=elements per chunk */
 int t8b200_plan_info(const t8b200_plan* plan, int64_t info[8]);
+/* The plan builder without a device (CPU-side checks of the host logic; the reference has no counterpart): same
+ * arguments as t8b200_plan_create, nothing is uploaded, the plan cannot be launched.  t8b200_plan_host_array returns a
+ * pointer into the plan's host arrays: which = 0 chunk headers (8 int32 per chunk: first element, count,
+ * halo | faces << 16, x-end | y-end << 16, z-end, overflow offset index or -1, overflow entry index, uniform area index
+ * or -1), 1 halo element indices (stride info[..] per chunk, -1 padded), 2 halo ranks, 3 face records (left slot bits
+ * 0-13, axis bits 14-15, right slot or wall code bits 16-31), 4 area index per record, 5 element -> face table (8 uint16
+ * per element: record << 1 | side, 0xFFFF none), 6 / 7 overflow offsets / entries, 8 area table, 9-12 normals and areas
+ * of general plans (as double). */
+int t8b200_plan_create_host(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
+                            const int32_t* face_neighbors, const void* face_normals, const void* face_surfaces,
+                            const int32_t* ranks, const int32_t* indices, int32_t n_xfaces,
+                            const int32_t* x_face_neighbors, const void* x_face_normals, const void* x_face_surfaces);
+int t8b200_plan_host_array(const t8b200_plan* plan, int which, const void** data, int64_t* count, int* elem_bytes);
 
 /* One fused RK stage.  in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's arrays (stage input, U^n, stage
  * output).  in_all: HOST array of 5 DEVICE tables (one pointer per rank) for ghost reads, or NULL when the plan has
@@ -156,6 +169,15 @@ int  t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int dim, 
                                 const void* x_face_normals, const void* x_face_surfaces,
                                 const int32_t* x_level_difference, const int32_t* x_neighbor_offset);
 void t8b200_subgrid_plan_destroy(t8b200_subgrid_plan* plan);
+/* host-only variant (see t8b200_plan_create_host) and access to the cell-level plan behind a subgrid plan */
+int t8b200_subgrid_plan_create_host(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local, int64_t n_ghost,
+                                    int32_t nf, int32_t nb, const int32_t* face_neighbors, const void* face_normals,
+                                    const void* face_surfaces, const int32_t* face_level_difference,
+                                    const int32_t* face_neighbor_offset, const void* volumes, const int32_t* ranks,
+                                    const int32_t* indices, int32_t n_xfaces, const int32_t* x_face_neighbors,
+                                    const void* x_face_normals, const void* x_face_surfaces,
+                                    const int32_t* x_level_difference, const int32_t* x_neighbor_offset);
+const t8b200_plan* t8b200_subgrid_plan_base(const t8b200_subgrid_plan* plan);
 /* as t8b200_plan_info, counted in cells */
 int t8b200_subgrid_plan_info(const t8b200_subgrid_plan* plan, int64_t info[8]);
 /* in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's cell arrays; in_all: tables for ghost reads or NULL;

@@ -120,7 +120,7 @@ subgrid_criteria_kernel(int64_t ne, const T* __restrict__ rho, const T* __restri
 
 template <typename T>
 int gradient_impl(const t8b200_plan* P, const T* rho, const T* const* rho_all, const T* vol, T* out, void* stream) {
-  if (!P || !rho || !vol || !out || (P->multi && !rho_all)) return cudaErrorInvalidValue;
+  if (!P || P->host_only || !rho || !vol || !out || (P->multi && !rho_all)) return cudaErrorInvalidValue;
   if (P->is_f64 != (sizeof(T) == 8)) return cudaErrorInvalidValue;
   if (P->n_chunks == 0) return 0;
   GradArgs<T> A{};

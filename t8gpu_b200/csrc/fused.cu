@@ -512,7 +512,7 @@ template <typename T>
 static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
                             const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream) {
   if (!P || stage < 1 || stage > 3 || !in || !out || !vol || (stage > 1 && !prev)) return cudaErrorInvalidValue;
-  if (P->is_f64 != (sizeof(T) == 8)) return cudaErrorInvalidValue;
+  if (P->is_f64 != (sizeof(T) == 8) || P->host_only) return cudaErrorInvalidValue;
   if (P->multi && !in_all) return cudaErrorInvalidValue;
   if (P->n_chunks == 0) return cudaSuccess;
   FusedArgs<T> A{};
@@ -576,16 +576,17 @@ void t8b_plan_free(t8b200_plan* P) { t8b200_plan_destroy(P); }
 // ============================================================================================================
 extern "C" {
 
-int t8b200_plan_create(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
-                       const int32_t* nbr, const void* normals, const void* areas, const int32_t* ranks,
-                       const int32_t* indices, int32_t nx, const int32_t* xnbr, const void* xnormals,
-                       const void* xareas) {
+static int plan_create_impl(t8b200_plan** out, int host_only, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
+                            int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
+                            const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                            const void* xnormals, const void* xareas) {
   if (!out || n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0) return cudaErrorInvalidValue;
   if ((nf + nb > 0) && (!nbr || !normals || !areas)) return cudaErrorInvalidValue;
   if (nx > 0 && (!xnbr || !xnormals || !xareas)) return cudaErrorInvalidValue;
   if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
   t8b200_plan* P = new t8b200_plan();
   P->is_f64      = is_f64 ? 1 : 0;
+  P->host_only   = host_only;
   int rc;
   if (is_f64) {
     MeshFaces<double> src{nf, nb, nx, nbr, (const double*)normals, (const double*)areas, ranks, indices, xnbr,
@@ -604,8 +605,55 @@ int t8b200_plan_create(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n
   return 0;
 }
 
+int t8b200_plan_create(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
+                       const int32_t* nbr, const void* normals, const void* areas, const int32_t* ranks,
+                       const int32_t* indices, int32_t nx, const int32_t* xnbr, const void* xnormals,
+                       const void* xareas) {
+  return plan_create_impl(out, 0, is_f64, n_local, n_ghost, nf, nb, nbr, normals, areas, ranks, indices, nx, xnbr,
+                          xnormals, xareas);
+}
+int t8b200_plan_create_host(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
+                            const int32_t* nbr, const void* normals, const void* areas, const int32_t* ranks,
+                            const int32_t* indices, int32_t nx, const int32_t* xnbr, const void* xnormals,
+                            const void* xareas) {
+  return plan_create_impl(out, 1, is_f64, n_local, n_ghost, nf, nb, nbr, normals, areas, ranks, indices, nx, xnbr,
+                          xnormals, xareas);
+}
+
+int t8b200_plan_host_array(const t8b200_plan* P, int which, const void** data, int64_t* count, int* elem_bytes) {
+  if (!P || !P->host || !data || !count || !elem_bytes) return cudaErrorInvalidValue;
+  const t8b200_plan_host& H = *P->host;
+  auto set = [&](const auto& v) {
+    *data       = v.data();
+    *count      = (int64_t)v.size();
+    *elem_bytes = (int)sizeof(v[0]);
+    return 0;
+  };
+  switch (which) {
+    case 0: return set(H.hdr);
+    case 1: return set(H.halo_elem);
+    case 2: return set(H.halo_rank);
+    case 3: return set(H.face_lr);
+    case 4: return set(H.face_ai);
+    case 5: return set(H.ell);
+    case 6: return set(H.ovf_off);
+    case 7: return set(H.ovf_ent);
+    case 8: return set(H.area_tab);
+    case 9: return set(H.fnx);
+    case 10: return set(H.fny);
+    case 11: return set(H.fnz);
+    case 12: return set(H.farea);
+  }
+  return cudaErrorInvalidValue;
+}
+
 void t8b200_plan_destroy(t8b200_plan* P) {
   if (!P) return;
+  if (P->host_only) {
+    delete P->host;
+    delete P;
+    return;
+  }
   cudaFree(P->hdr); cudaFree(P->halo_elem); cudaFree(P->halo_rank);
   cudaFree(P->face_lr); cudaFree(P->face_ai); cudaFree(P->fnx); cudaFree(P->fny); cudaFree(P->fnz); cudaFree(P->farea);
   cudaFree(P->area_tab); cudaFree(P->ell); cudaFree(P->ovf_off); cudaFree(P->ovf_ent);

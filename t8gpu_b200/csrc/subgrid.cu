@@ -389,7 +389,7 @@ struct SubgridFaces {
 }  // namespace
 
 template <typename T>
-static int sg_plan_build(t8b200_subgrid_plan* SP, int dim, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
+static int sg_plan_build(t8b200_subgrid_plan* SP, int host_only, int dim, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
                          const int32_t* nbr, const T* normals, const T* areas, const int32_t* level_diff,
                          const int32_t* offsets, const T* vol, const int32_t* ranks, const int32_t* indices, int32_t nx,
                          const int32_t* xnbr, const T* xnormals, const T* xareas, const int32_t* xld,
@@ -401,6 +401,7 @@ static int sg_plan_build(t8b200_subgrid_plan* SP, int dim, int64_t n_local, int6
   t8b200_plan* P = new t8b200_plan();
   SP->plan       = P;
   P->is_f64      = sizeof(T) == 8;
+  P->host_only   = host_only;
   P->vol_shift   = dim == 3 ? 6 : 4;
   P->vol_scale   = dim == 3 ? 1.0 / 64.0 : 1.0 / 16.0;
   return plan_build<T>(P, n_local * src.S(), n_ghost > 0, src);
@@ -408,7 +409,7 @@ static int sg_plan_build(t8b200_subgrid_plan* SP, int dim, int64_t n_local, int6
 
 extern "C" {
 
-int t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local, int64_t n_ghost,
+static int sg_plan_create_impl(t8b200_subgrid_plan** out, int host_only, int is_f64, int dim, int64_t n_local, int64_t n_ghost,
                                int32_t nf, int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
                                const int32_t* level_diff, const int32_t* offsets, const void* volumes,
                                const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
@@ -422,10 +423,10 @@ int t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int dim, i
   if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
   auto* SP = new t8b200_subgrid_plan();
   SP->dim  = dim;
-  int rc = is_f64 ? sg_plan_build<double>(SP, dim, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
+  int rc = is_f64 ? sg_plan_build<double>(SP, host_only, dim, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
                                           (const double*)areas, level_diff, offsets, (const double*)volumes, ranks,
                                           indices, nx, xnbr, (const double*)xnormals, (const double*)xareas, xld, xoff)
-                  : sg_plan_build<float>(SP, dim, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
+                  : sg_plan_build<float>(SP, host_only, dim, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
                                          (const float*)areas, level_diff, offsets, (const float*)volumes, ranks,
                                          indices, nx, xnbr, (const float*)xnormals, (const float*)xareas, xld, xoff);
   if (rc) {
@@ -435,6 +436,24 @@ int t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int dim, i
   *out = SP;
   return 0;
 }
+int t8b200_subgrid_plan_create(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local, int64_t n_ghost,
+                               int32_t nf, int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
+                               const int32_t* level_diff, const int32_t* offsets, const void* volumes,
+                               const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                               const void* xnormals, const void* xareas, const int32_t* xld, const int32_t* xoff) {
+  return sg_plan_create_impl(out, 0, is_f64, dim, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets,
+                             volumes, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
+}
+int t8b200_subgrid_plan_create_host(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local, int64_t n_ghost,
+                                    int32_t nf, int32_t nb, const int32_t* nbr, const void* normals,
+                                    const void* areas, const int32_t* level_diff, const int32_t* offsets,
+                                    const void* volumes, const int32_t* ranks, const int32_t* indices, int32_t nx,
+                                    const int32_t* xnbr, const void* xnormals, const void* xareas, const int32_t* xld,
+                                    const int32_t* xoff) {
+  return sg_plan_create_impl(out, 1, is_f64, dim, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets,
+                             volumes, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
+}
+const t8b200_plan* t8b200_subgrid_plan_base(const t8b200_subgrid_plan* SP) { return SP ? SP->plan : nullptr; }
 void t8b200_subgrid_plan_destroy(t8b200_subgrid_plan* SP) {
   if (!SP) return;
   t8b_plan_free(SP->plan);

@@ -34,6 +34,27 @@
 static constexpr int EC  = T8B_EC;  // elements per chunk == threads per CTA
 static constexpr int ELL = 8;    // face entries per element held in the fixed-width table
 
+// std::vector that does not value-initialise on resize: the large per-chunk arrays of the merge are written in full by
+// the parallel copy (payload + padding), a serial zero fill of hundreds of MB first would only add page-fault time
+template <typename T>
+struct default_init_allocator : std::allocator<T> {
+  template <typename U> struct rebind { using other = default_init_allocator<U>; };
+  template <typename U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <typename U, typename... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <typename T>
+using raw_vector = std::vector<T, default_init_allocator<T>>;
+
+// host copy of the plan arrays (t8b200_plan_create_host: the builder without a device, for CPU-side checks)
+struct t8b200_plan_host {
+  raw_vector<int32_t>   hdr, halo_elem, halo_rank;
+  raw_vector<uint32_t>  face_lr;
+  raw_vector<uint8_t>   face_ai;
+  raw_vector<uint16_t>  ell;
+  std::vector<uint16_t> ovf_off, ovf_ent;
+  std::vector<double>   area_tab, fnx, fny, fnz, farea;
+};
+
 struct t8b200_plan {
   int     is_f64     = 0;
   int64_t n_local    = 0;
@@ -63,19 +84,11 @@ struct t8b200_plan {
   // their element's volume: shift 6 / 4, scale 1/64 / 1/16, ssp_runge_kutta.inl:116)
   int    vol_shift = 0;
   double vol_scale = 1.0;
+  // host-only plans: arrays kept on the host, nothing uploaded, not launchable
+  int               host_only = 0;
+  t8b200_plan_host* host      = nullptr;
 };
 
-
-// std::vector that does not value-initialise on resize: the large per-chunk arrays of the merge are written in full by
-// the parallel copy (payload + padding), a serial zero fill of hundreds of MB first would only add page-fault time
-template <typename T>
-struct default_init_allocator : std::allocator<T> {
-  template <typename U> struct rebind { using other = default_init_allocator<U>; };
-  template <typename U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
-  template <typename U, typename... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
-};
-template <typename T>
-using raw_vector = std::vector<T, default_init_allocator<T>>;
 
 template <typename T, typename Alloc>
 static T* upload(const std::vector<T, Alloc>& v, int64_t& bytes, cudaError_t& err) {
@@ -509,6 +522,18 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   P->smem_bytes = sizeof(T) == 8 ? 8 * ((size_t)t8b200::NCELLQ * MS + 5 * (size_t)MF) : 32 * (size_t)MS + 20 * (size_t)MF;
 
   lap("merge");
+  P->cmp     = cmp ? 1 : 0;
+  P->n_areas = cmp ? (int)area_tab.size() : 0;
+  if (P->host_only) {
+    auto* Hc = new t8b200_plan_host();
+    Hc->hdr.swap(hdr); Hc->halo_elem.swap(halo_elem); Hc->halo_rank.swap(halo_rank); Hc->face_lr.swap(face_lr);
+    Hc->face_ai.swap(face_ai); Hc->ell.swap(ell); Hc->ovf_off.swap(ovf_off); Hc->ovf_ent.swap(ovf_ent);
+    if (cmp) Hc->area_tab.assign(area_tab.begin(), area_tab.end());
+    Hc->fnx.assign(fnx.begin(), fnx.end()); Hc->fny.assign(fny.begin(), fny.end());
+    Hc->fnz.assign(fnz.begin(), fnz.end()); Hc->farea.assign(far.begin(), far.end());
+    P->host = Hc;
+    return cudaSuccess;
+  }
   cudaError_t err = cudaSuccess;
   P->hdr       = upload(hdr, P->dev_bytes, err);
   P->halo_elem = upload(halo_elem, P->dev_bytes, err);

@@ -1,0 +1,291 @@
+"""CPU checks of the tile-plan builder (the host logic of the fused path) through the host-only entry points
+t8b200_plan_create_host / t8b200_plan_host_array: no device needed.
+
+Every array the stage kernel reads is checked against the connectivity it was built from: a chunk holds exactly the faces
+that touch its elements, each once; the halo is the sorted set of outside endpoints; records are in kernel order
+(x, y, z, walls; by left slot) with the canonical orientation, the axis in the record and the area through the table;
+the element -> face table lists, per element, its records in ascending order with the right side flags."""
+import ctypes as C
+import os
+from collections import Counter
+
+import numpy as np
+import pytest
+
+import oracle
+from util import hybrid_mesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EC = 256
+
+
+def _lib():
+    from t8gpu_b200 import build
+    L = C.CDLL(build.build())
+    L.t8b200_subgrid_plan_base.restype = C.c_void_p
+    return L
+
+
+def _p(a):
+    return None if a is None or len(a) == 0 else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(conn, k, dt):
+    v = conn.get(k)
+    return None if v is None or len(v) == 0 else np.ascontiguousarray(v, dtype=dt)
+
+
+def host_plan(L, conn, dtype):
+    keep = [_arr(conn, "face_neighbors", np.int32), _arr(conn, "face_normals", dtype), _arr(conn, "face_areas", dtype),
+            _arr(conn, "ranks", np.int32), _arr(conn, "indices", np.int32), _arr(conn, "x_face_neighbors", np.int32),
+            _arr(conn, "x_face_normals", dtype), _arr(conn, "x_face_areas", dtype)]
+    h = C.c_void_p()
+    rc = L.t8b200_plan_create_host(C.byref(h), int(dtype == np.float64), C.c_int64(int(conn["n_local"])),
+                                   C.c_int64(int(conn.get("n_ghost", 0))), int(conn["n_faces"]), int(conn["n_bfaces"]),
+                                   _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), _p(keep[4]),
+                                   int(conn.get("n_xfaces", 0)), _p(keep[5]), _p(keep[6]), _p(keep[7]))
+    assert rc == 0, rc
+    return h, keep
+
+
+def arrays(L, h):
+    names = ["hdr", "halo_elem", "halo_rank", "face_lr", "face_ai", "ell", "ovf_off", "ovf_ent", "area_tab", "fnx", "fny",
+             "fnz", "farea"]
+    dts = {1: np.uint8, 2: np.uint16, 4: np.int32, 8: np.float64}
+    out = {}
+    for which, name in enumerate(names):
+        data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
+        assert L.t8b200_plan_host_array(h, which, C.byref(data), C.byref(count), C.byref(eb)) == 0
+        n = count.value
+        if n == 0:
+            out[name] = np.zeros(0, dts[eb.value])
+            continue
+        buf = (C.c_char * (n * eb.value)).from_address(data.value)
+        a = np.frombuffer(buf, dtype=dts[eb.value]).copy()
+        out[name] = a.view(np.uint32) if name == "face_lr" else a
+    info = (C.c_int64 * 8)()
+    assert L.t8b200_plan_info(h, info) == 0
+    out["info"] = list(info)
+    return out
+
+
+def check_plan(conn, dtype, A, multi=False):
+    """Brute-force comparison of the plan arrays `A` with the reference-layout connectivity `conn`."""
+    nl, nf, nb = int(conn["n_local"]), int(conn["n_faces"]), int(conn["n_bfaces"])
+    nx = int(conn.get("n_xfaces", 0))
+    nbr = np.asarray(conn["face_neighbors"], np.int64)
+    l = np.concatenate([nbr[0:2 * nf:2], nbr[2 * nf:2 * nf + nb], np.asarray(conn.get("x_face_neighbors", []), np.int64)[0::2]])
+    r = np.concatenate([nbr[1:2 * nf:2], -np.ones(nb, np.int64), np.asarray(conn.get("x_face_neighbors", []), np.int64)[1::2]])
+    nd = len(conn["face_normals"]) // max(1, nf + nb)
+    nrm = np.concatenate([np.asarray(conn["face_normals"], np.float64).reshape(-1, nd),
+                          np.asarray(conn.get("x_face_normals", np.zeros(0)), np.float64).reshape(-1, nd)])
+    nrm = np.pad(nrm, ((0, 0), (0, 3 - nd)))
+    area = np.concatenate([np.asarray(conn["face_areas"], dtype).astype(np.float64),
+                           np.asarray(conn.get("x_face_areas", np.zeros(0)), dtype).astype(np.float64)])
+    ntot = nf + nb + nx
+    axis_aligned = np.all((np.abs(nrm) == 1).sum(1) == 1) and np.all((nrm != 0).sum(1) == 1)
+    nch = A["info"][0]
+    assert nch == len(A["hdr"]) // 8 and (nch > 0) == (nl > 0)
+    if nch == 0:
+        return
+    cmp_mode = len(A["area_tab"]) > 0
+    assert cmp_mode == (axis_aligned and len(np.unique(area)) <= 256)
+    HS, FS = len(A["halo_elem"]) // nch, len(A["face_lr"]) // nch
+    hdr = A["hdr"].reshape(nch, 8)
+    ell = A["ell"].reshape(-1, 8)
+    # element ranges tile [0, n_local) in order
+    assert hdr[0, 0] == 0 and np.all(hdr[1:, 0] == hdr[:-1, 0] + hdr[:-1, 1]) and hdr[-1, 0] + hdr[-1, 1] == nl
+    assert np.all(hdr[:, 1] <= EC) and np.all(hdr[:, 1] > 0)
+    # faces of every element range, brute force
+    touches = [[] for _ in range(nch)]
+    start = hdr[:, 0]
+    for f in range(ntot):
+        cs = set()
+        for e in (l[f], r[f]):
+            if 0 <= e < nl:
+                cs.add(int(np.searchsorted(start, e, side="right") - 1))
+        assert cs, "face without a local endpoint"
+        for c in cs:
+            touches[c].append(f)
+    ghost_of = {}
+    if multi:
+        rk, ix = np.asarray(conn["ranks"]), np.asarray(conn["indices"])
+        for g in range(nl, len(rk)):
+            ghost_of[(int(rk[g]), int(ix[g]))] = g
+    for c in range(nch):
+        e0, cnt, nh, nfc = hdr[c, 0], hdr[c, 1], hdr[c, 2] & 0xFFFF, hdr[c, 2] >> 16
+        x_end, y_end, z_end = hdr[c, 3] & 0xFFFF, hdr[c, 3] >> 16, hdr[c, 4]
+        he = A["halo_elem"][c * HS:(c + 1) * HS]
+        assert np.all(he[nh:] == -1)
+        if multi:
+            hr = A["halo_rank"][c * HS:(c + 1) * HS]
+            my = int(np.asarray(conn["ranks"])[0])
+            halo_ids = [int(he[i]) if hr[i] == my else ghost_of[(int(hr[i]), int(he[i]))] for i in range(nh)]
+        else:
+            halo_ids = [int(x) for x in he[:nh]]
+        want_halo = sorted({int(e) for f in touches[c] for e in (l[f], r[f]) if e >= 0 and not e0 <= e < e0 + cnt})
+        assert halo_ids == want_halo, c
+        glob = lambda s: e0 + s if s < EC else halo_ids[s - EC]   # noqa: E731
+        lr = A["face_lr"][c * FS:(c + 1) * FS]
+        assert nfc == len(touches[c]) and np.all(lr[nfc:] == 0)
+        got, want = Counter(), Counter()
+        prev_key = None
+        per_el = [[] for _ in range(cnt)]
+        for j in range(nfc):
+            sl, ax, sr = int(lr[j] & 0x3FFF), int((lr[j] >> 14) & 3), int(lr[j] >> 16)
+            if cmp_mode:
+                wall = j >= z_end
+                grp = 3 if wall else (0 if j < x_end else 1 if j < y_end else 2)
+                a = A["area_tab"][A["face_ai"][c * FS + j]]
+                if wall:
+                    code = sr & 7
+                    assert sr >> 3 == 0x1FFF and ax == 0
+                    got[(glob(sl), -1, code >> 1, 1 if code & 1 else -1, a)] += 1
+                else:
+                    assert ax == grp
+                    got[(glob(sl), glob(sr), ax, 1, a)] += 1
+                key = (grp, sl, sr)
+            else:
+                n3 = (A["fnx"][c * FS + j], A["fny"][c * FS + j], A["fnz"][c * FS + j])
+                got[(glob(sl), -1 if sr == 0xFFFF else glob(sr), n3, A["farea"][c * FS + j])] += 1
+                key = (0, sl, sr)
+            assert prev_key is None or prev_key <= key, (c, j)   # kernel order
+            prev_key = key
+            if sl < EC:
+                per_el[sl].append(j << 1)
+            if sr < EC:
+                per_el[sr].append((j << 1) | 1)
+        for f in touches[c]:
+            if cmp_mode:
+                axf = int(np.argmax(np.abs(nrm[f])))
+                sg = 1 if nrm[f, axf] > 0 else -1
+                if r[f] < 0:
+                    want[(int(l[f]), -1, axf, sg, area[f])] += 1
+                else:   # canonical orientation: the normal of the record is +e_axis
+                    a_, b_ = (int(l[f]), int(r[f])) if sg > 0 else (int(r[f]), int(l[f]))
+                    want[(a_, b_, axf, 1, area[f])] += 1
+            else:
+                want[(int(l[f]), int(r[f]), tuple(np.asarray(nrm[f], dtype).astype(np.float64)), area[f])] += 1
+        assert got == want, c
+        # element -> face table (+ overflow): the records of each element, ascending
+        oo, oe = hdr[c, 5], hdr[c, 6]
+        for i in range(cnt):
+            ent = [int(x) for x in ell[e0 + i] if x != 0xFFFF]
+            if oo >= 0:
+                off = A["ovf_off"][oo:oo + EC + 1]
+                ent += [int(x) for x in A["ovf_ent"][oe + off[i]:oe + off[i + 1]]]
+            assert ent == per_el[i], (c, i)
+            assert np.all(ell[e0 + i][min(len(per_el[i]), 8):] == 0xFFFF)
+        if cmp_mode:
+            ai = A["face_ai"][c * FS:c * FS + nfc]
+            assert hdr[c, 7] == (ai[0] if nfc and np.all(ai == ai[0]) else -1)
+
+
+def _forest(kind):
+    if kind == "hex3":
+        return oracle.Forest(3, 3)
+    if kind == "hex3_walls":
+        return oracle.Forest(3, 3, periodic=False)
+    if kind == "quad5":
+        return oracle.Forest(2, 5)
+    f = oracle.Forest(3, 2) if kind == "hex_amr" else oracle.Forest(2, 4, periodic=False)
+    lv, cent, vol, _ = f.elements()
+    crit = np.where(np.abs(cent[:, f.dim - 1] - 0.5) < 0.2, 20.0, 0.0)
+    return f.adapt(crit, 10.0, 1, 4 if kind == "hex_amr" else 6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["hex3", "hex3_walls", "quad5", "hex_amr", "quad_amr_walls"])
+def test_plan_arrays_match_connectivity(kind, dtype):
+    L = _lib()
+    conn = _forest(kind).connectivity(dtype=dtype)
+    h, keep = host_plan(L, conn, dtype)
+    try:
+        check_plan(conn, dtype, arrays(L, h))
+    finally:
+        L.t8b200_plan_destroy(h)
+
+
+def test_split_chunks_and_general_normals(monkeypatch):
+    L = _lib()
+    conn, vol, cent = hybrid_mesh(6, periodic=False, dtype=np.float64)
+    h, keep = host_plan(L, conn, np.float64)
+    A = arrays(L, h)
+    L.t8b200_plan_destroy(h)
+    assert len(A["area_tab"]) == 0 and len(A["fnx"]) > 0     # general geometry
+    check_plan(conn, np.float64, A)
+    # forced splitting: more chunks, same invariants
+    f = oracle.Forest(3, 3)
+    lv, cent, vol, _ = f.elements()
+    conn = f.adapt(np.where(np.abs(cent[:, 2] - 0.5) < 0.2, 20.0, 0.0), 10.0, 1, 4).connectivity(dtype=np.float64)
+    h, keep = host_plan(L, conn, np.float64)
+    n0 = arrays(L, h)["info"][0]
+    L.t8b200_plan_destroy(h)
+    monkeypatch.setenv("T8B200_TEST_MAX_HALO", "40")
+    h, keep = host_plan(L, conn, np.float64)
+    A = arrays(L, h)
+    L.t8b200_plan_destroy(h)
+    assert A["info"][0] > n0 and A["info"][1] <= 40
+    check_plan(conn, np.float64, A)
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_partitioned_plan(P):
+    """Ghost endpoints go through (rank, index); the faces owned by the lower rank are taken from the x-face arrays."""
+    L = _lib()
+    f = _forest("hex_amr")
+    for rank in range(P):
+        conn = f.connectivity(P, rank, dtype=np.float64)
+        h, keep = host_plan(L, conn, np.float64)
+        try:
+            check_plan(conn, np.float64, arrays(L, h), multi=True)
+        finally:
+            L.t8b200_plan_destroy(h)
+
+
+def test_subgrid_cell_plan():
+    """Cell-level plan of a Subgrid<4,4,4> forest with hanging faces: chunk statistics and conservation of the face
+    count (every cell face appears once per chunk it touches; inner faces of an element never leave its chunk)."""
+    L = _lib()
+    f = oracle.Forest(3, 1)
+    lv, cent, vol, _ = f.elements()
+    f = f.adapt(np.where(cent[:, 2] < 0.5, 1.0, 0.0), 0.02, 1, 2)
+    lv, cent, vol, _ = f.elements()
+    conn = f.connectivity(subgrid=True, dtype=np.float64)
+    keep = [_arr(conn, k, d) for k, d in (("face_neighbors", np.int32), ("face_normals", np.float64),
+                                          ("face_areas", np.float64), ("level_diff", np.int32), ("offsets", np.int32))]
+    vols = np.ascontiguousarray(vol, np.float64)
+    sh = C.c_void_p()
+    rc = L.t8b200_subgrid_plan_create_host(C.byref(sh), 1, 3, C.c_int64(f.num_elements), C.c_int64(0),
+                                           int(conn["n_faces"]), int(conn["n_bfaces"]), _p(keep[0]), _p(keep[1]),
+                                           _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(vols), None, None, 0, None, None,
+                                           None, None, None)
+    assert rc == 0
+    A = arrays(L, C.c_void_p(L.t8b200_subgrid_plan_base(sh)))
+    nch = A["info"][0]
+    ncell = f.num_elements * 64
+    # (blocks of 4 elements whose 2:1 halo exceeds the kernel's 256 slots are split)
+    assert nch >= (ncell + EC - 1) // EC and A["info"][1] <= 256 and len(A["area_tab"]) >= 2   # two levels: two areas
+    hdr = A["hdr"].reshape(nch, 8)
+    assert hdr[:, 1].sum() == ncell
+    # every cell has at least its 6 faces in the table (more where 2:1 faces hang), all entries valid record numbers
+    ell = A["ell"].reshape(-1, 8)
+    nent = (ell != 0xFFFF).sum(1)
+    assert nent.min() >= 6 and np.all(ell[:, :6] != 0xFFFF)
+    FS = len(A["face_lr"]) // nch
+    for c in range(nch):
+        nfc = hdr[c, 2] >> 16
+        e = ell[hdr[c, 0]:hdr[c, 0] + hdr[c, 1]]
+        assert (e[e != 0xFFFF] >> 1).max() < nfc <= FS
+    L.t8b200_subgrid_plan_destroy(sh)
+
+
+def test_host_plan_is_not_launchable():
+    L = _lib()
+    conn = _forest("hex3").connectivity(dtype=np.float64)
+    h, keep = host_plan(L, conn, np.float64)
+    ptr5 = (C.c_void_p * 5)()
+    assert L.t8b200_fused_stage_f64(h, 1, ptr5, None, None, ptr5, C.c_void_p(8), C.c_double(0.1), None, None) != 0
+    data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
+    assert L.t8b200_plan_host_array(h, 99, C.byref(data), C.byref(count), C.byref(eb)) != 0
+    L.t8b200_plan_destroy(h)
