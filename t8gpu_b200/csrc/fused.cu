@@ -282,6 +282,14 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 
   // ---- phase 1: software-pipelined over this thread's faces (record j+EC is in flight while j is evaluated)
   T smax = T(0);
+#ifdef T8B_SMAX_SMEM
+  // the running maximum of this thread lives in shared memory, not in two registers through the face loops
+  __shared__ T smax_s[SMAX ? EC : 1];
+  if (SMAX) smax_s[tid] = T(0);
+#define T8B_SMAX_UPDATE(s) do { if (want_smax && (s) > smax_s[tid]) smax_s[tid] = (s); } while (0)
+#else
+#define T8B_SMAX_UPDATE(s) do { if (want_smax) smax = fmax_(smax, (s)); } while (0)
+#endif
 #ifndef T8B_AXPERM
 #define T8B_AXPERM (sizeof(T) == 8)
 #endif
@@ -299,7 +307,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
           const Cell<T> L = sm.load_cell_axis(lr & 0x3FFFu, p0, p1, p2);
           const Cell<T> R = sm.load_cell_axis(lr >> 16, p0, p1, p2);
           s = kepes_flux_n<T, 0>(L, R, T(0), T(0), T(0), F);
-          if (want_smax) smax = fmax_(smax, s);
+          T8B_SMAX_UPDATE(s);
           if (SCALE) {
             const T ar = atab[A.face_ai[fb + j]];
 #pragma unroll
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
         else if (j < e1) s = kepes_flux_n<T, 1>(L, R, T(0), T(0), T(0), F);
         else s = kepes_flux_n<T, 2>(L, R, T(0), T(0), T(0), F);
 #endif
-        if (want_smax) smax = fmax_(smax, s);
+        T8B_SMAX_UPDATE(s);
         if (SCALE) {
           const T ar = atab[A.face_ai[fb + j]];
 #pragma unroll
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       const Cell<T> R = mirror(L, nx, ny, nz);
       T F[5];
       const T s = kepes_flux_n<T, -1>(L, R, nx, ny, nz, F);
-      if (want_smax) smax = fmax_(smax, s);
+      T8B_SMAX_UPDATE(s);
       if (area_idx < 0) {
         const T ar = atab[A.face_ai[fb + j]];
 #pragma unroll
@@ -362,7 +370,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       const Cell<T> R  = sr == 0xFFFF ? mirror(L, nx, ny, nz) : sm.load_cell(sr);
       T F[5];
       const T s = kepes_flux_n<T, -1>(L, R, nx, ny, nz, F);
-      if (want_smax) smax = fmax_(smax, s);
+      T8B_SMAX_UPDATE(s);
 #pragma unroll
       for (int k = 0; k < 5; k++) F[k] *= ar;
       sm.store_flux(j, F);
@@ -446,6 +454,9 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   }
 #endif
   if (SMAX) {
+#ifdef T8B_SMAX_SMEM
+    smax = smax_s[tid];
+#endif
     smax = warp_max(smax);
     if ((tid & 31) == 0) red[tid >> 5] = smax;
     __syncthreads();

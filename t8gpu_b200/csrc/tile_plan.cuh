@@ -260,6 +260,14 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   std::vector<Builder> builders(NT);
   parallel_ranges(nblocks, NT, [&](int t, int64_t blk0, int64_t blk1) {
     Builder& B = builders[t];
+    {   // sizes are known up to the splitting of blocks: no reallocation while the chunks are appended
+      const size_t nrec = (size_t)(face_off[blk1] - face_off[blk0]), nblk = (size_t)(blk1 - blk0);
+      B.face_lr.reserve(nrec);
+      if (cmp) B.face_ai.reserve(nrec);
+      else { B.fnx.reserve(nrec); B.fny.reserve(nrec); B.fnz.reserve(nrec); B.far.reserve(nrec); }
+      B.hdr.reserve(8 * nblk); B.halo_elem.reserve((size_t)EC * nblk); B.halo_rank.reserve((size_t)EC * nblk);
+      B.halo_off.reserve(nblk + 1); B.rec_off.reserve(nblk + 1);
+    }
     std::vector<int32_t> halo_tmp;
     std::vector<int64_t> cand, sub;
     uint16_t              el_cnt[EC];
