@@ -282,14 +282,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 
   // ---- phase 1: software-pipelined over this thread's faces (record j+EC is in flight while j is evaluated)
   T smax = T(0);
-#ifdef T8B_SMAX_SMEM
-  // the running maximum of this thread lives in shared memory, not in two registers through the face loops
-  __shared__ T smax_s[SMAX ? EC : 1];
-  if (SMAX) smax_s[tid] = T(0);
-#define T8B_SMAX_UPDATE(s) do { if (want_smax && (s) > smax_s[tid]) smax_s[tid] = (s); } while (0)
-#else
 #define T8B_SMAX_UPDATE(s) do { if (want_smax) smax = fmax_(smax, (s)); } while (0)
-#endif
 #ifndef T8B_AXPERM
 #define T8B_AXPERM (sizeof(T) == 8)
 #endif
@@ -454,9 +447,6 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   }
 #endif
   if (SMAX) {
-#ifdef T8B_SMAX_SMEM
-    smax = smax_s[tid];
-#endif
     smax = warp_max(smax);
     if ((tid & 31) == 0) red[tid >> 5] = smax;
     __syncthreads();
