@@ -271,6 +271,8 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     std::vector<int32_t> halo_tmp;
     std::vector<int64_t> cand, sub;
     uint16_t              el_cnt[EC];
+    int32_t               ht_key[1024];
+    uint16_t              ht_val[1024];
     std::vector<uint32_t> ovf_pairs;
     struct Rec { int grp, sl, sr; int64_t f; };
     std::vector<Rec>      recs, recs_sorted;
@@ -309,9 +311,21 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
         B.halo_rank.push_back(rk);
       }
       B.halo_off.push_back((int64_t)B.halo_elem.size());
+      // halo id -> slot through a small open-addressing table (the list is sorted, but a probe beats the bisection)
+      constexpr int HT = 1024;   // > 2 * (MS - EC) entries
+      static_assert(HT >= 2 * (MS - EC), "hash table of the halo slots too small");
+      for (int i = 0; i < HT; i++) ht_key[i] = -1;
+      for (int h = 0; h < nh; h++) {
+        unsigned k = ((unsigned)halo_tmp[h] * 2654435761u) >> 22;
+        while (ht_key[k] >= 0) k = (k + 1) & (HT - 1);
+        ht_key[k] = halo_tmp[h];
+        ht_val[k] = (uint16_t)(EC + h);
+      }
       auto slot_of = [&](int32_t id) -> int {
         if (id >= b0 && id < b1) return (int)(id - b0);
-        return EC + (int)(std::lower_bound(halo_tmp.begin(), halo_tmp.end(), id) - halo_tmp.begin());
+        unsigned k = ((unsigned)id * 2654435761u) >> 22;
+        while (ht_key[k] != id) k = (k + 1) & (HT - 1);
+        return ht_val[k];
       };
       // kernel order of the records: cmp -> x, y, z interior faces, then walls; inside a group by left slot, so that
       // the threads of a warp read neighbouring slots of the cell array (few bank conflicts whatever the numbering)
