@@ -182,6 +182,12 @@ extern "C" int t8b200_debug_phase_clocks(unsigned long long* out, int reset) {
 #define T8B_CLK(i)
 #endif
 
+// same for an address known to be 16-byte aligned (the size is rounded down to the granule)
+__device__ __forceinline__ void prefetch_l2_aligned(const void* p, unsigned bytes) {
+  bytes &= ~15u;
+  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // CTA = one chunk of EC consecutive elements.  MS / MF: compile-time strides of the shared-memory SoA arrays
 // (slots = EC own + halo; faces), so every shared access is base + index*sizeof(T) + immediate.
 //   phase 0: conserved -> per-cell quantities for the chunk's own elements (coalesced) and its halo (gather)
@@ -234,11 +240,16 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     // dispatched in index order): 8-12 state rows, 13-15 halo indices, face records, header.
     const int w  = tid >> 5;   // 0..7
     const int cw = c + A.wave;
-    if (A.pf_ptr[w]) prefetch_l2(A.pf_ptr[w] + (size_t)e0c * A.pf_unit[w], (unsigned)ecn * A.pf_unit[w]);
+    // (unsplit plans: chunk offsets are multiples of EC elements and the host only fills the table with 16-byte aligned
+    //  rows, so the address needs no alignment arithmetic)
+    if (A.pf_ptr[w]) {
+      if (SPLIT) prefetch_l2(A.pf_ptr[w] + (size_t)e0c * A.pf_unit[w], (unsigned)ecn * A.pf_unit[w]);
+      else prefetch_l2_aligned(A.pf_ptr[w] + (size_t)e0c * A.pf_unit[w], (unsigned)ecn * A.pf_unit[w]);
+    }
     if (!SPLIT && A.pf_ptr[w + 8] && cw < (int)gridDim.x) {
       const unsigned idx = w < 5 ? (unsigned)cw * EC : (unsigned)cw;
       const unsigned cnt = w < 5 ? (unsigned)min(EC, (int)A.n_local - cw * EC) : 1u;
-      prefetch_l2(A.pf_ptr[w + 8] + (size_t)idx * A.pf_unit[w + 8], cnt * A.pf_unit[w + 8]);
+      prefetch_l2_aligned(A.pf_ptr[w + 8] + (size_t)idx * A.pf_unit[w + 8], cnt * A.pf_unit[w + 8]);
     }
   }
   if (CMP && tid < A.n_areas) atab[tid] = A.area_tab[tid];
@@ -490,6 +501,10 @@ static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStrea
     B.pf_ptr[14] = (const char*)B.face_lr;   B.pf_unit[14] = (unsigned)B.fs * 4u;
     B.pf_ptr[15] = (const char*)B.hdr;       B.pf_unit[15] = 32u;
   }
+  for (int i = 0; i < 16; i++)   // the kernel's aligned prefetch path: rows and strides must be 16-byte granular
+    if (B.pf_ptr[i] && (((uintptr_t)B.pf_ptr[i] & 15u) || (((size_t)EC * B.pf_unit[i]) & 15u && i < 13) ||
+                        (i >= 13 && (B.pf_unit[i] & 15u))))
+      B.pf_ptr[i] = nullptr;
   k<<<P->n_chunks, EC, smem, st>>>(B);
   return cudaGetLastError();
 }
