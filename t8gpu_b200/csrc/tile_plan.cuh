@@ -324,7 +324,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
       auto slot_of = [&](int32_t id) -> int {
         if (id >= b0 && id < b1) return (int)(id - b0);
         unsigned k = ((unsigned)id * 2654435761u) >> 22;
-        while (ht_key[k] != id) k = (k + 1) & (HT - 1);
+        for (int probe = 0; ht_key[k] != id && probe < HT; probe++) k = (k + 1) & (HT - 1);   // always found
         return ht_val[k];
       };
       // kernel order of the records: cmp -> x, y, z interior faces, then walls; inside a group by left slot, so that
