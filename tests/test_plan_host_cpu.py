@@ -243,6 +243,86 @@ def test_partitioned_plan(P):
             L.t8b200_plan_destroy(h)
 
 
+def subgrid_cell_connectivity(conn, vol, levels):
+    """Cell-level connectivity of a Subgrid<4,4,4> forest in the reference layout, by brute force from the element-level
+    arrays of SubgridMeshConnectivityAccessor: the faces between the cells of an element (compute_inner_fluxes,
+    kernels.inl:335-662: area (cbrt(vol)/4)^2, normal +e_axis) and the 16 sub-faces of every element face
+    (compute_outer_fluxes, kernels.inl:717-802: left cell on the face plane, right cell = anchor + (i, j) at full or half
+    stride, area / 16)."""
+    ne, nf, nb = int(conn["n_local"]), int(conn["n_faces"]), int(conn["n_bfaces"])
+    nbr = np.asarray(conn["face_neighbors"], np.int64)
+    nrm = np.asarray(conn["face_normals"], np.float64).reshape(-1, 3)
+    area = np.asarray(conn["face_areas"], np.float64)
+    ld, off = np.asarray(conn["level_diff"]), np.asarray(conn["offsets"]).reshape(-1, 3)
+    pairs, normals, areas, walls, wnormals, wareas = [], [], [], [], [], []
+    flat = lambda c: c[0] + 4 * c[1] + 16 * c[2]   # noqa: E731
+    for e in range(ne):
+        a_in = (0.5 ** int(levels[e]) / 4.0) ** 2
+        for ax in range(3):
+            t1, t2 = [d for d in range(3) if d != ax]
+            for p in range(3):
+                for j in range(4):
+                    for i in range(4):
+                        cl, cr = [0, 0, 0], [0, 0, 0]
+                        cl[ax], cr[ax] = p, p + 1
+                        cl[t1] = cr[t1] = i
+                        cl[t2] = cr[t2] = j
+                        pairs.append((e * 64 + flat(cl), e * 64 + flat(cr)))
+                        n = [0.0, 0.0, 0.0]
+                        n[ax] = 1.0
+                        normals.append(n)
+                        areas.append(a_in)
+    for F in range(nf + nb):
+        wall = F >= nf
+        el = int(nbr[2 * F]) if not wall else int(nbr[2 * nf + (F - nf)])
+        er = int(nbr[2 * F + 1]) if not wall else -1
+        n = nrm[F]
+        ax = int(np.argmax(np.abs(n)))
+        t1, t2 = [d for d in range(3) if d != ax]
+        ds = 2 if wall or ld[F] == 0 else 1
+        for j in range(4):
+            for i in range(4):
+                cl = [0, 0, 0]
+                cl[ax] = 3 if n[ax] > 0 else 0
+                cl[t1], cl[t2] = i, j
+                if wall:
+                    walls.append(el * 64 + flat(cl))
+                    wnormals.append(list(n))
+                    wareas.append(area[F] / 16.0)
+                    continue
+                cr = [int(x) for x in off[F]]
+                cr[t1] += ds * i // 2
+                cr[t2] += ds * j // 2
+                pairs.append((el * 64 + flat(cl), er * 64 + flat(cr)))
+                normals.append(list(n))
+                areas.append(area[F] / 16.0)
+    return dict(n_local=ne * 64, n_ghost=0, n_faces=len(pairs), n_bfaces=len(walls),
+                face_neighbors=np.concatenate([np.asarray(pairs, np.int32).reshape(-1), np.asarray(walls, np.int32)]),
+                face_normals=np.asarray(normals + wnormals, np.float64).reshape(-1),
+                face_areas=np.asarray(areas + wareas, np.float64))
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_subgrid_cell_plan_matches_brute_force(periodic):
+    L = _lib()
+    f = oracle.Forest(3, 1, periodic=periodic)
+    lv, cent, vol, _ = f.elements()
+    f = f.adapt(np.where(cent[:, 2] < 0.5, 1.0, 0.0), 0.02, 1, 2)
+    lv, cent, vol, _ = f.elements()
+    conn = f.connectivity(subgrid=True, dtype=np.float64)
+    keep = [_arr(conn, k, d) for k, d in (("face_neighbors", np.int32), ("face_normals", np.float64),
+                                          ("face_areas", np.float64), ("level_diff", np.int32), ("offsets", np.int32))]
+    vols = np.ascontiguousarray(vol, np.float64)
+    sh = C.c_void_p()
+    assert L.t8b200_subgrid_plan_create_host(C.byref(sh), 1, 3, C.c_int64(f.num_elements), C.c_int64(0),
+                                             int(conn["n_faces"]), int(conn["n_bfaces"]), _p(keep[0]), _p(keep[1]),
+                                             _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(vols), None, None, 0, None,
+                                             None, None, None, None) == 0
+    A = arrays(L, C.c_void_p(L.t8b200_subgrid_plan_base(sh)))
+    L.t8b200_subgrid_plan_destroy(sh)
+    check_plan(subgrid_cell_connectivity(conn, vol, lv), np.float64, A)
+
+
 def test_subgrid_cell_plan():
     """Cell-level plan of a Subgrid<4,4,4> forest with hanging faces: chunk statistics and conservation of the face
     count (every cell face appears once per chunk it touches; inner faces of an element never leave its chunk)."""
