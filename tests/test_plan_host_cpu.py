@@ -296,10 +296,40 @@ def subgrid_cell_connectivity(conn, vol, levels):
                 pairs.append((el * 64 + flat(cl), er * 64 + flat(cr)))
                 normals.append(list(n))
                 areas.append(area[F] / 16.0)
-    return dict(n_local=ne * 64, n_ghost=0, n_faces=len(pairs), n_bfaces=len(walls),
-                face_neighbors=np.concatenate([np.asarray(pairs, np.int32).reshape(-1), np.asarray(walls, np.int32)]),
-                face_normals=np.asarray(normals + wnormals, np.float64).reshape(-1),
-                face_areas=np.asarray(areas + wareas, np.float64))
+    out = dict(n_local=ne * 64, n_ghost=0, n_faces=len(pairs), n_bfaces=len(walls),
+               face_neighbors=np.concatenate([np.asarray(pairs, np.int32).reshape(-1), np.asarray(walls, np.int32)]),
+               face_normals=np.asarray(normals + wnormals, np.float64).reshape(-1),
+               face_areas=np.asarray(areas + wareas, np.float64))
+    if int(conn.get("n_ghost", 0)) > 0:   # partition: ghost elements -> 64 ghost cells each, x-faces -> 16 sub-faces
+        ng, nx = int(conn["n_ghost"]), int(conn.get("n_xfaces", 0))
+        out["n_ghost"] = ng * 64
+        out["ranks"] = np.repeat(np.asarray(conn["ranks"], np.int32), 64)
+        out["indices"] = (np.repeat(np.asarray(conn["indices"], np.int64) * 64, 64) +
+                          np.tile(np.arange(64), ne + ng)).astype(np.int32)
+        xn = np.asarray(conn.get("x_face_neighbors", []), np.int64)
+        xnrm = np.asarray(conn.get("x_face_normals", []), np.float64).reshape(-1, 3)
+        xa, xld = np.asarray(conn.get("x_face_areas", []), np.float64), np.asarray(conn.get("x_level_diff", []))
+        xoff = np.asarray(conn.get("x_offsets", [])).reshape(-1, 3)
+        xp, xnn, xaa = [], [], []
+        for F in range(nx):
+            n = xnrm[F]
+            ax = int(np.argmax(np.abs(n)))
+            t1, t2 = [d for d in range(3) if d != ax]
+            ds = 2 if xld[F] == 0 else 1
+            for j in range(4):
+                for i in range(4):
+                    cl = [0, 0, 0]
+                    cl[ax] = 3 if n[ax] > 0 else 0
+                    cl[t1], cl[t2] = i, j
+                    cr = [int(x) for x in xoff[F]]
+                    cr[t1] += ds * i // 2
+                    cr[t2] += ds * j // 2
+                    xp.append((int(xn[2 * F]) * 64 + flat(cl), int(xn[2 * F + 1]) * 64 + flat(cr)))
+                    xnn.append(list(n))
+                    xaa.append(xa[F] / 16.0)
+        out.update(n_xfaces=len(xp), x_face_neighbors=np.asarray(xp, np.int32).reshape(-1),
+                   x_face_normals=np.asarray(xnn, np.float64).reshape(-1), x_face_areas=np.asarray(xaa, np.float64))
+    return out
 
 
 @pytest.mark.parametrize("periodic", [True, False])
@@ -321,6 +351,34 @@ def test_subgrid_cell_plan_matches_brute_force(periodic):
     A = arrays(L, C.c_void_p(L.t8b200_subgrid_plan_base(sh)))
     L.t8b200_subgrid_plan_destroy(sh)
     check_plan(subgrid_cell_connectivity(conn, vol, lv), np.float64, A)
+
+
+def test_subgrid_cell_plan_partitioned():
+    L = _lib()
+    f = oracle.Forest(3, 1)
+    lv, cent, vol, _ = f.elements()
+    f = f.adapt(np.where(cent[:, 2] < 0.5, 1.0, 0.0), 0.02, 1, 2)
+    lv, cent, vol, _ = f.elements()
+    P = 2
+    off = f.partition_offsets(P)
+    for rank in range(P):
+        conn = f.connectivity(P, rank, subgrid=True, dtype=np.float64)
+        names = [("face_neighbors", np.int32), ("face_normals", np.float64), ("face_areas", np.float64),
+                 ("level_diff", np.int32), ("offsets", np.int32), ("ranks", np.int32), ("indices", np.int32),
+                 ("x_face_neighbors", np.int32), ("x_face_normals", np.float64), ("x_face_areas", np.float64),
+                 ("x_level_diff", np.int32), ("x_offsets", np.int32)]
+        k = [_arr(conn, n_, d) for n_, d in names]
+        vols = np.ascontiguousarray(vol[off[rank]:off[rank + 1]], np.float64)
+        sh = C.c_void_p()
+        assert L.t8b200_subgrid_plan_create_host(
+            C.byref(sh), 1, 3, C.c_int64(int(conn["n_local"])), C.c_int64(int(conn["n_ghost"])), int(conn["n_faces"]),
+            int(conn["n_bfaces"]), _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]), _p(vols), _p(k[5]), _p(k[6]),
+            int(conn["n_xfaces"]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11])) == 0
+        A = arrays(L, C.c_void_p(L.t8b200_subgrid_plan_base(sh)))
+        L.t8b200_subgrid_plan_destroy(sh)
+        assert int(conn["n_ghost"]) > 0
+        cells = subgrid_cell_connectivity(conn, vols, lv[off[rank]:off[rank + 1]])
+        check_plan(cells, np.float64, A, multi=True)
 
 
 def test_subgrid_cell_plan():
