@@ -5,7 +5,8 @@
 //   header   8 x int32: first element, elements, nh | nfc << 16, e0 | e1 << 16, e2, ovf_off_base, ovf_ent_base, area
 //   halo     sorted unique elements outside the chunk that share a face with it (slot EC + h); fixed stride HS per
 //            chunk (padding = -1), so the indices can be requested without waiting for the header
-//   faces    one 32-bit record slotL | slotR << 16 per face touching the chunk, fixed stride FS per chunk.
+//   faces    one 32-bit record slotL (bits 0-13) | axis << 14 | slotR << 16 per face touching the chunk, fixed stride FS
+//            per chunk (axis: compressed interior faces only, else 0).
 //            Cartesian forests ("cmp": every normal +-e_axis, <= 256 distinct areas): records are put in canonical
 //            orientation (normal = +e_axis, sides swapped where the stored normal was -e_axis) and grouped by axis,
 //            [0,e0) x, [e0,e1) y, [e1,e2) z, then wall faces [e2,nfc) with the outward normal coded in the slotR field;
