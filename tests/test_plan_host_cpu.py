@@ -243,90 +243,90 @@ def test_partitioned_plan(P):
             L.t8b200_plan_destroy(h)
 
 
-def subgrid_cell_connectivity(conn, vol, levels):
-    """Cell-level connectivity of a Subgrid<4,4,4> forest in the reference layout, by brute force from the element-level
-    arrays of SubgridMeshConnectivityAccessor: the faces between the cells of an element (compute_inner_fluxes,
-    kernels.inl:335-662: area (cbrt(vol)/4)^2, normal +e_axis) and the 16 sub-faces of every element face
-    (compute_outer_fluxes, kernels.inl:717-802: left cell on the face plane, right cell = anchor + (i, j) at full or half
-    stride, area / 16)."""
+def subgrid_cell_connectivity(conn, vol, levels, dim=3):
+    """Cell-level connectivity of a Subgrid<4,4,4> (dim 3) / Subgrid<4,4> (dim 2) forest in the reference layout, by
+    brute force from the element-level arrays of SubgridMeshConnectivityAccessor: the faces between the cells of an
+    element (compute_inner_fluxes, kernels.inl:335-662: area (cbrt(vol)/4)^2 resp. sqrt(vol)/4, normal +e_axis) and
+    the 16 (4) sub-faces of every element face (compute_outer_fluxes, kernels.inl:717-802: left cell on the face
+    plane, right cell = anchor + (i, j) at full or half stride, area / 16 (4))."""
     ne, nf, nb = int(conn["n_local"]), int(conn["n_faces"]), int(conn["n_bfaces"])
+    S, TPF, NJ = (64, 16, 4) if dim == 3 else (16, 4, 1)
     nbr = np.asarray(conn["face_neighbors"], np.int64)
-    nrm = np.asarray(conn["face_normals"], np.float64).reshape(-1, 3)
-    area = np.asarray(conn["face_areas"], np.float64)
-    ld, off = np.asarray(conn["level_diff"]), np.asarray(conn["offsets"]).reshape(-1, 3)
+    ld = np.asarray(conn["level_diff"])
     pairs, normals, areas, walls, wnormals, wareas = [], [], [], [], [], []
     flat = lambda c: c[0] + 4 * c[1] + 16 * c[2]   # noqa: E731
+
+    def pad3(v):
+        return [float(x) for x in v] + [0.0] * (3 - len(v))
+
     for e in range(ne):
-        a_in = (0.5 ** int(levels[e]) / 4.0) ** 2
-        for ax in range(3):
-            t1, t2 = [d for d in range(3) if d != ax]
+        h = 0.5 ** int(levels[e]) / 4.0
+        a_in = h * h if dim == 3 else h
+        for ax in range(dim):
+            tang = [d for d in range(dim) if d != ax]
             for p in range(3):
-                for j in range(4):
+                for j in range(NJ):
                     for i in range(4):
                         cl, cr = [0, 0, 0], [0, 0, 0]
                         cl[ax], cr[ax] = p, p + 1
-                        cl[t1] = cr[t1] = i
-                        cl[t2] = cr[t2] = j
-                        pairs.append((e * 64 + flat(cl), e * 64 + flat(cr)))
+                        cl[tang[0]] = cr[tang[0]] = i
+                        if dim == 3:
+                            cl[tang[1]] = cr[tang[1]] = j
+                        pairs.append((e * S + flat(cl), e * S + flat(cr)))
                         n = [0.0, 0.0, 0.0]
                         n[ax] = 1.0
                         normals.append(n)
                         areas.append(a_in)
+
+    def outer(el, er, n, a, ldf, o, wall, out_pairs, out_n, out_a):
+        ax = int(np.argmax(np.abs(n)))
+        tang = [d for d in range(dim) if d != ax]
+        ds = 2 if wall or ldf == 0 else 1
+        for j in range(NJ):
+            for i in range(4):
+                cl = [0, 0, 0]
+                cl[ax] = 3 if n[ax] > 0 else 0
+                cl[tang[0]] = i
+                if dim == 3:
+                    cl[tang[1]] = j
+                if wall:
+                    walls.append(el * S + flat(cl))
+                    wnormals.append(pad3(n))
+                    wareas.append(a / TPF)
+                    continue
+                cr = [int(x) for x in o] + [0] * (3 - dim)
+                cr[tang[0]] += ds * i // 2
+                if dim == 3:
+                    cr[tang[1]] += ds * j // 2
+                out_pairs.append((el * S + flat(cl), er * S + flat(cr)))
+                out_n.append(pad3(n))
+                out_a.append(a / TPF)
+
+    nrm = np.asarray(conn["face_normals"], np.float64).reshape(-1, dim)
+    area = np.asarray(conn["face_areas"], np.float64)
+    off = np.asarray(conn["offsets"]).reshape(-1, dim)
     for F in range(nf + nb):
         wall = F >= nf
         el = int(nbr[2 * F]) if not wall else int(nbr[2 * nf + (F - nf)])
         er = int(nbr[2 * F + 1]) if not wall else -1
-        n = nrm[F]
-        ax = int(np.argmax(np.abs(n)))
-        t1, t2 = [d for d in range(3) if d != ax]
-        ds = 2 if wall or ld[F] == 0 else 1
-        for j in range(4):
-            for i in range(4):
-                cl = [0, 0, 0]
-                cl[ax] = 3 if n[ax] > 0 else 0
-                cl[t1], cl[t2] = i, j
-                if wall:
-                    walls.append(el * 64 + flat(cl))
-                    wnormals.append(list(n))
-                    wareas.append(area[F] / 16.0)
-                    continue
-                cr = [int(x) for x in off[F]]
-                cr[t1] += ds * i // 2
-                cr[t2] += ds * j // 2
-                pairs.append((el * 64 + flat(cl), er * 64 + flat(cr)))
-                normals.append(list(n))
-                areas.append(area[F] / 16.0)
-    out = dict(n_local=ne * 64, n_ghost=0, n_faces=len(pairs), n_bfaces=len(walls),
+        outer(el, er, nrm[F], area[F], 0 if wall else ld[F], None if wall else off[F], wall, pairs, normals, areas)
+    out = dict(n_local=ne * S, n_ghost=0, n_faces=len(pairs), n_bfaces=len(walls),
                face_neighbors=np.concatenate([np.asarray(pairs, np.int32).reshape(-1), np.asarray(walls, np.int32)]),
                face_normals=np.asarray(normals + wnormals, np.float64).reshape(-1),
                face_areas=np.asarray(areas + wareas, np.float64))
-    if int(conn.get("n_ghost", 0)) > 0:   # partition: ghost elements -> 64 ghost cells each, x-faces -> 16 sub-faces
+    if int(conn.get("n_ghost", 0)) > 0:   # partition: ghost elements -> S ghost cells each, x-faces -> TPF sub-faces
         ng, nx = int(conn["n_ghost"]), int(conn.get("n_xfaces", 0))
-        out["n_ghost"] = ng * 64
-        out["ranks"] = np.repeat(np.asarray(conn["ranks"], np.int32), 64)
-        out["indices"] = (np.repeat(np.asarray(conn["indices"], np.int64) * 64, 64) +
-                          np.tile(np.arange(64), ne + ng)).astype(np.int32)
+        out["n_ghost"] = ng * S
+        out["ranks"] = np.repeat(np.asarray(conn["ranks"], np.int32), S)
+        out["indices"] = (np.repeat(np.asarray(conn["indices"], np.int64) * S, S) +
+                          np.tile(np.arange(S), ne + ng)).astype(np.int32)
         xn = np.asarray(conn.get("x_face_neighbors", []), np.int64)
-        xnrm = np.asarray(conn.get("x_face_normals", []), np.float64).reshape(-1, 3)
+        xnrm = np.asarray(conn.get("x_face_normals", []), np.float64).reshape(-1, dim)
         xa, xld = np.asarray(conn.get("x_face_areas", []), np.float64), np.asarray(conn.get("x_level_diff", []))
-        xoff = np.asarray(conn.get("x_offsets", [])).reshape(-1, 3)
+        xoff = np.asarray(conn.get("x_offsets", [])).reshape(-1, dim)
         xp, xnn, xaa = [], [], []
         for F in range(nx):
-            n = xnrm[F]
-            ax = int(np.argmax(np.abs(n)))
-            t1, t2 = [d for d in range(3) if d != ax]
-            ds = 2 if xld[F] == 0 else 1
-            for j in range(4):
-                for i in range(4):
-                    cl = [0, 0, 0]
-                    cl[ax] = 3 if n[ax] > 0 else 0
-                    cl[t1], cl[t2] = i, j
-                    cr = [int(x) for x in xoff[F]]
-                    cr[t1] += ds * i // 2
-                    cr[t2] += ds * j // 2
-                    xp.append((int(xn[2 * F]) * 64 + flat(cl), int(xn[2 * F + 1]) * 64 + flat(cr)))
-                    xnn.append(list(n))
-                    xaa.append(xa[F] / 16.0)
+            outer(int(xn[2 * F]), int(xn[2 * F + 1]), xnrm[F], xa[F], xld[F], xoff[F], False, xp, xnn, xaa)
         out.update(n_xfaces=len(xp), x_face_neighbors=np.asarray(xp, np.int32).reshape(-1),
                    x_face_normals=np.asarray(xnn, np.float64).reshape(-1), x_face_areas=np.asarray(xaa, np.float64))
     return out
@@ -351,6 +351,27 @@ def test_subgrid_cell_plan_matches_brute_force(periodic):
     A = arrays(L, C.c_void_p(L.t8b200_subgrid_plan_base(sh)))
     L.t8b200_subgrid_plan_destroy(sh)
     check_plan(subgrid_cell_connectivity(conn, vol, lv), np.float64, A)
+
+
+def test_subgrid_cell_plan_2d_matches_brute_force():
+    """Subgrid<4,4>: 16 cells per element, 4 sub-faces per element face, 2-component normals and offsets."""
+    L = _lib()
+    f = oracle.Forest(2, 2, periodic=False)
+    lv, cent, vol, _ = f.elements()
+    f = f.adapt(np.where(cent[:, 1] < 0.5, 1.0, 0.0), 0.02, 1, 3)
+    lv, cent, vol, _ = f.elements()
+    conn = f.connectivity(subgrid=True, dtype=np.float64)
+    keep = [_arr(conn, k, d) for k, d in (("face_neighbors", np.int32), ("face_normals", np.float64),
+                                          ("face_areas", np.float64), ("level_diff", np.int32), ("offsets", np.int32))]
+    vols = np.ascontiguousarray(vol, np.float64)
+    sh = C.c_void_p()
+    assert L.t8b200_subgrid_plan_create_host(C.byref(sh), 1, 2, C.c_int64(f.num_elements), C.c_int64(0),
+                                             int(conn["n_faces"]), int(conn["n_bfaces"]), _p(keep[0]), _p(keep[1]),
+                                             _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(vols), None, None, 0, None,
+                                             None, None, None, None) == 0
+    A = arrays(L, C.c_void_p(L.t8b200_subgrid_plan_base(sh)))
+    L.t8b200_subgrid_plan_destroy(sh)
+    check_plan(subgrid_cell_connectivity(conn, vol, lv, dim=2), np.float64, A)
 
 
 def test_subgrid_cell_plan_partitioned():
