@@ -271,9 +271,11 @@ inline int cell_ax(int dim, int ax, int x, int a, int b) {
   return ax == 0 ? x + 4 * a + 16 * b : (ax == 1 ? a + 4 * x + 16 * b : a + 4 * b + 16 * x);
 }
 
-template <typename T>
+// DIM is a template parameter: the plan builder asks for the endpoints of every cell face several times, and with
+// compile-time cell / face counts the decoding of a face id needs no integer division by a run-time value
+template <typename T, int DIM>
 struct SubgridFaces {
-  int            dim;
+  static constexpr int dim = DIM;
   int64_t        n_local;  // elements
   int32_t        nf, nb, nx;
   const int32_t* nbr;
@@ -284,9 +286,9 @@ struct SubgridFaces {
   const T *      xnormals, *xareas;
   const int32_t *xld, *xoff;
   std::vector<T> inner_area;   // per element: area of the faces between its cells (prepare())
-  int     S() const { return dim == 3 ? 64 : 16; }
-  int     TPF() const { return dim == 3 ? 16 : 4; }
-  int     IPE() const { return dim * 3 * TPF(); }   // inner faces per element: dim axes x 3 planes x TPF
+  static constexpr int S() { return DIM == 3 ? 64 : 16; }
+  static constexpr int TPF() { return DIM == 3 ? 16 : 4; }
+  static constexpr int IPE() { return DIM * 3 * TPF(); }   // inner faces per element: dim axes x 3 planes x TPF
   int64_t n_inner() const { return n_local * IPE(); }
   int64_t num_faces() const { return n_inner() + ((int64_t)nf + nb + nx) * TPF(); }
 
@@ -388,14 +390,34 @@ struct SubgridFaces {
 };
 }  // namespace
 
+template <typename T, int DIM>
+static int sg_plan_build_dim(t8b200_subgrid_plan* SP, int host_only, int64_t n_local, int64_t n_ghost, int32_t nf,
+                             int32_t nb, const int32_t* nbr, const T* normals, const T* areas,
+                             const int32_t* level_diff, const int32_t* offsets, const T* vol, const int32_t* ranks,
+                             const int32_t* indices, int32_t nx, const int32_t* xnbr, const T* xnormals,
+                             const T* xareas, const int32_t* xld, const int32_t* xoff);
+
 template <typename T>
 static int sg_plan_build(t8b200_subgrid_plan* SP, int host_only, int dim, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
                          const int32_t* nbr, const T* normals, const T* areas, const int32_t* level_diff,
                          const int32_t* offsets, const T* vol, const int32_t* ranks, const int32_t* indices, int32_t nx,
                          const int32_t* xnbr, const T* xnormals, const T* xareas, const int32_t* xld,
                          const int32_t* xoff) {
-  SubgridFaces<T> src{dim, n_local, nf, nb, nx, nbr, normals, areas, level_diff, offsets, vol, ranks, indices, xnbr,
-                      xnormals, xareas, xld, xoff, {}};
+  if (dim == 2) return sg_plan_build_dim<T, 2>(SP, host_only, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff,
+                                               offsets, vol, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
+  return sg_plan_build_dim<T, 3>(SP, host_only, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets, vol,
+                                 ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
+}
+
+template <typename T, int DIM>
+static int sg_plan_build_dim(t8b200_subgrid_plan* SP, int host_only, int64_t n_local, int64_t n_ghost, int32_t nf,
+                             int32_t nb, const int32_t* nbr, const T* normals, const T* areas,
+                             const int32_t* level_diff, const int32_t* offsets, const T* vol, const int32_t* ranks,
+                             const int32_t* indices, int32_t nx, const int32_t* xnbr, const T* xnormals,
+                             const T* xareas, const int32_t* xld, const int32_t* xoff) {
+  constexpr int dim = DIM;
+  SubgridFaces<T, DIM> src{n_local, nf, nb, nx, nbr, normals, areas, level_diff, offsets, vol, ranks, indices, xnbr,
+                           xnormals, xareas, xld, xoff, {}};
   src.prepare();
   if ((n_local + n_ghost) * src.S() > 0x7FFFFFF0LL) return cudaErrorInvalidValue;
   t8b200_plan* P = new t8b200_plan();
