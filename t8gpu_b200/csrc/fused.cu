@@ -36,6 +36,7 @@ struct FusedArgs {
   int             wave;  // CTAs resident on the device at once = distance of the next-wave prefetch (0: off)
   const char*     pf_ptr[16];   // L2 prefetch table: base pointer (null: skip) and bytes per index
   unsigned        pf_unit[16];
+  const int32_t*  chunk_list;   // SPLIT variants: chunk id per CTA (plans whose structured chunks run in structured.cu)
   const uint4*    ell;
   const uint16_t* ovf_off;
   const uint16_t* ovf_ent;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   const Smem<T, MS, MF> sm(smem_raw);
   __shared__ T atab[CMP ? 256 : 1];
   __shared__ T red[EC / 32];
-  const int c   = blockIdx.x;
+  const int c   = (SPLIT && A.chunk_list) ? __ldg(A.chunk_list + blockIdx.x) : blockIdx.x;
   const int tid = threadIdx.x;
 #ifdef T8B_PHASE_CLOCKS
   long long clk[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -509,7 +510,7 @@ static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStrea
     if (B.pf_ptr[i] && (((uintptr_t)B.pf_ptr[i] & 15u) || (((size_t)EC * B.pf_unit[i]) & 15u && i < 13) ||
                         (i >= 13 && (B.pf_unit[i] & 15u))))
       B.pf_ptr[i] = nullptr;
-  k<<<P->n_chunks, EC, smem, st>>>(B);
+  k<<<B.chunk_list ? P->n_generic : P->n_chunks, EC, smem, st>>>(B);
   return cudaGetLastError();
 }
 
@@ -521,11 +522,12 @@ static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_
 #define T8B_MINB64 3
 #endif
   constexpr int B0 = sizeof(T) == 8 ? T8B_MINB64 : 5;
+  const bool split = P->split || A.chunk_list;   // a chunk list goes through the header-driven variant
   if (A.speed_max)
-    return P->split ? launch_variant<T, MS, MF, B0, CMP, true, true>(P, A, st)
-                    : launch_variant<T, MS, MF, B0, CMP, false, true>(P, A, st);
-  return P->split ? launch_variant<T, MS, MF, B0, CMP, true, false>(P, A, st)
-                  : launch_variant<T, MS, MF, B0, CMP, false, false>(P, A, st);
+    return split ? launch_variant<T, MS, MF, B0, CMP, true, true>(P, A, st)
+                 : launch_variant<T, MS, MF, B0, CMP, false, true>(P, A, st);
+  return split ? launch_variant<T, MS, MF, B0, CMP, true, false>(P, A, st)
+               : launch_variant<T, MS, MF, B0, CMP, false, false>(P, A, st);
 }
 
 template <typename T>
@@ -552,6 +554,11 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
   A.stage = stage; A.multi = P->multi; A.my_rank = P->my_rank;
   cudaStream_t st = (cudaStream_t)stream;
   if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), st));
+  if (P->n_struct) {   // the structured chunks (structured.cu); what is left goes through the chunk list
+    const int rc = t8b_structured_stage_run<T>(P, stage, in, in_all, prev, out, vol, dt, speed_max, stream);
+    if (rc != 0 || P->n_generic == 0) return rc;
+    A.chunk_list = P->g_list;
+  }
   return P->cmp ? launch_fused<T, true>(P, A, st) : launch_fused<T, false>(P, A, st);
 }
 
@@ -663,6 +670,10 @@ int t8b200_plan_host_array(const t8b200_plan* P, int which, const void** data, i
     case 10: return set(H.fny);
     case 11: return set(H.fnz);
     case 12: return set(H.farea);
+    case 13: return set(H.s_rec);
+    case 14: return set(H.s_halo);
+    case 15: return set(H.s_hrank);
+    case 16: return set(H.g_list);
   }
   return cudaErrorInvalidValue;
 }
@@ -677,6 +688,7 @@ void t8b200_plan_destroy(t8b200_plan* P) {
   cudaFree(P->hdr); cudaFree(P->halo_elem); cudaFree(P->halo_rank);
   cudaFree(P->face_lr); cudaFree(P->face_ai); cudaFree(P->fnx); cudaFree(P->fny); cudaFree(P->fnz); cudaFree(P->farea);
   cudaFree(P->area_tab); cudaFree(P->ell); cudaFree(P->ovf_off); cudaFree(P->ovf_ent);
+  cudaFree(P->s_rec); cudaFree(P->s_halo); cudaFree(P->s_hrank); cudaFree(P->g_list);
   delete P;
 }
 

@@ -1,0 +1,242 @@
+// Fused RK stage for the STRUCTURED chunks of a tile plan (box_layout.cuh): 256 consecutive elements / cells that form
+// an 8 x 8 x 4 box with 256 single same-size face neighbours around it -- every chunk of a uniform hexahedral forest
+// (BASELINE config 2), of a uniform Subgrid<4,4,4> forest (config 4), and the uniform regions of adaptive ones.  The
+// generic kernel (fused.cu) keeps every other chunk (hanging faces, walls, general normals, 2-D, ragged ends).
+//
+// Same three phases as the generic kernel, but nothing is looked up:
+//   phase 0  own conserved values (coalesced) and the 256 halo elements (gather through the per-chunk halo list, the
+//            only plan data this kernel reads: 1 KB per chunk) -> 7 cell quantities in shared memory; the own cell stays
+//            in registers
+//   phase 1  every thread evaluates the three faces on the LOWER side of its element (left cell from shared memory,
+//            right cell = its own registers), threads 0-127 one of the 128 faces on the upper box boundary
+//   phase 2  out = RK combination of (sum of the three lower fluxes - sum of the three upper fluxes), indices arithmetic
+// No face records, no element -> face table, no signs, no per-face branches; shared-memory accesses of the face phase
+// are bank-conflict free by construction of the halo slots.
+//
+// Reference behaviour replaced (not translated): one stage of CompressibleEulerSolver::iterate
+// (examples/compressible_euler/solver.cu:78-112) and of SubgridCompressibleEulerSolver::iterate
+// (examples/subgrid/solver.inl:156-194) on the uniform parts of the mesh.
+#include <algorithm>
+#include <cstdlib>
+
+#include "../../include/t8gpu_b200.h"
+#include "box_layout.cuh"
+#include "common.cuh"
+#include "euler_flux.cuh"
+#include "tile_plan.cuh"
+
+using namespace t8b200;
+
+template <typename T>
+struct SArgs {
+  const int4*    rec;     // per structured chunk: first element, area index, chunk id, -
+  const int32_t* halo;    // 256 per chunk, thread order (box_layout.cuh), index into the owner's arrays
+  const int32_t* hrank;   // owner rank (multi only)
+  const T*       area_tab;
+  const T*       in[5];
+  const T* const* in_all[5];
+  const T*       prev[5];
+  T*             out[5];
+  const T*       vol;
+  int            vol_shift;
+  T              vol_scale;
+  T              dt;
+  T*             speed_max;
+  int            stage, multi, my_rank;
+  int            dense;   // every chunk of the plan is structured: chunk b = elements [256 b, 256 b + 256), one area
+  int            area0;
+  int            wave;    // CTAs resident at once (distance of the next-wave L2 prefetch), 0: off
+  int            pf_ok;   // rows are 16-byte aligned: bulk L2 prefetch hints allowed
+};
+
+__device__ __forceinline__ void s_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <typename T, int NS>
+__device__ __forceinline__ Cell<T> s_load_cell(const T* cq, int s) {
+  Cell<T> q;
+  q.rho = cq[0 * NS + s]; q.hx = cq[1 * NS + s]; q.hy = cq[2 * NS + s]; q.hz = cq[3 * NS + s];
+  q.kp  = cq[4 * NS + s]; q.b  = cq[5 * NS + s]; q.q  = cq[6 * NS + s];
+  return q;
+}
+template <typename T, int NS>
+__device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
+  cq[0 * NS + s] = q.rho; cq[1 * NS + s] = q.hx; cq[2 * NS + s] = q.hy; cq[3 * NS + s] = q.hz;
+  cq[4 * NS + s] = q.kp;  cq[5 * NS + s] = q.b;  cq[6 * NS + s] = q.q;
+}
+
+#ifndef T8B_S_MINB
+#define T8B_S_MINB 3
+#endif
+#ifndef T8B_S_OWNREG   // 1: the thread's own cell stays in registers through the face phase; 0: re-read per face
+#define T8B_S_OWNREG 1
+#endif
+
+template <typename T, class L, bool SMAX>
+__global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const __grid_constant__ SArgs<T> A) {
+  constexpr int NS = L::NSLOT, NF = BoxCommon::NFLUX;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* const cq = reinterpret_cast<T*>(smem_raw);   // [7][NS]
+  T* const fl = cq + NCELLQ * NS;                 // [5][NF]
+  __shared__ T red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+
+  // ---- phase 0: every independent global load first
+  int e0 = b * 256, area_idx = A.area0;
+  if (!A.dense) {
+    const int4 r = __ldg(A.rec + b);
+    e0 = r.x; area_idx = r.y;
+  }
+  const int e    = e0 + tid;
+  const int hidx = __ldg(A.halo + b * 256 + tid);
+  int       hrk  = A.my_rank;
+  if (A.multi) hrk = __ldg(A.hrank + b * 256 + tid);
+  const T u0 = A.in[0][e], u1 = A.in[1][e], u2 = A.in[2][e], u3 = A.in[3][e], u4 = A.in[4][e];
+  if (A.pf_ok && (tid & 31) == 0) {
+    // L2 prefetch hints, one or two per warp: the phase-2 operands of this chunk (rows of U^n, volume) and the streams
+    // of the chunk that takes over this CTA slot about one wave later (CTAs are dispatched in index order)
+    const int w = tid >> 5;
+    if (w < 5) { if (A.stage != 1) s_prefetch_l2(A.prev[w] + e0, 256u * sizeof(T)); }
+    else if (w == 5 && A.vol_shift == 0) s_prefetch_l2(A.vol + e0, 256u * sizeof(T));
+    const int bw = b + A.wave;
+    if (A.dense && A.wave > 0 && bw < (int)gridDim.x) {
+      if (w < 5) s_prefetch_l2(A.in[w] + bw * 256, 256u * sizeof(T));
+      else if (w == 5) s_prefetch_l2(A.halo + bw * 256, 1024u);
+    }
+  }
+  T g0, g1, g2, g3, g4;
+  if (A.multi && hrk != A.my_rank) {   // ghost: through the [var][rank] tables (a peer GPU's array over NVLink)
+    g0 = A.in_all[0][hrk][hidx]; g1 = A.in_all[1][hrk][hidx]; g2 = A.in_all[2][hrk][hidx];
+    g3 = A.in_all[3][hrk][hidx]; g4 = A.in_all[4][hrk][hidx];
+  } else {
+    g0 = A.in[0][hidx]; g1 = A.in[1][hidx]; g2 = A.in[2][hidx]; g3 = A.in[3][hidx]; g4 = A.in[4][hidx];
+  }
+  const Cell<T> C = to_cell(u0, u1, u2, u3, u4);
+  s_store_cell<T, NS>(cq, tid, C);
+  s_store_cell<T, NS>(cq, L::thread_slot(tid), to_cell(g0, g1, g2, g3, g4));
+  __syncthreads();
+
+  // ---- phase 1
+  T smax = T(0);
+#define T8B_S_FACE(D)                                                                                              \
+  {                                                                                                                \
+    const int sl = L::at_lower(tid, D) ? L::halo_slot(D, 0, L::compact(tid, D)) : L::lower_own(tid, D);            \
+    const Cell<T> Lc = s_load_cell<T, NS>(cq, sl);                                                                 \
+    const Cell<T> Rc = T8B_S_OWNREG ? C : s_load_cell<T, NS>(cq, tid);                                             \
+    T       F[5];                                                                                                  \
+    const T s = kepes_flux_n<T, D>(Lc, Rc, T(0), T(0), T(0), F);                                                   \
+    if (SMAX) smax = fmax_(smax, s);                                                                               \
+    _Pragma("unroll") for (int k = 0; k < 5; k++) fl[k * NF + D * 256 + tid] = F[k];                               \
+  }
+  T8B_S_FACE(0)
+  T8B_S_FACE(1)
+  T8B_S_FACE(2)
+#undef T8B_S_FACE
+  if (tid < 128) {   // the 128 faces on the upper box boundary: warp 0 x+, warp 1 y+, warps 2-3 z+
+    const int d = tid < 64 ? tid >> 5 : 2, idx = tid < 64 ? tid & 31 : tid - 64;
+    const int p0 = d, p1 = d == 2 ? 0 : d + 1, p2 = d == 0 ? 2 : d - 1;   // cyclic axis permutation: one flux copy
+    const int sl = L::upper_elem(idx, d), sr = L::halo_slot(d, 1, idx);
+    Cell<T> Lc, Rc;
+    Lc.rho = cq[sl]; Lc.hx = cq[(1 + p0) * NS + sl]; Lc.hy = cq[(1 + p1) * NS + sl]; Lc.hz = cq[(1 + p2) * NS + sl];
+    Lc.kp = cq[4 * NS + sl]; Lc.b = cq[5 * NS + sl]; Lc.q = cq[6 * NS + sl];
+    Rc.rho = cq[sr]; Rc.hx = cq[(1 + p0) * NS + sr]; Rc.hy = cq[(1 + p1) * NS + sr]; Rc.hz = cq[(1 + p2) * NS + sr];
+    Rc.kp = cq[4 * NS + sr]; Rc.b = cq[5 * NS + sr]; Rc.q = cq[6 * NS + sr];
+    T       F[5];
+    const T s = kepes_flux_n<T, 0>(Lc, Rc, T(0), T(0), T(0), F);
+    if (SMAX) smax = fmax_(smax, s);
+    const int j = 768 + tid;   // == BoxCommon::upper_flux(d, idx)
+    fl[j] = F[0]; fl[(1 + p0) * NF + j] = F[1]; fl[(1 + p1) * NF + j] = F[2]; fl[(1 + p2) * NF + j] = F[3];
+    fl[4 * NF + j] = F[4];
+  }
+
+  // ---- phase 2: operands requested before the barrier
+  const int stage = A.stage;
+  T         base[5];
+  T         vol = A.vol[e >> A.vol_shift] * A.vol_scale;
+#pragma unroll
+  for (int k = 0; k < 5; k++) base[k] = A.in[k][e];
+  if (stage != 1) {
+    const T cp = stage == 2 ? T(0.75) : T(0.33333333333333), ci = stage == 2 ? T(0.25) : T(0.66666666666666);
+#pragma unroll
+    for (int k = 0; k < 5; k++) base[k] = cp * A.prev[k][e] + ci * base[k];
+  }
+  T sc = fast_rcp(vol) * A.dt;
+  if (stage == 2) sc *= T(0.25);
+  if (stage == 3) sc *= T(0.66666666666666);
+  sc *= A.area_tab[area_idx];
+  const int ux = L::at_upper(tid, 0) ? BoxCommon::upper_flux(0, L::compact(tid, 0)) : L::upper_own(tid, 0);
+  const int uy = L::at_upper(tid, 1) ? BoxCommon::upper_flux(1, L::compact(tid, 1)) : 256 + L::upper_own(tid, 1);
+  const int uz = L::at_upper(tid, 2) ? BoxCommon::upper_flux(2, L::compact(tid, 2)) : 512 + L::upper_own(tid, 2);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const T* f = fl + k * NF;
+    const T  acc = ((f[tid] + f[256 + tid]) + f[512 + tid]) - ((f[ux] + f[uy]) + f[uz]);
+    A.out[k][e] = base[k] + sc * acc;
+  }
+  if (SMAX) {
+    smax = warp_max(smax);
+    if ((tid & 31) == 0) red[tid >> 5] = smax;
+    __syncthreads();
+    if (tid == 0) {
+      T m = red[0];
+#pragma unroll
+      for (int w = 1; w < 8; w++) m = fmax_(m, red[w]);
+      atomic_max_nonneg(A.speed_max, m);
+    }
+  }
+}
+
+template <typename T, class L, bool SMAX>
+static int s_launch(const t8b200_plan* P, SArgs<T>& A, cudaStream_t st) {
+  auto             k    = structured_stage_kernel<T, L, SMAX>;
+  constexpr size_t smem = sizeof(T) * ((size_t)NCELLQ * L::NSLOT + 5 * (size_t)BoxCommon::NFLUX);
+  // the opt-in above 48 KB is per device: cached per device id (not once per process)
+  static int resident[64];
+  int        dev = 0;
+  T8B_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (resident[dev] == 0) {
+    T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0, per_sm = 0;
+    T8B_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    T8B_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, smem));
+    resident[dev] = std::max(1, sms * per_sm);
+  }
+  static const int wave_knob = getenv("T8B200_WAVE") ? atoi(getenv("T8B200_WAVE")) : -1;
+  A.wave = wave_knob >= 0 ? wave_knob : resident[dev];
+  k<<<P->n_struct, 256, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
+template <typename T>
+int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
+                             const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream) {
+  if (P->n_struct == 0) return cudaSuccess;
+  SArgs<T> A{};
+  A.rec = reinterpret_cast<const int4*>(P->s_rec); A.halo = P->s_halo; A.hrank = P->s_hrank;
+  A.area_tab = (const T*)P->area_tab;
+  bool aligned = ((uintptr_t)vol & 15u) == 0 && ((uintptr_t)P->s_halo & 15u) == 0;
+  for (int k = 0; k < 5; k++) {
+    A.in[k]     = in[k];
+    A.in_all[k] = in_all ? in_all[k] : nullptr;
+    A.prev[k]   = stage > 1 ? prev[k] : in[k];
+    A.out[k]    = out[k];
+    aligned     = aligned && ((uintptr_t)A.in[k] & 15u) == 0 && ((uintptr_t)A.prev[k] & 15u) == 0;
+  }
+  A.vol = vol; A.vol_shift = P->vol_shift; A.vol_scale = (T)P->vol_scale; A.dt = dt; A.speed_max = speed_max;
+  A.stage = stage; A.multi = P->multi; A.my_rank = P->my_rank;
+  A.dense = (P->n_struct == P->n_chunks && !P->split) ? 1 : 0;
+  A.area0 = P->s_area0;
+  A.pf_ok = aligned ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (P->box_layout == 1)
+    return speed_max ? s_launch<T, SubgridBox, true>(P, A, st) : s_launch<T, SubgridBox, false>(P, A, st);
+  return speed_max ? s_launch<T, MortonBox, true>(P, A, st) : s_launch<T, MortonBox, false>(P, A, st);
+}
+template int t8b_structured_stage_run<float>(const t8b200_plan*, int, const float* const*, const float* const* const*,
+                                             const float* const*, float* const*, const float*, float, float*, void*);
+template int t8b_structured_stage_run<double>(const t8b200_plan*, int, const double* const*,
+                                              const double* const* const*, const double* const*, double* const*,
+                                              const double*, double, double*, void*);

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/t8gpu_b200.h"
+#include "box_layout.cuh"
 #include "euler_flux.cuh"
 
 #ifndef T8B_EC
@@ -54,6 +55,7 @@ struct t8b200_plan_host {
   raw_vector<uint16_t>  ell;
   std::vector<uint16_t> ovf_off, ovf_ent;
   std::vector<double>   area_tab, fnx, fny, fnz, farea;
+  std::vector<int32_t>  s_rec, s_halo, s_hrank, g_list;   // structured chunks (box_layout.cuh)
 };
 
 struct t8b200_plan {
@@ -81,6 +83,14 @@ struct t8b200_plan {
   uint4*    ell      = nullptr;  // n_chunks * EC
   uint16_t* ovf_off  = nullptr;  // (EC + 1) per chunk that has overflow entries
   uint16_t* ovf_ent  = nullptr;
+  // structured chunks (box_layout.cuh, structured.cu): 8 x 8 x 4 boxes with 256 single same-size neighbours
+  int      box_layout = -1;     // layout the builder tested the chunks against: 0 MortonBox, 1 SubgridBox, -1 none
+  int      n_struct = 0, n_generic = 0;
+  int      s_area0  = 0;        // area index shared by all chunks (dense plans)
+  int32_t* s_rec    = nullptr;  // 4 per structured chunk: first element, area index, chunk id, 0
+  int32_t* s_halo   = nullptr;  // 256 per structured chunk, thread order, index into the owner's arrays
+  int32_t* s_hrank  = nullptr;  // owner ranks (multi only)
+  int32_t* g_list   = nullptr;  // chunk ids left to the generic kernel (n_generic entries; only when n_struct > 0)
   // volume lookup of the stage kernel: volume of element e = vol[e >> vol_shift] * vol_scale (subgrid cells share
   // their element's volume: shift 6 / 4, scale 1/64 / 1/16, ssp_runge_kutta.inl:116)
   int    vol_shift = 0;
@@ -255,9 +265,22 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     std::vector<uint8_t>  face_ai;
     std::vector<T>        fnx, fny, fnz, far;
     std::vector<uint16_t> ovf_off, ovf_ent;
+    std::vector<uint8_t>  s_flag;             // per chunk: structured?
+    std::vector<int32_t>  s_halo, s_hrank;    // 256 per structured chunk
     int  max_halo = 0, max_faces = 0, rc = 0;
     bool split = false;
   };
+  // structured chunks: which box layout the chunks of this plan can have (unstructured plans: t8code hexahedra in
+  // Morton order; cell-level plans of Subgrid<4,4,4>: 4 sibling elements); T8B200_STRUCTURED=0 leaves every chunk to the
+  // generic kernel
+  static const bool structured_on = !(getenv("T8B200_STRUCTURED") && atoi(getenv("T8B200_STRUCTURED")) == 0);
+  const int box_layout = (structured_on && EC == 256 && MS - EC >= 256) ? (P->vol_shift == 6 ? 1 : P->vol_shift == 0 ? 0 : -1) : -1;
+  P->box_layout = box_layout;
+  int thread_of_slot[2][t8b200::SubgridBox::NSLOT];   // inverse of thread_slot() per layout
+  for (int h = 0; h < 256; h++) {
+    thread_of_slot[0][t8b200::MortonBox::thread_slot(h)]  = h;
+    thread_of_slot[1][t8b200::SubgridBox::thread_slot(h)] = h;
+  }
   std::vector<Builder> builders(NT);
   parallel_ranges(nblocks, NT, [&](int t, int64_t blk0, int64_t blk1) {
     Builder& B = builders[t];
@@ -424,6 +447,47 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
         }
         B.ovf_off.push_back((uint16_t)q);
       }
+      // structured?  full chunk, compressed geometry with one area, no walls, exactly 256 halo elements and 896 faces,
+      // and the faces are those of the box: inside the box along the layout's index arithmetic, across its boundary to
+      // ONE halo element per boundary element and direction (no hanging faces)
+      bool structured = false;
+      if (box_layout >= 0 && cmp && uniform && area0 >= 0 && b1 - b0 == 256 && (b0 & 255) == 0 && seg[3] == 0 &&
+          nh == 256 && nfc == t8b200::BoxCommon::NFLUX) {
+        int16_t lo[3][256], hi[3][256];
+        std::fill(&lo[0][0], &lo[0][0] + 3 * 256, (int16_t)-1);
+        std::fill(&hi[0][0], &hi[0][0] + 3 * 256, (int16_t)-1);
+        structured = true;
+        for (int j = 0; j < nfc && structured; j++) {   // canonical orientation: normal +e_grp from sl to sr
+          const int d = recs[j].grp, sl = recs[j].sl, sr = recs[j].sr;
+          if (sl < 256) { if (hi[d][sl] != -1) structured = false; hi[d][sl] = (int16_t)sr; }
+          if (sr < 256) { if (lo[d][sr] != -1) structured = false; lo[d][sr] = (int16_t)sl; }
+        }
+        auto test = [&](auto tag) {
+          using L = decltype(tag);
+          const int* inv = thread_of_slot[box_layout];
+          int32_t hl[256], hr[256];
+          for (int t = 0; t < 256 && structured; t++)
+            for (int d = 0; d < 3; d++) {
+              const int l = lo[d][t], u = hi[d][t];
+              if (L::at_lower(t, d) ? l < 256 : l != L::lower_own(t, d)) { structured = false; break; }
+              if (L::at_upper(t, d) ? u < 256 : u != L::upper_own(t, d)) { structured = false; break; }
+              if (L::at_lower(t, d)) {
+                const int h = inv[L::halo_slot(d, 0, L::compact(t, d))], q = (int)B.halo_elem.size() - nh + (l - 256);
+                hl[h] = B.halo_elem[q]; hr[h] = B.halo_rank[q];
+              }
+              if (L::at_upper(t, d)) {
+                const int h = inv[L::halo_slot(d, 1, L::compact(t, d))], q = (int)B.halo_elem.size() - nh + (u - 256);
+                hl[h] = B.halo_elem[q]; hr[h] = B.halo_rank[q];
+              }
+            }
+          if (structured) {
+            B.s_halo.insert(B.s_halo.end(), hl, hl + 256);
+            B.s_hrank.insert(B.s_hrank.end(), hr, hr + 256);
+          }
+        };
+        if (structured) { if (box_layout == 1) test(t8b200::SubgridBox{}); else test(t8b200::MortonBox{}); }
+      }
+      B.s_flag.push_back(structured ? 1 : 0);
       return 0;
     };
     // chunk [b0,b1) from the candidate faces of its block; halves it while it does not fit
@@ -493,6 +557,13 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   raw_vector<uint8_t>  face_ai(cmp ? (size_t)nchunks * FS : 0);
   raw_vector<T>        fnx(cmp ? 0 : (size_t)nchunks * FS), fny(fnx.size()), fnz(fnx.size()), far(fnx.size());
   std::vector<uint16_t> ovf_off(n_ovf_off), ovf_ent(n_ovf_ent);
+  struct BFlags { std::vector<uint8_t> flag; std::vector<int32_t> halo, hrank; };
+  std::vector<BFlags> builders_flags(NT);
+  for (int t = 0; t < NT; t++) {
+    builders_flags[t].flag.swap(builders[t].s_flag);
+    builders_flags[t].halo.swap(builders[t].s_halo);
+    builders_flags[t].hrank.swap(builders[t].s_hrank);
+  }
   {
     std::vector<int>    chunk_base(NT + 1, 0);
     std::vector<size_t> oo_base(NT + 1, 0), oe_base(NT + 1, 0);
@@ -533,6 +604,25 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
       }
     });
   }
+  // structured chunks: records and halo lists in chunk order, the other chunk ids for the generic kernel
+  std::vector<int32_t> s_rec, s_halo, s_hrank, g_list;
+  {
+    int c = 0;
+    for (auto& B : builders_flags) {
+      for (size_t i = 0, q = 0; i < B.flag.size(); i++, c++) {
+        if (B.flag[i]) {
+          s_rec.push_back(hdr[(size_t)c * 8]); s_rec.push_back(hdr[(size_t)c * 8 + 7]); s_rec.push_back(c); s_rec.push_back(0);
+          s_halo.insert(s_halo.end(), B.halo.begin() + q * 256, B.halo.begin() + (q + 1) * 256);
+          if (multi) s_hrank.insert(s_hrank.end(), B.hrank.begin() + q * 256, B.hrank.begin() + (q + 1) * 256);
+          q++;
+        } else g_list.push_back(c);
+      }
+    }
+    P->n_struct  = (int)(s_rec.size() / 4);
+    P->n_generic = P->n_struct ? (int)g_list.size() : nchunks;
+    P->s_area0   = P->n_struct ? s_rec[1] : 0;
+    if (!P->n_struct) g_list.clear();
+  }
   P->n_halo     = n_halo;
   P->n_records  = n_rec;
   P->hs = HS;
@@ -554,6 +644,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     if (cmp) Hc->area_tab.assign(area_tab.begin(), area_tab.end());
     Hc->fnx.assign(fnx.begin(), fnx.end()); Hc->fny.assign(fny.begin(), fny.end());
     Hc->fnz.assign(fnz.begin(), fnz.end()); Hc->farea.assign(far.begin(), far.end());
+    Hc->s_rec.swap(s_rec); Hc->s_halo.swap(s_halo); Hc->s_hrank.swap(s_hrank); Hc->g_list.swap(g_list);
     P->host = Hc;
     return cudaSuccess;
   }
@@ -576,6 +667,12 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   P->ell     = reinterpret_cast<uint4*>(upload(ell, P->dev_bytes, err));
   P->ovf_off = upload(ovf_off, P->dev_bytes, err);
   P->ovf_ent = upload(ovf_ent, P->dev_bytes, err);
+  if (P->n_struct) {
+    P->s_rec  = upload(s_rec, P->dev_bytes, err);
+    P->s_halo = upload(s_halo, P->dev_bytes, err);
+    if (P->multi) P->s_hrank = upload(s_hrank, P->dev_bytes, err);
+    if (P->n_generic) P->g_list = upload(g_list, P->dev_bytes, err);
+  }
   lap("upload");
   return err;
 }
@@ -584,4 +681,8 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
 template <typename T>
 int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
                         const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream);
+// defined in structured.cu: the structured chunks of the plan (no-op when it has none)
+template <typename T>
+int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
+                             const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream);
 void t8b_plan_free(t8b200_plan* P);

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B builds of the library: tools/build_variant.py NAME [-DFLAG ...] compiles csrc/fused.cu and csrc/subgrid.cu with
+"""A/B builds of the library: tools/build_variant.py NAME [-DFLAG ...] compiles csrc/fused.cu, csrc/structured.cu and csrc/subgrid.cu with
 the extra flags and links them with the other objects into t8gpu_b200/build/variants/libNAME.so (git-ignored, travels
 with gpurun).  Select at run time with T8GPU_B200_LIB=<path>, so several variants are timed in ONE gpurun call."""
 import os
@@ -19,7 +19,7 @@ def main():
     os.makedirs(vdir, exist_ok=True)
     objs, procs = [], []
     for s in B.SOURCES:
-        if s in ("fused.cu", "subgrid.cu"):
+        if s in ("fused.cu", "subgrid.cu", "structured.cu"):
             obj = os.path.join(vdir, name + "_" + s.replace(".cu", ".o"))
             cmd = [B._nvcc()] + B.NVCC_FLAGS + flags + ["-c", os.path.join(B.CSRC, s), "-o", obj]
             procs.append(subprocess.Popen(cmd))
