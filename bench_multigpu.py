@@ -3,8 +3,17 @@
 Each rank owns one tree of a periodic brick of unit trees refined to `--level` (16.8 M hexes per GPU at level 8):
 brick (2,1,1) / (2,2,1) / (2,2,2) for 2 / 4 / 8 GPUs.  Ghost states are read directly from the neighbour GPUs'
 live state arrays through peer-mapped pointers (NVLink); every rank evaluates all faces of its own elements
-(owner computes, no remote atomics).  One tiny NCCL all-reduce per RK stage orders the stages across ranks on the
-device (no host synchronisation inside a step); the stage-3 one carries the max wave speed (CFL reduction)."""
+(owner computes, no remote atomics).
+
+Stage ordering across ranks (T8B200_SYNC):
+  kernel (default)  the stage kernels order themselves: the chunks that read ghost elements run first, wait for the
+                    peers' previous stage and the last of them signals this stage to every peer through the
+                    peer-mapped mailboxes (csrc/peer_sync.cuh); all other chunks never wait.  The CFL reduction is one
+                    32-thread mailbox kernel per step (on a side stream while dt is fixed, on the compute stream when
+                    the next dt depends on it).
+  peer              one mailbox barrier kernel per stage (round-1 scheme)
+  nccl              one 1-element NCCL all-reduce per stage
+No host synchronisation inside a step in any mode."""
 import json
 import os
 import time
@@ -12,14 +21,37 @@ import time
 import torch
 import torch.distributed as dist
 
-from t8gpu_b200.multi import BRICK, exchange_wires, global_max_wave_speed, row_pointers, stage_barrier, timestep
+from t8gpu_b200.multi import BRICK, exchange_wires, global_max_wave_speed, row_pointers, stage_barrier
+
+CFL = 0.7   # examples/compressible_euler/solver.h:37
+
+
+def pin_to_gpu_numa_node(device):
+    """Host threads (and the pinned staging buffers they first-touch) onto the CPUs next to this rank's GPU."""
+    try:
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = torch.cuda.get_device_properties(device).pci_domain_id
+        dev = torch.cuda.get_device_properties(device).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
 
 
 class MultiGpuEuler:
-    def __init__(self, level, dtype, rank, world, device, brick=None):
+    def __init__(self, level, dtype, rank, world, device, brick=None, sync=None):
         import t8gpu_b200 as tb
         from t8gpu_b200.solver import NB_STEPS, NVAR
         self.tb, self.rank, self.world, self.device, self.dtype = tb, rank, world, device, dtype
+        self.sync = sync or os.environ.get("T8B200_SYNC", "kernel")
         brick = brick or BRICK[world]
         esz = 8 if dtype == torch.float64 else 4
         conn = tb.cartesian_uniform_connectivity(3, level, dtype, world, rank, device=device, brick=brick)
@@ -37,20 +69,30 @@ class MultiGpuEuler:
         bases = [self.shared.ptr if r == rank else self.shared.open_peer(wires[r][0]) for r in range(world)]
         rows = row_pointers(bases, caps, NVAR, NB_STEPS, esz)
         self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
-        # stage barrier + CFL max over peer memory (T8B200_SYNC=nccl: 1-element NCCL all-reduces instead)
         self.mail = None
-        if os.environ.get("T8B200_SYNC", "peer") == "peer":
+        if self.sync in ("kernel", "peer", "none"):
             self.mail = tb.PeerMailboxes(rank, world, device)
             mw = exchange_wires(dist, self.mail.handle, 0, world, device)
             self.mail.exchange([h for h, _ in mw])
-            self.speed_loc = torch.zeros(1, dtype=dtype, device=device)
+        self.speed_loc = torch.zeros(1, dtype=dtype, device=device)
         self.plan = tb.Plan(tb.conn_to_host(conn), dtype)
         tb.init_kelvin_helmholtz(3, conn["centroids"], self.variables(0))
         self.next, self.prev = 0, 3
         self.speed_max = torch.zeros(1, dtype=dtype, device=device)
         self.token = torch.zeros(1, dtype=dtype, device=device)
+        self.dt_dev = torch.zeros(1, dtype=dtype, device=device)
+        self.length = 0.5 ** level                # the length scale of compute_timestep (solver.cu:225-228)
+        self.side = torch.cuda.Stream(device=device)
+        self.side_done = None
         torch.cuda.synchronize()
         dist.barrier()
+        self.publish()
+
+    def publish(self):
+        """The state was written outside the stage kernels (initial data, upload): a full barrier before any rank reads
+        ghosts, which also starts the stage-epoch sequence the self-ordering kernels continue."""
+        if self.mail is not None and self.sync != "none":
+            self.mail.barrier()
 
     def variables(self, step):
         from t8gpu_b200.solver import NVAR
@@ -60,27 +102,66 @@ class MultiGpuEuler:
         from t8gpu_b200.solver import NB_STEPS, NVAR
         return self.buffer[NVAR * NB_STEPS, :self.n]
 
-    def iterate(self, dt):
+    def state(self):
+        return self.buffer[self.next * 5:(self.next + 1) * 5, :self.n]
+
+    def iterate(self, dt, adaptive=False):
+        """One RK3 step.  adaptive: dt is read from self.dt_dev (device) and the next dt = min(dt, cfl h / vmax) is
+        written there after the global CFL reduction (compute_timestep, solver.cu:213-229) -- no host round trip."""
         self.next, self.prev = self.prev, self.next
         prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
         vol, T = self.volume(), self.tables
-        if self.mail is not None:   # barriers and the CFL reduction through the peers' mailboxes (NVLink stores)
-            self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev])
-            self.mail.barrier()
-            self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1])
-            self.mail.barrier()
-            self.plan.stage(3, s2, prev, nxt, vol, dt, in_all=T[2], speed_max=self.speed_loc)
+        dtd = self.dt_dev if adaptive else None
+        if self.sync == "kernel":
+            m = self.mail
+            self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev], dt_dev=dtd, sync=m)
+            self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1], dt_dev=dtd, sync=m)
+            main = torch.cuda.current_stream()
+            if self.side_done is not None:
+                main.wait_event(self.side_done)           # the previous reduction has read speed_loc
+                self.side_done = None
+            self.plan.stage(3, s2, prev, nxt, vol, dt, in_all=T[2], speed_max=self.speed_loc, dt_dev=dtd, sync=m)
+            if adaptive:                                  # the next step's kernels need the reduced value
+                m.barrier(self.speed_loc, self.speed_max)
+                self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
+                return 5
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                m.barrier(self.speed_loc, self.speed_max)
+                self.side_done = torch.cuda.Event()
+                self.side_done.record(self.side)
+            return 4                                               # 3 stage kernels + the CFL reduction
+        if self.mail is not None:   # "peer": barriers and the CFL reduction through the peers' mailboxes
+            bar = (lambda *a: None) if self.sync == "none" else self.mail.barrier
+            self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev], dt_dev=dtd)
+            bar()
+            self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1], dt_dev=dtd)
+            bar()
+            self.plan.stage(3, s2, prev, nxt, vol, dt, in_all=T[2], speed_max=self.speed_loc, dt_dev=dtd)
             self.mail.barrier(self.speed_loc, self.speed_max)
+            if adaptive:
+                self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
             return 6                                               # 3 stage kernels + 3 barrier kernels
-        self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev])
+        self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev], dt_dev=dtd)
         stage_barrier(dist, self.token)                            # device-side, on the compute stream
-        self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1])
+        self.plan.stage(2, s1, prev, s2, vol, dt, in_all=T[1], dt_dev=dtd)
         stage_barrier(dist, self.token)
-        self.plan.stage(3, s2, prev, nxt, vol, dt, in_all=T[2], speed_max=self.speed_max)
+        self.plan.stage(3, s2, prev, nxt, vol, dt, in_all=T[2], speed_max=self.speed_max, dt_dev=dtd)
         global_max_wave_speed(dist, self.speed_max)                # barrier + global CFL reduction
+        if adaptive:
+            self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
         return 3
 
+    def drain(self):
+        """Joins the side stream (the last CFL reduction) into the compute stream."""
+        if self.side_done is not None:
+            torch.cuda.current_stream().wait_event(self.side_done)
+            self.side_done = None
+
     def close(self):
+        self.drain()
         torch.cuda.synchronize()
         dist.barrier()
         self.plan = None
@@ -89,9 +170,40 @@ class MultiGpuEuler:
         self.shared.close()
 
 
+def bitwise_parity(dtype, rank, world, device, level=4, steps=3):
+    """Owner-computes is deterministic: the N-rank run must be BITWISE equal to the one-rank run of the same brick.
+    Every rank steps the small brick under the production protocol (self-ordering kernels, peer ghost reads), then
+    compares its slice with a one-rank solve of the whole brick done on its own GPU."""
+    import t8gpu_b200 as tb
+    dt = 0.1 * 2.0 ** -level
+    sol = MultiGpuEuler(level, dtype, rank, world, device)
+    c1 = tb.cartesian_uniform_connectivity(3, level, dtype, 1, 0, device=device, brick=BRICK[world])
+    one = tb.EulerSolver(tb.conn_to_host(c1), c1["volumes"].cpu().numpy(), dtype, device=device)
+    tb.init_kelvin_helmholtz(3, c1["centroids"], one.variables(one.next))
+    n1 = int(c1["n_local"])
+    off = [n1 * r // world for r in range(world + 1)]
+    equal_ic = bool(torch.equal(one.state()[:, off[rank]:off[rank + 1]], sol.state()))
+    for _ in range(steps):
+        one.iterate(dt)
+        sol.iterate(dt)
+    sol.drain()
+    torch.cuda.synchronize()
+    same = equal_ic and bool(torch.equal(one.state()[:, off[rank]:off[rank + 1]], sol.state()))
+    vm = abs(float(one.max_wave_speed().item()) - float(sol.speed_max.item())) == 0.0
+    flag = torch.tensor([1.0 if (same and vm) else 0.0], dtype=torch.float64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    sol.close()
+    ok = bool(flag.item() == 1.0)
+    return {"vs": "one-rank run of the same brick (level %d trees, %d elements)" % (level, n1), "steps": steps,
+            "bitwise_equal": ok, "checked": "conserved variables of every rank + reduced max wave speed"}
+
+
 def run_multi(args, rank, world, device):
     from bench import ALG_BYTES, ClockSampler, measured_peak
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    ncpu = pin_to_gpu_numa_node(device)
+    parity = bitwise_parity(dtype, rank, world, device)
+    assert parity["bitwise_equal"], "the %d-rank run differs from the one-rank run of the same brick" % world
     t0 = time.time()
     sol = MultiGpuEuler(args.level, dtype, rank, world, device)
     t_setup = time.time() - t0
@@ -100,6 +212,7 @@ def run_multi(args, rank, world, device):
     stream = torch.cuda.current_stream()
     for _ in range(args.warmup):
         sol.iterate(dt)
+    sol.drain()
     torch.cuda.synchronize()
     dist.barrier()
     sampler = ClockSampler(device.index)
@@ -114,6 +227,7 @@ def run_multi(args, rank, world, device):
     ev0.record(stream)
     for _ in range(args.steps):
         launches += sol.iterate(dt)
+    sol.drain()
     ev1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
@@ -124,35 +238,37 @@ def run_multi(args, rank, world, device):
     vmax = float(sol.speed_max.item())
     assert vmax > 0 and vmax == vmax
 
-    # e2e: same protocol as the 1-GPU arm (state upload from pinned host, per-step D2H of the reduced max wave speed
-    # with the next dt computed on the host, state download), max over ranks
+    # e2e: the same job through host buffers: state uploaded from pinned host memory, K x [iterate with the CFL rule:
+    # global max wave speed -> next dt, both kept on the device; dt and vmax of every step are copied to the host
+    # asynchronously], state downloaded.  No host synchronisation inside the loop; max over ranks.
     u_host = torch.empty((5, n), dtype=dtype).pin_memory()
-    state = sol.buffer[sol.next * 5:(sol.next + 1) * 5, :n]
-    u_host.copy_(state)
+    u_host.copy_(sol.state())
     out_host = torch.empty((5, n), dtype=dtype).pin_memory()
-    vmax_host = torch.empty(1, dtype=dtype).pin_memory()
+    hist = torch.zeros((args.steps, 2), dtype=dtype).pin_memory()
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    sol.buffer[sol.next * 5:(sol.next + 1) * 5, :n].copy_(u_host, non_blocking=True)
-    dist.all_reduce(sol.token, op=dist.ReduceOp.MAX)   # every rank's upload is complete before neighbours read it
-    cur_dt = dt
-    for _ in range(args.steps):
-        sol.iterate(cur_dt)
-        vmax_host.copy_(sol.speed_max, non_blocking=True)
-        stream.synchronize()
-        cur_dt = timestep(float(vmax_host[0]), 0.7, args.level, dt_cap=dt)
-    out_host.copy_(sol.buffer[sol.next * 5:(sol.next + 1) * 5, :n], non_blocking=True)
+    sol.state().copy_(u_host, non_blocking=True)
+    sol.dt_dev.fill_(dt)
+    sol.publish()                    # every rank's upload is complete before neighbours read it
+    if sol.sync == "nccl":
+        dist.all_reduce(sol.token, op=dist.ReduceOp.MAX)
+    for k in range(args.steps):
+        sol.iterate(dt, adaptive=True)
+        hist[k, 0:1].copy_(sol.dt_dev, non_blocking=True)
+        hist[k, 1:2].copy_(sol.speed_max, non_blocking=True)
+    out_host.copy_(sol.state(), non_blocking=True)
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
+    assert bool((hist[:, 0] > 0).all()) and bool((hist[:, 0] <= dt).all()) and bool((hist[:, 1] > 0).all())
 
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     info = sol.plan.info
-    nfaces, nghost = sol.n_faces, sol.n_ghost
+    nfaces, nghost, sync = sol.n_faces, sol.n_ghost, sol.sync
     sol.close()
     if rank == 0:
         esz = 8 if args.dtype == "f64" else 4
@@ -162,6 +278,14 @@ def run_multi(args, rank, world, device):
         ms_per_step = ms / args.steps
         achieved = alg * n / (ms_per_step * 1e-3) / 1e9   # per GPU
         state_bytes = 5 * n * esz
+        sync_text = {"kernel": "stage kernels order themselves through peer-memory mailboxes (ghost-reading chunks first: "
+                               "wait for the peers' previous stage, last one signals; interior chunks never wait); CFL "
+                               "max over ranks = one 32-thread mailbox kernel per step",
+                     "peer": "peer-memory mailbox barrier kernel per RK stage on the compute stream; stage 3 carries "
+                             "the max wave speed",
+                     "nccl": "1 NCCL all-reduce (1 element) per RK stage on the compute stream; stage 3 carries the max "
+                             "wave speed",
+                     "none": "NO stage ordering (timing experiment, results invalid)"}[sync]
         line = {"metric": "cell-updates/s per RK3 step", "value": total * args.steps / (ms * 1e-3),
                 "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -172,22 +296,20 @@ def run_multi(args, rank, world, device):
                            "elements_per_gpu": n, "faces_per_gpu": nfaces, "ghosts_per_gpu": nghost,
                            "partition": "one tree (one t8code SFC partition) per GPU; ghosts read from peer GPUs "
                                         "over NVLink (cudaIpc-mapped state arrays), owner-computes boundary faces",
-                           "sync": ("peer-memory mailbox barrier per RK stage on the compute stream (NVLink stores + "
-                                    "acquire spin); stage 3 carries the max wave speed" if os.environ.get(
-                                        "T8B200_SYNC", "peer") == "peer" else
-                                    "1 NCCL all-reduce (1 element) per RK stage on the compute stream; stage 3 "
-                                    "carries the max wave speed"), "l2": "inputs larger than L2",
-                           "host_setup_s": round(t_setup, 2), "host_cores": os.cpu_count(), "plan": info},
-                "clocks": clocks,
+                           "sync": sync_text, "l2": "inputs larger than L2",
+                           "host_setup_s": round(t_setup, 2), "host_cores": os.cpu_count(),
+                           "host_cpus_bound_to_gpu_numa_node": ncpu, "plan": info},
+                "clocks": clocks, "parity": parity,
                 "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",
                         "h2d_bytes_per_step": (state_bytes / args.steps + esz) * world,
-                        "d2h_bytes_per_step": (state_bytes / args.steps + esz) * world,
+                        "d2h_bytes_per_step": (state_bytes / args.steps + 2 * esz) * world,
                         "ms_per_step": e2e_ms / args.steps,
-                        "protocol": "pinned-host state in, K x (iterate + D2H max wave speed + host dt), state out"},
+                        "protocol": "pinned-host state in, K x (iterate with dt on the device: global CFL max -> next "
+                                    "dt, no host synchronisation; async D2H of dt and vmax per step), state out"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": src,
-                             "kernel": "fused_stage_kernel", "note": "per GPU"},
+                             "kernel": "structured_stage_kernel", "note": "per GPU"},
                 "max_wave_speed": vmax}
         print(json.dumps(line))
     dist.destroy_process_group()

@@ -70,6 +70,7 @@ class SubgridBrick:
             self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
             self.mail = tb.PeerMailboxes(rank, world, device)
             self.mail.exchange([h for h, _ in exchange_wires(dist, self.mail.handle, 0, world, device)])
+        self.sync = os.environ.get("T8B200_SYNC", "kernel")
         t0 = time.time()
         self.plan = tb.SubgridPlan(tb.conn_to_host(conn), self.vol.cpu().numpy(), dtype)
         self.t_plan = time.time() - t0
@@ -78,6 +79,13 @@ class SubgridBrick:
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+            self.publish()
+
+    def publish(self):
+        """State written outside the stage kernels: full barrier before any rank reads ghosts (starts / continues the
+        stage-epoch sequence of the self-ordering kernels)."""
+        if self.mail is not None:
+            self.mail.barrier()
 
     def variables(self, step):
         return [self.buffer[step * 5 + k, :self.n] for k in range(5)]
@@ -89,10 +97,12 @@ class SubgridBrick:
         self.next, self.prev = self.prev, self.next
         prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
         T, launches = self.tables, 0
+        own_order = self.mail is not None and self.sync == "kernel"   # the stage kernels order themselves
         for stage, sin, vin, vout in ((1, self.prev, prev, s1), (2, 1, s1, s2), (3, 2, s2, nxt)):
-            self.plan.stage(stage, vin, prev if stage > 1 else None, vout, self.vol, dt, in_all=T[sin])
+            self.plan.stage(stage, vin, prev if stage > 1 else None, vout, self.vol, dt, in_all=T[sin],
+                            sync=self.mail if own_order else None)
             launches += 1
-            if self.mail is not None:   # every rank has written stage s before any rank reads it as ghost data
+            if self.mail is not None and not own_order:   # barrier kernel per stage (T8B200_SYNC=peer)
                 self.mail.barrier()
                 launches += 1
         return launches
@@ -160,8 +170,7 @@ def run_subgrid(args, rank, world, device):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     sol.state().copy_(u_host, non_blocking=True)
-    if sol.mail is not None:
-        sol.mail.barrier()                     # every rank's upload is complete before neighbours read it
+    sol.publish()                              # every rank's upload is complete before neighbours read it
     for _ in range(args.steps):
         sol.iterate(dt)
         probe.copy_(sol.state()[0, :1], non_blocking=True)
@@ -189,7 +198,8 @@ def run_subgrid(args, rank, world, device):
                                        "adaptation" % (BRICK[world], level, ne, n, total, args.dtype),
                            "cells_per_gpu": n, "element_faces_per_gpu": nfaces, "ghost_elements_per_gpu": nghost,
                            "partition": "one tree per GPU; ghost cells read from peer GPUs over NVLink, owner-computes "
-                                        "boundary faces; peer-memory mailbox barrier per RK stage" if world > 1 else
+                                        "boundary faces; stage kernels order themselves through peer-memory mailboxes "
+                                        "(ghost-reading chunks first)" if world > 1 else
                                         "one rank", "l2": "inputs larger than L2 (%.0f MB of state per stage)" %
                                                           (2 * state_bytes / 1e6),
                            "host_setup_s": round(t_setup, 2), "tile_plan_host_s": round(t_plan, 2),

@@ -21,6 +21,7 @@
 #include <t8_forest/t8_forest_partition.h>
 #include <t8gpu/memory/subgrid_memory_manager.h>
 #include <t8gpu/utils/cuda.h>
+#include <t8gpu/utils/meta.h>
 #include <t8gpu_b200.h>
 #include <thrust/device_vector.h>
 #include <thrust/host_vector.h>
@@ -378,8 +379,88 @@ namespace t8gpu {
           x.normals.data(), x.areas.data(), x.level_diff.data(), x.offset.data()));
     }
 
-    // (VTK output of the cell data -- save_variables_to_vtk / column_major_to_z_order,
-    // subgrid_mesh_manager.inl:1007-1124 -- is I/O outside the hot path and not mirrored: SURVEY f-4.)
+    // ---- output (subgrid_mesh_manager.h:355-446, .inl:1007-1208)
+
+    /// Cell data of one variable, one value per CELL, written on the forest refined log2(extent) more times so that
+    /// every cell is a leaf (the reference's scheme, subgrid_mesh_manager.inl:1066-1124).  The permutation to that
+    /// forest's leaf order and the widening to double run on the device (t8b200_subgrid_z_order), one copy to the host.
+    void save_variable_to_vtk(step_index_type step, variable_index_type variable, std::string const& prefix) const {
+      size_t const                  cells = static_cast<size_t>(m_num_local_elements) * SubgridType::size;
+      thrust::device_vector<double> z_ordered(cells);
+      float_type const* const       from = static_cast<float_type const*>(this->get_own_variable(step, variable));
+      if constexpr (sizeof(float_type) == 8)
+        T8GPU_CUDA_CHECK_ERROR(t8b200_subgrid_z_order_f64(dim, m_num_local_elements, (double const*)from,
+                                                          thrust::raw_pointer_cast(z_ordered.data()), nullptr));
+      else
+        T8GPU_CUDA_CHECK_ERROR(t8b200_subgrid_z_order_f32(dim, m_num_local_elements, (float const*)from,
+                                                          thrust::raw_pointer_cast(z_ordered.data()), nullptr));
+      thrust::host_vector<double> host = z_ordered;
+
+      constexpr int levels = meta::log2_v<SubgridType::template extent<0>>;
+      t8_forest_t   fine   = m_forest;
+      for (int l = 0; l < levels; l++) {   // every element -> its 2^dim children, `levels` times
+        t8_forest_t next{};
+        t8_forest_init(&next);
+        if (l == 0) t8_forest_ref(fine);   // set_adapt consumes one reference of its source; m_forest stays ours
+        t8_forest_set_adapt(next, fine, refine_everything, false);
+        t8_forest_commit(next);
+        fine = next;
+      }
+      t8_vtk_data_field_t field{};
+      field.type = T8_VTK_SCALAR;
+      std::strncpy(field.description, "variables", BUFSIZ - 1);
+      field.data = host.data();
+      t8_forest_write_vtk_ext(fine, prefix.c_str(), true, true, true, true, false, false, false, 1, &field);
+      if (levels > 0) t8_forest_unref(&fine);
+    }
+
+    /// The element mesh alone (subgrid_mesh_manager.inl:1126-1142).
+    void save_mesh_to_vtk(std::string const& prefix) const {
+      t8_forest_write_vtk_ext(m_forest, prefix.c_str(), true, true, true, true, false, false, false, 0, nullptr);
+    }
+
+    /// Host copy of a variable, owning wrapper around t8_vtk_data_field_t (subgrid_mesh_manager.h:388-417).
+    class HostVariableInfo {
+      friend SubgridMeshManager;
+      HostVariableInfo(t8_vtk_data_type_t type, std::unique_ptr<double[]>&& data, std::string const& name)
+          : m_data{std::move(data)} {
+        m_field.type = type;
+        m_field.data = m_data.get();
+        std::strncpy(m_field.description, name.c_str(), BUFSIZ - 1);
+        m_field.description[BUFSIZ - 1] = '\0';
+      }
+
+     public:
+      HostVariableInfo()                   = default;
+      HostVariableInfo(HostVariableInfo&&) = default;
+      ~HostVariableInfo()                  = default;
+
+     private:
+      std::unique_ptr<double[]> m_data;
+      t8_vtk_data_field_t       m_field{};
+    };
+
+    /// As the reference (subgrid_mesh_manager.inl:1144-1161): the first num_local_elements values of the variable's
+    /// array, widened to double.
+    [[nodiscard]] HostVariableInfo get_host_scalar_variable(step_index_type step, variable_index_type variable,
+                                                            std::string const& name) const {
+      auto data = std::make_unique<double[]>(static_cast<size_t>(m_num_local_elements));
+      fetch_head(step, variable, data.get(), 1);
+      return HostVariableInfo{T8_VTK_SCALAR, std::move(data), name};
+    }
+    /// Three variables interleaved per entry (subgrid_mesh_manager.inl:1163-1183).
+    [[nodiscard]] HostVariableInfo get_host_vector_variable(step_index_type step, std::array<variable_index_type, 3> variable,
+                                                            std::string const& name) const {
+      auto data = std::make_unique<double[]>(3 * static_cast<size_t>(m_num_local_elements));
+      for (int c = 0; c < 3; c++) fetch_head(step, variable[c], data.get() + c, 3);
+      return HostVariableInfo{T8_VTK_VECTOR, std::move(data), name};
+    }
+    /// The reference's body is commented out (subgrid_mesh_manager.inl:1185-1208): the fields are per element while the
+    /// data is per cell.  Kept callable with the same effect: nothing is written.
+    void save_variables_to_vtk(std::vector<HostVariableInfo> host_variables, std::string const& prefix) const {
+      (void)host_variables;
+      (void)prefix;
+    }
 
     [[nodiscard]] SubgridMeshConnectivityAccessor<float_type, SubgridType> get_connectivity_information() const {
       return {thrust::raw_pointer_cast(m_device_ranks.data()),
@@ -492,6 +573,19 @@ namespace t8gpu {
         v[idx] = static_cast<float_type>(t8_forest_element_volume(forest, tree, element));
       });
       return v;
+    }
+    /// t8code adapt callback that refines every element (the cells of a subgrid as leaves, for output)
+    static int refine_everything(t8_forest_t, t8_forest_t, t8_locidx_t, t8_locidx_t, t8_eclass_scheme_c*, int const,
+                                 int const, t8_element_t*[]) {
+      return 1;
+    }
+    /// first num_local_elements values of a variable's array -> out[i * stride], widened to double
+    void fetch_head(step_index_type step, variable_index_type variable, double* out, int stride) const {
+      thrust::host_vector<float_type> h(m_num_local_elements);
+      if (m_num_local_elements > 0)
+        T8GPU_CUDA_CHECK_ERROR(cudaMemcpy(h.data(), static_cast<float_type const*>(this->get_own_variable(step, variable)),
+                                          sizeof(float_type) * m_num_local_elements, cudaMemcpyDeviceToHost));
+      for (t8_locidx_t i = 0; i < m_num_local_elements; i++) out[static_cast<size_t>(i) * stride] = static_cast<double>(h[i]);
     }
     /// host copy of the (remapped) volumes: the plan needs them for the areas of the faces between cells
     void fetch_volumes() {

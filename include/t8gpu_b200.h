@@ -231,13 +231,64 @@ int t8b200_shared_free(void* dev_ptr);
 /* Stage barrier + max-reduction between the GPUs of one node over peer memory; stays on the stream.  Replaces the
  * cudaDeviceSynchronize() + MPI_Barrier pairs of iterate() (examples/compressible_euler/solver.cu:98-99, ...) and the
  * MPI_Allreduce(MAX) of compute_timestep (solver.cu:219-223).
- * mailboxes_dev: DEVICE array of nranks pointers; entry p is rank p's mailbox (nranks slots of 16 bytes, zero-initialised,
- *   allocated with t8b200_shared_alloc and mapped here with t8b200_shared_open).  Every rank stores (value, epoch) into
- *   its slot of every mailbox, then waits until all slots of its own mailbox carry `epoch` (strictly increasing, > 0,
- *   the same on all ranks).  value_dev: device scalar (float or double per value_is_f64) or NULL (pure barrier);
- *   out_max_dev: receives the maximum over the ranks, or NULL.  nranks <= 32. */
+ * mailboxes_dev: DEVICE array of nranks pointers; entry p is rank p's mailbox: 4 * nranks slots of 16 bytes,
+ *   zero-initialised, allocated with t8b200_shared_alloc and mapped here with t8b200_shared_open.  Slots [0, 2 nranks)
+ *   carry stage epochs, [2 nranks, 4 nranks) (value, epoch) pairs of the CFL reduction; each class is double-buffered by
+ *   epoch parity (csrc/peer_sync.cuh).  Every rank stores (value, epoch) into its slot of every mailbox, then waits
+ *   until all slots of its own mailbox carry `epoch`.
+ * epoch: > 0, the same on all ranks, consecutive PER CLASS: calls without a value (and the stage kernels of
+ *   t8b200_fused_stage_sync_*, which signal the same slots) share one sequence, calls with a value another.
+ * value_dev: device scalar (float or double per value_is_f64) or NULL (pure barrier); out_max_dev: receives the
+ *   maximum over the ranks, or NULL.  nranks <= 32. */
 int t8b200_peer_barrier(int nranks, int rank, long long epoch, void* const* mailboxes_dev, const void* value_dev,
                         int value_is_f64, void* out_max_dev, void* stream);
+
+/* CompressibleEulerSolver::compute_timestep's formula (examples/compressible_euler/solver.cu:225-228) on the device:
+ *   *dt_dev = cfl * length / *speed_max_dev, capped by dt_cap when dt_cap > 0 (length = 0.5^max_level in the example).
+ * With t8b200_fused_stage_sync_* reading dt from dt_dev, a time loop with the CFL rule needs no device -> host copy
+ * and no host synchronisation per step (the reference's thrust::reduce returns through the host, solver.cu:214-217). */
+int t8b200_timestep_f32(const float* speed_max_dev, float cfl, float length, float dt_cap, float* dt_dev, void* stream);
+int t8b200_timestep_f64(const double* speed_max_dev, double cfl, double length, double dt_cap, double* dt_dev,
+                        void* stream);
+
+/* t8b200_fused_stage_* with (i) the time step read from device memory and (ii) the stage ordering between the GPUs done
+ * by the stage kernel itself instead of a barrier between the launches:
+ *   dt_dev != NULL: the kernels read dt from *dt_dev (written earlier on the stream, e.g. by t8b200_timestep_*); `dt` is
+ *     ignored.
+ *   sync != NULL (plans with ghosts): the chunks that read ghost elements ("partition-boundary chunks", scheduled first)
+ *     wait until every peer has signalled `wait_epoch` (0: no wait), and the last of them to finish signals
+ *     `signal_epoch` (0: no signal) to every peer; all other chunks neither wait nor signal, so they overlap the
+ *     peers' skew.  Call pattern for consecutive stage launches k = 1, 2, 3, ... on every rank: wait_epoch = k - 1,
+ *     signal_epoch = k (the very first launch after the state was written by other means must be preceded by a
+ *     t8b200_peer_barrier, whose epoch continues the same sequence).  Replaces solver.cu:98-99,111-112,... as
+ *     t8b200_peer_barrier does, minus one launch per stage and minus the lock step of the interior.
+ *   No output may alias an input of the same call (in / prev / in_all rows vs out rows): cudaErrorInvalidValue. */
+typedef struct {
+  int          nranks, rank;
+  void* const* mailboxes_dev; /* as t8b200_peer_barrier */
+  unsigned*    counter_dev;   /* device, one zero-initialised unsigned owned by this rank */
+} t8b200_stage_sync;
+int t8b200_fused_stage_sync_f32(const t8b200_plan* plan, int stage, const float* const* in,
+                                const float* const* const* in_all, const float* const* prev, float* const* out,
+                                const float* vol, float dt, const float* dt_dev, float* speed_max_dev,
+                                const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
+                                void* stream);
+int t8b200_fused_stage_sync_f64(const t8b200_plan* plan, int stage, const double* const* in,
+                                const double* const* const* in_all, const double* const* prev, double* const* out,
+                                const double* vol, double dt, const double* dt_dev, double* speed_max_dev,
+                                const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
+                                void* stream);
+/* the same for the subgrid stage (no wave-speed reduction: the reference's subgrid solver has none) */
+int t8b200_subgrid_fused_stage_sync_f32(const t8b200_subgrid_plan* plan, int stage, const float* const* in,
+                                        const float* const* const* in_all, const float* const* prev,
+                                        float* const* out, const float* vol, float dt, const float* dt_dev,
+                                        const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
+                                        void* stream);
+int t8b200_subgrid_fused_stage_sync_f64(const t8b200_subgrid_plan* plan, int stage, const double* const* in,
+                                        const double* const* const* in_all, const double* const* prev,
+                                        double* const* out, const double* vol, double dt, const double* dt_dev,
+                                        const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
+                                        void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
  * 5. Device-side remap of variables and volumes after t8code adapt / partition (which stay on the host).
@@ -300,6 +351,19 @@ int t8b200_subgrid_criteria_f64(int dim, int64_t n_elements, const double* rho, 
  * (device, 3 per point, float_type).  u: HOST array of 5 device pointers. */
 int t8b200_init_kelvin_helmholtz_f32(int dim, int64_t n, const float* centers, float* const* u, void* stream);
 int t8b200_init_kelvin_helmholtz_f64(int dim, int64_t n, const double* centers, double* const* u, void* stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * 7. Output path of the subgrid manager (the step after the hot path when a run writes VTK)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Replaces column_major_to_z_order<<<N, Subgrid::block_size>>> + the device -> host copy of a float_type temporary +
+ * the host loop widening float to double (t8gpu/mesh/subgrid_mesh_manager.inl:1007-1049, :1057-1064, :1106-1109):
+ *   to[e * S + morton(i, j, k)] = (double) from[e * S + i + 4 j + 16 k],  S = 64 (dim 3) or 16 (dim 2),
+ * morton = bit interleave x, y, z (x lowest) -- the leaf order of the forest refined twice more, which is the element
+ * order t8_forest_write_vtk_ext expects.  from: device, n_elements * S cells of one variable; to: device, n_elements *
+ * S doubles, must not alias from. */
+int t8b200_subgrid_z_order_f32(int dim, int64_t n_elements, const float* from, double* to, void* stream);
+int t8b200_subgrid_z_order_f64(int dim, int64_t n_elements, const double* from, double* to, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,90 @@ LIBS = {
 }
 
 
+# The same reference translation units compiled against the PRODUCT's header mirror (include/t8gpu/) instead of the
+# reference's own t8gpu/ headers: the reference's unmodified example solvers running on this repo's managers.
+#     libmirror_uns_f32.so / _f64.so, libmirror_sg_f32.so / _f64.so   (same harness, same C symbols as libref_*)
+MIRROR_INC = os.path.join(os.path.dirname(HERE), "include")
+PRODUCT_LIBDIR = os.path.join(os.path.dirname(HERE), "t8gpu_b200")
+# every translation unit of the reference's examples (compile check of the mirror: SURVEY 8(b) source compatibility)
+EXAMPLE_TUS = ["examples/compressible_euler/kernels.cu", "examples/compressible_euler/solver.cu",
+               "examples/compressible_euler/main.cu", "examples/subgrid/kernels_2d.cu", "examples/subgrid/kernels_3d.cu",
+               "examples/subgrid/solver_2d.cu", "examples/subgrid/solver_3d.cu", "examples/subgrid/main_2d.cu",
+               "examples/subgrid/main_3d.cu"]
+
+
+def mirror_available():
+    return all(os.path.exists(os.path.join(OUT, "libmirror_%s_%s.so" % (k, p))) for k in LIBS for p in ("f32", "f64"))
+
+
+def _run_jobs(jobs, verbose=False, width=6):
+    running, pending = [], list(jobs)
+    while pending or running:
+        while pending and len(running) < width:
+            j = pending.pop(0)
+            running.append((j, subprocess.Popen(j[1], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        j, p = running.pop(0)
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(" ".join(j[1]) + "\n" + out)
+            raise RuntimeError("build failed: %s" % j[0])
+        if verbose:
+            sys.stderr.write("built %s\n" % j[0])
+
+
+def _mirror_deps():
+    deps = [os.path.join(SHIM, "t8mini.cpp"), os.path.join(SHIM, "t8.h"), os.path.join(HERE, "miniforest.c"),
+            os.path.join(MIRROR_INC, "t8gpu_b200.h")]
+    for d in (HARN, os.path.join(MIRROR_INC, "t8gpu")):
+        for dp, _, fs in os.walk(d):
+            deps += [os.path.join(dp, f) for f in fs]
+    return deps
+
+
+def build_mirror(force=False, verbose=False):
+    """The reference's example solvers (unmodified, from /root/reference) over include/t8gpu/ -> libmirror_*.so.
+    Also compiles the three main*.cu (objects only): all nine example TUs build against the mirror."""
+    if not os.path.isdir(REF):
+        return False
+    if mirror_available() and not force:
+        oldest = min(os.path.getmtime(os.path.join(OUT, "libmirror_%s_%s.so" % (k, p))) for k in LIBS for p in ("f32", "f64"))
+        if oldest > max(os.path.getmtime(d) for d in _mirror_deps()):
+            return True
+    objdir = os.path.join(OUT, "obj_mirror")
+    os.makedirs(objdir, exist_ok=True)
+    jobs, by_lib = [], {}
+    for prec in ("f32", "f64"):
+        inc = ["-I", MIRROR_INC, "-I", SHIM] + (["-DT8GPU_FLOAT_TYPE=double"] if prec == "f64" else [])
+        for kind, (tus, harness, exdir) in LIBS.items():
+            objs = by_lib.setdefault((kind, prec), [])
+            for tu in tus:
+                obj = os.path.join(objdir, "%s_%s_%s.o" % (kind, prec, os.path.basename(tu).replace(".cu", "")))
+                jobs.append((obj, ["nvcc"] + FLAGS + inc + ["-c", os.path.join(REF, tu), "-o", obj]))
+                objs.append(obj)
+            obj = os.path.join(objdir, "%s_%s_harness.o" % (kind, prec))
+            jobs.append((obj, ["nvcc"] + FLAGS + inc + ["-DT8B200_MIRROR_BUILD", "-I", os.path.join(REF, exdir), "-c",
+                                                        os.path.join(HARN, harness), "-o", obj]))
+            objs.append(obj)
+    inc = ["-I", MIRROR_INC, "-I", SHIM]
+    for tu in EXAMPLE_TUS:
+        if "main" in tu:
+            obj = os.path.join(objdir, "main_%s.o" % tu.replace("/", "_").replace(".cu", ""))
+            jobs.append((obj, ["nvcc"] + FLAGS + inc + ["-c", os.path.join(REF, tu), "-o", obj]))
+    common = []
+    for src, lang in ((os.path.join(SHIM, "t8mini.cpp"), "c++"), (os.path.join(HERE, "miniforest.c"), "c")):
+        obj = os.path.join(objdir, os.path.basename(src).split(".")[0] + ".o")
+        cmd = (["g++", "-std=c++17"] if lang == "c++" else ["gcc", "-std=gnu11"]) + ["-O2", "-fPIC", "-I", SHIM, "-c", src, "-o", obj]
+        jobs.append((obj, cmd))
+        common.append(obj)
+    _run_jobs(jobs, verbose)
+    for (kind, prec), objs in by_lib.items():
+        so = os.path.join(OUT, "libmirror_%s_%s.so" % (kind, prec))
+        subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs + common +
+                              ["-L", PRODUCT_LIBDIR, "-lt8gpu_b200", "-Xlinker", "-rpath=" + PRODUCT_LIBDIR, "-Xlinker",
+                               "-rpath=$ORIGIN/../../t8gpu_b200"])
+    return True
+
+
 def available():
     return all(os.path.exists(os.path.join(OUT, "libref_%s_%s.so" % (k, p))) for k in LIBS for p in ("f32", "f64"))
 
@@ -97,3 +181,4 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_mirror(force="--force" in sys.argv, verbose=True))

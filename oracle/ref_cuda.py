@@ -15,18 +15,27 @@ OUT = os.path.join(HERE, "_ref")
 _LIBS = {}
 
 
-def _path(kind, prec):
-    return os.path.join(OUT, "libref_%s_%s.so" % (kind, prec))
+def _path(kind, prec, mirror=False):
+    return os.path.join(OUT, "lib%s_%s_%s.so" % ("mirror" if mirror else "ref", kind, prec))
 
 
 def available():
     return all(os.path.exists(_path(k, p)) for k in ("uns", "sg") for p in ("f32", "f64"))
 
 
-def _lib(kind, prec):
-    key = (kind, prec)
+def mirror_available():
+    """libmirror_*: the SAME unmodified reference example solvers + harness, compiled against the product's header
+    mirror (include/t8gpu/) instead of the reference's t8gpu/ headers, linked with libt8gpu_b200.so."""
+    return all(os.path.exists(_path(k, p, True)) for k in ("uns", "sg") for p in ("f32", "f64"))
+
+
+def _lib(kind, prec, mirror=False):
+    key = (kind, prec, mirror)
     if key not in _LIBS:
-        L = C.CDLL(_path(kind, prec))
+        L = C.CDLL(_path(kind, prec, mirror))
+        L.t8mini_vtk_prefix.restype = C.c_char_p
+        L.t8mini_vtk_field_name.restype = C.c_char_p
+        L.t8mini_vtk_field.restype = C.c_int64
         L.ref_create.restype = C.c_void_p
         L.ref_time_steps.restype = C.c_double
         if kind == "uns":
@@ -44,11 +53,11 @@ class RefSolver:
     """kind="uns": t8gpu::CompressibleEulerSolver over MeshManager<VariableList,StepList,3>;
     kind="sg": SubgridCompressibleEulerSolver<Subgrid<4,4,4>> (dim 3) / <Subgrid<4,4>> (dim 2)."""
 
-    def __init__(self, kind, dtype, dim, level, periodic=True):
+    def __init__(self, kind, dtype, dim, level, periodic=True, mirror=False):
         self.kind, self.dim = kind, dim
         self.dtype = np.dtype(dtype)
         self.prec = "f64" if self.dtype == np.float64 else "f32"
-        self.L = _lib(kind, self.prec)
+        self.L = _lib(kind, self.prec, mirror)
         self.h = C.c_void_p(self.L.ref_create(dim, level, int(periodic)))
         self.cells_per_element = (64 if dim == 3 else 16) if kind == "sg" else 1
 
@@ -129,6 +138,26 @@ class RefSolver:
 
     def time_steps(self, dt, warmup, steps):
         return self.L.ref_time_steps(self.h, C.c_double(dt), warmup, steps)
+
+    # ---- output path: what the solver's save_* members hand to t8_forest_write_vtk_ext (captured by t8mini)
+    def save(self, what, prefix):
+        """what: "conserved" (uns: save_conserved_variables_to_vtk), "density" / "mesh" (sg: save_density_to_vtk /
+        save_mesh_to_vtk).  Returns the captured call: dict(calls, n_elements, dim, min_level, max_level, prefix,
+        fields=[(name, array)])."""
+        fn = {"conserved": "ref_save_conserved", "density": "ref_save_density", "mesh": "ref_save_mesh"}[what]
+        getattr(self.L, fn)(self.h, prefix.encode())
+        err = self.L.ref_last_cuda_error()
+        assert err == 0, "CUDA error %d" % err
+        info = (C.c_int64 * 6)()
+        self.L.t8mini_vtk_info(info)
+        fields = []
+        for k in range(info[1]):
+            n = self.L.t8mini_vtk_field(k, None, C.c_int64(0))
+            a = np.zeros(n, np.float64)
+            self.L.t8mini_vtk_field(k, _p(a), C.c_int64(n))
+            fields.append((self.L.t8mini_vtk_field_name(k).decode(), a))
+        return dict(calls=info[0], n_elements=info[2], dim=info[3], min_level=info[4], max_level=info[5],
+                    prefix=self.L.t8mini_vtk_prefix().decode(), fields=fields)
 
 
 def bench(args):

@@ -155,4 +155,8 @@ double ref_time_steps(void* h, double dt, int warmup, int steps) { return DISPAT
 void   ref_mesh_adapt(void* h, const T* crit) { DISPATCH(h, mesh_adapt(s, crit)); }
 void   ref_criteria(void* h, T* out) { DISPATCH(h, criteria(s, out)); }
 int    ref_last_cuda_error() { return (int)cudaGetLastError(); }
+// output path: SubgridCompressibleEulerSolver::save_density_to_vtk / save_mesh_to_vtk (solver.inl:268-279) ->
+// SubgridMeshManager::save_variable_to_vtk / save_mesh_to_vtk (subgrid_mesh_manager.inl:1051-1142)
+void ref_save_density(void* h, const char* prefix) { DISPATCH(h, s->save_density_to_vtk(prefix)); cudaDeviceSynchronize(); }
+void ref_save_mesh(void* h, const char* prefix) { DISPATCH(h, s->save_mesh_to_vtk(prefix)); }
 }

@@ -145,4 +145,10 @@ void ref_criteria(void* h, T* out) {
   cudaMemset(m.get_own_variable(Fluxes, Rho), 0, sizeof(T) * n);
 }
 int ref_last_cuda_error() { return (int)cudaGetLastError(); }
+// output path: CompressibleEulerSolver::save_conserved_variables_to_vtk (solver.cu:177-186) ->
+// MeshManager::get_host_{scalar,vector}_variable + save_variables_to_vtk (mesh_manager.inl:515-623)
+void ref_save_conserved(void* h, const char* prefix) {
+  static_cast<CompressibleEulerSolver*>(h)->save_conserved_variables_to_vtk(prefix);
+  cudaDeviceSynchronize();
+}
 }

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <string>
 #include <vector>
 
 extern "C" {
@@ -229,7 +230,50 @@ void t8_forest_ghost_exchange_data(t8_forest_t, sc_array*) {}
 void t8_forest_partition_data(t8_forest_t, t8_forest_t, const sc_array* in, sc_array* out) {
   memcpy(out->array, in->array, in->elem_size * in->elem_count);
 }
-int t8_forest_write_vtk_ext(t8_forest_t, const char*, int, int, int, int, int, int, int, int, t8_vtk_data_field_t*) {
+// No file is written (t8code's VTK writer is not restated); the call is captured so that tests can check WHAT the
+// managers hand to t8code: the forest (element count, levels) and the data fields.
+struct t8mini_vtk_capture {
+  int                 calls = 0, num_data = 0, dim = 0, min_level = 0, max_level = 0;
+  int64_t             n_elements = 0;
+  std::string         prefix;
+  std::vector<int>    types;
+  std::vector<std::string>         names;
+  std::vector<std::vector<double>> data;
+};
+static t8mini_vtk_capture g_vtk;
+
+int t8_forest_write_vtk_ext(t8_forest_t F, const char* prefix, int, int, int, int, int, int, int, int num_data,
+                            t8_vtk_data_field_t* fields) {
+  g_vtk.calls++;
+  g_vtk.prefix     = prefix ? prefix : "";
+  g_vtk.num_data   = num_data;
+  g_vtk.dim        = F->dim;
+  g_vtk.n_elements = mf_num_elements(F->f);
+  g_vtk.min_level = MAXL; g_vtk.max_level = 0;
+  for (auto const& e : F->elems) {
+    g_vtk.min_level = e.level < g_vtk.min_level ? e.level : g_vtk.min_level;
+    g_vtk.max_level = e.level > g_vtk.max_level ? e.level : g_vtk.max_level;
+  }
+  g_vtk.types.clear(); g_vtk.names.clear(); g_vtk.data.clear();
+  for (int k = 0; k < num_data; k++) {
+    const int comps = fields[k].type == T8_VTK_VECTOR ? 3 : 1;
+    g_vtk.types.push_back((int)fields[k].type);
+    g_vtk.names.emplace_back(fields[k].description);
+    g_vtk.data.emplace_back(fields[k].data, fields[k].data + (size_t)comps * g_vtk.n_elements);
+  }
   return 1;
+}
+// test access to the capture: info = calls, num_data, n_elements, dim, min_level, max_level
+void t8mini_vtk_info(int64_t info[6]) {
+  info[0] = g_vtk.calls; info[1] = g_vtk.num_data; info[2] = g_vtk.n_elements; info[3] = g_vtk.dim;
+  info[4] = g_vtk.min_level; info[5] = g_vtk.max_level;
+}
+const char* t8mini_vtk_prefix(void) { return g_vtk.prefix.c_str(); }
+const char* t8mini_vtk_field_name(int k) { return k < (int)g_vtk.names.size() ? g_vtk.names[k].c_str() : ""; }
+int64_t t8mini_vtk_field(int k, double* out, int64_t cap) {   // returns the number of doubles of field k (copies <= cap)
+  if (k < 0 || k >= (int)g_vtk.data.size()) return -1;
+  const int64_t n = (int64_t)g_vtk.data[k].size();
+  if (out) memcpy(out, g_vtk.data[k].data(), sizeof(double) * (size_t)(n < cap ? n : cap));
+  return n;
 }
 }  // extern "C"

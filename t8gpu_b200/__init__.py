@@ -208,13 +208,27 @@ class Plan:
             lib().t8b200_plan_destroy(self._h)
             self._h = None
 
-    def stage(self, stage, inp, prev, out, vol, dt, in_all=None, speed_max=None, stream=None):
+    def stage(self, stage, inp, prev, out, vol, dt, in_all=None, speed_max=None, stream=None, dt_dev=None,
+              sync=None):
+        """One fused RK stage.  dt_dev: device scalar holding the time step (then `dt` is ignored); sync: a
+        PeerMailboxes whose stage epochs order this launch against the peers inside the kernel (boundary chunks wait
+        for the previous launch of every peer, the last of them signals this one)."""
         s, ft = _sfx(self.dtype)
-        fn = getattr(lib(), "t8b200_fused_stage_" + s)
-        check(fn(self._h, stage, ptrs(inp), in_all.host if in_all is not None else None,
-                 ptrs(prev) if prev is not None else None, ptrs(out), C.c_void_p(vol.data_ptr()), ft(dt),
-                 C.c_void_p(speed_max.data_ptr() if speed_max is not None else None), stream_ptr(stream)),
-              "fused_stage")
+        if dt_dev is None and sync is None:
+            fn = getattr(lib(), "t8b200_fused_stage_" + s)
+            check(fn(self._h, stage, ptrs(inp), in_all.host if in_all is not None else None,
+                     ptrs(prev) if prev is not None else None, ptrs(out), C.c_void_p(vol.data_ptr()), ft(dt),
+                     C.c_void_p(speed_max.data_ptr() if speed_max is not None else None), stream_ptr(stream)),
+                  "fused_stage")
+            return
+        wait, signal = sync.next_stage() if sync is not None else (0, 0)
+        check(getattr(lib(), "t8b200_fused_stage_sync_" + s)(
+            self._h, stage, ptrs(inp), in_all.host if in_all is not None else None,
+            ptrs(prev) if prev is not None else None, ptrs(out), C.c_void_p(vol.data_ptr()), ft(dt),
+            C.c_void_p(dt_dev.data_ptr() if dt_dev is not None else None),
+            C.c_void_p(speed_max.data_ptr() if speed_max is not None else None),
+            C.byref(sync.struct) if sync is not None else None, C.c_longlong(wait), C.c_longlong(signal),
+            stream_ptr(stream)), "fused_stage_sync")
 
 
 class SubgridPlan:
@@ -257,12 +271,21 @@ class SubgridPlan:
             lib().t8b200_subgrid_plan_destroy(self._h)
             self._h = None
 
-    def stage(self, stage, inp, prev, out, vol, dt, in_all=None, stream=None):
+    def stage(self, stage, inp, prev, out, vol, dt, in_all=None, stream=None, dt_dev=None, sync=None):
         s, ft = _sfx(self.dtype)
-        check(getattr(lib(), "t8b200_subgrid_fused_stage_" + s)(
+        if dt_dev is None and sync is None:
+            check(getattr(lib(), "t8b200_subgrid_fused_stage_" + s)(
+                self._h, stage, ptrs(inp), in_all.host if in_all is not None else None,
+                ptrs(prev) if prev is not None else None, ptrs(out), C.c_void_p(vol.data_ptr()), ft(dt),
+                stream_ptr(stream)), "subgrid_fused_stage")
+            return
+        wait, signal = sync.next_stage() if sync is not None else (0, 0)
+        check(getattr(lib(), "t8b200_subgrid_fused_stage_sync_" + s)(
             self._h, stage, ptrs(inp), in_all.host if in_all is not None else None,
             ptrs(prev) if prev is not None else None, ptrs(out), C.c_void_p(vol.data_ptr()), ft(dt),
-            stream_ptr(stream)), "subgrid_fused_stage")
+            C.c_void_p(dt_dev.data_ptr() if dt_dev is not None else None),
+            C.byref(sync.struct) if sync is not None else None, C.c_longlong(wait), C.c_longlong(signal),
+            stream_ptr(stream)), "subgrid_fused_stage_sync")
 
 
 # ------------------------------------------------------------------------------------------------ Cartesian meshes
@@ -361,6 +384,20 @@ def subgrid_criteria(dim, rho, vol, out=None, stream=None):
     return out
 
 
+def subgrid_z_order(dim, cells, out=None, stream=None):
+    """column_major_to_z_order + widening to double (output path of SubgridMeshManager::save_variable_to_vtk): cells =
+    device tensor of n_elements * 64 (16) values of one variable -> float64 tensor in the Morton order of the cells."""
+    torch = _torch()
+    s, _ = _sfx(cells.dtype)
+    S = 64 if dim == 3 else 16
+    if out is None:
+        out = torch.empty(cells.numel(), dtype=torch.float64, device=cells.device)
+    check(getattr(lib(), "t8b200_subgrid_z_order_" + s)(int(dim), C.c_int64(cells.numel() // S),
+                                                        C.c_void_p(cells.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                        stream_ptr(stream)), "subgrid_z_order")
+    return out
+
+
 class SharedBuffer:
     """A device allocation that other processes on this node can map (cudaIpc handle exchange is up to the caller).
     `.tensor(shape, dtype)` views it as a torch tensor; `.handle` is the 64-byte IPC handle."""
@@ -404,17 +441,27 @@ class SharedBuffer:
             self.ptr = None
 
 
+class _StageSyncStruct(C.Structure):
+    _fields_ = [("nranks", C.c_int), ("rank", C.c_int), ("mailboxes_dev", C.c_void_p), ("counter_dev", C.c_void_p)]
+
+
 class PeerMailboxes:
-    """Mailboxes of t8b200_peer_barrier: one SharedBuffer of nranks 16-byte slots per rank, mapped on every rank.
-    `exchange(handles)`: handles = list over ranks of the 64-byte IPC handles (this rank's own entry is ignored)."""
+    """Mailboxes of t8b200_peer_barrier / t8b200_fused_stage_sync_*: one SharedBuffer of 4 * nranks 16-byte slots per
+    rank, mapped on every rank (layout in csrc/peer_sync.cuh).
+    `exchange(handles)`: handles = list over ranks of the 64-byte IPC handles (this rank's own entry is ignored).
+    Two epoch sequences, consecutive per class on every rank: `stage_epoch` (barriers without a value and the stage
+    kernels that order themselves) and `cfl_epoch` (barriers that carry the max wave speed)."""
 
     def __init__(self, rank, nranks, device):
         torch = _torch()
         self.rank, self.nranks, self.device = rank, nranks, device
         # a whole 2 MiB granule of its own, so that the IPC handle maps exactly this buffer
-        self.buf = SharedBuffer(max(16 * nranks, 2 << 20), device)
-        self.epoch = 0
+        self.buf = SharedBuffer(max(64 * nranks, 2 << 20), device)
+        self.stage_epoch = 0
+        self.cfl_epoch = 0
         self.table = None
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.struct = None
 
     @property
     def handle(self):
@@ -423,16 +470,31 @@ class PeerMailboxes:
     def exchange(self, handles):
         torch = _torch()
         ptrs_ = [self.buf.ptr if r == self.rank else self.buf.open_peer(handles[r]) for r in range(self.nranks)]
+        self.set_table(ptrs_)
+
+    def set_table(self, ptrs_):
+        """ptrs_: mailbox address of every rank as seen from this rank's device."""
+        torch = _torch()
         self.table = torch.tensor(ptrs_, dtype=torch.int64).to(self.device)
+        self.struct = _StageSyncStruct(self.nranks, self.rank, self.table.data_ptr(), self.counter.data_ptr())
+
+    def next_stage(self):
+        """(wait_epoch, signal_epoch) of the next self-ordering stage launch."""
+        self.stage_epoch += 1
+        return self.stage_epoch - 1, self.stage_epoch
 
     def barrier(self, value=None, out=None, stream=None):
-        """Stage barrier on `stream`; with value / out (device scalars) also the maximum over the ranks."""
-        self.epoch += 1
+        """Barrier kernel on `stream`; with value / out (device scalars) also the maximum over the ranks."""
         is64 = 1
         if value is not None:
             s, _ = _sfx(value.dtype)
             is64 = int(s == "f64")
-        check(lib().t8b200_peer_barrier(self.nranks, self.rank, C.c_longlong(self.epoch),
+            self.cfl_epoch += 1
+            epoch = self.cfl_epoch
+        else:
+            self.stage_epoch += 1
+            epoch = self.stage_epoch
+        check(lib().t8b200_peer_barrier(self.nranks, self.rank, C.c_longlong(epoch),
                                         C.c_void_p(self.table.data_ptr()),
                                         C.c_void_p(value.data_ptr() if value is not None else None), is64,
                                         C.c_void_p(out.data_ptr() if out is not None else None), stream_ptr(stream)),
@@ -440,6 +502,13 @@ class PeerMailboxes:
 
     def close(self):
         self.buf.close()
+
+
+def timestep(speed_max, cfl, length, dt_cap, dt_dev, stream=None):
+    """compute_timestep's formula on the device: dt_dev <- min(dt_cap, cfl * length / speed_max) (dt_cap <= 0: none)."""
+    s, ft = _sfx(speed_max.dtype)
+    check(getattr(lib(), "t8b200_timestep_" + s)(C.c_void_p(speed_max.data_ptr()), ft(cfl), ft(length), ft(dt_cap),
+                                                 C.c_void_p(dt_dev.data_ptr()), stream_ptr(stream)), "timestep")
 
 
 class PointerTables:

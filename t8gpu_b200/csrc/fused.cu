@@ -18,6 +18,7 @@
 #include "../../include/t8gpu_b200.h"
 #include "common.cuh"
 #include "euler_flux.cuh"
+#include "peer_sync.cuh"
 #include "tile_plan.cuh"
 
 using namespace t8b200;
@@ -48,6 +49,9 @@ struct FusedArgs {
   int             vol_shift;
   T               vol_scale;
   T               dt;
+  const T*        dt_ptr;       // non-null: the time step is read from device memory (t8b200_timestep_*)
+  StageSync       sync;         // multi-GPU stage ordering done by the kernel itself (mailboxes == nullptr: off)
+  int             n_boundary;   // the first n_boundary CTAs are partition-boundary chunks (they read ghost elements)
   T*              speed_max;
   int64_t         n_local;
   int             stage;
@@ -277,6 +281,13 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     load_halo(idx, rk, a0, a1, a2, a3, a4);
     sm.store_cell(EC + h, to_cell(a0, a1, a2, a3, a4));
   };
+  // partition-boundary chunk: the peers' previous stage must be complete before their elements are read (everything
+  // requested so far is this rank's own data or plan data)
+  const bool bnd = SPLIT && A.sync.mailboxes != nullptr && (int)blockIdx.x < A.n_boundary;
+  if (bnd && A.sync.wait_epoch > 0) {
+    if (tid < 32) stage_wait(A.sync, tid);
+    __syncthreads();
+  }
   // the gathers of the halo states are issued before the own elements are converted: the two latencies overlap
   T g0 = T(1), g1 = T(0), g2 = T(0), g3 = T(0), g4 = T(1);
   if (hidx >= 0) load_halo(hidx, hrk, g0, g1, g2, g3, g4);
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     const int4 h1b = __ldg(A.hdr + 2 * c + 1);
     ovf = make_int2(h1b.y, h1b.z);
   }
-  T sc = fast_rcp(vol) * A.dt;   // before the barrier: the reciprocal chain hides in the wait
+  T sc = fast_rcp(vol) * (A.dt_ptr ? __ldg(A.dt_ptr) : A.dt);   // before the barrier: the reciprocal chain hides in the wait
   if (stage == 2) sc *= T(0.25);
   if (stage == 3) sc *= T(0.66666666666666);
   T8B_CLK(3);
@@ -472,6 +483,10 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
       atomic_max_nonneg(A.speed_max, m);
     }
   }
+  if (bnd && A.sync.signal_epoch > 0) {   // every store of this chunk precedes the count (and the flag behind it)
+    __syncthreads();
+    if (tid == 0) stage_signal(A.sync);
+  }
 }
 
 template <typename T, int MS, int MF, int MINB, bool CMP, bool SPLIT, bool SMAX>
@@ -482,18 +497,22 @@ static int launch_variant(const t8b200_plan* P, const FusedArgs<T>& A, cudaStrea
 #else
   constexpr size_t smem = Smem<T, MS, MF>::bytes;
 #endif
-  static int resident = -1;   // CTAs of this variant the device holds at once
-  if (resident < 0) {
+  // CTAs of this variant the device holds at once; the opt-in above 48 KB of shared memory is per device, so it is
+  // set and cached per device id (a process-wide flag broke a second device / a device reset)
+  static int resident[64];
+  int        dev = 0;
+  T8B_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (resident[dev] == 0) {
     T8B_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 0, per_sm = 0;
-    T8B_TRY(cudaGetDevice(&dev));
+    int sms = 0, per_sm = 0;
     T8B_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     T8B_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, EC, smem));
-    resident = std::max(1, sms * per_sm);
+    resident[dev] = std::max(1, sms * per_sm);
   }
   FusedArgs<T> B = A;
   static const int wave_knob = getenv("T8B200_WAVE") ? atoi(getenv("T8B200_WAVE")) : -1;   // tuning knob
-  B.wave = wave_knob >= 0 ? wave_knob : resident;
+  B.wave = wave_knob >= 0 ? wave_knob : resident[dev];
   for (int k = 0; k < 16; k++) { B.pf_ptr[k] = nullptr; B.pf_unit[k] = 0; }
   for (int k = 0; k < 5; k++) {
     if (B.stage != 1) { B.pf_ptr[k] = (const char*)B.prev[k]; B.pf_unit[k] = sizeof(T); }
@@ -532,10 +551,19 @@ static int launch_fused(const t8b200_plan* P, const FusedArgs<T>& A, cudaStream_
 
 template <typename T>
 static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
-                            const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream) {
+                            const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
+                            const T* dt_dev = nullptr, const t8b200_stage_sync* sync = nullptr,
+                            long long wait_epoch = 0, long long signal_epoch = 0) {
   if (!P || stage < 1 || stage > 3 || !in || !out || !vol || (stage > 1 && !prev)) return cudaErrorInvalidValue;
   if (P->is_f64 != (sizeof(T) == 8) || P->host_only) return cudaErrorInvalidValue;
   if (P->multi && !in_all) return cudaErrorInvalidValue;
+  // CTAs read halo states from `in` (or the peers' `in`) while other CTAs write `out`: an in-place call would race
+  // silently; the reference-shaped rk3_stage tolerates out == prev, this entry point does not
+  for (int k = 0; k < 5; k++)
+    if (!in[k] || !out[k] || out[k] == in[k] || (stage > 1 && (!prev[k] || out[k] == prev[k]))) return cudaErrorInvalidValue;
+  if (sync && (sync->nranks < 1 || sync->nranks > 32 || sync->rank < 0 || sync->rank >= sync->nranks ||
+               !sync->mailboxes_dev || !sync->counter_dev || wait_epoch < 0 || signal_epoch < 0 || !P->multi))
+    return cudaErrorInvalidValue;
   if (P->n_chunks == 0) return cudaSuccess;
   FusedArgs<T> A{};
   A.hdr = reinterpret_cast<const int4*>(P->hdr);
@@ -552,13 +580,23 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
   }
   A.vol = vol; A.vol_shift = P->vol_shift; A.vol_scale = (T)P->vol_scale; A.dt = dt; A.speed_max = speed_max; A.n_local = P->n_local;
   A.stage = stage; A.multi = P->multi; A.my_rank = P->my_rank;
+  A.dt_ptr = dt_dev;
+  StageSync S{};
+  if (sync) {
+    S.mailboxes = (PeerSlot* const*)sync->mailboxes_dev; S.counter = sync->counter_dev;
+    S.wait_epoch = wait_epoch; S.signal_epoch = signal_epoch;
+    S.nranks = sync->nranks; S.rank = sync->rank; S.n_boundary_total = P->nb_struct + P->nb_generic;
+    A.sync = S;
+    A.n_boundary = P->nb_generic;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), st));
   if (P->n_struct) {   // the structured chunks (structured.cu); what is left goes through the chunk list
-    const int rc = t8b_structured_stage_run<T>(P, stage, in, in_all, prev, out, vol, dt, speed_max, stream);
+    const int rc = t8b_structured_stage_run<T>(P, stage, in, in_all, prev, out, vol, dt, speed_max, stream, dt_dev,
+                                               sync ? &S : nullptr);
     if (rc != 0 || P->n_generic == 0) return rc;
-    A.chunk_list = P->g_list;
   }
+  if (P->g_list) A.chunk_list = P->g_list;   // structured chunks elsewhere and / or boundary-first order (multi)
   return P->cmp ? launch_fused<T, true>(P, A, st) : launch_fused<T, false>(P, A, st);
 }
 
@@ -588,13 +626,17 @@ struct MeshFaces {
 
 template <typename T>
 int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
-                        const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream) {
-  return fused_stage_impl<T>(P, stage, in, in_all, prev, out, vol, dt, speed_max, stream);
+                        const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
+                        const T* dt_dev, const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch) {
+  return fused_stage_impl<T>(P, stage, in, in_all, prev, out, vol, dt, speed_max, stream, dt_dev, sync, wait_epoch,
+                             signal_epoch);
 }
 template int t8b_fused_stage_run<float>(const t8b200_plan*, int, const float* const*, const float* const* const*,
-                                        const float* const*, float* const*, const float*, float, float*, void*);
+                                        const float* const*, float* const*, const float*, float, float*, void*,
+                                        const float*, const t8b200_stage_sync*, long long, long long);
 template int t8b_fused_stage_run<double>(const t8b200_plan*, int, const double* const*, const double* const* const*,
-                                         const double* const*, double* const*, const double*, double, double*, void*);
+                                         const double* const*, double* const*, const double*, double, double*, void*,
+                                         const double*, const t8b200_stage_sync*, long long, long long);
 
 void t8b_plan_free(t8b200_plan* P) { t8b200_plan_destroy(P); }
 
@@ -708,6 +750,22 @@ int t8b200_fused_stage_f64(const t8b200_plan* plan, int stage, const double* con
                            const double* const* const* in_all, const double* const* prev, double* const* out,
                            const double* vol, double dt, double* speed_max_dev, void* stream) {
   return fused_stage_impl<double>(plan, stage, in, in_all, prev, out, vol, dt, speed_max_dev, stream);
+}
+int t8b200_fused_stage_sync_f32(const t8b200_plan* plan, int stage, const float* const* in,
+                                const float* const* const* in_all, const float* const* prev, float* const* out,
+                                const float* vol, float dt, const float* dt_dev, float* speed_max_dev,
+                                const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
+                                void* stream) {
+  return fused_stage_impl<float>(plan, stage, in, in_all, prev, out, vol, dt, speed_max_dev, stream, dt_dev, sync,
+                                 wait_epoch, signal_epoch);
+}
+int t8b200_fused_stage_sync_f64(const t8b200_plan* plan, int stage, const double* const* in,
+                                const double* const* const* in_all, const double* const* prev, double* const* out,
+                                const double* vol, double dt, const double* dt_dev, double* speed_max_dev,
+                                const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
+                                void* stream) {
+  return fused_stage_impl<double>(plan, stage, in, in_all, prev, out, vol, dt, speed_max_dev, stream, dt_dev, sync,
+                                  wait_epoch, signal_epoch);
 }
 
 }  // extern "C"

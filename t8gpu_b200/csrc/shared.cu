@@ -5,6 +5,7 @@
 
 #include "../../include/t8gpu_b200.h"
 #include "common.cuh"
+#include "peer_sync.cuh"
 
 extern "C" {
 
@@ -35,33 +36,31 @@ int t8b200_shared_free(void* dev_ptr) { return dev_ptr ? cudaFree(dev_ptr) : 0; 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Stage barrier + max-reduction between the GPUs of one node over peer memory (one process per GPU).
-// Replaces cudaDeviceSynchronize() + MPI_Barrier between the phases of iterate() (examples/compressible_euler/
-// solver.cu:98-99, ...) and the MPI_Allreduce(MAX) of compute_timestep (solver.cu:219-223) without leaving the stream:
-// every rank stores (value, epoch) into its slot of EVERY rank's mailbox through the peer-mapped pointers (NVLink),
-// then waits until all slots of its own mailbox carry the epoch.  One warp, one lane per rank.  Kernels of different
-// ranks run on different GPUs, so none of them can keep another from being scheduled.
+// Stage barrier + max-reduction between the GPUs of one node over peer memory (one process per GPU); mailbox layout
+// and protocol in peer_sync.cuh.  One warp, one lane per rank: every rank stores (value, epoch) into its slot of EVERY
+// rank's mailbox through the peer-mapped pointers (NVLink), then waits until all slots of its own mailbox carry the
+// epoch.  Kernels of different ranks run on different GPUs, so none of them can keep another from being scheduled.
+// Two slot classes with their own epoch sequences: without a value the stage slots (the same ones the stage kernels
+// signal through when they order themselves, t8b200_fused_stage_sync_*), with a value the CFL slots.
 namespace {
-struct Slot { double value; long long epoch; };
+using t8b200::PeerSlot;
 
-__global__ void peer_barrier_kernel(int nranks, int rank, long long epoch, Slot* const* mailboxes, const void* value,
+__global__ void peer_barrier_kernel(int nranks, int rank, long long epoch, PeerSlot* const* mailboxes, const void* value,
                                     int value_is_f64, void* out_max) {
   const int lane = threadIdx.x;
+  const int base = (value ? 2 * nranks : 0) + (int)(epoch & 1) * nranks;
   double    v    = 0.0;
   if (value) v = value_is_f64 ? *(const double*)value : (double)*(const float*)value;
   if (lane < nranks) {
-    Slot* s = mailboxes[lane] + rank;
+    PeerSlot* s = mailboxes[lane] + base + rank;
     // value first, then the epoch with release semantics at system scope (the reader acquires the epoch)
     asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&s->value), "d"(v) : "memory");
-    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(&s->epoch), "l"(epoch) : "memory");
+    t8b200::peer_store_epoch(s, epoch);
   }
   double m = 0.0;
   if (lane < nranks) {
-    const Slot* s = mailboxes[rank] + lane;
-    long long   e;
-    do {
-      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(e) : "l"(&s->epoch) : "memory");
-    } while (e < epoch);
+    const PeerSlot* s = mailboxes[rank] + base + lane;
+    while (t8b200::peer_load_epoch(s) < epoch) {}
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(m) : "l"(&s->value) : "memory");
   }
   if (out_max) {
@@ -71,12 +70,34 @@ __global__ void peer_barrier_kernel(int nranks, int rank, long long epoch, Slot*
     }
   }
 }
+
+// CompressibleEulerSolver::compute_timestep (examples/compressible_euler/solver.cu:225-228) without leaving the device:
+// dt = cfl * length / vmax, optionally capped; the stage kernels of the next step read it from dt_out.
+template <typename T>
+__global__ void timestep_kernel(const T* vmax, T cfl, T length, T dt_cap, T* dt_out) {
+  T dt = cfl * length / *vmax;
+  if (dt_cap > T(0) && !(dt < dt_cap)) dt = dt_cap;   // also catches vmax == 0 (inf) and NaN
+  *dt_out = dt;
+}
 }  // namespace
 
 extern "C" int t8b200_peer_barrier(int nranks, int rank, long long epoch, void* const* mailboxes_dev,
                                    const void* value_dev, int value_is_f64, void* out_max_dev, void* stream) {
   if (nranks < 1 || nranks > 32 || rank < 0 || rank >= nranks || epoch <= 0 || !mailboxes_dev) return cudaErrorInvalidValue;
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(nranks, rank, epoch, (Slot* const*)mailboxes_dev, value_dev,
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(nranks, rank, epoch, (PeerSlot* const*)mailboxes_dev, value_dev,
                                                           value_is_f64, out_max_dev);
+  return cudaGetLastError();
+}
+
+extern "C" int t8b200_timestep_f32(const float* speed_max_dev, float cfl, float length, float dt_cap, float* dt_dev,
+                                   void* stream) {
+  if (!speed_max_dev || !dt_dev) return cudaErrorInvalidValue;
+  timestep_kernel<float><<<1, 1, 0, (cudaStream_t)stream>>>(speed_max_dev, cfl, length, dt_cap, dt_dev);
+  return cudaGetLastError();
+}
+extern "C" int t8b200_timestep_f64(const double* speed_max_dev, double cfl, double length, double dt_cap, double* dt_dev,
+                                   void* stream) {
+  if (!speed_max_dev || !dt_dev) return cudaErrorInvalidValue;
+  timestep_kernel<double><<<1, 1, 0, (cudaStream_t)stream>>>(speed_max_dev, cfl, length, dt_cap, dt_dev);
   return cudaGetLastError();
 }

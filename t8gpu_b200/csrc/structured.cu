@@ -23,6 +23,7 @@
 #include "box_layout.cuh"
 #include "common.cuh"
 #include "euler_flux.cuh"
+#include "peer_sync.cuh"
 #include "tile_plan.cuh"
 
 using namespace t8b200;
@@ -41,6 +42,9 @@ struct SArgs {
   int            vol_shift;
   T              vol_scale;
   T              dt;
+  const T*       dt_ptr;  // non-null: the time step is read from device memory (t8b200_timestep_*)
+  StageSync      sync;    // multi-GPU stage ordering done by the kernel itself (mailboxes == nullptr: off)
+  int            n_boundary;   // the first n_boundary CTAs are partition-boundary chunks (they read ghost elements)
   T*             speed_max;
   int            stage, multi, my_rank;
   int            dense;   // every chunk of the plan is structured: chunk b = elements [256 b, 256 b + 256), one area
@@ -93,6 +97,13 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
   int       hrk  = A.my_rank;
   if (A.multi) hrk = __ldg(A.hrank + b * 256 + tid);
   const T u0 = A.in[0][e], u1 = A.in[1][e], u2 = A.in[2][e], u3 = A.in[3][e], u4 = A.in[4][e];
+  // partition-boundary chunk: the peers' previous stage must be complete before their elements are read (the loads
+  // above are this rank's own data and already in flight)
+  const bool bnd = A.sync.mailboxes != nullptr && b < A.n_boundary;
+  if (bnd && A.sync.wait_epoch > 0) {
+    if (tid < 32) stage_wait(A.sync, tid);
+    __syncthreads();
+  }
   if (A.pf_ok && (tid & 31) == 0) {
     // L2 prefetch hints, one or two per warp: the phase-2 operands of this chunk (rows of U^n, volume) and the streams
     // of the chunk that takes over this CTA slot about one wave later (CTAs are dispatched in index order)
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
 #pragma unroll
     for (int k = 0; k < 5; k++) base[k] = cp * A.prev[k][e] + ci * base[k];
   }
-  T sc = fast_rcp(vol) * A.dt;
+  T sc = fast_rcp(vol) * (A.dt_ptr ? __ldg(A.dt_ptr) : A.dt);
   if (stage == 2) sc *= T(0.25);
   if (stage == 3) sc *= T(0.66666666666666);
   sc *= A.area_tab[area_idx];
@@ -185,6 +196,10 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
       for (int w = 1; w < 8; w++) m = fmax_(m, red[w]);
       atomic_max_nonneg(A.speed_max, m);
     }
+  }
+  if (bnd && A.sync.signal_epoch > 0) {   // every store of this chunk precedes the count (and the flag behind it)
+    __syncthreads();
+    if (tid == 0) stage_signal(A.sync);
   }
 }
 
@@ -212,9 +227,13 @@ static int s_launch(const t8b200_plan* P, SArgs<T>& A, cudaStream_t st) {
 
 template <typename T>
 int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
-                             const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream) {
+                             const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
+                             const T* dt_dev, const StageSync* sync) {
   if (P->n_struct == 0) return cudaSuccess;
   SArgs<T> A{};
+  A.dt_ptr = dt_dev;
+  if (sync) A.sync = *sync;
+  A.n_boundary = P->nb_struct;
   A.rec = reinterpret_cast<const int4*>(P->s_rec); A.halo = P->s_halo; A.hrank = P->s_hrank;
   A.area_tab = (const T*)P->area_tab;
   bool aligned = ((uintptr_t)vol & 15u) == 0 && ((uintptr_t)P->s_halo & 15u) == 0;
@@ -227,7 +246,7 @@ int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in
   }
   A.vol = vol; A.vol_shift = P->vol_shift; A.vol_scale = (T)P->vol_scale; A.dt = dt; A.speed_max = speed_max;
   A.stage = stage; A.multi = P->multi; A.my_rank = P->my_rank;
-  A.dense = (P->n_struct == P->n_chunks && !P->split) ? 1 : 0;
+  A.dense = (P->n_struct == P->n_chunks && !P->split && !P->multi) ? 1 : 0;   // multi: boundary chunks come first
   A.area0 = P->s_area0;
   A.pf_ok = aligned ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -236,7 +255,8 @@ int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in
   return speed_max ? s_launch<T, MortonBox, true>(P, A, st) : s_launch<T, MortonBox, false>(P, A, st);
 }
 template int t8b_structured_stage_run<float>(const t8b200_plan*, int, const float* const*, const float* const* const*,
-                                             const float* const*, float* const*, const float*, float, float*, void*);
+                                             const float* const*, float* const*, const float*, float, float*, void*,
+                                             const float*, const StageSync*);
 template int t8b_structured_stage_run<double>(const t8b200_plan*, int, const double* const*,
                                               const double* const* const*, const double* const*, double* const*,
-                                              const double*, double, double*, void*);
+                                              const double*, double, double*, void*, const double*, const StageSync*);

@@ -497,4 +497,22 @@ int t8b200_subgrid_fused_stage_f64(const t8b200_subgrid_plan* SP, int stage, con
   if (!SP) return cudaErrorInvalidValue;
   return t8b_fused_stage_run<double>(SP->plan, stage, in, in_all, prev, out, vol, dt, nullptr, stream);
 }
+int t8b200_subgrid_fused_stage_sync_f32(const t8b200_subgrid_plan* SP, int stage, const float* const* in,
+                                        const float* const* const* in_all, const float* const* prev,
+                                        float* const* out, const float* vol, float dt, const float* dt_dev,
+                                        const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
+                                        void* stream) {
+  if (!SP) return cudaErrorInvalidValue;
+  return t8b_fused_stage_run<float>(SP->plan, stage, in, in_all, prev, out, vol, dt, nullptr, stream, dt_dev, sync,
+                                    wait_epoch, signal_epoch);
+}
+int t8b200_subgrid_fused_stage_sync_f64(const t8b200_subgrid_plan* SP, int stage, const double* const* in,
+                                        const double* const* const* in_all, const double* const* prev,
+                                        double* const* out, const double* vol, double dt, const double* dt_dev,
+                                        const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
+                                        void* stream) {
+  if (!SP) return cudaErrorInvalidValue;
+  return t8b_fused_stage_run<double>(SP->plan, stage, in, in_all, prev, out, vol, dt, nullptr, stream, dt_dev, sync,
+                                     wait_epoch, signal_epoch);
+}
 }

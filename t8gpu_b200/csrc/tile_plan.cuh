@@ -90,7 +90,10 @@ struct t8b200_plan {
   int32_t* s_rec    = nullptr;  // 4 per structured chunk: first element, area index, chunk id, 0
   int32_t* s_halo   = nullptr;  // 256 per structured chunk, thread order, index into the owner's arrays
   int32_t* s_hrank  = nullptr;  // owner ranks (multi only)
-  int32_t* g_list   = nullptr;  // chunk ids left to the generic kernel (n_generic entries; only when n_struct > 0)
+  int32_t* g_list   = nullptr;  // chunk ids left to the generic kernel (n_generic entries; when n_struct > 0 or multi)
+  // multi: partition-boundary chunks (some halo element lives on another rank) come first in s_rec / s_halo / s_hrank
+  // and in g_list, so that the stage kernels can wait for / signal the peers from those chunks alone (peer_sync.cuh)
+  int      nb_struct = 0, nb_generic = 0;
   // volume lookup of the stage kernel: volume of element e = vol[e >> vol_shift] * vol_scale (subgrid cells share
   // their element's volume: shift 6 / 4, scale 1/64 / 1/16, ssp_runge_kutta.inl:116)
   int    vol_shift = 0;
@@ -621,7 +624,36 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     P->n_struct  = (int)(s_rec.size() / 4);
     P->n_generic = P->n_struct ? (int)g_list.size() : nchunks;
     P->s_area0   = P->n_struct ? s_rec[1] : 0;
-    if (!P->n_struct) g_list.clear();
+    if (!P->n_struct && !multi) g_list.clear();
+    if (multi) {
+      // partition-boundary chunks first (stable): the stage kernels order themselves against the peers from those
+      // chunks alone (peer_sync.cuh); every rank must signal, so a rank without any gets one nominal boundary chunk
+      const int32_t me = P->my_rank;
+      std::vector<uint8_t> sb(P->n_struct, 0), gb(g_list.size(), 0);
+      for (int q = 0; q < P->n_struct; q++)
+        for (int i = 0; i < 256; i++)
+          if (s_hrank[(size_t)q * 256 + i] != me) { sb[q] = 1; break; }
+      for (size_t q = 0; q < g_list.size(); q++) {
+        const size_t c = (size_t)g_list[q];
+        for (int h = 0; h < HS; h++)
+          if (halo_elem[c * HS + h] >= 0 && halo_rank[c * HS + h] != me) { gb[q] = 1; break; }
+      }
+      std::vector<int32_t> r2, h2, k2, g2;
+      r2.reserve(s_rec.size()); h2.reserve(s_halo.size()); k2.reserve(s_hrank.size()); g2.reserve(g_list.size());
+      for (int pass = 1; pass >= 0; pass--) {
+        for (int q = 0; q < P->n_struct; q++)
+          if (sb[q] == pass) {
+            r2.insert(r2.end(), s_rec.begin() + (size_t)q * 4, s_rec.begin() + (size_t)q * 4 + 4);
+            h2.insert(h2.end(), s_halo.begin() + (size_t)q * 256, s_halo.begin() + (size_t)q * 256 + 256);
+            k2.insert(k2.end(), s_hrank.begin() + (size_t)q * 256, s_hrank.begin() + (size_t)q * 256 + 256);
+          }
+        for (size_t q = 0; q < g_list.size(); q++)
+          if (gb[q] == pass) g2.push_back(g_list[q]);
+        if (pass == 1) { P->nb_struct = (int)(r2.size() / 4); P->nb_generic = (int)g2.size(); }
+      }
+      s_rec.swap(r2); s_halo.swap(h2); s_hrank.swap(k2); g_list.swap(g2);
+      if (P->nb_struct + P->nb_generic == 0 && nchunks > 0) { if (P->n_struct) P->nb_struct = 1; else P->nb_generic = 1; }
+    }
   }
   P->n_halo     = n_halo;
   P->n_records  = n_rec;
@@ -671,18 +703,22 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     P->s_rec  = upload(s_rec, P->dev_bytes, err);
     P->s_halo = upload(s_halo, P->dev_bytes, err);
     if (P->multi) P->s_hrank = upload(s_hrank, P->dev_bytes, err);
-    if (P->n_generic) P->g_list = upload(g_list, P->dev_bytes, err);
   }
+  if (!g_list.empty()) P->g_list = upload(g_list, P->dev_bytes, err);
   lap("upload");
   return err;
 }
 
-// defined in fused.cu (explicitly instantiated for float and double)
+namespace t8b200 { struct StageSync; }
+// defined in fused.cu (explicitly instantiated for float and double); dt_dev / sync: see t8b200_fused_stage_sync_*
 template <typename T>
 int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
-                        const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream);
+                        const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
+                        const T* dt_dev = nullptr, const t8b200_stage_sync* sync = nullptr, long long wait_epoch = 0,
+                        long long signal_epoch = 0);
 // defined in structured.cu: the structured chunks of the plan (no-op when it has none)
 template <typename T>
 int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
-                             const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream);
+                             const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
+                             const T* dt_dev, const t8b200::StageSync* sync);
 void t8b_plan_free(t8b200_plan* P);

@@ -196,3 +196,24 @@ def test_bench_subgrid_brick_ranks_agree_with_one_rank(cuda):
                 plans[r].stage(stage, v(sin), v(prv), v(sout), conns[r]["volumes"], dt, in_all=tabs[sin])
         got = np.concatenate([bufs[r][nxt * 5:(nxt + 1) * 5].cpu().numpy() for r in range(P)], axis=1)
         assert rel_linf(got, one.state().cpu().numpy()) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_z_order_output_kernel(cuda, dim, dtype):
+    """t8b200_subgrid_z_order: out[e*S + morton(i,j,k)] = double(in[e*S + i + 4j + 16k])
+    (column_major_to_z_order, t8gpu/mesh/subgrid_mesh_manager.inl:1007-1049, plus the host widening loop :1106-1109)."""
+    import t8gpu_b200
+    S = 64 if dim == 3 else 16
+    n = 1000
+    x = torch.rand(n * S, dtype=dtype, device=cuda)
+    got = t8gpu_b200.subgrid_z_order(dim, x).cpu().numpy()
+    perm = np.zeros(S, np.int64)
+    for flat in range(S):
+        i, j, k = flat & 3, (flat >> 2) & 3, flat >> 4
+        mo = 0
+        for l in range(2):
+            mo |= ((i >> l) & 1) << (dim * l) | ((j >> l) & 1) << (dim * l + 1) | (((k >> l) & 1) << (dim * l + 2) if dim == 3 else 0)
+        perm[mo] = flat
+    want = x.cpu().numpy().astype(np.float64).reshape(n, S)[:, perm].reshape(-1)
+    assert got.dtype == np.float64 and np.array_equal(got, want)
