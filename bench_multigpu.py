@@ -6,7 +6,12 @@ live state arrays through peer-mapped pointers (NVLink); every rank evaluates al
 (owner computes, no remote atomics).
 
 Stage ordering across ranks (T8B200_SYNC):
-  kernel (default)  the stage kernels order themselves: the chunks that read ghost elements run first, wait for the
+  pull (default)    ghost tail: every rank keeps local copies of its ghosts behind its own elements; per stage one
+                    mailbox barrier kernel, one bandwidth-bound pull kernel that copies the ghosts from the peers' rows
+                    over NVLink (no pack / unpack on the owner's side), then the SINGLE-rank stage kernel, which reads
+                    no peer memory (direct peer loads inside the stage kernel cost +8 % per step: the NVLink latency
+                    is exposed in every chunk at the partition boundary).  The stage-3 barrier carries the CFL max.
+  kernel            direct peer loads; the stage kernels order themselves: the chunks that read ghost elements run first, wait for the
                     peers' previous stage and the last of them signals this stage to every peer through the
                     peer-mapped mailboxes (csrc/peer_sync.cuh); all other chunks never wait.  The CFL reduction is one
                     32-thread mailbox kernel per step (on a side stream while dt is fixed, on the compute stream when
@@ -51,14 +56,15 @@ class MultiGpuEuler:
         import t8gpu_b200 as tb
         from t8gpu_b200.solver import NB_STEPS, NVAR
         self.tb, self.rank, self.world, self.device, self.dtype = tb, rank, world, device, dtype
-        self.sync = sync or os.environ.get("T8B200_SYNC", "kernel")
+        self.sync = sync or os.environ.get("T8B200_SYNC", "pull")
         brick = brick or BRICK[world]
         esz = 8 if dtype == torch.float64 else 4
         conn = tb.cartesian_uniform_connectivity(3, level, dtype, world, rank, device=device, brick=brick)
         self.n = int(conn["n_local"])
         self.n_faces = int(conn["n_faces"]) + int(conn["n_xfaces"])
         self.n_ghost = int(conn["n_ghost"])
-        self.cap = (self.n + 31) // 32 * 32
+        self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync == "pull")
+        self.cap = (self.n + self.plan.n_tail + 31) // 32 * 32     # own elements, then the ghost tail
         nrows = NVAR * NB_STEPS + 1
         self.shared = tb.SharedBuffer(nrows * self.cap * esz, device)
         self.buffer = self.shared.tensor((nrows, self.cap), dtype)
@@ -70,12 +76,11 @@ class MultiGpuEuler:
         rows = row_pointers(bases, caps, NVAR, NB_STEPS, esz)
         self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
         self.mail = None
-        if self.sync in ("kernel", "peer", "none"):
+        if self.sync in ("pull", "kernel", "peer", "none"):
             self.mail = tb.PeerMailboxes(rank, world, device)
             mw = exchange_wires(dist, self.mail.handle, 0, world, device)
             self.mail.exchange([h for h, _ in mw])
         self.speed_loc = torch.zeros(1, dtype=dtype, device=device)
-        self.plan = tb.Plan(tb.conn_to_host(conn), dtype)
         tb.init_kelvin_helmholtz(3, conn["centroids"], self.variables(0))
         self.next, self.prev = 0, 3
         self.speed_max = torch.zeros(1, dtype=dtype, device=device)
@@ -92,7 +97,10 @@ class MultiGpuEuler:
         """The state was written outside the stage kernels (initial data, upload): a full barrier before any rank reads
         ghosts, which also starts the stage-epoch sequence the self-ordering kernels continue."""
         if self.mail is not None and self.sync != "none":
-            self.mail.barrier()
+            if self.sync == "pull":    # same class as the barrier that ends a step (it precedes the first pull)
+                self.mail.barrier(self.speed_loc, self.speed_max)
+            else:
+                self.mail.barrier()
 
     def variables(self, step):
         from t8gpu_b200.solver import NVAR
@@ -112,6 +120,20 @@ class MultiGpuEuler:
         prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
         vol, T = self.volume(), self.tables
         dtd = self.dt_dev if adaptive else None
+        if self.sync == "pull":
+            m, P = self.mail, self.plan
+            P.pull(prev, T[self.prev])                    # the peers' U^n is complete (barrier of the previous step)
+            P.stage(1, prev, None, s1, vol, dt, dt_dev=dtd)
+            m.barrier()
+            P.pull(s1, T[1])
+            P.stage(2, s1, prev, s2, vol, dt, dt_dev=dtd)
+            m.barrier()
+            P.pull(s2, T[2])
+            P.stage(3, s2, prev, nxt, vol, dt, speed_max=self.speed_loc, dt_dev=dtd)
+            m.barrier(self.speed_loc, self.speed_max)     # stage barrier + CFL max over the ranks
+            if adaptive:
+                self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
+            return 9 + int(adaptive)                      # 3 x (pull, stage, barrier)
         if self.sync == "kernel":
             m = self.mail
             self.plan.stage(1, prev, None, s1, vol, dt, in_all=T[self.prev], dt_dev=dtd, sync=m)
@@ -125,6 +147,9 @@ class MultiGpuEuler:
                 m.barrier(self.speed_loc, self.speed_max)
                 self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
                 return 5
+            if os.environ.get("T8B200_CFL_SIDE", "1") == "0":   # experiment: the reduction on the compute stream
+                m.barrier(self.speed_loc, self.speed_max)
+                return 4
             ev = torch.cuda.Event()
             ev.record(main)
             self.side.wait_event(ev)
@@ -203,7 +228,8 @@ def run_multi(args, rank, world, device):
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     ncpu = pin_to_gpu_numa_node(device)
     parity = bitwise_parity(dtype, rank, world, device)
-    assert parity["bitwise_equal"], "the %d-rank run differs from the one-rank run of the same brick" % world
+    if os.environ.get("T8B200_SYNC") != "none":   # (the timing experiment without stage ordering is expected to differ)
+        assert parity["bitwise_equal"], "the %d-rank run differs from the one-rank run of the same brick" % world
     t0 = time.time()
     sol = MultiGpuEuler(args.level, dtype, rank, world, device)
     t_setup = time.time() - t0
@@ -233,6 +259,9 @@ def run_multi(args, rank, world, device):
     dist.barrier()
     tw1 = time.time()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+    every = [torch.zeros_like(ms) for _ in range(world)]
+    dist.all_gather(every, ms)
+    per_rank_ms = [round(float(t.item()) / args.steps, 4) for t in every]
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     vmax = float(sol.speed_max.item())
@@ -278,7 +307,11 @@ def run_multi(args, rank, world, device):
         ms_per_step = ms / args.steps
         achieved = alg * n / (ms_per_step * 1e-3) / 1e9   # per GPU
         state_bytes = 5 * n * esz
-        sync_text = {"kernel": "stage kernels order themselves through peer-memory mailboxes (ghost-reading chunks first: "
+        sync_text = {"pull": "ghost tail: per stage one peer-memory mailbox barrier kernel + one pull kernel copying the "
+                             "ghosts from the peers' rows over NVLink into local copies behind the own elements, then "
+                             "the single-rank stage kernel (no peer memory inside it); the stage-3 barrier carries the "
+                             "CFL max",
+                     "kernel": "stage kernels order themselves through peer-memory mailboxes (ghost-reading chunks first: "
                                "wait for the peers' previous stage, last one signals; interior chunks never wait); CFL "
                                "max over ranks = one 32-thread mailbox kernel per step",
                      "peer": "peer-memory mailbox barrier kernel per RK stage on the compute stream; stage 3 carries "
@@ -298,7 +331,8 @@ def run_multi(args, rank, world, device):
                                         "over NVLink (cudaIpc-mapped state arrays), owner-computes boundary faces",
                            "sync": sync_text, "l2": "inputs larger than L2",
                            "host_setup_s": round(t_setup, 2), "host_cores": os.cpu_count(),
-                           "host_cpus_bound_to_gpu_numa_node": ncpu, "plan": info},
+                           "host_cpus_bound_to_gpu_numa_node": ncpu, "per_rank_ms_per_step": per_rank_ms,
+                           "plan": info},
                 "clocks": clocks, "parity": parity,
                 "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",
                         "h2d_bytes_per_step": (state_bytes / args.steps + esz) * world,

@@ -58,8 +58,12 @@ class SubgridBrick:
         self.n = self.ne * 64
         self.n_faces = int(conn["n_faces"]) + int(conn["n_xfaces"])
         self.n_ghost = int(conn["n_ghost"])
-        self.cap = (self.n + 31) // 32 * 32
         self.vol = conn["volumes"]
+        self.sync = os.environ.get("T8B200_SYNC", "pull") if world > 1 else "single"
+        t0 = time.time()
+        self.plan = tb.SubgridPlan(tb.conn_to_host(conn), self.vol.cpu().numpy(), dtype, ghost_tail=self.sync == "pull")
+        self.t_plan = time.time() - t0
+        self.cap = (self.n + self.plan.n_tail + 31) // 32 * 32     # own cells, then the ghost-cell tail
         self.shared = tb.SharedBuffer(NVAR * NB_STEPS * self.cap * esz, device)
         self.buffer = self.shared.tensor((NVAR * NB_STEPS, self.cap), dtype)
         self.tables, self.mail = {s: None for s in range(NB_STEPS)}, None
@@ -70,10 +74,6 @@ class SubgridBrick:
             self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
             self.mail = tb.PeerMailboxes(rank, world, device)
             self.mail.exchange([h for h, _ in exchange_wires(dist, self.mail.handle, 0, world, device)])
-        self.sync = os.environ.get("T8B200_SYNC", "kernel")
-        t0 = time.time()
-        self.plan = tb.SubgridPlan(tb.conn_to_host(conn), self.vol.cpu().numpy(), dtype)
-        self.t_plan = time.time() - t0
         tb.init_kelvin_helmholtz(3, cell_centers(conn["centroids"], level, dtype), self.variables(0))
         self.next, self.prev = 0, 3
         torch.cuda.synchronize()
@@ -98,11 +98,15 @@ class SubgridBrick:
         prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
         T, launches = self.tables, 0
         own_order = self.mail is not None and self.sync == "kernel"   # the stage kernels order themselves
+        pull = self.mail is not None and self.sync == "pull"          # ghost-cell tail, single-rank stage kernels
         for stage, sin, vin, vout in ((1, self.prev, prev, s1), (2, 1, s1, s2), (3, 2, s2, nxt)):
-            self.plan.stage(stage, vin, prev if stage > 1 else None, vout, self.vol, dt, in_all=T[sin],
-                            sync=self.mail if own_order else None)
+            if pull:
+                self.plan.pull(vin, T[sin])
+                launches += 1
+            self.plan.stage(stage, vin, prev if stage > 1 else None, vout, self.vol, dt,
+                            in_all=None if pull else T[sin], sync=self.mail if own_order else None)
             launches += 1
-            if self.mail is not None and not own_order:   # barrier kernel per stage (T8B200_SYNC=peer)
+            if self.mail is not None and not own_order:   # barrier kernel per stage
                 self.mail.barrier()
                 launches += 1
         return launches
@@ -198,8 +202,8 @@ def run_subgrid(args, rank, world, device):
                                        "adaptation" % (BRICK[world], level, ne, n, total, args.dtype),
                            "cells_per_gpu": n, "element_faces_per_gpu": nfaces, "ghost_elements_per_gpu": nghost,
                            "partition": "one tree per GPU; ghost cells read from peer GPUs over NVLink, owner-computes "
-                                        "boundary faces; stage kernels order themselves through peer-memory mailboxes "
-                                        "(ghost-reading chunks first)" if world > 1 else
+                                        "boundary faces; per stage a mailbox barrier kernel, a pull kernel filling the local "
+                                        "ghost-cell copies, then the single-rank stage kernel" if world > 1 else
                                         "one rank", "l2": "inputs larger than L2 (%.0f MB of state per stage)" %
                                                           (2 * state_bytes / 1e6),
                            "host_setup_s": round(t_setup, 2), "tile_plan_host_s": round(t_plan, 2),

@@ -141,6 +141,35 @@ int t8b200_plan_create_host(t8b200_plan** out, int is_f64, int64_t n_local, int6
                             const int32_t* x_face_neighbors, const void* x_face_normals, const void* x_face_surfaces);
 int t8b200_plan_host_array(const t8b200_plan* plan, int which, const void** data, int64_t* count, int* elem_bytes);
 
+/* Ghost tail.  The reference keeps no ghost layer: kernels dereference the owner's arrays directly
+ * (t8gpu/memory/shared_device_vector.h:25-29), which over NVLink exposes the peer-load latency inside every chunk that
+ * touches the partition boundary (measured: +8 % per step on 2 GPUs).  A plan created with *_ghost_tail gives every ghost
+ * element its chunks read a LOCAL copy at index n_local + j of this rank's own rows (rows need n_local +
+ * t8b200_plan_ghost_tail_count() entries), the halo entries point there, and t8b200_ghost_pull_* fills the copies from
+ * the peers' rows in one bandwidth-bound kernel before each stage: no pack / unpack on the owner's side, no ghost
+ * buffers to exchange, the [var][rank] tables (get_all_variables) stay the interface.  The stage entry points then need no
+ * in_all (it is ignored).  Arguments as t8b200_plan_create. */
+int t8b200_plan_create_ghost_tail(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
+                                  int32_t nb, const int32_t* face_neighbors, const void* face_normals,
+                                  const void* face_surfaces, const int32_t* ranks, const int32_t* indices,
+                                  int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
+                                  const void* x_face_surfaces);
+int t8b200_plan_create_ghost_tail_host(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
+                                       int32_t nb, const int32_t* face_neighbors, const void* face_normals,
+                                       const void* face_surfaces, const int32_t* ranks, const int32_t* indices,
+                                       int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
+                                       const void* x_face_surfaces);
+/* tail entries of the plan (0 for plans without a ghost tail), -1 for a NULL plan; host arrays 17 / 18 of
+ * t8b200_plan_host_array: owner rank / index in the owner's rows of every tail entry */
+int64_t t8b200_plan_ghost_tail_count(const t8b200_plan* plan);
+/* rows[k][n_local + j] = rows_all[k][rank_j][index_j] for every tail entry j and variable k < nvar (<= 8).
+ * rows: HOST array of nvar DEVICE pointers (this rank's rows of one step); rows_all: HOST array of nvar DEVICE tables
+ * (one pointer per rank; MemoryAccessorAll).  The owners' rows must be complete (t8b200_peer_barrier before). */
+int t8b200_ghost_pull_f32(const t8b200_plan* plan, int nvar, float* const* rows, const float* const* const* rows_all,
+                          void* stream);
+int t8b200_ghost_pull_f64(const t8b200_plan* plan, int nvar, double* const* rows, const double* const* const* rows_all,
+                          void* stream);
+
 /* One fused RK stage.  in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's arrays (stage input, U^n, stage
  * output).  in_all: HOST array of 5 DEVICE tables (one pointer per rank) for ghost reads, or NULL when the plan has
  * no ghosts.  vol: device, per element.  speed_max_dev: device scalar receiving max(|uHat|+aHat) over the faces of
@@ -177,6 +206,16 @@ int t8b200_subgrid_plan_create_host(t8b200_subgrid_plan** out, int is_f64, int d
                                     const int32_t* indices, int32_t n_xfaces, const int32_t* x_face_neighbors,
                                     const void* x_face_normals, const void* x_face_surfaces,
                                     const int32_t* x_level_difference, const int32_t* x_neighbor_offset);
+/* ghost-tail variant (see t8b200_plan_create_ghost_tail); tail entries are CELLS: rows need n_local * 64 (16) +
+ * t8b200_plan_ghost_tail_count(t8b200_subgrid_plan_base(plan)) entries, pulled with t8b200_ghost_pull_* on the base plan */
+int t8b200_subgrid_plan_create_ghost_tail(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local,
+                                          int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* face_neighbors,
+                                          const void* face_normals, const void* face_surfaces,
+                                          const int32_t* face_level_difference, const int32_t* face_neighbor_offset,
+                                          const void* volumes, const int32_t* ranks, const int32_t* indices,
+                                          int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
+                                          const void* x_face_surfaces, const int32_t* x_level_difference,
+                                          const int32_t* x_neighbor_offset);
 const t8b200_plan* t8b200_subgrid_plan_base(const t8b200_subgrid_plan* plan);
 /* as t8b200_plan_info, counted in cells */
 int t8b200_subgrid_plan_info(const t8b200_subgrid_plan* plan, int64_t info[8]);

@@ -31,6 +31,7 @@ def lib():
                 "There is no CPU fallback for this path.")
         _LIB = C.CDLL(LIB_PATH)
         _LIB.t8b200_plan_destroy.restype = None
+        _LIB.t8b200_plan_ghost_tail_count.restype = C.c_int64
         _LIB.t8b200_cartesian_connectivity_free.restype = None
         if hasattr(_LIB, "t8b200_solver_destroy"):
             _LIB.t8b200_solver_destroy.restype = None
@@ -168,10 +169,12 @@ def subgrid_boundary_flux(conn, vars_own_tab, flux_own_tab, stream=None):
 class Plan:
     """Tile plan: the reference-layout connectivity re-laid out per chunk of elements."""
 
-    def __init__(self, conn, dtype):
+    def __init__(self, conn, dtype, ghost_tail=False):
         """conn: dict of HOST numpy arrays in the reference layout (as MeshManager::compute_connectivity_information
         builds them): n_local, n_ghost, n_faces, n_bfaces, face_neighbors, face_normals, face_areas, and for
-        multi-rank ranks, indices, optionally x_face_* (faces whose ghost neighbour belongs to a lower rank)."""
+        multi-rank ranks, indices, optionally x_face_* (faces whose ghost neighbour belongs to a lower rank).
+        ghost_tail: the ghosts get local copies behind this rank's own elements (rows need n_local + n_tail entries),
+        filled by pull() before each stage; the stage kernels then read no peer memory."""
         import numpy as np
         _torch()
         s, _ = _sfx(dtype)
@@ -193,11 +196,13 @@ class Plan:
             return None if a is None else a.ctypes.data_as(C.c_void_p)
 
         h = C.c_void_p()
-        check(lib().t8b200_plan_create(C.byref(h), int(s == "f64"), C.c_int64(int(conn["n_local"])),
-                                       C.c_int64(int(conn.get("n_ghost", 0))), int(conn["n_faces"]),
-                                       int(conn["n_bfaces"]), p(nbr), p(nrm), p(ar), p(rk), p(ix), nx, p(xn), p(xr),
-                                       p(xa)), "plan_create")
+        create = lib().t8b200_plan_create_ghost_tail if ghost_tail else lib().t8b200_plan_create
+        check(create(C.byref(h), int(s == "f64"), C.c_int64(int(conn["n_local"])),
+                     C.c_int64(int(conn.get("n_ghost", 0))), int(conn["n_faces"]),
+                     int(conn["n_bfaces"]), p(nbr), p(nrm), p(ar), p(rk), p(ix), nx, p(xn), p(xr),
+                     p(xa)), "plan_create")
         self._h = h
+        self.n_tail = int(lib().t8b200_plan_ghost_tail_count(h))
         info = (C.c_int64 * 8)()
         check(lib().t8b200_plan_info(self._h, info), "plan_info")
         self.info = dict(n_chunks=info[0], max_halo=info[1], max_faces=info[2], smem_bytes=info[3],
@@ -207,6 +212,13 @@ class Plan:
         if getattr(self, "_h", None) and lib is not None:   # `lib` is gone when the interpreter shuts down
             lib().t8b200_plan_destroy(self._h)
             self._h = None
+
+    def pull(self, rows, rows_all, stream=None):
+        """Ghost tail <- the owners' rows (t8b200_ghost_pull).  rows: this rank's per-variable tensors of one step (with
+        the tail behind the n_local own entries); rows_all: RankTables / PointerTables of the same step."""
+        s, _ = _sfx(self.dtype)
+        check(getattr(lib(), "t8b200_ghost_pull_" + s)(self._h, len(rows), ptrs(rows), rows_all.host,
+                                                       stream_ptr(stream)), "ghost_pull")
 
     def stage(self, stage, inp, prev, out, vol, dt, in_all=None, speed_max=None, stream=None, dt_dev=None,
               sync=None):
@@ -234,7 +246,7 @@ class Plan:
 class SubgridPlan:
     """Cell-level tile plan for the fused Subgrid<4,4,4> / Subgrid<4,4> stage kernel."""
 
-    def __init__(self, conn, volumes, dtype):
+    def __init__(self, conn, volumes, dtype, ghost_tail=False):
         import numpy as np
         _torch()
         s, _ = _sfx(dtype)
@@ -255,12 +267,16 @@ class SubgridPlan:
                 arr("indices", np.int32), arr("x_face_neighbors", np.int32), arr("x_face_normals", npdt),
                 arr("x_face_areas", npdt), arr("x_level_diff", np.int32), arr("x_offsets", np.int32)]
         h = C.c_void_p()
-        check(lib().t8b200_subgrid_plan_create(
+        create = lib().t8b200_subgrid_plan_create_ghost_tail if ghost_tail else lib().t8b200_subgrid_plan_create
+        check(create(
             C.byref(h), int(s == "f64"), dim, C.c_int64(int(conn["n_local"])), C.c_int64(int(conn.get("n_ghost", 0))),
             int(conn["n_faces"]), int(conn["n_bfaces"]), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]), p(keep[4]),
             p(vols), p(keep[5]), p(keep[6]), int(conn.get("n_xfaces", 0)), p(keep[7]), p(keep[8]), p(keep[9]),
             p(keep[10]), p(keep[11])), "subgrid_plan_create")
         self._h = h
+        lib().t8b200_subgrid_plan_base.restype = C.c_void_p
+        self._base = C.c_void_p(lib().t8b200_subgrid_plan_base(h))
+        self.n_tail = int(lib().t8b200_plan_ghost_tail_count(self._base))
         info = (C.c_int64 * 8)()
         check(lib().t8b200_subgrid_plan_info(self._h, info), "subgrid_plan_info")
         self.info = dict(n_chunks=info[0], max_halo=info[1], max_faces=info[2], smem_bytes=info[3],
@@ -270,6 +286,12 @@ class SubgridPlan:
         if getattr(self, "_h", None) and lib is not None:
             lib().t8b200_subgrid_plan_destroy(self._h)
             self._h = None
+
+    def pull(self, rows, rows_all, stream=None):
+        """Ghost-cell tail <- the owners' cell rows (t8b200_ghost_pull on the cell-level plan)."""
+        s, _ = _sfx(self.dtype)
+        check(getattr(lib(), "t8b200_ghost_pull_" + s)(self._base, len(rows), ptrs(rows), rows_all.host,
+                                                       stream_ptr(stream)), "ghost_pull")
 
     def stage(self, stage, inp, prev, out, vol, dt, in_all=None, stream=None, dt_dev=None, sync=None):
         s, ft = _sfx(self.dtype)

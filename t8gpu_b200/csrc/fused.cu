@@ -51,7 +51,6 @@ struct FusedArgs {
   T               dt;
   const T*        dt_ptr;       // non-null: the time step is read from device memory (t8b200_timestep_*)
   StageSync       sync;         // multi-GPU stage ordering done by the kernel itself (mailboxes == nullptr: off)
-  int             n_boundary;   // the first n_boundary CTAs are partition-boundary chunks (they read ghost elements)
   T*              speed_max;
   int64_t         n_local;
   int             stage;
@@ -204,7 +203,9 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
   const Smem<T, MS, MF> sm(smem_raw);
   __shared__ T atab[CMP ? 256 : 1];
   __shared__ T red[EC / 32];
-  const int c   = (SPLIT && A.chunk_list) ? __ldg(A.chunk_list + blockIdx.x) : blockIdx.x;
+  // chunk list entries: chunk id, bit 30 = partition-boundary chunk (tile_plan.cuh)
+  const int cl  = (SPLIT && A.chunk_list) ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
+  const int c   = cl & 0x3FFFFFFF;
   const int tid = threadIdx.x;
 #ifdef T8B_PHASE_CLOCKS
   long long clk[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -266,6 +267,8 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
 
   auto load_halo = [&](int idx, int rk, T& a0, T& a1, T& a2, T& a3, T& a4) {
     if (A.multi && rk != A.my_rank) {   // ghost: through the [var][rank] tables (a peer GPU's array over NVLink)
+      // self-ordering launches: the owner's previous stage must be complete before its element is read
+      if (A.sync.mailboxes != nullptr) stage_wait_owner(A.sync, rk);
       a0 = A.in_all[0][rk][idx]; a1 = A.in_all[1][rk][idx]; a2 = A.in_all[2][rk][idx];
       a3 = A.in_all[3][rk][idx]; a4 = A.in_all[4][rk][idx];
     } else {
@@ -281,13 +284,8 @@ __global__ void __launch_bounds__(EC, MINB) fused_stage_kernel(const __grid_cons
     load_halo(idx, rk, a0, a1, a2, a3, a4);
     sm.store_cell(EC + h, to_cell(a0, a1, a2, a3, a4));
   };
-  // partition-boundary chunk: the peers' previous stage must be complete before their elements are read (everything
-  // requested so far is this rank's own data or plan data)
-  const bool bnd = SPLIT && A.sync.mailboxes != nullptr && (int)blockIdx.x < A.n_boundary;
-  if (bnd && A.sync.wait_epoch > 0) {
-    if (tid < 32) stage_wait(A.sync, tid);
-    __syncthreads();
-  }
+  // partition-boundary chunk of a launch that orders itself against the peers: it signals when it is done
+  const bool bnd = SPLIT && A.sync.mailboxes != nullptr && (cl >> 30) != 0;
   // the gathers of the halo states are issued before the own elements are converted: the two latencies overlap
   T g0 = T(1), g1 = T(0), g2 = T(0), g3 = T(0), g4 = T(1);
   if (hidx >= 0) load_halo(hidx, hrk, g0, g1, g2, g3, g4);
@@ -556,13 +554,14 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
                             long long wait_epoch = 0, long long signal_epoch = 0) {
   if (!P || stage < 1 || stage > 3 || !in || !out || !vol || (stage > 1 && !prev)) return cudaErrorInvalidValue;
   if (P->is_f64 != (sizeof(T) == 8) || P->host_only) return cudaErrorInvalidValue;
-  if (P->multi && !in_all) return cudaErrorInvalidValue;
+  if (P->multi && !P->ghost_tail && !in_all) return cudaErrorInvalidValue;   // (ghost-tail plans read no peer memory)
   // CTAs read halo states from `in` (or the peers' `in`) while other CTAs write `out`: an in-place call would race
   // silently; the reference-shaped rk3_stage tolerates out == prev, this entry point does not
   for (int k = 0; k < 5; k++)
     if (!in[k] || !out[k] || out[k] == in[k] || (stage > 1 && (!prev[k] || out[k] == prev[k]))) return cudaErrorInvalidValue;
   if (sync && (sync->nranks < 1 || sync->nranks > 32 || sync->rank < 0 || sync->rank >= sync->nranks ||
-               !sync->mailboxes_dev || !sync->counter_dev || wait_epoch < 0 || signal_epoch < 0 || !P->multi))
+               !sync->mailboxes_dev || !sync->counter_dev || wait_epoch < 0 || signal_epoch < 0 || !P->multi ||
+               P->ghost_tail))
     return cudaErrorInvalidValue;
   if (P->n_chunks == 0) return cudaSuccess;
   FusedArgs<T> A{};
@@ -579,7 +578,7 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
     A.out[k]    = out[k];
   }
   A.vol = vol; A.vol_shift = P->vol_shift; A.vol_scale = (T)P->vol_scale; A.dt = dt; A.speed_max = speed_max; A.n_local = P->n_local;
-  A.stage = stage; A.multi = P->multi; A.my_rank = P->my_rank;
+  A.stage = stage; A.multi = P->multi && !P->ghost_tail; A.my_rank = P->my_rank;
   A.dt_ptr = dt_dev;
   StageSync S{};
   if (sync) {
@@ -587,7 +586,6 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
     S.wait_epoch = wait_epoch; S.signal_epoch = signal_epoch;
     S.nranks = sync->nranks; S.rank = sync->rank; S.n_boundary_total = P->nb_struct + P->nb_generic;
     A.sync = S;
-    A.n_boundary = P->nb_generic;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), st));
@@ -655,7 +653,8 @@ static int plan_create_impl(t8b200_plan** out, int host_only, int is_f64, int64_
   if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
   t8b200_plan* P = new t8b200_plan();
   P->is_f64      = is_f64 ? 1 : 0;
-  P->host_only   = host_only;
+  P->host_only   = host_only & 1;   // flags: bit 0 host-only plan, bit 1 ghost tail
+  P->ghost_tail  = (host_only >> 1) & 1;
   int rc;
   if (is_f64) {
     MeshFaces<double> src{nf, nb, nx, nbr, (const double*)normals, (const double*)areas, ranks, indices, xnbr,
@@ -689,6 +688,22 @@ int t8b200_plan_create_host(t8b200_plan** out, int is_f64, int64_t n_local, int6
                           xnormals, xareas);
 }
 
+int t8b200_plan_create_ghost_tail(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
+                                  int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
+                                  const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                                  const void* xnormals, const void* xareas) {
+  return plan_create_impl(out, 2, is_f64, n_local, n_ghost, nf, nb, nbr, normals, areas, ranks, indices, nx, xnbr,
+                          xnormals, xareas);
+}
+int t8b200_plan_create_ghost_tail_host(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
+                                       int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
+                                       const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                                       const void* xnormals, const void* xareas) {
+  return plan_create_impl(out, 3, is_f64, n_local, n_ghost, nf, nb, nbr, normals, areas, ranks, indices, nx, xnbr,
+                          xnormals, xareas);
+}
+int64_t t8b200_plan_ghost_tail_count(const t8b200_plan* P) { return P ? P->n_pull : -1; }
+
 int t8b200_plan_host_array(const t8b200_plan* P, int which, const void** data, int64_t* count, int* elem_bytes) {
   if (!P || !P->host || !data || !count || !elem_bytes) return cudaErrorInvalidValue;
   const t8b200_plan_host& H = *P->host;
@@ -716,6 +731,8 @@ int t8b200_plan_host_array(const t8b200_plan* P, int which, const void** data, i
     case 14: return set(H.s_halo);
     case 15: return set(H.s_hrank);
     case 16: return set(H.g_list);
+    case 17: return set(H.pull_rank);
+    case 18: return set(H.pull_idx);
   }
   return cudaErrorInvalidValue;
 }
@@ -731,6 +748,7 @@ void t8b200_plan_destroy(t8b200_plan* P) {
   cudaFree(P->face_lr); cudaFree(P->face_ai); cudaFree(P->fnx); cudaFree(P->fny); cudaFree(P->fnz); cudaFree(P->farea);
   cudaFree(P->area_tab); cudaFree(P->ell); cudaFree(P->ovf_off); cudaFree(P->ovf_ent);
   cudaFree(P->s_rec); cudaFree(P->s_halo); cudaFree(P->s_hrank); cudaFree(P->g_list);
+  cudaFree(P->pull_rank); cudaFree(P->pull_idx);
   delete P;
 }
 

@@ -38,20 +38,23 @@ __device__ __forceinline__ long long peer_load_epoch(const PeerSlot* s) {
   return e;
 }
 
-// Called by ONE warp of a boundary chunk before it touches ghost data: lane r spins on rank r's stage slot.
-__device__ __forceinline__ void stage_wait(const StageSync& S, int lane) {
-  if (lane < S.nranks && lane != S.rank) {
-    const PeerSlot* s = S.mailboxes[S.rank] + (S.wait_epoch & 1) * S.nranks + lane;
+// Called by a THREAD about to read an element owned by rank `owner` (a ghost): waits until that rank has signalled
+// the awaited epoch.  The acquire is per thread and in front of the thread's own peer loads, so no CTA-wide step is
+// needed, threads that read this rank's own elements never wait, and a chunk only waits for the ranks it reads from.
+__device__ __forceinline__ void stage_wait_owner(const StageSync& S, int owner) {
+  if (S.wait_epoch > 0) {
+    const PeerSlot* s = S.mailboxes[S.rank] + (S.wait_epoch & 1) * S.nranks + owner;
     while (peer_load_epoch(s) < S.wait_epoch) {}
   }
-  __syncwarp();
 }
 
 // Called by ONE thread of a boundary chunk after a CTA barrier that follows the chunk's last global store: counts the
-// chunk; the last one publishes the epoch to every peer (release at system scope; the fences order the other CTAs'
-// stores, observed through the counter, before the flag).
+// chunk; the last one publishes the epoch to every peer.  Ordering: every chunk releases its stores at GPU scope
+// before it counts (fence + atomic), the last chunk acquires the count and releases at SYSTEM scope in front of the
+// flag -- causality order is transitive, so a peer that acquires the flag sees the stores of all chunks, while only
+// one thread per stage pays for a system-scope fence.
 __device__ __forceinline__ void stage_signal(const StageSync& S) {
-  __threadfence_system();
+  __threadfence();
   const unsigned done = atomicAdd(S.counter, 1u);
   if (done + 1u == (unsigned)S.n_boundary_total) {
     *S.counter = 0u;   // every boundary chunk of this stage has counted; the next stage starts from zero

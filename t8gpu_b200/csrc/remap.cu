@@ -10,6 +10,7 @@
 //   t8gpu/mesh/subgrid_mesh_manager.inl:1216-1283 partition_variable_data, partition_volume_data
 #include "../../include/t8gpu_b200.h"
 #include "common.cuh"
+#include "tile_plan.cuh"
 
 namespace {
 
@@ -111,6 +112,22 @@ partition_kernel(int nvar, int64_t n_new_cells, int cpe, const int32_t* __restri
   if (c == 0 && vn) vn[e] = vo[rk][indices[e]];
 }
 
+// Ghost tail of a plan built with t8b200_plan_create_ghost_tail: tail entry j of every variable row <- entry idx[j] of
+// rank rk[j]'s row (peer memory over NVLink).  One thread per (entry, variable): every load of the exchange is in flight
+// at once, so the pull is bound by NVLink bandwidth, not by the latency a stage kernel would expose per chunk.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ghost_pull_kernel(int nvar, int64_t n_pull, int64_t tail, const int32_t* __restrict__ rk, const int32_t* __restrict__ idx,
+                  Ptrs<T> own, TablesC<T> all) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_pull * nvar) return;
+  const int64_t j = g % n_pull;
+  const int     l = (int)(g / n_pull);
+#pragma unroll
+  for (int k = 0; k < MAXV; k++)
+    if (k == l) own.p[k][tail + j] = all.p[k][rk[j]][idx[j]];
+}
+
 template <typename T>
 int adapt_impl(int dim_subgrid, int nvar, int64_t n_new, const int32_t* ad, const T* const* uo, T* const* un,
                const T* vo, T* vn, void* stream) {
@@ -148,7 +165,29 @@ int partition_impl(int nvar, int64_t n_new, int cpe, const int32_t* ranks, const
 }
 }  // namespace
 
+template <typename T>
+static int ghost_pull_impl(const t8b200_plan* P, int nvar, T* const* rows, const T* const* const* rows_all, void* stream) {
+  if (!P || !P->ghost_tail || P->host_only || nvar < 1 || nvar > MAXV || (P->is_f64 != (sizeof(T) == 8))) return cudaErrorInvalidValue;
+  if (P->n_pull == 0) return 0;
+  if (!rows || !rows_all) return cudaErrorInvalidValue;
+  Ptrs<T>    o{};
+  TablesC<T> a{};
+  for (int k = 0; k < nvar; k++) { o.p[k] = rows[k]; a.p[k] = rows_all[k]; }
+  const int64_t total = P->n_pull * nvar;
+  ghost_pull_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nvar, P->n_pull, P->n_local,
+                                                                                          P->pull_rank, P->pull_idx, o, a);
+  return cudaGetLastError();
+}
+
 extern "C" {
+int t8b200_ghost_pull_f32(const t8b200_plan* plan, int nvar, float* const* rows, const float* const* const* rows_all,
+                          void* stream) {
+  return ghost_pull_impl<float>(plan, nvar, rows, rows_all, stream);
+}
+int t8b200_ghost_pull_f64(const t8b200_plan* plan, int nvar, double* const* rows, const double* const* const* rows_all,
+                          void* stream) {
+  return ghost_pull_impl<double>(plan, nvar, rows, rows_all, stream);
+}
 int t8b200_adapt_remap_f32(int subgrid_dim, int nvar, int64_t n_new, const int32_t* adapt_data,
                            const float* const* vars_old, float* const* vars_new, const float* vol_old, float* vol_new,
                            void* stream) {

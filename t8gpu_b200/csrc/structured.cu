@@ -44,7 +44,6 @@ struct SArgs {
   T              dt;
   const T*       dt_ptr;  // non-null: the time step is read from device memory (t8b200_timestep_*)
   StageSync      sync;    // multi-GPU stage ordering done by the kernel itself (mailboxes == nullptr: off)
-  int            n_boundary;   // the first n_boundary CTAs are partition-boundary chunks (they read ghost elements)
   T*             speed_max;
   int            stage, multi, my_rank;
   int            dense;   // every chunk of the plan is structured: chunk b = elements [256 b, 256 b + 256), one area
@@ -77,7 +76,9 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 #define T8B_S_OWNREG 1
 #endif
 
-template <typename T, class L, bool SMAX>
+// MULTI: plans with ghosts (peer tables, owner ranks, self-ordering against the peers); its own instantiation so that
+// single-rank launches do not carry its registers (the kernel sits at the 80-register cap of 3 CTAs per SM)
+template <typename T, class L, bool SMAX, bool MULTI>
 __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const __grid_constant__ SArgs<T> A) {
   constexpr int NS = L::NSLOT, NF = BoxCommon::NFLUX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -87,23 +88,20 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
   const int b = blockIdx.x, tid = threadIdx.x;
 
   // ---- phase 0: every independent global load first
-  int e0 = b * 256, area_idx = A.area0;
+  int  e0 = b * 256, area_idx = A.area0;
+  bool bnd = false;   // partition-boundary chunk (reads ghost elements) of a launch that orders itself against the peers
   if (!A.dense) {
     const int4 r = __ldg(A.rec + b);
     e0 = r.x; area_idx = r.y;
+    bnd = MULTI && r.w != 0 && A.sync.mailboxes != nullptr;
+  } else if (MULTI && A.sync.mailboxes != nullptr) {
+    bnd = __ldg(reinterpret_cast<const int*>(A.rec + b) + 3) != 0;   // off the critical path: only the flag is read
   }
   const int e    = e0 + tid;
   const int hidx = __ldg(A.halo + b * 256 + tid);
   int       hrk  = A.my_rank;
-  if (A.multi) hrk = __ldg(A.hrank + b * 256 + tid);
+  if (MULTI) hrk = __ldg(A.hrank + b * 256 + tid);
   const T u0 = A.in[0][e], u1 = A.in[1][e], u2 = A.in[2][e], u3 = A.in[3][e], u4 = A.in[4][e];
-  // partition-boundary chunk: the peers' previous stage must be complete before their elements are read (the loads
-  // above are this rank's own data and already in flight)
-  const bool bnd = A.sync.mailboxes != nullptr && b < A.n_boundary;
-  if (bnd && A.sync.wait_epoch > 0) {
-    if (tid < 32) stage_wait(A.sync, tid);
-    __syncthreads();
-  }
   if (A.pf_ok && (tid & 31) == 0) {
     // L2 prefetch hints, one or two per warp: the phase-2 operands of this chunk (rows of U^n, volume) and the streams
     // of the chunk that takes over this CTA slot about one wave later (CTAs are dispatched in index order)
@@ -117,7 +115,9 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
     }
   }
   T g0, g1, g2, g3, g4;
-  if (A.multi && hrk != A.my_rank) {   // ghost: through the [var][rank] tables (a peer GPU's array over NVLink)
+  if (MULTI && hrk != A.my_rank) {   // ghost: through the [var][rank] tables (a peer GPU's array over NVLink)
+    // self-ordering launches: the owner's previous stage must be complete before its element is read
+    if (A.sync.mailboxes != nullptr) stage_wait_owner(A.sync, hrk);
     g0 = A.in_all[0][hrk][hidx]; g1 = A.in_all[1][hrk][hidx]; g2 = A.in_all[2][hrk][hidx];
     g3 = A.in_all[3][hrk][hidx]; g4 = A.in_all[4][hrk][hidx];
   } else {
@@ -197,15 +197,15 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
       atomic_max_nonneg(A.speed_max, m);
     }
   }
-  if (bnd && A.sync.signal_epoch > 0) {   // every store of this chunk precedes the count (and the flag behind it)
+  if (MULTI && bnd && A.sync.signal_epoch > 0) {   // every store of this chunk precedes the count (and the flag behind it)
     __syncthreads();
     if (tid == 0) stage_signal(A.sync);
   }
 }
 
-template <typename T, class L, bool SMAX>
+template <typename T, class L, bool SMAX, bool MULTI>
 static int s_launch(const t8b200_plan* P, SArgs<T>& A, cudaStream_t st) {
-  auto             k    = structured_stage_kernel<T, L, SMAX>;
+  auto             k    = structured_stage_kernel<T, L, SMAX, MULTI>;
   constexpr size_t smem = sizeof(T) * ((size_t)NCELLQ * L::NSLOT + 5 * (size_t)BoxCommon::NFLUX);
   // the opt-in above 48 KB is per device: cached per device id (not once per process)
   static int resident[64];
@@ -233,7 +233,6 @@ int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in
   SArgs<T> A{};
   A.dt_ptr = dt_dev;
   if (sync) A.sync = *sync;
-  A.n_boundary = P->nb_struct;
   A.rec = reinterpret_cast<const int4*>(P->s_rec); A.halo = P->s_halo; A.hrank = P->s_hrank;
   A.area_tab = (const T*)P->area_tab;
   bool aligned = ((uintptr_t)vol & 15u) == 0 && ((uintptr_t)P->s_halo & 15u) == 0;
@@ -245,14 +244,19 @@ int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in
     aligned     = aligned && ((uintptr_t)A.in[k] & 15u) == 0 && ((uintptr_t)A.prev[k] & 15u) == 0;
   }
   A.vol = vol; A.vol_shift = P->vol_shift; A.vol_scale = (T)P->vol_scale; A.dt = dt; A.speed_max = speed_max;
-  A.stage = stage; A.multi = P->multi; A.my_rank = P->my_rank;
-  A.dense = (P->n_struct == P->n_chunks && !P->split && !P->multi) ? 1 : 0;   // multi: boundary chunks come first
+  A.stage = stage; A.multi = P->multi && !P->ghost_tail; A.my_rank = P->my_rank;
+  A.dense = (P->n_struct == P->n_chunks && !P->split) ? 1 : 0;   // (such plans keep their chunks in element order)
+  static const bool no_dense = getenv("T8B200_TEST_NODENSE") != nullptr;   // timing experiment
+  if (no_dense) A.dense = 0;
   A.area0 = P->s_area0;
   A.pf_ok = aligned ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (P->box_layout == 1)
-    return speed_max ? s_launch<T, SubgridBox, true>(P, A, st) : s_launch<T, SubgridBox, false>(P, A, st);
-  return speed_max ? s_launch<T, MortonBox, true>(P, A, st) : s_launch<T, MortonBox, false>(P, A, st);
+  auto pick = [&](auto layout) {
+    using L = decltype(layout);
+    if (A.multi) return speed_max ? s_launch<T, L, true, true>(P, A, st) : s_launch<T, L, false, true>(P, A, st);
+    return speed_max ? s_launch<T, L, true, false>(P, A, st) : s_launch<T, L, false, false>(P, A, st);
+  };
+  return P->box_layout == 1 ? pick(SubgridBox{}) : pick(MortonBox{});
 }
 template int t8b_structured_stage_run<float>(const t8b200_plan*, int, const float* const*, const float* const* const*,
                                              const float* const*, float* const*, const float*, float, float*, void*,

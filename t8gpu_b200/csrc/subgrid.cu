@@ -423,7 +423,8 @@ static int sg_plan_build_dim(t8b200_subgrid_plan* SP, int host_only, int64_t n_l
   t8b200_plan* P = new t8b200_plan();
   SP->plan       = P;
   P->is_f64      = sizeof(T) == 8;
-  P->host_only   = host_only;
+  P->host_only   = host_only & 1;   // flags: bit 0 host-only plan, bit 1 ghost tail
+  P->ghost_tail  = (host_only >> 1) & 1;
   P->vol_shift   = dim == 3 ? 6 : 4;
   P->vol_scale   = dim == 3 ? 1.0 / 64.0 : 1.0 / 16.0;
   return plan_build<T>(P, n_local * src.S(), n_ghost > 0, src);
@@ -473,6 +474,15 @@ int t8b200_subgrid_plan_create_host(t8b200_subgrid_plan** out, int is_f64, int d
                                     const int32_t* xnbr, const void* xnormals, const void* xareas, const int32_t* xld,
                                     const int32_t* xoff) {
   return sg_plan_create_impl(out, 1, is_f64, dim, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets,
+                             volumes, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
+}
+int t8b200_subgrid_plan_create_ghost_tail(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local,
+                                          int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* nbr,
+                                          const void* normals, const void* areas, const int32_t* level_diff,
+                                          const int32_t* offsets, const void* volumes, const int32_t* ranks,
+                                          const int32_t* indices, int32_t nx, const int32_t* xnbr, const void* xnormals,
+                                          const void* xareas, const int32_t* xld, const int32_t* xoff) {
+  return sg_plan_create_impl(out, 2, is_f64, dim, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets,
                              volumes, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
 }
 const t8b200_plan* t8b200_subgrid_plan_base(const t8b200_subgrid_plan* SP) { return SP ? SP->plan : nullptr; }

@@ -56,6 +56,7 @@ struct t8b200_plan_host {
   std::vector<uint16_t> ovf_off, ovf_ent;
   std::vector<double>   area_tab, fnx, fny, fnz, farea;
   std::vector<int32_t>  s_rec, s_halo, s_hrank, g_list;   // structured chunks (box_layout.cuh)
+  std::vector<int32_t>  pull_rank, pull_idx;              // ghost tail
 };
 
 struct t8b200_plan {
@@ -98,6 +99,13 @@ struct t8b200_plan {
   // their element's volume: shift 6 / 4, scale 1/64 / 1/16, ssp_runge_kutta.inl:116)
   int    vol_shift = 0;
   double vol_scale = 1.0;
+  // ghost tail (t8b200_plan_create_ghost_tail): every ghost element a chunk reads has a LOCAL copy at index
+  // n_local + j of this rank's own rows, filled before each stage by t8b200_ghost_pull_* from the peers' rows; the
+  // halo entries point there (owner rank = this rank), so the stage kernels never touch peer memory
+  int      ghost_tail = 0;
+  int64_t  n_pull     = 0;
+  int32_t* pull_rank  = nullptr;   // device, n_pull: owner rank of tail entry j
+  int32_t* pull_idx   = nullptr;   // device, n_pull: its index in the owner's rows
   // host-only plans: arrays kept on the host, nothing uploaded, not launchable
   int               host_only = 0;
   t8b200_plan_host* host      = nullptr;
@@ -638,22 +646,80 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
         for (int h = 0; h < HS; h++)
           if (halo_elem[c * HS + h] >= 0 && halo_rank[c * HS + h] != me) { gb[q] = 1; break; }
       }
+      // order of the launches: boundary chunk j of nb sits at position floor(j W / nb) of the first W = max(nb, n/2)
+      // positions, interior chunks fill the rest in element order -- all boundary chunks are done (and signalled) about
+      // half way through the kernel, without a first wave made of nothing but NVLink-latency-bound chunks
+      // (T8B200_BND_ORDER=first: all of them first; =natural: element order).  The flag travels with the chunk:
+      // s_rec[4 q + 3] = 1, g_list entry | 1 << 30.
+      static const int order_mode = getenv("T8B200_BND_ORDER") ? (getenv("T8B200_BND_ORDER")[0] == 'f' ? 1 : getenv("T8B200_BND_ORDER")[0] == 'n' ? 2 : 0) : 0;
+      // plans whose chunks are all structured and unsplit keep the element order: chunk b = elements [256 b, 256 b + 256)
+      // needs no record load in front of the kernel's first loads (measured: +4.5 % per step with it), and their
+      // boundary chunks are scattered over the launch by the Morton order anyway
+      const bool keep_order = order_mode == 2 || (P->n_struct == nchunks && !split);
+      auto arrange = [&](const std::vector<uint8_t>& flag) {
+        const size_t n = flag.size();
+        std::vector<size_t> bl, il, order;
+        for (size_t q = 0; q < n; q++) (flag[q] ? bl : il).push_back(q);
+        order.reserve(n);
+        if (keep_order) { for (size_t q = 0; q < n; q++) order.push_back(q); return order; }
+        if (order_mode == 1 || bl.empty()) { order = bl; order.insert(order.end(), il.begin(), il.end()); return order; }
+        const size_t nb = bl.size(), W = std::max(nb, n / 2);
+        size_t ib = 0, ii = 0;
+        for (size_t pos = 0; pos < n; pos++) {
+          const bool want_b = ib < nb && (pos >= W || ib * W / nb <= pos || ii >= il.size());
+          if (want_b) order.push_back(bl[ib++]); else order.push_back(il[ii++]);
+        }
+        return order;
+      };
       std::vector<int32_t> r2, h2, k2, g2;
       r2.reserve(s_rec.size()); h2.reserve(s_halo.size()); k2.reserve(s_hrank.size()); g2.reserve(g_list.size());
-      for (int pass = 1; pass >= 0; pass--) {
-        for (int q = 0; q < P->n_struct; q++)
-          if (sb[q] == pass) {
-            r2.insert(r2.end(), s_rec.begin() + (size_t)q * 4, s_rec.begin() + (size_t)q * 4 + 4);
-            h2.insert(h2.end(), s_halo.begin() + (size_t)q * 256, s_halo.begin() + (size_t)q * 256 + 256);
-            k2.insert(k2.end(), s_hrank.begin() + (size_t)q * 256, s_hrank.begin() + (size_t)q * 256 + 256);
-          }
-        for (size_t q = 0; q < g_list.size(); q++)
-          if (gb[q] == pass) g2.push_back(g_list[q]);
-        if (pass == 1) { P->nb_struct = (int)(r2.size() / 4); P->nb_generic = (int)g2.size(); }
+      for (size_t q : arrange(sb)) {
+        r2.insert(r2.end(), s_rec.begin() + q * 4, s_rec.begin() + q * 4 + 4);
+        r2.back() = sb[q];
+        h2.insert(h2.end(), s_halo.begin() + q * 256, s_halo.begin() + q * 256 + 256);
+        k2.insert(k2.end(), s_hrank.begin() + q * 256, s_hrank.begin() + q * 256 + 256);
+        P->nb_struct += sb[q];
+      }
+      for (size_t q : arrange(gb)) {
+        g2.push_back(g_list[q] | (gb[q] ? (1 << 30) : 0));
+        P->nb_generic += gb[q];
       }
       s_rec.swap(r2); s_halo.swap(h2); s_hrank.swap(k2); g_list.swap(g2);
-      if (P->nb_struct + P->nb_generic == 0 && nchunks > 0) { if (P->n_struct) P->nb_struct = 1; else P->nb_generic = 1; }
+      if (P->nb_struct + P->nb_generic == 0 && nchunks > 0) {   // no ghosts at all: one nominal boundary chunk
+        if (P->n_struct) { s_rec[3] = 1; P->nb_struct = 1; } else { g_list[0] |= 1 << 30; P->nb_generic = 1; }
+      }
     }
+  }
+  // ghost tail: distinct (owner rank, remote index) pairs of the halo entries that live on other ranks, sorted ->
+  // tail slot j; the entries are redirected to this rank's own rows at n_local + j.  The boundary flags above were
+  // computed from the true owners and stay.
+  std::vector<int32_t> pull_rank, pull_idx;
+  if (P->ghost_tail && multi) {
+    const int32_t me = P->my_rank;
+    std::vector<uint64_t> keys;
+    auto collect = [&](const auto& elem, const auto& rank) {
+      for (size_t i = 0; i < elem.size(); i++)
+        if (elem[i] >= 0 && rank[i] != me) keys.push_back(((uint64_t)(uint32_t)rank[i] << 32) | (uint32_t)elem[i]);
+    };
+    collect(halo_elem, halo_rank);
+    collect(s_halo, s_hrank);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    if ((int64_t)keys.size() + n_local > 0x7FFFFF00LL) return cudaErrorInvalidValue;
+    auto redirect = [&](auto& elem, auto& rank) {
+      for (size_t i = 0; i < elem.size(); i++)
+        if (elem[i] >= 0 && rank[i] != me) {
+          const uint64_t k = ((uint64_t)(uint32_t)rank[i] << 32) | (uint32_t)elem[i];
+          elem[i] = (int32_t)(n_local + (std::lower_bound(keys.begin(), keys.end(), k) - keys.begin()));
+          rank[i] = me;
+        }
+    };
+    redirect(halo_elem, halo_rank);
+    redirect(s_halo, s_hrank);
+    pull_rank.resize(keys.size());
+    pull_idx.resize(keys.size());
+    for (size_t j = 0; j < keys.size(); j++) { pull_rank[j] = (int32_t)(keys[j] >> 32); pull_idx[j] = (int32_t)(keys[j] & 0xFFFFFFFFu); }
+    P->n_pull = (int64_t)keys.size();
   }
   P->n_halo     = n_halo;
   P->n_records  = n_rec;
@@ -677,6 +743,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     Hc->fnx.assign(fnx.begin(), fnx.end()); Hc->fny.assign(fny.begin(), fny.end());
     Hc->fnz.assign(fnz.begin(), fnz.end()); Hc->farea.assign(far.begin(), far.end());
     Hc->s_rec.swap(s_rec); Hc->s_halo.swap(s_halo); Hc->s_hrank.swap(s_hrank); Hc->g_list.swap(g_list);
+    Hc->pull_rank.swap(pull_rank); Hc->pull_idx.swap(pull_idx);
     P->host = Hc;
     return cudaSuccess;
   }
@@ -705,6 +772,10 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     if (P->multi) P->s_hrank = upload(s_hrank, P->dev_bytes, err);
   }
   if (!g_list.empty()) P->g_list = upload(g_list, P->dev_bytes, err);
+  if (P->n_pull) {
+    P->pull_rank = upload(pull_rank, P->dev_bytes, err);
+    P->pull_idx  = upload(pull_idx, P->dev_bytes, err);
+  }
   lap("upload");
   return err;
 }

@@ -114,7 +114,7 @@ def test_layout_is_a_bijection_and_bank_conflict_free(L):
 def structured_arrays(lib, h):
     out = {}
     for which, name in ((0, "hdr"), (13, "s_rec"), (14, "s_halo"), (15, "s_hrank"), (16, "g_list"), (8, "area_tab"),
-                        (4, "face_ai")):
+                        (4, "face_ai"), (1, "halo_elem"), (2, "halo_rank")):
         data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
         assert lib.t8b200_plan_host_array(h, which, C.byref(data), C.byref(count), C.byref(eb)) == 0
         n = count.value
@@ -166,8 +166,31 @@ def check_structured(conn, A, L, multi=False, expect_some=True, expect_all=False
         rk, ix = np.asarray(conn["ranks"]), np.asarray(conn["indices"])
         my = int(rk[0])
     s_chunks = set(int(c) for c in rec[:, 2])
-    assert sorted(s_chunks | set(int(c) for c in A["g_list"])) == (list(range(nch)) if len(rec) else sorted(A["g_list"]))
-    assert not (s_chunks & set(int(c) for c in A["g_list"]))
+    # generic chunk list: chunk id, bit 30 = partition-boundary chunk (multi-rank plans list every generic chunk)
+    g_ids = [int(c) & 0x3FFFFFFF for c in A["g_list"]]
+    g_bnd = {int(c) & 0x3FFFFFFF: bool(int(c) >> 30) for c in A["g_list"]}
+    assert len(set(g_ids)) == len(g_ids)
+    assert sorted(s_chunks | set(g_ids)) == (list(range(nch)) if (len(rec) or multi) else sorted(g_ids))
+    assert not (s_chunks & set(g_ids))
+    if multi:
+        # boundary flags: a chunk is flagged iff one of its halo elements lives on another rank; flagged chunks are
+        # spread over the first half of their launch (all done and signalled about half way through the kernel)
+        hs = len(A["halo_elem"]) // nch
+        he, hr = A["halo_elem"].reshape(nch, hs), A["halo_rank"].reshape(nch, hs)
+        for c in range(nch):
+            want = bool(((he[c] >= 0) & (hr[c] != my)).any())
+            got = bool(rec[np.nonzero(rec[:, 2] == c)[0][0], 3]) if c in s_chunks else g_bnd[c]
+            assert got == want, (c, got, want)
+        all_structured = len(rec) == nch and all(int(hdr[c, 1]) == 256 and int(hdr[c, 0]) == 256 * c for c in range(nch))
+        if all_structured:      # such plans keep the element order (chunk b = elements [256 b, 256 b + 256))
+            assert [int(c) for c in rec[:, 2]] == list(range(nch))
+        for flags in ([bool(x) for x in rec[:, 3]], [g_bnd[c] for c in g_ids]):
+            nb, n = sum(flags), len(flags)
+            if nb and not all_structured:
+                last = max(i for i, f in enumerate(flags) if f)
+                assert last < max(nb, n // 2) + 1, (last, nb, n)
+    else:
+        assert not any(rec[:, 3])
     if expect_all:
         assert len(rec) == nch
     if expect_some:

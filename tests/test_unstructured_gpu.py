@@ -345,22 +345,29 @@ def test_self_ordering_stage_kernels_bitwise(cuda, brick, P, dtype):
     ns = [int(c["n_local"]) for c in conns]
     off = np.concatenate([[0], np.cumsum(ns)])
     plans = [tb.Plan(tb.conn_to_host(c), dtype) for c in conns]
+    tail_plans = [tb.Plan(tb.conn_to_host(c), dtype, ghost_tail=True) for c in conns]
     mails = [tb.PeerMailboxes(r, P, cuda) for r in range(P)]
     for m in mails:
         m.set_table([x.buf.ptr for x in mails])     # same device: the mailboxes are plain device pointers
     dt_dev = torch.tensor([dt], dtype=dtype, device=cuda)
 
-    def run(ordered_by_kernels):
+    def run(mode):
+        """mode: "plain" (ordered by the launch sequence, direct ghost reads), "kernel" (self-ordering stage kernels, dt
+        from device memory), "tail" (ghost tail: pull kernel, then stage kernels that read no other rank's rows)."""
+        pl = tail_plans if mode == "tail" else plans
+        cols = [ns[r] + pl[r].n_tail for r in range(P)]
+        if mode == "tail":
+            assert all(pl[r].n_tail == int(conns[r]["n_ghost"]) for r in range(P))
         bufs = []
         for r in range(P):
-            b = torch.zeros((NVAR * NB_STEPS + 1, ns[r]), dtype=dtype, device=cuda)
-            b[NVAR * NB_STEPS] = conns[r]["volumes"]
-            b[0:5] = torch.as_tensor(u0[:, off[r]:off[r + 1]]).to(cuda)
+            b = torch.zeros((NVAR * NB_STEPS + 1, cols[r]), dtype=dtype, device=cuda)
+            b[NVAR * NB_STEPS, :ns[r]] = conns[r]["volumes"]
+            b[0:5, :ns[r]] = torch.as_tensor(u0[:, off[r]:off[r + 1]]).to(cuda)
             bufs.append(b)
         tabs = {s: tb.RankTables([[bufs[r][s * NVAR + k] for k in range(NVAR)] for r in range(P)], cuda)
                 for s in range(NB_STEPS)}
         vmax = [torch.zeros(1, dtype=dtype, device=cuda) for _ in range(P)]
-        if ordered_by_kernels:
+        if mode == "kernel":
             # "state written by other means": a t8b200_peer_barrier starts the epoch sequence on real GPUs; the ranks
             # emulated here share one stream, where a barrier kernel would wait for kernels behind it, so its effect
             # (every stage slot of parity e & 1 carries epoch e) is written directly
@@ -373,17 +380,23 @@ def test_self_ordering_stage_kernels_bitwise(cuda, brick, P, dtype):
         for it in range(4):
             nxt, prv = prv, nxt
             for stage, sin, sout in ((1, prv, 1), (2, 1, 2), (3, 2, nxt)):
+                if mode == "tail":
+                    for r in range(P):
+                        pl[r].pull([bufs[r][sin * NVAR + k] for k in range(NVAR)], tabs[sin])
                 for r in range(P):
                     v = lambda s: [bufs[r][s * NVAR + k] for k in range(NVAR)]  # noqa: E731
-                    kw = dict(dt_dev=dt_dev, sync=mails[r]) if ordered_by_kernels else {}
-                    plans[r].stage(stage, v(sin), v(prv), v(sout), bufs[r][NVAR * NB_STEPS], 0.0 if kw else dt,
-                                   in_all=tabs[sin], speed_max=vmax[r] if stage == 3 else None, **kw)
+                    kw = dict(dt_dev=dt_dev, sync=mails[r]) if mode == "kernel" else {}
+                    pl[r].stage(stage, v(sin), v(prv), v(sout), bufs[r][NVAR * NB_STEPS], 0.0 if kw else dt,
+                                in_all=None if mode == "tail" else tabs[sin],
+                                speed_max=vmax[r] if stage == 3 else None, **kw)
         torch.cuda.synchronize()
-        return (np.concatenate([bufs[r][nxt * NVAR:(nxt + 1) * NVAR].cpu().numpy() for r in range(P)], axis=1),
+        return (np.concatenate([bufs[r][nxt * NVAR:(nxt + 1) * NVAR, :ns[r]].cpu().numpy() for r in range(P)], axis=1),
                 max(float(x.item()) for x in vmax))
 
-    plain, vm_plain = run(False)
-    own, vm_own = run(True)
+    plain, vm_plain = run("plain")
+    own, vm_own = run("kernel")
+    tail, vm_tail = run("tail")
+    assert np.array_equal(tail, plain) and vm_tail == vm_plain
     for it in range(4):
         one.iterate(dt)
     ref = one.state().cpu().numpy()
