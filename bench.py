@@ -110,6 +110,176 @@ def build_problem(level, dtype_name, rank, nranks, device, rotate=False, mode="f
     return sol, info
 
 
+def fp64_peak():
+    """Measured FP64 rate of this pool's B200 (tools/fp64_peak.cu, record in profiles/r2_fp64_peak.txt): FMA/s."""
+    p = os.path.join(ROOT, "profiles", "r2_fp64_peak.txt")
+    best = 0.0
+    if os.path.exists(p):
+        for ln in open(p):
+            if "TFMA/s" in ln:
+                try:
+                    best = max(best, float(ln.split(":")[1].split("TFMA/s")[0]))
+                except Exception:
+                    pass
+    return (best or 16.5) * 1e12, ("profiles/r2_fp64_peak.txt" if best else "fallback 16.5 TFMA/s")
+
+
+def profile_record(dtype_name):
+    """Per-launch counters of the dominant kernel from the committed ncu capture (profiles/traffic_*.json)."""
+    tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % dtype_name)
+    try:
+        return json.load(open(tp))
+    except Exception:
+        return {}
+
+
+def time_loop(sol, dt, steps, stream):
+    import torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    ev0.record(stream)
+    for _ in range(steps):
+        launches += sol.iterate(dt)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1), launches
+
+
+def e2e_unstructured(sol, dt, level, steps, stream):
+    """The same job through the public API with HOST buffers: state uploaded from pinned host memory, K x [iterate with
+    the CFL rule: stage-3 max wave speed -> next dt, both kept on the device (t8b200_timestep); dt and vmax of every
+    step copied to the host asynchronously], state downloaded -- all inside the timed region, no host synchronisation
+    inside the loop (the reference's compute_timestep returns through the host, solver.cu:214-217)."""
+    import torch
+    n = sol.n
+    u_host = torch.empty((5, n), dtype=sol.dtype).pin_memory()
+    u_host.copy_(sol.state())
+    out_host = torch.empty((5, n), dtype=sol.dtype).pin_memory()
+    hist = torch.zeros((steps, 2), dtype=sol.dtype).pin_memory()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sol.state().copy_(u_host, non_blocking=True)
+    sol.dt_dev.fill_(dt)
+    for k in range(steps):
+        sol.iterate(dt, adaptive=True, length=0.5 ** level)
+        hist[k, 0:1].copy_(sol.dt_dev, non_blocking=True)
+        hist[k, 1:2].copy_(sol.speed_max, non_blocking=True)
+    out_host.copy_(sol.state(), non_blocking=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert bool((hist[:, 0] > 0).all()) and bool((hist[:, 0] <= dt).all()) and bool((hist[:, 1] > 0).all())
+    esz = sol.state().element_size()
+    sb = 5 * n * esz
+    return {"value": n * steps / (ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": sb / steps + esz,
+            "d2h_bytes_per_step": sb / steps + 2 * esz, "ms_per_step": ms / steps,
+            "protocol": "pinned-host state in, K x (iterate with dt on the device: stage-3 CFL max -> next dt, no host "
+                        "synchronisation; async D2H of dt and vmax per step), state out"}
+
+
+def parity_unstructured(sol, level, dtype_name, steps=3):
+    """After the timing: the measured configuration against the reference's OWN CUDA kernels (oracle/_ref, the checker)
+    from the same Kelvin-Helmholtz state, relative L-infinity after each of `steps` steps (tolerance: north star)."""
+    import numpy as np
+    import torch
+    tol = 1e-12 if dtype_name == "f64" else 1e-5
+    npdt = np.float64 if dtype_name == "f64" else np.float32
+    dt = 0.1 * 2.0 ** -level
+    try:
+        from oracle import ref_cuda
+        have_ref = ref_cuda.available()
+    except Exception:
+        have_ref = False
+    if not have_ref:
+        return {"vs": "unavailable (oracle/_ref not built)", "ok": None}
+    import t8gpu_b200 as tb
+    t0 = time.time()
+    conn = tb.cartesian_uniform_connectivity(3, level, sol.dtype, 1, 0, device=sol.device)
+    tb.init_kelvin_helmholtz(3, conn["centroids"], sol.variables(sol.next))
+    del conn
+    u0 = sol.state().cpu().numpy().astype(npdt)
+    ref = ref_cuda.RefSolver("uns", npdt, 3, level, True)   # the reference's mesh manager + kernels, unmodified
+    ref.set_state(u0)
+    errs = []
+    for _ in range(steps):
+        ref.iterate(dt)
+        sol.iterate(dt)
+        a, b = sol.state().cpu().numpy().astype(np.float64), ref.get_state().astype(np.float64)
+        scale = np.abs(b).max(axis=1)
+        scale = np.where(scale < 1e-3 * scale.max(), scale.max(), scale)   # tests/util.py: rel_linf
+        errs.append(float((np.abs(a - b).max(axis=1) / scale).max()))
+    ref.close()
+    ok = all(e <= (k + 1) * tol for k, e in enumerate(errs))
+    return {"vs": "reference CUDA kernels (oracle/_ref, examples/compressible_euler compiled unmodified)",
+            "level": level, "elements": int(u0.shape[1]), "steps": steps, "rel_linf_after_step": errs,
+            "tolerance_per_step": tol, "ok": ok, "seconds": round(time.time() - t0, 1),
+            "note": "a variable whose magnitude is < 1e-3 of the state is measured against the state scale "
+                    "(rho_v2 == 0 in this set-up)"}
+
+
+def measure_unstructured(level, dtype_name, steps, warmup, device, rotate=False, mode="fused", e2e=True, parity=True,
+                         sampler_index=0):
+    """One unstructured measurement: device-resident rate, e2e, roofline (HBM + FP64 pipe), parity."""
+    import torch
+    dt = 0.1 * 2.0 ** -level
+    sol, info = build_problem(level, dtype_name, 0, 1, device, rotate=rotate, mode=mode)
+    n = info["n"]
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        sol.iterate(dt)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(sampler_index)
+    sampler.start()
+    time.sleep(0.3)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ms, launches = time_loop(sol, dt, steps, stream)
+    clocks = sampler.stop(t0, time.time())
+    ms_per_step = ms / steps
+    vmax = float(sol.max_wave_speed().item())
+    assert vmax > 0 and vmax == vmax, "wave speed is not finite: the run diverged"
+    out = {"n": n, "ms_per_step": ms_per_step, "value": n * steps / (ms * 1e-3), "launches": launches,
+           "clocks": clocks, "max_wave_speed": vmax, "info": info}
+    if e2e and mode == "fused":
+        out["e2e"] = e2e_unstructured(sol, dt, level, steps, stream)
+    peak, peak_src = measured_peak()
+    alg = ALG_BYTES[("hex", dtype_name)]
+    achieved = alg * n / (ms_per_step * 1e-3) / 1e9
+    rec = profile_record(dtype_name) if (mode == "fused" and not rotate) else {}
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": rec.get("dram_bytes_per_launch"), "peak_source": peak_src,
+            "kernel": rec.get("kernel", "structured_stage_kernel" if mode == "fused" else
+                              "flux_faces_kernel + rk3_stage_kernel"),
+            "alg_bytes_per_launch": alg * n / 3.0, "avg_launch_ms": ms_per_step / 3.0}
+    if dtype_name == "f64" and rec.get("fp64_thread_inst_per_launch"):
+        # the second roofline (SURVEY 8d): executed FP64 instructions of the committed ncu capture / live launch time
+        # against the measured FP64 rate -- this, not HBM, is the pipe the kernel is closest to
+        pk, pk_src = fp64_peak()
+        rate = rec["fp64_thread_inst_per_launch"] / (ms_per_step / 3.0 * 1e-3)
+        roof["fp64_pipe"] = {"achieved": rate, "peak": pk, "unit": "FP64 thread-instructions/s", "frac": rate / pk,
+                             "thread_inst_per_launch": rec["fp64_thread_inst_per_launch"],
+                             "per_element_stage": rec["fp64_thread_inst_per_launch"] / n, "peak_source": pk_src,
+                             "floor_ms_per_step": 3e3 * rec["fp64_thread_inst_per_launch"] / pk}
+        roof["limiter"] = ("latency of the per-face FP64 dependency chain at 24 warps per SM (ncu: FP64 pipe %s %% busy, "
+                           "issue slots %s %%, DRAM %s %% of peak): neither roofline is saturated; the FP64 pipe is the "
+                           "nearer one" % (rec.get("fp64_pipe_busy_pct", "52-58"), rec.get("issue_active_pct", "54-57"),
+                                           rec.get("dram_pct_of_peak", "26-35")))
+    out["roofline"] = roof
+    if parity and mode == "fused" and not rotate:
+        out["parity"] = parity_unstructured(sol, level, dtype_name)
+    return out
+
+
+def short(m, keys=("ms_per_step", "value", "clocks", "parity")):
+    d = {k: m[k] for k in keys if k in m}
+    d["roofline_frac"] = m["roofline"]["frac"]
+    d["roofline_achieved_gbs"] = m["roofline"]["achieved"]
+    if "e2e" in m:
+        d["e2e_ms_per_step"] = m["e2e"]["ms_per_step"]
+    return d
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -134,93 +304,42 @@ def run_ours(args):
         return run_multi(args, rank, world, device)
 
     dtype_name = args.dtype
-    dt = 0.1 * 2.0 ** -args.level
-    sol, info = build_problem(args.level, dtype_name, 0, 1, device, rotate=args.rotate, mode=args.mode)
-    n = info["n"]
-    stream = torch.cuda.current_stream()
-
-    # ---------------- device-resident throughput ("value")
-    for _ in range(args.warmup):
-        sol.iterate(dt)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    torch.cuda.synchronize()
-    t0 = time.time()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        launches += sol.iterate(dt)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    t1 = time.time()
-    clocks = sampler.stop(t0, t1)
-    ms = ev0.elapsed_time(ev1)
-    ms_per_step = ms / args.steps
-    value = n * args.steps / (ms * 1e-3)
-    vmax = float(sol.max_wave_speed().item())
-    assert vmax > 0 and vmax == vmax, "wave speed is not finite: the run diverged"
-
-    # ---------------- end to end through the public API with host buffers ("e2e")
-    # job = upload the initial state from pinned host memory, K x [iterate(dt); read back the stage-3 maximum wave
-    # speed (the CFL reduction) and compute the next dt on the host], download the final state.  All inside the
-    # timed region; copies are amortised over K steps exactly as in a real run of the reference's main loop.
-    u_host = torch.empty((5, n), dtype=sol.dtype).pin_memory()
-    u_host.copy_(sol.state())
-    out_host = torch.empty((5, n), dtype=sol.dtype).pin_memory()
-    vmax_host = torch.empty(1, dtype=sol.dtype).pin_memory()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    sol.state().copy_(u_host, non_blocking=True)
-    cur_dt = dt
-    for _ in range(args.steps):
-        sol.iterate(cur_dt)
-        vmax_host.copy_(sol.max_wave_speed(), non_blocking=True)
-        stream.synchronize()
-        # CompressibleEulerSolver::compute_timestep (solver.cu:225-228), capped by the fixed dt of the config
-        cur_dt = min(dt, 0.7 * 0.5 ** args.level / float(vmax_host[0]))
-    out_host.copy_(sol.state(), non_blocking=True)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
+    m = measure_unstructured(args.level, dtype_name, args.steps, args.warmup, device, rotate=args.rotate,
+                             mode=args.mode, parity=not args.no_parity, sampler_index=local)
+    n, info = m["n"], m["info"]
     esz = 8 if dtype_name == "f64" else 4
-    state_bytes = 5 * n * esz
-    e2e = {"value": n * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",
-           "h2d_bytes_per_step": state_bytes / args.steps + esz, "d2h_bytes_per_step": state_bytes / args.steps + esz,
-           "ms_per_step": e2e_ms / args.steps,
-           "protocol": "pinned-host state in, K x (iterate + D2H max wave speed + host dt), state out"}
-
-    peak, peak_src = measured_peak()
-    alg = ALG_BYTES[("hex", dtype_name)]
-    achieved = alg * n / (ms_per_step * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % dtype_name)
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic if args.mode == "fused" and not args.rotate else None, "peak_source": peak_src,
-                "kernel": "fused_stage_kernel" if args.mode == "fused" else "flux_faces_kernel + rk3_stage_kernel",
-                "alg_bytes_per_launch": alg * n / 3.0, "avg_launch_ms": ms_per_step / 3.0}
-
-    line = {"metric": "cell-updates/s per RK3 step", "value": value, "unit": "cell-updates/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+    line = {"metric": "cell-updates/s per RK3 step", "value": m["value"], "unit": "cell-updates/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
             "config": {"workload": "kelvin_helmholtz 3D uniform periodic hex mesh level %d (%d elements) %s, "
                                    "fixed dt, no adaptation" % (args.level, n, dtype_name),
                        "elements_per_gpu": n, "faces_per_gpu": info["faces"], "l2": "inputs larger than L2 "
-                       "(%.0f MB of state per stage)" % (2 * state_bytes / 1e6),
+                       "(%.0f MB of state per stage)" % (2 * 5 * n * esz / 1e6),
                        "mode": ("fused tile plan" if args.mode == "fused" else "reference-shaped kernels, reference schedule") +
                                (", general normals (mesh rotated)" if args.rotate else ""),
                        "host_setup_s": {"connectivity_device": info["t_connectivity_s"],
-                                        "tile_plan_host": info["t_plan_s"], "host_cores": os.cpu_count()}},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "max_wave_speed": vmax}
+                                        "tile_plan": info["t_plan_s"], "host_cores": os.cpu_count()}},
+            "clocks": m["clocks"], "gpu_launches": m["launches"], "roofline": m["roofline"],
+            "max_wave_speed": m["max_wave_speed"]}
+    if "e2e" in m:
+        line["e2e"] = m["e2e"]
+    if "parity" in m:
+        line["parity"] = m["parity"]
+    del m
+    torch.cuda.empty_cache()
+    if not args.no_secondary and args.mode == "fused" and not args.rotate:
+        # the other precisions / workloads of the path, short runs, so that they are measured by the same command
+        from bench_subgrid import measure_subgrid
+        sec = {}
+        st = max(10, min(args.steps, 30))
+        other = "f32" if dtype_name == "f64" else "f64"
+        sec["unstructured_" + other] = short(measure_unstructured(args.level, other, st, args.warmup, device, e2e=False,
+                                                                  parity=not args.no_parity, sampler_index=local))
+        torch.cuda.empty_cache()
+        for dn in ("f64", "f32"):
+            sec["subgrid_" + dn] = measure_subgrid(6, dn, st, args.warmup, device, parity=not args.no_parity)
+            torch.cuda.empty_cache()
+        line["secondary"] = sec
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dtype_name)
     print(json.dumps(line))
@@ -268,6 +387,8 @@ def main():
                     help="uniform refinement level per GPU (default 8 = 16.8M hexes; subgrid: 6 = 16.8M cells)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timing comparison with oracle/_ref")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short fp32 / subgrid runs of the default line")
     ap.add_argument("--rotate", action="store_true", help="rotate the mesh in space: general-normal path of the plan")
     ap.add_argument("--mode", default="fused", choices=["fused", "unfused"],
                     help="unfused = the reference's schedule through the reference-shaped drop-in kernels")

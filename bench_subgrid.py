@@ -121,6 +121,72 @@ class SubgridBrick:
         self.shared.close()
 
 
+def parity_subgrid(sol, level, dtype_name, steps=3):
+    """The measured configuration against the reference's own subgrid kernels (oracle/_ref, the checker) from the same
+    Kelvin-Helmholtz cell state; relative L-infinity after each step."""
+    import numpy as np
+    tol = 1e-12 if dtype_name == "f64" else 1e-5
+    npdt = np.float64 if dtype_name == "f64" else np.float32
+    try:
+        from oracle import ref_cuda
+        if not ref_cuda.available():
+            raise RuntimeError
+    except Exception:
+        return {"vs": "unavailable (oracle/_ref not built)", "ok": None}
+    t0 = time.time()
+    dt = 0.1 * 2.0 ** -(level + 2)
+    u0 = sol.state().cpu().numpy().astype(npdt)
+    ref = ref_cuda.RefSolver("sg", npdt, 3, level, True)
+    ref.set_state(u0)
+    errs = []
+    for _ in range(steps):
+        ref.iterate(dt)
+        sol.iterate(dt)
+        a, b = sol.state().cpu().numpy().astype(np.float64), ref.get_state().astype(np.float64)
+        scale = np.abs(b).max(axis=1)
+        scale = np.where(scale < 1e-3 * scale.max(), scale.max(), scale)
+        errs.append(float((np.abs(a - b).max(axis=1) / scale).max()))
+    ref.close()
+    return {"vs": "reference CUDA kernels (oracle/_ref, examples/subgrid compiled unmodified)", "level": level,
+            "cells": int(u0.shape[1]), "steps": steps, "rel_linf_after_step": errs, "tolerance_per_step": tol,
+            "ok": all(e <= (k + 1) * tol for k, e in enumerate(errs)), "seconds": round(time.time() - t0, 1)}
+
+
+def measure_subgrid(level, dtype_name, steps, warmup, device, parity=True):
+    """Short single-GPU Subgrid<4,4,4> run for the `secondary` block of the default bench line."""
+    from bench import ClockSampler, measured_peak
+    dtype = torch.float64 if dtype_name == "f64" else torch.float32
+    sol = SubgridBrick(level, dtype, 0, 1, device)
+    dt = 0.1 * 2.0 ** -(level + 2)
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        sol.iterate(dt)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(steps):
+        sol.iterate(dt)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop(t0, time.time())
+    ms_per_step = ev0.elapsed_time(ev1) / steps
+    assert bool(torch.isfinite(sol.state()).all()), "the run diverged"
+    peak, _ = measured_peak()
+    achieved = ALG_CELL_BYTES[dtype_name] * sol.n / (ms_per_step * 1e-3) / 1e9
+    out = {"workload": "Subgrid<4,4,4>, uniform periodic hex forest level %d (%d cells) %s" % (level, sol.n, dtype_name),
+           "ms_per_step": ms_per_step, "value": sol.n / (ms_per_step * 1e-3), "clocks": clocks,
+           "roofline_frac": achieved / peak, "roofline_achieved_gbs": achieved,
+           "alg_bytes_per_cell_step": ALG_CELL_BYTES[dtype_name], "tile_plan_s": round(sol.t_plan, 2)}
+    if parity:
+        out["parity"] = parity_subgrid(sol, level, dtype_name)
+    sol.close()
+    return out
+
+
 def run_subgrid(args, rank, world, device):
     import torch.distributed as dist
     from bench import ClockSampler, measured_peak

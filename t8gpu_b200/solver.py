@@ -41,6 +41,7 @@ class EulerSolver:
         self.next, self.prev = STEP0, STEP3
         self.speed = torch.zeros(max(1, self.nf + self.nb), dtype=dtype, device=self.device)
         self.speed_max = torch.zeros(1, dtype=dtype, device=self.device)
+        self.dt_dev = torch.zeros(1, dtype=dtype, device=self.device)   # time step kept on the device (adaptive=True)
         self.plan = None
         if mode == "fused":
             self.plan = Plan(conn_host, dtype)
@@ -67,16 +68,24 @@ class EulerSolver:
         return self.buffer[self.next * NVAR:(self.next + 1) * NVAR, :self.n]
 
     # --- CompressibleEulerSolver::iterate (solver.cu:75-175) -------------------------------------------
-    def iterate(self, dt, stream=None):
-        from . import flux_faces, rk3_stage
+    def iterate(self, dt, stream=None, adaptive=False, length=None):
+        """One RK3 step.  adaptive (fused mode): the step uses the dt stored in self.dt_dev and leaves the next one
+        there, min(dt, cfl * length / vmax) with vmax the stage-3 maximum wave speed (compute_timestep,
+        solver.cu:213-229) -- computed on the device, no copy to the host, no synchronisation."""
+        from . import flux_faces, rk3_stage, timestep
         self.next, self.prev = self.prev, self.next
         prev = self.variables(self.prev)
         s1, s2, nxt = self.variables(STEP1), self.variables(STEP2), self.variables(self.next)
         vol = self.volume()
         if self.mode == "fused":
-            self.plan.stage(1, prev, None, s1, vol, dt, stream=stream)
-            self.plan.stage(2, s1, prev, s2, vol, dt, stream=stream)
-            self.plan.stage(3, s2, prev, nxt, vol, dt, speed_max=self.speed_max, stream=stream)
+            dtd = self.dt_dev if adaptive else None
+            self.plan.stage(1, prev, None, s1, vol, dt, stream=stream, dt_dev=dtd)
+            self.plan.stage(2, s1, prev, s2, vol, dt, stream=stream, dt_dev=dtd)
+            self.plan.stage(3, s2, prev, nxt, vol, dt, speed_max=self.speed_max, stream=stream, dt_dev=dtd)
+            if adaptive:
+                timestep(self.speed_max, self.cfl, 0.5 ** self.max_level if length is None else length, dt,
+                         self.dt_dev, stream)
+                return 4
             return 3
         fl = self.variables(FLUXES)
         T = self._tables
