@@ -63,7 +63,12 @@ class MultiGpuEuler:
         self.n = int(conn["n_local"])
         self.n_faces = int(conn["n_faces"]) + int(conn["n_xfaces"])
         self.n_ghost = int(conn["n_ghost"])
-        self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync == "pull")
+        t0 = time.time()
+        self.plan = tb.Plan.from_device(conn, dtype, ghost_tail=self.sync == "pull")     # no D2H of the connectivity
+        if self.plan is None:
+            self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync == "pull")
+        torch.cuda.synchronize()
+        self.t_plan = time.time() - t0
         self.cap = (self.n + self.plan.n_tail + 31) // 32 * 32     # own elements, then the ghost tail
         nrows = NVAR * NB_STEPS + 1
         self.shared = tb.SharedBuffer(nrows * self.cap * esz, device)
@@ -297,7 +302,7 @@ def run_multi(args, rank, world, device):
 
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     info = sol.plan.info
-    nfaces, nghost, sync = sol.n_faces, sol.n_ghost, sol.sync
+    nfaces, nghost, sync, t_plan = sol.n_faces, sol.n_ghost, sol.sync, sol.t_plan
     sol.close()
     if rank == 0:
         esz = 8 if args.dtype == "f64" else 4
@@ -330,7 +335,8 @@ def run_multi(args, rank, world, device):
                            "partition": "one tree (one t8code SFC partition) per GPU; ghosts read from peer GPUs "
                                         "over NVLink (cudaIpc-mapped state arrays), owner-computes boundary faces",
                            "sync": sync_text, "l2": "inputs larger than L2",
-                           "host_setup_s": round(t_setup, 2), "host_cores": os.cpu_count(),
+                           "host_setup_s": round(t_setup, 2), "tile_plan_s": round(t_plan, 3),
+                           "tile_plan_built_on": info.get("built_on", "host"), "host_cores": os.cpu_count(),
                            "host_cpus_bound_to_gpu_numa_node": ncpu, "per_rank_ms_per_step": per_rank_ms,
                            "plan": info},
                 "clocks": clocks, "parity": parity,

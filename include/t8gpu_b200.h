@@ -170,6 +170,24 @@ int t8b200_ghost_pull_f32(const t8b200_plan* plan, int nvar, float* const* rows,
 int t8b200_ghost_pull_f64(const t8b200_plan* plan, int nvar, double* const* rows, const double* const* const* rows_all,
                           void* stream);
 
+/* The plan built ON THE DEVICE from DEVICE connectivity arrays (same arguments as t8b200_plan_create, all pointers device
+ * pointers): no device -> host copy of the connectivity, no host loop -- for the meshes whose every block of 256
+ * consecutive elements is an 8 x 8 x 4 box of same-size hexahedra with 256 single same-size face neighbours (uniform
+ * forests and brick partitions: the arrays t8b200_cartesian_*_connectivity leaves on the device).  Returns
+ * cudaErrorNotSupported (801) for any other mesh (hanging faces, walls, general normals, n_local not a multiple of 256):
+ * the caller then copies the arrays to the host and uses t8b200_plan_create.  The plan holds the halo lists of its
+ * chunks (equal, entry for entry, to arrays 13-15 / 17-18 of the host builder) and serves t8b200_fused_stage_*,
+ * t8b200_ghost_pull_* and t8b200_gradient_criteria_*.  ghost_tail != 0: as t8b200_plan_create_ghost_tail.
+ * Replaces the upload half of MeshManager::compute_connectivity_information (t8gpu/mesh/mesh_manager.inl:442-480). */
+int t8b200_plan_create_device(t8b200_plan** out, int is_f64, int ghost_tail, int64_t n_local, int64_t n_ghost,
+                              int32_t nf, int32_t nb, const int32_t* face_neighbors, const void* face_normals,
+                              const void* face_surfaces, const int32_t* ranks, const int32_t* indices,
+                              int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
+                              const void* x_face_surfaces, void* stream);
+/* test access: one of the structured / ghost-tail DEVICE arrays of a plan copied to the host (which = 13, 14, 15, 17,
+ * 18 as t8b200_plan_host_array numbers them); returns the element count (host_out may be NULL), -1 on error */
+int64_t t8b200_plan_device_array(const t8b200_plan* plan, int which, int32_t* host_out, int64_t capacity);
+
 /* One fused RK stage.  in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's arrays (stage input, U^n, stage
  * output).  in_all: HOST array of 5 DEVICE tables (one pointer per rank) for ghost reads, or NULL when the plan has
  * no ghosts.  vol: device, per element.  speed_max_dev: device scalar receiving max(|uHat|+aHat) over the faces of

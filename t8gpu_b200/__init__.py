@@ -32,6 +32,7 @@ def lib():
         _LIB = C.CDLL(LIB_PATH)
         _LIB.t8b200_plan_destroy.restype = None
         _LIB.t8b200_plan_ghost_tail_count.restype = C.c_int64
+        _LIB.t8b200_plan_device_array.restype = C.c_int64
         _LIB.t8b200_cartesian_connectivity_free.restype = None
         if hasattr(_LIB, "t8b200_solver_destroy"):
             _LIB.t8b200_solver_destroy.restype = None
@@ -207,6 +208,51 @@ class Plan:
         check(lib().t8b200_plan_info(self._h, info), "plan_info")
         self.info = dict(n_chunks=info[0], max_halo=info[1], max_faces=info[2], smem_bytes=info[3],
                          device_bytes=info[4], face_records=info[5], halo_entries=info[6], chunk=info[7])
+
+    @classmethod
+    def from_device(cls, conn, dtype, ghost_tail=False, stream=None):
+        """Plan built on the device from DEVICE connectivity tensors (t8b200_plan_create_device): no copy of the
+        connectivity to the host.  Returns None when the mesh is not made of structured chunks only (the caller then
+        uses Plan(conn_to_host(conn), ...))."""
+        _torch()
+        s, _ = _sfx(dtype)
+
+        def p(k):
+            t = conn.get(k)
+            return None if t is None or t.numel() == 0 else C.c_void_p(t.data_ptr())
+
+        nx = int(conn.get("n_xfaces", 0))
+        ng = int(conn.get("n_ghost", 0))
+        h = C.c_void_p()
+        rc = lib().t8b200_plan_create_device(
+            C.byref(h), int(s == "f64"), int(bool(ghost_tail)), C.c_int64(int(conn["n_local"])), C.c_int64(ng),
+            int(conn["n_faces"]), int(conn["n_bfaces"]), p("face_neighbors"), p("face_normals"), p("face_areas"),
+            p("ranks") if ng else None, p("indices") if ng else None, nx, p("x_face_neighbors") if nx else None,
+            p("x_face_normals") if nx else None, p("x_face_areas") if nx else None, stream_ptr(stream))
+        if rc == 801:   # cudaErrorNotSupported: not a structured-only mesh
+            return None
+        check(rc, "plan_create_device")
+        self = cls.__new__(cls)
+        self.dtype, self._h = dtype, h
+        self.n_tail = int(lib().t8b200_plan_ghost_tail_count(h))
+        info = (C.c_int64 * 8)()
+        check(lib().t8b200_plan_info(self._h, info), "plan_info")
+        self.info = dict(n_chunks=info[0], max_halo=info[1], max_faces=info[2], smem_bytes=info[3],
+                         device_bytes=info[4], face_records=info[5], halo_entries=info[6], chunk=info[7],
+                         built_on="device")
+        return self
+
+    def device_array(self, which):
+        """Structured / ghost-tail arrays of the plan copied from the device (13 s_rec, 14 s_halo, 15 s_hrank, 17
+        pull_rank, 18 pull_idx) -> numpy int32."""
+        import numpy as np
+        n = lib().t8b200_plan_device_array(self._h, which, None, C.c_int64(0))
+        if n < 0:
+            raise CudaError("plan_device_array(%d)" % which)
+        a = np.zeros(n, np.int32)
+        if n:
+            lib().t8b200_plan_device_array(self._h, which, a.ctypes.data_as(C.c_void_p), C.c_int64(n))
+        return a
 
     def __del__(self):
         if getattr(self, "_h", None) and lib is not None:   # `lib` is gone when the interpreter shuts down

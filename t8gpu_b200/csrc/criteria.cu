@@ -78,6 +78,33 @@ __global__ void __launch_bounds__(EC) gradient_criteria_kernel(const __grid_cons
   A.out[e] = acc / cbrt(A.vol[e >> A.vol_shift] * A.vol_scale);   // solver.cu:243
 }
 
+// Plans built on the device (device_plan.cu) carry only the halo lists of their structured chunks: the six neighbours
+// of an element follow from the box layout, no face records.
+template <typename T, class L>
+__global__ void __launch_bounds__(256)
+structured_gradient_kernel(const int32_t* __restrict__ s_halo, const int32_t* __restrict__ s_hrank, int multi,
+                           int my_rank, const T* __restrict__ rho, const T* const* __restrict__ rho_all,
+                           const T* __restrict__ vol, T* __restrict__ out) {
+  __shared__ T  r[L::NSLOT];
+  const int     b = blockIdx.x, t = threadIdx.x;
+  const int64_t e = (int64_t)b * 256 + t;
+  const int     hidx = s_halo[(int64_t)b * 256 + t];
+  const int     hrk  = multi ? s_hrank[(int64_t)b * 256 + t] : my_rank;
+  const T       mine = rho[e];
+  r[t] = mine;
+  r[L::thread_slot(t)] = (multi && hrk != my_rank) ? rho_all[hrk][hidx] : rho[hidx];
+  __syncthreads();
+  T acc = T(0);
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const int lo = L::at_lower(t, d) ? L::halo_slot(d, 0, L::compact(t, d)) : L::lower_own(t, d);
+    const int up = L::at_upper(t, d) ? L::halo_slot(d, 1, L::compact(t, d)) : L::upper_own(t, d);
+    acc += t8b200::fabs_(mine - r[lo]);
+    acc += t8b200::fabs_(r[up] - mine);
+  }
+  out[e] = acc / cbrt(vol[e]);   // solver.cu:243
+}
+
 // EPB elements per CTA; all threads stage the densities (coalesced), the first EPB threads walk one element each.
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
@@ -120,15 +147,21 @@ subgrid_criteria_kernel(int64_t ne, const T* __restrict__ rho, const T* __restri
 
 template <typename T>
 int gradient_impl(const t8b200_plan* P, const T* rho, const T* const* rho_all, const T* vol, T* out, void* stream) {
-  if (!P || P->host_only || !rho || !vol || !out || (P->multi && !rho_all)) return cudaErrorInvalidValue;
+  if (!P || P->host_only || !rho || !vol || !out || (P->multi && !P->ghost_tail && !rho_all)) return cudaErrorInvalidValue;
   if (P->is_f64 != (sizeof(T) == 8)) return cudaErrorInvalidValue;
   if (P->n_chunks == 0) return 0;
+  if (!P->hdr) {   // device-built plan: every chunk is a structured box of hexahedra
+    if (P->n_struct != P->n_chunks || P->box_layout != 0 || P->vol_shift != 0) return cudaErrorInvalidValue;
+    structured_gradient_kernel<T, t8b200::MortonBox><<<P->n_chunks, 256, 0, (cudaStream_t)stream>>>(
+        P->s_halo, P->s_hrank, P->multi && !P->ghost_tail, P->my_rank, rho, rho_all, vol, out);
+    return cudaGetLastError();
+  }
   GradArgs<T> A{};
   A.hdr = reinterpret_cast<const int4*>(P->hdr);
   A.halo_elem = P->halo_elem; A.halo_rank = P->halo_rank; A.face_lr = P->face_lr;
   A.ell = P->ell; A.ovf_off = P->ovf_off; A.ovf_ent = P->ovf_ent;
   A.rho = rho; A.rho_all = rho_all; A.vol = vol; A.out = out; A.n_local = P->n_local;
-  A.hs = P->hs; A.fs = P->fs; A.split = P->split; A.multi = P->multi; A.cmp = P->cmp;
+  A.hs = P->hs; A.fs = P->fs; A.split = P->split; A.multi = P->multi && !P->ghost_tail; A.cmp = P->cmp;
   A.vol_shift = P->vol_shift; A.vol_scale = (T)P->vol_scale;
   gradient_criteria_kernel<T><<<P->n_chunks, EC, 0, (cudaStream_t)stream>>>(A);
   return cudaGetLastError();

@@ -21,7 +21,7 @@ class EulerSolver:
 
     cfl = 0.7  # solver.h:37
 
-    def __init__(self, conn_host, volumes, dtype, device=None, mode="fused", max_level=4):
+    def __init__(self, conn_host, volumes, dtype, device=None, mode="fused", max_level=4, plan=None):
         import numpy as np
         import torch
         from . import Plan, RankTables, conn_to_device
@@ -36,7 +36,8 @@ class EulerSolver:
         # 128-byte aligned rows: capacity padded to a multiple of 32 elements
         self.capacity = max(32, (self.n + 31) // 32 * 32)
         self.buffer = torch.zeros((NVAR * NB_STEPS + 1, self.capacity), dtype=dtype, device=self.device)
-        vol = torch.as_tensor(np.ascontiguousarray(volumes)).to(dtype).to(self.device)
+        vol = (volumes if isinstance(volumes, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(volumes)))
+        vol = vol.to(dtype).to(self.device)
         self.buffer[NVAR * NB_STEPS, :self.n] = vol
         self.next, self.prev = STEP0, STEP3
         self.speed = torch.zeros(max(1, self.nf + self.nb), dtype=dtype, device=self.device)
@@ -44,7 +45,7 @@ class EulerSolver:
         self.dt_dev = torch.zeros(1, dtype=dtype, device=self.device)   # time step kept on the device (adaptive=True)
         self.plan = None
         if mode == "fused":
-            self.plan = Plan(conn_host, dtype)
+            self.plan = plan if plan is not None else Plan(conn_host, dtype)   # plan: e.g. Plan.from_device(...)
         else:
             self.conn = conn_to_device({k: conn_host[k] for k in
                                         ("face_neighbors", "face_normals", "face_areas")}, dtype, self.device)

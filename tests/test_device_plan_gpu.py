@@ -1,0 +1,114 @@
+"""f-2: the tile plan built on the device (t8b200_plan_create_device) from device-resident connectivity arrays equals the
+host builder's plan array by array (structured-chunk records, halo lists in thread order, owner ranks, partition-boundary
+flags, ghost-tail redirection and pull lists), gives bitwise the same states, and reports meshes it does not cover."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import rel_linf
+
+pytestmark = pytest.mark.gpu
+
+
+def host_arrays(conn_host, dtype, ghost_tail):
+    """Arrays 13-15, 17-18 of the HOST builder (host-only plan: nothing uploaded)."""
+    import t8gpu_b200 as tb
+    lib = tb.lib()
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+
+    def arr(k, dt):
+        v = conn_host.get(k)
+        return None if v is None or len(v) == 0 else np.ascontiguousarray(v, dtype=dt)
+
+    def p(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    keep = [arr("face_neighbors", np.int32), arr("face_normals", npdt), arr("face_areas", npdt), arr("ranks", np.int32),
+            arr("indices", np.int32), arr("x_face_neighbors", np.int32), arr("x_face_normals", npdt),
+            arr("x_face_areas", npdt)]
+    ng = int(conn_host.get("n_ghost", 0))
+    h = C.c_void_p()
+    fn = lib.t8b200_plan_create_ghost_tail_host if ghost_tail else lib.t8b200_plan_create_host
+    assert fn(C.byref(h), int(dtype == torch.float64), C.c_int64(int(conn_host["n_local"])), C.c_int64(ng),
+              int(conn_host["n_faces"]), int(conn_host["n_bfaces"]), p(keep[0]), p(keep[1]), p(keep[2]),
+              p(keep[3]) if ng else None, p(keep[4]) if ng else None, int(conn_host.get("n_xfaces", 0)), p(keep[5]),
+              p(keep[6]), p(keep[7])) == 0
+    out = {}
+    for which in (13, 14, 15, 17, 18):
+        data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
+        assert lib.t8b200_plan_host_array(h, which, C.byref(data), C.byref(count), C.byref(eb)) == 0
+        n = count.value
+        out[which] = (np.frombuffer((C.c_char * (n * 4)).from_address(data.value), dtype=np.int32).copy() if n
+                      else np.zeros(0, np.int32))
+    lib.t8b200_plan_destroy(h)
+    return out
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("level", [4, 5])
+def test_uniform_forest_plan_equals_host_builder(cuda, level, dtype):
+    import t8gpu_b200 as tb
+    conn = tb.cartesian_uniform_connectivity(3, level, dtype, 1, 0, device=cuda)
+    plan = tb.Plan.from_device(conn, dtype)
+    assert plan is not None and plan.info["n_chunks"] == int(conn["n_local"]) // 256
+    host = host_arrays(tb.conn_to_host(conn), dtype, False)
+    for which in (13, 14):
+        assert np.array_equal(plan.device_array(which), host[which]), which
+    assert plan.device_array(15).size == 0 and plan.n_tail == 0
+    # the same states, bit for bit, as with the host-built plan; criteria agree to rounding (different summation order)
+    a = tb.EulerSolver(tb.conn_to_host(conn), conn["volumes"], dtype, device=cuda)
+    b = tb.EulerSolver(None or tb.conn_to_host(conn), conn["volumes"], dtype, device=cuda, plan=plan)
+    tb.init_kelvin_helmholtz(3, conn["centroids"], a.variables(a.next))
+    rng = np.random.default_rng(3)
+    u0 = a.state().cpu().numpy() * (1 + 0.02 * rng.uniform(-1, 1, (5, a.n)))
+    a.set_state(u0)
+    b.set_state(u0)
+    dt = 0.1 * 2.0 ** -level
+    for _ in range(3):
+        a.iterate(dt)
+        b.iterate(dt)
+    assert torch.equal(a.state(), b.state()) and torch.equal(a.max_wave_speed(), b.max_wave_speed())
+    ca = tb.gradient_criteria(a.plan, a.state()[0], a.volume()).cpu().numpy()
+    cb = tb.gradient_criteria(plan, b.state()[0], b.volume()).cpu().numpy()
+    assert np.abs(ca - cb).max() <= (1e-13 if dtype == torch.float64 else 1e-5) * np.abs(ca).max()
+
+
+@pytest.mark.parametrize("ghost_tail", [False, True])
+@pytest.mark.parametrize("brick,P", [((2, 1, 1), 2), ((2, 2, 1), 4)])
+def test_partitioned_brick_plan_equals_host_builder(cuda, brick, P, ghost_tail):
+    import t8gpu_b200 as tb
+    dtype = torch.float64
+    for r in range(P):
+        conn = tb.cartesian_uniform_connectivity(3, 4, dtype, P, r, device=cuda, brick=brick)
+        plan = tb.Plan.from_device(conn, dtype, ghost_tail=ghost_tail)
+        assert plan is not None
+        host = host_arrays(tb.conn_to_host(conn), dtype, ghost_tail)
+        for which in (13, 14, 15, 17, 18):
+            assert np.array_equal(plan.device_array(which), host[which]), (which, r)
+        if ghost_tail:
+            assert plan.n_tail == host[17].size == int(conn["n_ghost"])
+            assert (plan.device_array(15) == r).all()
+        else:
+            assert plan.device_array(13).reshape(-1, 4)[:, 3].sum() > 0      # partition-boundary chunks are flagged
+
+
+def test_meshes_outside_the_device_builder_are_reported(cuda):
+    """Hanging faces, walls, general normals: cudaErrorNotSupported -> None, the caller falls back to the host builder."""
+    import t8gpu_b200 as tb
+    f = oracle.Forest(3, 4)
+    lv, cent, vol, _ = f.elements()
+    amr = f.adapt(np.where(np.abs(cent[:, 2] - 0.5) < 0.2, 20.0, 0.0), 10.0, 1, 5)
+    walls = oracle.Forest(3, 4, periodic=False)
+    small = tb.conn_to_device(oracle.Forest(3, 3).connectivity(dtype=np.float64), torch.float64, cuda)
+    assert tb.Plan.from_device(small, torch.float64) is None     # 8 elements across: a box is its own neighbour
+    for forest in (amr, walls):
+        conn = tb.conn_to_device(forest.connectivity(dtype=np.float64), torch.float64, cuda)
+        assert tb.Plan.from_device(conn, torch.float64) is None
+    conn = tb.conn_to_device(f.connectivity(dtype=np.float64), torch.float64, cuda)
+    assert tb.Plan.from_device(conn, torch.float64) is not None
+    q, _ = np.linalg.qr(np.random.default_rng(7).normal(size=(3, 3)))
+    conn["face_normals"] = (conn["face_normals"].view(-1, 3) @ torch.as_tensor(q.T).to(cuda)).reshape(-1).contiguous()
+    assert tb.Plan.from_device(conn, torch.float64) is None

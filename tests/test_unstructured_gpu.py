@@ -325,15 +325,16 @@ def test_hybrid_tet_prism_hex_mesh(cuda, periodic, shuffle, mode, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("brick,P", [((2, 1, 1), 2), ((2, 2, 1), 4)])
-def test_self_ordering_stage_kernels_bitwise(cuda, brick, P, dtype):
+@pytest.mark.parametrize("brick,P,L", [((2, 1, 1), 2, 3), ((2, 2, 1), 4, 3), ((2, 1, 1), 2, 4)])
+def test_self_ordering_stage_kernels_bitwise(cuda, brick, P, L, dtype):
     """t8b200_fused_stage_sync_*: the stage kernels order themselves through the mailboxes (partition-boundary chunks
     first: wait for the peers' previous launch, the last one signals) and read dt from device memory.  P ranks emulated
     on one device, stage after stage (so no kernel ever waits for a later one).  Owner-computes is deterministic: the
     result must be BITWISE the one-rank run of the same brick, and bitwise the run ordered by plain launches."""
     import t8gpu_b200 as tb
     from t8gpu_b200.solver import NB_STEPS, NVAR
-    L, dt = 3, 0.1 * 2.0 ** -3
+    # level 3: generic chunks (a tree 8 elements across is its own neighbour); level 4: structured chunks
+    dt = 0.1 * 2.0 ** -L
     c1 = tb.cartesian_uniform_connectivity(3, L, dtype, 1, 0, brick=brick)
     n1 = int(c1["n_local"])
     one = tb.EulerSolver(tb.conn_to_host(c1), c1["volumes"].cpu().numpy(), dtype, device=cuda)
