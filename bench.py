@@ -302,6 +302,12 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    if args.workload == "amr":
+        from bench_amr import run_amr
+        run_amr(args, rank, world, device, dist if world > 1 else None)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "subgrid":
         from bench_subgrid import run_subgrid
         run_subgrid(args, rank, world, device)
@@ -349,6 +355,8 @@ def run_ours(args):
         for dn in ("f64", "f32"):
             sec["subgrid_" + dn] = measure_subgrid(6, dn, st, args.warmup, device, parity=not args.no_parity)
             torch.cuda.empty_cache()
+        from bench_amr import amr_secondary
+        sec["amr_c3"] = amr_secondary(dtype_name, 0, 1, device)
         line["secondary"] = sec
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dtype_name)
@@ -391,8 +399,12 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="unstructured", choices=["unstructured", "subgrid"],
-                    help="unstructured = BASELINE configs[1] (the headline); subgrid = configs[3], Subgrid<4,4,4>")
+    ap.add_argument("--workload", default="unstructured", choices=["unstructured", "subgrid", "amr"],
+                    help="unstructured = BASELINE configs[1] (the headline); subgrid = configs[3], Subgrid<4,4,4>; "
+                         "amr = configs[2], adapt + repartition every --every steps")
+    ap.add_argument("--every", type=int, default=10, help="amr: steps between adapts")
+    ap.add_argument("--cycles", type=int, default=3, help="amr: adapt cycles")
+    ap.add_argument("--check", action="store_true", help="amr: compare with a one-rank run of the same forest sequence")
     ap.add_argument("--level", type=int, default=None,
                     help="uniform refinement level per GPU (default 8 = 16.8M hexes; subgrid: 6 = 16.8M cells)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
@@ -405,7 +417,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.level is None:
+    if args.level is None and args.workload != "amr":
         args.level = 6 if args.workload == "subgrid" else 8
     if args.impl == "reference":
         return run_reference(args)

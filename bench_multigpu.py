@@ -304,6 +304,12 @@ def run_multi(args, rank, world, device):
     info = sol.plan.info
     nfaces, nghost, sync, t_plan = sol.n_faces, sol.n_ghost, sol.sync, sol.t_plan
     sol.close()
+    secondary = {}
+    if not getattr(args, "no_secondary", False):
+        # BASELINE config 3 across the same ranks: adapt + repartition every 10 steps (short run, compared with the
+        # one-rank run of the same forest sequence)
+        from bench_amr import amr_secondary
+        secondary["amr_c3"] = amr_secondary(args.dtype, rank, world, device, dist)
     if rank == 0:
         esz = 8 if args.dtype == "f64" else 4
         total = n * world
@@ -339,7 +345,7 @@ def run_multi(args, rank, world, device):
                            "tile_plan_built_on": info.get("built_on", "host"), "host_cores": os.cpu_count(),
                            "host_cpus_bound_to_gpu_numa_node": ncpu, "per_rank_ms_per_step": per_rank_ms,
                            "plan": info},
-                "clocks": clocks, "parity": parity,
+                "clocks": clocks, "parity": parity, "secondary": secondary,
                 "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",
                         "h2d_bytes_per_step": (state_bytes / args.steps + esz) * world,
                         "d2h_bytes_per_step": (state_bytes / args.steps + 2 * esz) * world,
