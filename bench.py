@@ -302,6 +302,12 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    if args.workload == "hybrid":
+        from bench_hybrid import run_hybrid
+        run_hybrid(args, rank, world, device, dist if world > 1 else None)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "amr":
         from bench_amr import run_amr
         run_amr(args, rank, world, device, dist if world > 1 else None)
@@ -399,9 +405,10 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="unstructured", choices=["unstructured", "subgrid", "amr"],
+    ap.add_argument("--workload", default="unstructured", choices=["unstructured", "subgrid", "amr", "hybrid"],
                     help="unstructured = BASELINE configs[1] (the headline); subgrid = configs[3], Subgrid<4,4,4>; "
-                         "amr = configs[2], adapt + repartition every --every steps")
+                         "amr = configs[2], adapt + repartition every --every steps; hybrid = configs[4], mixed "
+                         "hex + prism + tet mesh, strong scaling (--level = tiles per direction, 648 * level^3 elements)")
     ap.add_argument("--every", type=int, default=10, help="amr: steps between adapts")
     ap.add_argument("--cycles", type=int, default=3, help="amr: adapt cycles")
     ap.add_argument("--check", action="store_true", help="amr: compare with a one-rank run of the same forest sequence")
@@ -417,7 +424,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.level is None and args.workload != "amr":
+    if args.level is None and args.workload not in ("amr", "hybrid"):
         args.level = 6 if args.workload == "subgrid" else 8
     if args.impl == "reference":
         return run_reference(args)
