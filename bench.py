@@ -363,6 +363,12 @@ def run_ours(args):
             torch.cuda.empty_cache()
         from bench_amr import amr_secondary
         sec["amr_c3"] = amr_secondary(dtype_name, 0, 1, device)
+        sec["subgrid_amr_c4"] = amr_secondary(dtype_name, 0, 1, device, subgrid=True)
+        from bench_hybrid import run_hybrid
+        h = run_hybrid(argparse.Namespace(dtype=dtype_name, level=12, steps=st, warmup=args.warmup), 0, 1, device,
+                       emit=False)
+        sec["hybrid_c5"] = {"workload": h["config"]["workload"], "ms_per_step": h["ms_per_step"], "value": h["value"],
+                            "roofline_frac": h["roofline"]["frac"], "parity": h["parity"]}
         line["secondary"] = sec
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dtype_name)
@@ -412,6 +418,7 @@ def main():
     ap.add_argument("--every", type=int, default=10, help="amr: steps between adapts")
     ap.add_argument("--cycles", type=int, default=3, help="amr: adapt cycles")
     ap.add_argument("--check", action="store_true", help="amr: compare with a one-rank run of the same forest sequence")
+    ap.add_argument("--subgrid", action="store_true", help="amr: Subgrid<4,4,4> elements (BASELINE configs[3] with AMR)")
     ap.add_argument("--level", type=int, default=None,
                     help="uniform refinement level per GPU (default 8 = 16.8M hexes; subgrid: 6 = 16.8M cells)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])

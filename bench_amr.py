@@ -34,7 +34,9 @@ def pad32(n):
 class RankMesh:
     """One rank's partition of one forest: connectivity, plan (ghost tail), MemoryManager-layout rows, peer tables."""
 
-    def __init__(self, forest, rank, world, device, dtype, dist, rows=26):
+    def __init__(self, forest, rank, world, device, dtype, dist, rows=26, subgrid=False):
+        """subgrid: Subgrid<4,4,4> cells (64 per element) in the variable rows, cell-level plan; the per-element volumes
+        sit in the last row (first n entries) so that the partition remap can pull them from the peers."""
         import t8gpu_b200 as tb
         from t8gpu_b200.multi import exchange_wires
         self.tb, self.rank, self.world, self.device, self.dtype = tb, rank, world, device, dtype
@@ -42,13 +44,18 @@ class RankMesh:
         esz = 8 if dtype == torch.float64 else 4
         t0 = time.time()
         self.off = forest.partition_offsets(world)
-        conn = forest.connectivity(world, rank, dtype=npdt)
+        conn = forest.connectivity(world, rank, subgrid=subgrid, dtype=npdt)
         self.t_conn = time.time() - t0
         self.n = int(conn["n_local"])
+        self.S = 64 if subgrid else 1
+        self.nc = self.n * self.S                          # entries of a variable row (cells)
         t0 = time.time()
         self.plan = None
         lv = forest.elements()[0]
-        if lv.min() == lv.max() and self.n % 256 == 0:     # uniform: the device builder applies
+        if subgrid:
+            lvol = forest.elements()[2][self.off[rank]:self.off[rank + 1]].astype(npdt)
+            self.plan = tb.SubgridPlan(conn, lvol, dtype, ghost_tail=world > 1)
+        elif lv.min() == lv.max() and self.n % 256 == 0:     # uniform: the device builder applies
             keys = ("face_neighbors", "face_normals", "face_areas", "ranks", "indices", "x_face_neighbors",
                     "x_face_normals", "x_face_areas")
             cd = tb.conn_to_device({k: conn[k] for k in keys}, dtype, device)
@@ -58,7 +65,7 @@ class RankMesh:
             self.plan = tb.Plan(conn, dtype, ghost_tail=world > 1)
         torch.cuda.synchronize()
         self.t_plan = time.time() - t0
-        self.cap = pad32(self.n + self.plan.n_tail)
+        self.cap = pad32(self.nc + self.plan.n_tail)
         self.rows = rows
         self.shared = None
         if world > 1:
@@ -73,11 +80,8 @@ class RankMesh:
         self._tables = {}
         self.esz = esz
 
-    def row(self, k):
-        return self.buffer[k, :self.n]
-
     def vars(self, step):
-        return [self.buffer[step * 5 + k, :self.n] for k in range(5)]
+        return [self.buffer[step * 5 + k, :self.nc] for k in range(5)]
 
     def volume(self):
         return self.buffer[25, :self.n] if self.rows == 26 else self.buffer[5, :self.n]
@@ -103,19 +107,22 @@ class RankMesh:
 
 
 class AmrRun:
-    def __init__(self, level, max_level, dtype, rank, world, device, dist):
+    def __init__(self, level, max_level, dtype, rank, world, device, dist, subgrid=False):
         import oracle                      # the t8code stand-in (host forest); see the module docstring
         import t8gpu_b200 as tb
-        self.tb, self.oracle, self.dist = tb, oracle, dist
+        self.tb, self.oracle, self.dist, self.subgrid = tb, oracle, dist, subgrid
         self.rank, self.world, self.device, self.dtype, self.max_level = rank, world, device, dtype, max_level
         self.npdt = np.float64 if dtype == torch.float64 else np.float32
         self.forest = oracle.Forest(3, level)
-        self.mesh = RankMesh(self.forest, rank, world, device, dtype, dist)
+        self.mesh = RankMesh(self.forest, rank, world, device, dtype, dist, subgrid=subgrid)
         lv, cent, vol, _ = self.forest.elements()
         o0, o1 = self.mesh.off[rank], self.mesh.off[rank + 1]
         self.mesh.volume().copy_(torch.as_tensor(vol[o0:o1].astype(self.npdt)))
-        tb.init_kelvin_helmholtz(3, torch.as_tensor(np.ascontiguousarray(cent[o0:o1].astype(self.npdt))).to(device).reshape(-1),
-                                 self.mesh.vars(0))
+        centres = torch.as_tensor(np.ascontiguousarray(cent[o0:o1].astype(self.npdt))).to(device).reshape(-1)
+        if subgrid:                        # centres of the 4 x 4 x 4 cells (examples/subgrid/solver.inl:13-35)
+            from bench_subgrid import cell_centers
+            centres = cell_centers(centres, level, dtype)
+        tb.init_kelvin_helmholtz(3, centres, self.mesh.vars(0))
         self.next, self.prev = 0, 3
         self.mail = None
         if world > 1:
@@ -140,8 +147,11 @@ class AmrRun:
         for stage, sin, vin, vout in ((1, self.prev, prev, s1), (2, 1, s1, s2), (3, 2, s2, nxt)):
             if mail is not None:
                 P.pull(vin, m.tables(sin))
-            P.stage(stage, vin, prev if stage > 1 else None, vout, vol, dt,
-                    speed_max=self.speed_loc if stage == 3 else None)
+            if self.subgrid:
+                P.stage(stage, vin, prev if stage > 1 else None, vout, vol, dt)
+            else:
+                P.stage(stage, vin, prev if stage > 1 else None, vout, vol, dt,
+                        speed_max=self.speed_loc if stage == 3 else None)
             if mail is not None:
                 if stage == 3:
                     mail.barrier(self.speed_loc, self.speed_max)
@@ -149,7 +159,7 @@ class AmrRun:
                     mail.barrier()
 
     def state(self):
-        return self.mesh.buffer[self.next * 5:(self.next + 1) * 5, :self.mesh.n]
+        return self.mesh.buffer[self.next * 5:(self.next + 1) * 5, :self.mesh.nc]
 
     def adapt(self, T):
         """One adapt + repartition cycle; T accumulates the seconds of its parts."""
@@ -157,9 +167,14 @@ class AmrRun:
         m, f = self.mesh, self.forest
         # ---- criteria (device), gathered over the ranks
         t = time.time()
-        if self.mail is not None:
-            m.plan.pull(m.vars(self.next), m.tables(self.next))     # the criterion reads the ghosts' densities
-        crit = tb.gradient_criteria(m.plan, m.buffer[self.next * 5, :m.n], m.volume()) * CRIT_SCALE
+        if self.subgrid:      # H1 seminorm of the density inside each element (no ghosts), threshold of the example
+            crit = tb.subgrid_criteria(3, m.buffer[self.next * 5, :m.nc], m.volume())
+            threshold = 0.02
+        else:
+            if self.mail is not None:
+                m.plan.pull(m.vars(self.next), m.tables(self.next))     # the criterion reads the ghosts' densities
+            crit = tb.gradient_criteria(m.plan, m.buffer[self.next * 5, :m.n], m.volume()) * CRIT_SCALE
+            threshold = THRESHOLD
         counts = np.diff(m.off)
         if world > 1:
             pad = torch.zeros(int(counts.max()), dtype=self.dtype, device=dev)
@@ -173,7 +188,7 @@ class AmrRun:
         T["criteria_device+gather"] += time.time() - t
         # ---- forest: adapt + balance + repartition on the host (t8code's part; mini-forest stand-in)
         t = time.time()
-        f2 = f.adapt(crit_h, THRESHOLD, 1, self.max_level, nranks=world)
+        f2 = f.adapt(crit_h, threshold, 1, self.max_level, nranks=world)
         amap = f.adapt_map(f2)
         n_new = f2.num_elements
         lo = np.searchsorted(amap[:-1], m.off, side="left")      # adapted, not yet repartitioned: rank q holds [lo[q], lo[q+1])
@@ -183,15 +198,15 @@ class AmrRun:
         # ---- adapt remap into a peer-visible intermediate (5 variables + volume)
         t = time.time()
         n_mid = int(lo[rank + 1] - lo[rank])
-        mid = RankMidBuffer(n_mid, rank, world, dev, self.dtype, dist, tb)
+        mid = RankMidBuffer(n_mid, rank, world, dev, self.dtype, dist, tb, m.S)
         ad = torch.as_tensor((amap[lo[rank]:lo[rank + 1] + 1] - m.off[rank]).astype(np.int32)).to(dev)
-        tb.adapt_remap(ad, m.vars(self.next), mid.vars(), m.volume(), mid.volume(), 0)
+        tb.adapt_remap(ad, m.vars(self.next), mid.vars(), m.volume(), mid.volume(), 3 if self.subgrid else 0)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         T["adapt_remap_device"] += time.time() - t
         # ---- new partition: connectivity (host) + plan + rows
-        new = RankMesh(f2, rank, world, dev, self.dtype, dist)
+        new = RankMesh(f2, rank, world, dev, self.dtype, dist, subgrid=self.subgrid)
         T["connectivity_host(t8code stand-in)"] += new.t_conn
         T["tile_plan"] += new.t_plan
         # ---- partition remap: pull the new elements from the ranks that hold them
@@ -200,7 +215,7 @@ class AmrRun:
         owner = (np.searchsorted(lo, g, side="right") - 1).astype(np.int32)
         index = (g - lo[owner]).astype(np.int32)
         tb.partition_remap(torch.as_tensor(owner).to(dev), torch.as_tensor(index).to(dev), new.vars(0), mid.tables(),
-                           new.volume(), mid.volume_table(), 1)
+                           new.volume(), mid.volume_table(), m.S)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -211,18 +226,18 @@ class AmrRun:
         self.mesh, self.forest = new, f2
         self.next, self.prev = 0, 3
         self.sync_all()
-        return dict(elements=int(n_new), local=int(new.n), moved_between_ranks=moved,
+        return dict(elements=int(n_new), cells=int(n_new) * m.S, local=int(new.n), moved_between_ranks=moved,
                     chunks=int(new.plan.info["n_chunks"]), plan_built_on=new.plan.info.get("built_on", "host")), crit_h
 
 
 class RankMidBuffer:
     """The adapted, not yet repartitioned elements of one rank: 5 variable rows + the volume row, peer-visible."""
 
-    def __init__(self, n, rank, world, device, dtype, dist, tb):
+    def __init__(self, n, rank, world, device, dtype, dist, tb, S=1):
         from t8gpu_b200.multi import exchange_wires
-        self.n, self.world, self.device, self.tb = n, world, device, tb
+        self.n, self.world, self.device, self.tb, self.S = n, world, device, tb, S
         self.esz = 8 if dtype == torch.float64 else 4
-        self.cap = pad32(n)
+        self.cap = pad32(n * S)
         self.shared = None
         if world > 1:
             self.shared = tb.SharedBuffer(6 * self.cap * self.esz, device)
@@ -235,7 +250,7 @@ class RankMidBuffer:
             self.caps, self.bases = [self.cap], [self.buffer.data_ptr()]
 
     def vars(self):
-        return [self.buffer[k, :self.n] for k in range(5)]
+        return [self.buffer[k, :self.n * self.S] for k in range(5)]
 
     def volume(self):
         return self.buffer[5, :self.n]
@@ -261,11 +276,24 @@ class OneRankShadow:
         self.tb, self.run = tb, run
         f = run.forest
         lv, cent, vol, _ = f.elements()
-        self.sol = tb.EulerSolver(f.connectivity(dtype=run.npdt), vol.astype(run.npdt), run.dtype, device=run.device,
-                                  max_level=run.max_level)
-        tb.init_kelvin_helmholtz(3, torch.as_tensor(np.ascontiguousarray(cent.astype(run.npdt))).to(run.device).reshape(-1),
-                                 self.sol.variables(self.sol.next))
+        self.sol = self.make(f)
+        centres = torch.as_tensor(np.ascontiguousarray(cent.astype(run.npdt))).to(run.device).reshape(-1)
+        if run.subgrid:
+            from bench_subgrid import cell_centers
+            centres = cell_centers(centres, int(lv[0]), run.dtype)
+        tb.init_kelvin_helmholtz(3, centres, self.sol.variables(self.sol.next))
         self.steps, self.worst = 0, 0.0
+
+    def make(self, f):
+        run, tb = self.run, self.tb
+        vol = f.elements()[2].astype(run.npdt)
+        if run.subgrid:
+            return tb.SubgridEulerSolver(f.connectivity(subgrid=True, dtype=run.npdt), vol, run.dtype, device=run.device,
+                                         mode="fused")
+        return tb.EulerSolver(f.connectivity(dtype=run.npdt), vol, run.dtype, device=run.device, max_level=run.max_level)
+
+    def volume(self):
+        return self.sol.vol if self.run.subgrid else self.sol.volume()
 
     def iterate(self, dt):
         self.sol.iterate(dt)
@@ -274,24 +302,24 @@ class OneRankShadow:
     def compare(self):
         run = self.run
         o0, o1 = run.mesh.off[run.rank], run.mesh.off[run.rank + 1]
+        S = run.mesh.S
         a = run.state().cpu().numpy().astype(np.float64)
-        b = self.sol.state()[:, o0:o1].cpu().numpy().astype(np.float64)
+        b = self.sol.state()[:, o0 * S:o1 * S].cpu().numpy().astype(np.float64)
         full = self.sol.state().cpu().numpy().astype(np.float64)
         scale = np.abs(full).max(axis=1)
         scale = np.where(scale < 1e-3 * scale.max(), scale.max(), scale)
         err = float((np.abs(a - b).max(axis=1) / scale).max()) if a.size else 0.0
-        same_vol = bool(torch.equal(run.mesh.volume(), self.sol.volume()[o0:o1]))
+        same_vol = bool(torch.equal(run.mesh.volume(), self.volume()[o0:o1]))
         self.worst = max(self.worst, err)
         return err, same_vol
 
     def adapt(self, f_old, f_new):
         tb, run = self.tb, self.run
         amap = f_old.adapt_map(f_new)
-        lv, cent, vol, _ = f_new.elements()
-        new = tb.EulerSolver(f_new.connectivity(dtype=run.npdt), vol.astype(run.npdt), run.dtype, device=run.device,
-                             max_level=run.max_level)
+        new, old_vol = self.make(f_new), self.volume()
+        new_vol = new.vol if run.subgrid else new.volume()
         tb.adapt_remap(torch.as_tensor(amap).to(run.device), self.sol.variables(self.sol.next), new.variables(new.next),
-                       self.sol.volume(), new.volume(), 0)
+                       old_vol, new_vol, 3 if run.subgrid else 0)
         self.sol = new
 
 
@@ -299,13 +327,14 @@ def run_amr(args, rank, world, device, dist=None, emit=True):
     """Returns (and on rank 0 prints) the JSON line of the AMR workload."""
     from bench import ClockSampler
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
-    level = args.level if args.level is not None else 5
+    subgrid = bool(getattr(args, "subgrid", False))
+    level = args.level if args.level is not None else (3 if subgrid else 5)
     max_level = level + 2
     every, cycles = args.every, args.cycles
     tol = 1e-12 if args.dtype == "f64" else 1e-5
-    run = AmrRun(level, max_level, dtype, rank, world, device, dist)
+    run = AmrRun(level, max_level, dtype, rank, world, device, dist, subgrid=subgrid)
     shadow = OneRankShadow(run) if args.check else None
-    dt = 0.1 * 2.0 ** -max_level
+    dt = 0.1 * 2.0 ** -(max_level + (2 if subgrid else 0))
     T = {k: 0.0 for k in ("criteria_device+gather", "forest_host(t8code stand-in)", "adapt_remap_device",
                           "connectivity_host(t8code stand-in)", "tile_plan", "partition_remap_device")}
     hist, t_step, updates, checks = [], 0.0, 0, []
@@ -318,7 +347,7 @@ def run_amr(args, rank, world, device, dist=None, emit=True):
         sampler.start()
     wall0 = time.time()
     for cyc in range(cycles):
-        n_total = run.forest.num_elements
+        n_total = run.forest.num_elements * run.mesh.S
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -365,9 +394,9 @@ def run_amr(args, rank, world, device, dist=None, emit=True):
     line = {"metric": "cell-updates/s per RK3 step", "value": updates / t_step, "unit": "cell-updates/s", "n_gpus": world,
             "steps": every * cycles, "warmup": 3, "ms_per_step": t_step / (every * cycles) * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "kelvin_helmholtz 3D adaptive periodic hex forest (levels 1..%d, start uniform level %d), "
+            "config": {"workload": "kelvin_helmholtz 3D %sadaptive periodic hex forest (levels 1..%d, start uniform level %d), "
                                    "adapt + repartition every %d steps, %d cycles, %d GPU(s)" %
-                                   (max_level, level, every, cycles, world),
+                                   ("Subgrid<4,4,4> on an " if subgrid else "", max_level, level, every, cycles, world),
                        "host_forest": "oracle.Forest: mini-forest stand-in for t8code (absent in this image), replicated "
                                       "on every rank; mesh management only -- stepping, criteria, remaps and plan build "
                                       "are the product",
@@ -382,10 +411,11 @@ def run_amr(args, rank, world, device, dist=None, emit=True):
     return line
 
 
-def amr_secondary(dtype_name, rank, world, device, dist=None, level=5, every=10, cycles=2):
-    """Short config-3 run for the `secondary` block of the default bench lines (with the one-rank comparison)."""
+def amr_secondary(dtype_name, rank, world, device, dist=None, level=None, every=10, cycles=2, subgrid=False):
+    """Short config-3 (subgrid: config-4) run for the `secondary` block of the default bench lines (with the one-rank
+    comparison)."""
     import argparse
-    a = argparse.Namespace(level=level, every=every, cycles=cycles, check=True, dtype=dtype_name)
+    a = argparse.Namespace(level=level, every=every, cycles=cycles, check=True, dtype=dtype_name, subgrid=subgrid)
     line = run_amr(a, rank, world, device, dist, emit=False)
     c, par = line["config"], line["parity"]
     return {"workload": c["workload"], "stepping_cell_updates_per_s": line["value"], "ms_per_step": line["ms_per_step"],

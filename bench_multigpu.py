@@ -310,6 +310,15 @@ def run_multi(args, rank, world, device):
         # one-rank run of the same forest sequence)
         from bench_amr import amr_secondary
         secondary["amr_c3"] = amr_secondary(args.dtype, rank, world, device, dist)
+        secondary["subgrid_amr_c4"] = amr_secondary(args.dtype, rank, world, device, dist, subgrid=True)
+        # BASELINE config 5 (strong scaling: the SAME mixed-element mesh on every GPU count)
+        import argparse
+        from bench_hybrid import run_hybrid
+        h = run_hybrid(argparse.Namespace(dtype=args.dtype, level=24, steps=20, warmup=3), rank, world, device, dist,
+                       emit=False)
+        secondary["hybrid_c5"] = {"workload": h["config"]["workload"], "ms_per_step": h["ms_per_step"],
+                                  "value": h["value"], "scaling": "strong", "roofline_frac_per_gpu": h["roofline"]["frac"],
+                                  "parity": h["parity"]}
     if rank == 0:
         esz = 8 if args.dtype == "f64" else 4
         total = n * world
