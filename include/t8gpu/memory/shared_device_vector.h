@@ -77,8 +77,12 @@ namespace t8gpu {
         size_t        capacity;
         int           fresh;
       };
+      /// The new allocation is made and published BEFORE the old one is freed, and the old one is freed only after every
+      /// peer has closed its mapping of it (exchange() ends with a barrier when a rank published a new buffer): freeing an
+      /// exported allocation that is still imported elsewhere is undefined behaviour (the reference frees first,
+      /// shared_device_vector.inl:249-283).
       void reallocate_and_exchange(size_t size, size_t want_capacity) {
-        if (m_base[m_rank]) T8GPU_CUDA_CHECK_ERROR(t8b200_shared_free(m_base[m_rank]));
+        T* const old   = m_base[m_rank];
         m_base[m_rank] = nullptr;
         m_size         = size;
         size_t cap     = (want_capacity + 31) / 32 * 32;  // 128-byte aligned rows for 4- and 8-byte T
@@ -91,13 +95,16 @@ namespace t8gpu {
         }
         m_wire.capacity = cap;
         exchange(true);
+        if (old) T8GPU_CUDA_CHECK_ERROR(t8b200_shared_free(old));
       }
       void exchange(bool fresh) {
         m_wire.fresh = fresh ? 1 : 0;
         std::vector<Wire> all(m_nb_ranks);
         all[m_rank] = m_wire;
         MPI_Allgather(MPI_IN_PLACE, 0, MPI_DATATYPE_NULL, all.data(), sizeof(Wire), MPI_BYTE, m_comm);
+        bool any_fresh = false;
         for (int r = 0; r < m_nb_ranks; r++) {
+          any_fresh = any_fresh || all[r].fresh;
           if (r != m_rank && all[r].fresh) {
             if (m_base[r]) T8GPU_CUDA_CHECK_ERROR(t8b200_shared_close(m_base[r]));
             m_base[r] = nullptr;
@@ -112,14 +119,23 @@ namespace t8gpu {
             m_rows[k * m_nb_ranks + r] = m_base[r] ? m_base[r] + k * m_cap[r] : nullptr;
         }
         m_device_rows = m_rows;
+        if (any_fresh && m_nb_ranks > 1) MPI_Barrier(m_comm);   // every stale mapping is closed: old buffers may be freed
       }
+      /// collective (destruction and move-assignment of the managers are, as in the reference): every rank first closes
+      /// its mappings of the peers' buffers, then -- after a barrier -- frees its own.
       void release() {
+        bool owns = false;
         for (int r = 0; r < m_nb_ranks; r++) {
           if (!m_base.empty() && m_base[r]) {
-            if (r == m_rank) t8b200_shared_free(m_base[r]);
-            else t8b200_shared_close(m_base[r]);
+            if (r == m_rank) { owns = true; continue; }
+            t8b200_shared_close(m_base[r]);
             m_base[r] = nullptr;
           }
+        }
+        if (m_nb_ranks > 1) MPI_Barrier(m_comm);
+        if (owns) {
+          t8b200_shared_free(m_base[m_rank]);
+          m_base[m_rank] = nullptr;
         }
       }
       void steal(SharedRows&& o) {

@@ -95,6 +95,17 @@ static double time_steps(S* s, double dt, int warmup, int steps) {
   return (double)ms;
 }
 
+// The reference never initialises its flux accumulators: a new allocation (constructor, or a resize that had to grow,
+// SURVEY App. D-14) holds whatever the allocator hands back, and iterate() accumulates into it.  On a fresh device that
+// is zero; inside a long test process it is recycled memory.  The harness clears the array where the reference relies on
+// it being zero -- nothing else of the reference's state is touched.
+template <typename S>
+static void zero_fluxes(S* s) {
+  size_t n = (size_t)s->m_mesh_manager.get_num_local_elements() * S::subgrid_type::size;
+  for (int k = 0; k < 5; k++)
+    cudaMemset(static_cast<T*>(s->m_mesh_manager.get_own_variable(Fluxes, static_cast<VariableList>(k))), 0, sizeof(T) * n);
+}
+
 template <typename S>
 static void mesh_adapt(S* s, const T* crit) {
   int n = s->m_mesh_manager.get_num_local_elements();
@@ -102,6 +113,7 @@ static void mesh_adapt(S* s, const T* crit) {
   s->m_mesh_manager.adapt(c, s->next);      // subgrid_mesh_manager.inl:427-558
   s->m_mesh_manager.partition(s->next);     // :1282-1369 (as SubgridCompressibleEulerSolver::adapt, solver.inl:342-344)
   s->m_mesh_manager.compute_connectivity_information();
+  zero_fluxes(s);
   cudaDeviceSynchronize();
 }
 
@@ -131,6 +143,7 @@ void* ref_create(int dim, int level, int periodic) {
     h->s3 = new S3(sc_MPI_COMM_WORLD, scheme, cmesh, forest);
   else
     h->s2 = new S2(sc_MPI_COMM_WORLD, scheme, cmesh, forest);
+  DISPATCH(h, zero_fluxes(s));
   return h;
 }
 void ref_destroy(void* h) {
@@ -150,7 +163,7 @@ void ref_iterate(void* h, double dt, int nsteps) {
   for (int i = 0; i < nsteps; i++) DISPATCH(h, s->iterate(static_cast<T>(dt)));
   cudaDeviceSynchronize();
 }
-void   ref_adapt(void* h) { DISPATCH(h, s->adapt()); cudaDeviceSynchronize(); }
+void   ref_adapt(void* h) { DISPATCH(h, s->adapt()); DISPATCH(h, zero_fluxes(s)); cudaDeviceSynchronize(); }
 double ref_time_steps(void* h, double dt, int warmup, int steps) { return DISPATCH(h, time_steps(s, dt, warmup, steps)); }
 void   ref_mesh_adapt(void* h, const T* crit) { DISPATCH(h, mesh_adapt(s, crit)); }
 void   ref_criteria(void* h, T* out) { DISPATCH(h, criteria(s, out)); }

@@ -41,6 +41,14 @@ __global__ static void crit_div(T const* fluxes_rho, T const* volume, T* criteri
   criteria[i] = fluxes_rho[i] / cbrt(volume[i]);   // solver.cu:243
 }
 
+// The reference never initialises its flux accumulators after a (re)allocation; inside a long test
+// process that memory is recycled.  The harness clears the array where the reference relies on it being zero.
+static void zero_fluxes(CompressibleEulerSolver* s) {
+  int n = s->m_mesh_manager.get_num_local_elements();
+  for (int k = 0; k < 5; k++)
+    cudaMemset(s->m_mesh_manager.get_own_variable(Fluxes, static_cast<VariableList>(k)), 0, sizeof(T) * n);
+}
+
 extern "C" {
 
 int ref_float_size() { return (int)sizeof(T); }
@@ -49,7 +57,9 @@ void* ref_create(int dim, int level, int periodic) {
   t8_scheme_cxx_t* scheme = t8_scheme_new_default_cxx();
   t8_cmesh_t       cmesh  = t8mini_cmesh_new_cube(dim, periodic);
   t8_forest_t      forest = t8_forest_new_uniform(cmesh, scheme, level, true, sc_MPI_COMM_WORLD);
-  return new CompressibleEulerSolver(sc_MPI_COMM_WORLD, scheme, cmesh, forest);
+  auto* s = new CompressibleEulerSolver(sc_MPI_COMM_WORLD, scheme, cmesh, forest);
+  zero_fluxes(s);
+  return s;
 }
 void ref_destroy(void* h) { delete static_cast<CompressibleEulerSolver*>(h); }
 
@@ -95,7 +105,11 @@ void ref_iterate(void* h, double dt, int nsteps) {
   cudaDeviceSynchronize();
 }
 double ref_compute_timestep(void* h) { return (double)static_cast<CompressibleEulerSolver*>(h)->compute_timestep(); }
-void   ref_adapt(void* h) { static_cast<CompressibleEulerSolver*>(h)->adapt(); cudaDeviceSynchronize(); }
+void   ref_adapt(void* h) {
+  static_cast<CompressibleEulerSolver*>(h)->adapt();
+  zero_fluxes(static_cast<CompressibleEulerSolver*>(h));
+  cudaDeviceSynchronize();
+}
 
 // milliseconds for `steps` calls of the reference's own iterate() (its cudaDeviceSynchronize()s included), CUDA events
 double ref_time_steps(void* h, double dt, int warmup, int steps) {
@@ -125,6 +139,7 @@ void ref_mesh_adapt(void* h, const T* crit) {
   s->m_mesh_manager.compute_connectivity_information();
   s->m_device_face_speed_estimate.resize(s->m_mesh_manager.get_num_local_faces() +
                                          s->m_mesh_manager.get_num_local_boundary_faces());
+  zero_fluxes(s);
   cudaDeviceSynchronize();
 }
 // Refinement criteria exactly as CompressibleEulerSolver::adapt computes them (solver.cu:246-271): the reference's own

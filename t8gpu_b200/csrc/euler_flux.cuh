@@ -107,9 +107,17 @@ T8B_HD Cell<T> to_cell(T rho, T mx, T my, T mz, T e) {
   const T kappa = T(1.4), km1 = T(1.4) - T(1);
   T hm2 = T(0.5) * (mx * mx + my * my + mz * mz);
   T pr  = km1 * (e * rho - hm2);       // p * rho
-  T r   = fast_rcp(pr * rho);          // 1 / (p rho^2): one reciprocal serves 1/rho and 1/p
-  T hsr = (T(0.5) * r) * pr;           // 1 / (2 rho)
-  T t   = r * rho;                     // 1 / (p rho)
+  T hsr, t;
+  if (sizeof(T) == 8) {
+    T r = fast_rcp(pr * rho);          // 1 / (p rho^2): one reciprocal serves 1/rho and 1/p (fp64 is FP64-pipe bound)
+    hsr = (T(0.5) * r) * pr;           // 1 / (2 rho)
+    t   = r * rho;                     // 1 / (p rho)
+  } else {
+    // fp32: p rho^2 leaves the float range for densities / pressures around 1e+-13 (flushed to zero or overflowed,
+    // where the reference's separate divides are still finite): two reciprocals, one MUFU more per cell
+    hsr = T(0.5) * fast_rcp(rho);
+    t   = fast_rcp(pr);
+  }
   c.rho = rho;
   c.hx  = hsr * mx;
   c.hy  = hsr * my;

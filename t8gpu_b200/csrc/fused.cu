@@ -555,6 +555,7 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
   if (!P || stage < 1 || stage > 3 || !in || !out || !vol || (stage > 1 && !prev)) return cudaErrorInvalidValue;
   if (P->is_f64 != (sizeof(T) == 8) || P->host_only) return cudaErrorInvalidValue;
   if (P->multi && !P->ghost_tail && !in_all) return cudaErrorInvalidValue;   // (ghost-tail plans read no peer memory)
+  if (P->n_chunks == 0) return cudaSuccess;   // a rank without elements: nothing to do (its rows may be null)
   // CTAs read halo states from `in` (or the peers' `in`) while other CTAs write `out`: an in-place call would race
   // silently; the reference-shaped rk3_stage tolerates out == prev, this entry point does not
   for (int k = 0; k < 5; k++)

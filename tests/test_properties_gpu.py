@@ -134,3 +134,27 @@ def test_empty_rank_and_bad_arguments(cuda):
     assert L.t8b200_max_speed_f64(None, z64, C.c_void_p(out.data_ptr()), None) == 0
     torch.cuda.synchronize()
     assert float(out[0]) == 0.0
+
+
+@pytest.mark.parametrize("scale", [1e-13, 1e13])
+@pytest.mark.parametrize("mode", ["fused", "unfused"])
+def test_fp32_dynamic_range(cuda, mode, scale):
+    """Densities / pressures around 1e-13 and 1e+13 in fp32: the per-cell staging must not leave the float
+    range where the reference's separate divides stay finite.  The equations are invariant under (rho, p) -> s (rho, p),
+    so the step from the scaled state is compared with the fp32 oracle on the same scaled state."""
+    import oracle
+    import t8gpu_b200
+    from util import TOL, perturbed_kh, rel_linf
+    f = oracle.Forest(3, 3)
+    conn = f.connectivity(dtype=np.float32)
+    u0, vol = perturbed_kh(f, np.float32, seed=11)
+    us = (u0.astype(np.float64) * scale).astype(np.float32)
+    dt = 0.1 * 2.0 ** -3
+    ref, _, _ = oracle.iterate(conn, vol, us, dt)
+    assert np.isfinite(ref).all()
+    sol = t8gpu_b200.EulerSolver(conn, vol, torch.float32, device=cuda, mode=mode)
+    sol.set_state(us)
+    sol.iterate(dt)
+    got = sol.state().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel_linf(got, ref) <= TOL[np.dtype(np.float32)]

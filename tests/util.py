@@ -12,6 +12,8 @@ def rel_linf(a, b):
     the momentum/state scale instead of its own ~0 maximum."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
+    if not (np.isfinite(a).all() and np.isfinite(b).all()):
+        return float("inf")          # a NaN must never compare as "equal"
     scale_all = np.abs(b).max()
     worst = 0.0
     for k in range(a.shape[0]):
