@@ -11,6 +11,11 @@ Stage ordering across ranks (T8B200_SYNC):
                     over NVLink (no pack / unpack on the owner's side), then the SINGLE-rank stage kernel, which reads
                     no peer memory (direct peer loads inside the stage kernel cost +8 % per step: the NVLink latency
                     is exposed in every chunk at the partition boundary).  The stage-3 barrier carries the CFL max.
+  overlap           ghost tail as in `pull`, with every stage launched in two passes (t8b200_fused_stage_part): the
+                    chunks that read no ghost copy on the compute stream right behind the previous stage, while a
+                    second (high-priority) stream does barrier -> pull -> the partition-boundary chunks.  Measured
+                    SLOWER than `pull` on 2 GPUs (2.61 vs 2.50 ms per step): the boundary pass does not fill the GPU and
+                    the interior pass of the next stage has to wait for it.  Kept as an option.
   kernel            direct peer loads; the stage kernels order themselves: the chunks that read ghost elements run first, wait for the
                     peers' previous stage and the last of them signals this stage to every peer through the
                     peer-mapped mailboxes (csrc/peer_sync.cuh); all other chunks never wait.  The CFL reduction is one
@@ -64,9 +69,9 @@ class MultiGpuEuler:
         self.n_faces = int(conn["n_faces"]) + int(conn["n_xfaces"])
         self.n_ghost = int(conn["n_ghost"])
         t0 = time.time()
-        self.plan = tb.Plan.from_device(conn, dtype, ghost_tail=self.sync == "pull")     # no D2H of the connectivity
+        self.plan = tb.Plan.from_device(conn, dtype, ghost_tail=self.sync in ("pull", "overlap"))     # no D2H
         if self.plan is None:
-            self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync == "pull")
+            self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync in ("pull", "overlap"))
         torch.cuda.synchronize()
         self.t_plan = time.time() - t0
         self.cap = (self.n + self.plan.n_tail + 31) // 32 * 32     # own elements, then the ghost tail
@@ -81,7 +86,7 @@ class MultiGpuEuler:
         rows = row_pointers(bases, caps, NVAR, NB_STEPS, esz)
         self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
         self.mail = None
-        if self.sync in ("pull", "kernel", "peer", "none"):
+        if self.sync in ("overlap", "pull", "kernel", "peer", "none"):
             self.mail = tb.PeerMailboxes(rank, world, device)
             mw = exchange_wires(dist, self.mail.handle, 0, world, device)
             self.mail.exchange([h for h, _ in mw])
@@ -92,8 +97,11 @@ class MultiGpuEuler:
         self.token = torch.zeros(1, dtype=dtype, device=device)
         self.dt_dev = torch.zeros(1, dtype=dtype, device=device)
         self.length = 0.5 ** level                # the length scale of compute_timestep (solver.cu:225-228)
-        self.side = torch.cuda.Stream(device=device)
+        # high priority: the boundary pass must get SM slots ahead of the interior pass' remaining chunks, or it would
+        # run at the tail of the stage and the next interior pass (which needs it) could not start
+        self.side = torch.cuda.Stream(device=device, priority=-1)
         self.side_done = None
+        self.ev_b = None
         torch.cuda.synchronize()
         dist.barrier()
         self.publish()
@@ -102,8 +110,13 @@ class MultiGpuEuler:
         """The state was written outside the stage kernels (initial data, upload): a full barrier before any rank reads
         ghosts, which also starts the stage-epoch sequence the self-ordering kernels continue."""
         if self.mail is not None and self.sync != "none":
-            if self.sync == "pull":    # same class as the barrier that ends a step (it precedes the first pull)
+            if self.sync in ("pull", "overlap"):    # same class as the barrier that ends a step (precedes the first pull)
                 self.mail.barrier(self.speed_loc, self.speed_max)
+                if self.sync == "overlap":          # the second stream continues from here
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream())
+                    self.side.wait_event(ev)
+                    self.ev_b = None
             else:
                 self.mail.barrier()
 
@@ -125,6 +138,41 @@ class MultiGpuEuler:
         prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
         vol, T = self.volume(), self.tables
         dtd = self.dt_dev if adaptive else None
+        if self.sync == "overlap":
+            m, P, main, side = self.mail, self.plan, torch.cuda.current_stream(), self.side
+            for stage, sin, vin, vout in ((1, self.prev, prev, s1), (2, 1, s1, s2), (3, 2, s2, nxt)):
+                sm = self.speed_loc if stage == 3 else None
+                pv = prev if stage > 1 else None
+                # compute stream: the chunks without ghosts, as soon as this rank's previous stage is complete
+                if self.ev_b is not None:
+                    main.wait_event(self.ev_b)
+                if not P.stage_part(stage, 1, vin, pv, vout, vol, dt, speed_max=sm, dt_dev=dtd):
+                    self.sync = "pull"                    # not a structured-only plan: serial scheme from here on
+                    self.next, self.prev = self.prev, self.next
+                    main.wait_stream(side)
+                    return self.iterate(dt, adaptive)
+                ev_a = torch.cuda.Event()
+                ev_a.record(main)
+                # second stream: pull the ghosts of this stage (the peers' previous stage is complete: barrier below /
+                # publish()), then the partition-boundary chunks; then announce this stage once both passes are done
+                with torch.cuda.stream(side):
+                    P.pull(vin, T[sin])
+                    P.stage_part(stage, 2, vin, pv, vout, vol, dt, speed_max=sm, dt_dev=dtd)
+                    self.ev_b = torch.cuda.Event()
+                    self.ev_b.record(side)
+                    side.wait_event(ev_a)
+                    if stage == 3:
+                        m.barrier(self.speed_loc, self.speed_max)     # stage barrier + CFL max over the ranks
+                        self.speed_loc.zero_()                        # both passes of the next stage 3 max into it
+                        if adaptive:
+                            self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
+                            self.ev_b = torch.cuda.Event()            # the next step's kernels read the new dt
+                            self.ev_b.record(side)
+                    else:
+                        m.barrier()
+            self.side_done = torch.cuda.Event()
+            self.side_done.record(side)
+            return 15 + int(adaptive)                     # 3 x (interior pass, pull, boundary pass, barrier) + memsets
         if self.sync == "pull":
             m, P = self.mail, self.plan
             P.pull(prev, T[self.prev])                    # the peers' U^n is complete (barrier of the previous step)
@@ -327,7 +375,11 @@ def run_multi(args, rank, world, device):
         ms_per_step = ms / args.steps
         achieved = alg * n / (ms_per_step * 1e-3) / 1e9   # per GPU
         state_bytes = 5 * n * esz
-        sync_text = {"pull": "ghost tail: per stage one peer-memory mailbox barrier kernel + one pull kernel copying the "
+        sync_text = {"overlap": "ghost tail; every stage in two passes: the chunks without ghosts on the compute stream right "
+                                "behind the previous stage, on a second stream mailbox barrier -> pull kernel (ghost "
+                                "copies from the peers' rows over NVLink) -> the partition-boundary chunks; the stage-3 "
+                                "barrier carries the CFL max",
+                     "pull": "ghost tail: per stage one peer-memory mailbox barrier kernel + one pull kernel copying the "
                              "ghosts from the peers' rows over NVLink into local copies behind the own elements, then "
                              "the single-rank stage kernel (no peer memory inside it); the stage-3 barrier carries the "
                              "CFL max",

@@ -335,6 +335,20 @@ int t8b200_fused_stage_sync_f64(const t8b200_plan* plan, int stage, const double
                                 const double* vol, double dt, const double* dt_dev, double* speed_max_dev,
                                 const t8b200_stage_sync* sync, long long wait_epoch, long long signal_epoch,
                                 void* stream);
+/* A stage of a ghost-tail plan in TWO launches, so that the exchange of the ghosts hides behind the interior:
+ *   part 1  every chunk that reads no ghost copy (launched over all chunks; the partition-boundary ones leave at once).
+ *           Needs nothing from the peers: the caller launches it right behind the previous stage.
+ *   part 2  the partition-boundary chunks only; the caller launches it (typically on a second stream) after
+ *           t8b200_peer_barrier + t8b200_ghost_pull_* of this stage.
+ * Both parts together write exactly what t8b200_fused_stage_* writes (bitwise) and max into speed_max_dev, which the
+ * caller zeroes before BOTH parts (they may run in either order on two streams).  For ghost-tail plans whose chunks are all structured (e.g. from t8b200_plan_create_device); other plans:
+ * cudaErrorNotSupported, use t8b200_fused_stage_* after the pull.  dt_dev as in t8b200_fused_stage_sync_*. */
+int t8b200_fused_stage_part_f32(const t8b200_plan* plan, int stage, int part, const float* const* in,
+                                const float* const* prev, float* const* out, const float* vol, float dt,
+                                const float* dt_dev, float* speed_max_dev, void* stream);
+int t8b200_fused_stage_part_f64(const t8b200_plan* plan, int stage, int part, const double* const* in,
+                                const double* const* prev, double* const* out, const double* vol, double dt,
+                                const double* dt_dev, double* speed_max_dev, void* stream);
 /* the same for the subgrid stage (no wave-speed reduction: the reference's subgrid solver has none) */
 int t8b200_subgrid_fused_stage_sync_f32(const t8b200_subgrid_plan* plan, int stage, const float* const* in,
                                         const float* const* const* in_all, const float* const* prev,

@@ -266,6 +266,19 @@ class Plan:
         check(getattr(lib(), "t8b200_ghost_pull_" + s)(self._h, len(rows), ptrs(rows), rows_all.host,
                                                        stream_ptr(stream)), "ghost_pull")
 
+    def stage_part(self, stage, part, inp, prev, out, vol, dt, speed_max=None, stream=None, dt_dev=None):
+        """One pass of a stage split in two (t8b200_fused_stage_part): part 1 = the chunks that read no ghost copy,
+        part 2 = the partition-boundary chunks.  Returns False when the plan does not support the split."""
+        s, ft = _sfx(self.dtype)
+        rc = getattr(lib(), "t8b200_fused_stage_part_" + s)(
+            self._h, stage, part, ptrs(inp), ptrs(prev) if prev is not None else None, ptrs(out),
+            C.c_void_p(vol.data_ptr()), ft(dt), C.c_void_p(dt_dev.data_ptr() if dt_dev is not None else None),
+            C.c_void_p(speed_max.data_ptr() if speed_max is not None else None), stream_ptr(stream))
+        if rc == 801:
+            return False
+        check(rc, "fused_stage_part")
+        return True
+
     def stage(self, stage, inp, prev, out, vol, dt, in_all=None, speed_max=None, stream=None, dt_dev=None,
               sync=None):
         """One fused RK stage.  dt_dev: device scalar holding the time step (then `dt` is ignored); sync: a

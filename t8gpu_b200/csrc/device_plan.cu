@@ -13,6 +13,7 @@
 #include <thrust/copy.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
+#include <thrust/iterator/counting_iterator.h>
 #include <thrust/sort.h>
 #include <thrust/unique.h>
 
@@ -112,10 +113,6 @@ box_kernel(int64_t n_local, const int32_t* __restrict__ nb6, const int32_t* __re
   }
 }
 
-struct IsGhost {
-  int me;
-  __device__ bool operator()(const thrust::tuple<int32_t, int32_t>& x) const { return thrust::get<0>(x) != me; }
-};
 
 __global__ void ghost_keys_kernel(int64_t n, const int32_t* __restrict__ halo, const int32_t* __restrict__ hrank, int me,
                                   unsigned long long* __restrict__ keys, unsigned long long* count) {
@@ -133,6 +130,10 @@ __global__ void redirect_kernel(int64_t n, int32_t* __restrict__ halo, int32_t* 
   halo[i]  = (int32_t)(n_local + lo);
   hrank[i] = me;
 }
+struct IsBoundary {
+  const int32_t* s_rec;
+  __device__ bool operator()(int q) const { return s_rec[4 * (size_t)q + 3] != 0; }
+};
 __global__ void split_keys_kernel(int64_t n, const unsigned long long* __restrict__ keys, int32_t* __restrict__ rk,
                                   int32_t* __restrict__ ix) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,6 +214,12 @@ int device_plan_impl(t8b200_plan** out, int flags_in, int64_t n_local, int64_t n
       T8B_TRY(cudaMemcpyAsync(P->s_rec + 3, &one, sizeof(one), cudaMemcpyHostToDevice, st));
       P->nb_struct = 1;
     }
+    // ids of the partition-boundary chunks, ascending (the "boundary pass" of the split stage launches)
+    T8B_TRY(dev_alloc(&P->blist, sizeof(int32_t) * (size_t)P->nb_struct));
+    thrust::copy_if(thrust::cuda::par.on(st), thrust::counting_iterator<int>(0), thrust::counting_iterator<int>(nchunks),
+                    thrust::device_ptr<int32_t>(P->blist), IsBoundary{P->s_rec});
+    T8B_TRY(cudaGetLastError());
+    T8B_TRY(cudaStreamSynchronize(st));
   }
   if (P->ghost_tail && multi) {
     // distinct (owner rank, remote index) pairs of the ghost entries, sorted -> tail slots; entries redirected
@@ -272,6 +279,7 @@ int64_t t8b200_plan_device_array(const t8b200_plan* P, int which, int32_t* host_
     case 15: src = P->s_hrank; n = P->multi ? 256 * (int64_t)P->n_struct : 0; break;
     case 17: src = P->pull_rank; n = P->n_pull; break;
     case 18: src = P->pull_idx; n = P->n_pull; break;
+    case 19: src = P->blist; n = P->blist ? P->nb_struct : 0; break;
     default: return -1;
   }
   if (host_out && n > 0 && src) {

@@ -599,6 +599,23 @@ static int fused_stage_impl(const t8b200_plan* P, int stage, const T* const* in,
   return P->cmp ? launch_fused<T, true>(P, A, st) : launch_fused<T, false>(P, A, st);
 }
 
+// One pass of a stage split into "interior" (part 1: every chunk is launched, the partition-boundary ones leave at once)
+// and "boundary" (part 2: the partition-boundary chunks only) launches, for ghost-tail plans whose chunks are all
+// structured: part 1 needs no ghost copies, so it runs while the barrier and the pull of this stage proceed on another
+// stream; part 2 follows the pull.  Both parts max into speed_max (cleared by the caller before both).
+template <typename T>
+static int fused_stage_part_impl(const t8b200_plan* P, int stage, int part, const T* const* in, const T* const* prev,
+                                 T* const* out, const T* vol, T dt, const T* dt_dev, T* speed_max, void* stream) {
+  if (!P || stage < 1 || stage > 3 || (part != 1 && part != 2) || !in || !out || !vol || (stage > 1 && !prev)) return cudaErrorInvalidValue;
+  if (P->is_f64 != (sizeof(T) == 8) || P->host_only) return cudaErrorInvalidValue;
+  if (!P->multi || !P->ghost_tail || P->n_struct != P->n_chunks || P->split || !P->blist) return cudaErrorNotSupported;
+  for (int k = 0; k < 5; k++)
+    if (!in[k] || !out[k] || out[k] == in[k] || (stage > 1 && (!prev[k] || out[k] == prev[k]))) return cudaErrorInvalidValue;
+  // (speed_max is NOT zeroed here: the two passes run on different streams in either order; the caller clears it
+  // before both)
+  return t8b_structured_stage_run<T>(P, stage, in, nullptr, prev, out, vol, dt, speed_max, stream, dt_dev, nullptr, part);
+}
+
 // Face source over the arrays behind MeshConnectivityAccessor<float_type,3> (t8gpu/mesh/mesh_manager.h:159-166):
 // global face ids [0,nf) interior, [nf,nf+nb) boundary, then the extra partition-boundary faces.
 template <typename T>
@@ -734,6 +751,7 @@ int t8b200_plan_host_array(const t8b200_plan* P, int which, const void** data, i
     case 16: return set(H.g_list);
     case 17: return set(H.pull_rank);
     case 18: return set(H.pull_idx);
+    case 19: return set(H.blist);
   }
   return cudaErrorInvalidValue;
 }
@@ -749,7 +767,7 @@ void t8b200_plan_destroy(t8b200_plan* P) {
   cudaFree(P->face_lr); cudaFree(P->face_ai); cudaFree(P->fnx); cudaFree(P->fny); cudaFree(P->fnz); cudaFree(P->farea);
   cudaFree(P->area_tab); cudaFree(P->ell); cudaFree(P->ovf_off); cudaFree(P->ovf_ent);
   cudaFree(P->s_rec); cudaFree(P->s_halo); cudaFree(P->s_hrank); cudaFree(P->g_list);
-  cudaFree(P->pull_rank); cudaFree(P->pull_idx);
+  cudaFree(P->pull_rank); cudaFree(P->pull_idx); cudaFree(P->blist);
   delete P;
 }
 
@@ -769,6 +787,16 @@ int t8b200_fused_stage_f64(const t8b200_plan* plan, int stage, const double* con
                            const double* const* const* in_all, const double* const* prev, double* const* out,
                            const double* vol, double dt, double* speed_max_dev, void* stream) {
   return fused_stage_impl<double>(plan, stage, in, in_all, prev, out, vol, dt, speed_max_dev, stream);
+}
+int t8b200_fused_stage_part_f32(const t8b200_plan* plan, int stage, int part, const float* const* in,
+                                const float* const* prev, float* const* out, const float* vol, float dt,
+                                const float* dt_dev, float* speed_max_dev, void* stream) {
+  return fused_stage_part_impl<float>(plan, stage, part, in, prev, out, vol, dt, dt_dev, speed_max_dev, stream);
+}
+int t8b200_fused_stage_part_f64(const t8b200_plan* plan, int stage, int part, const double* const* in,
+                                const double* const* prev, double* const* out, const double* vol, double dt,
+                                const double* dt_dev, double* speed_max_dev, void* stream) {
+  return fused_stage_part_impl<double>(plan, stage, part, in, prev, out, vol, dt, dt_dev, speed_max_dev, stream);
 }
 int t8b200_fused_stage_sync_f32(const t8b200_plan* plan, int stage, const float* const* in,
                                 const float* const* const* in_all, const float* const* prev, float* const* out,

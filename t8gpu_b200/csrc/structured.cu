@@ -46,6 +46,7 @@ struct SArgs {
   StageSync      sync;    // multi-GPU stage ordering done by the kernel itself (mailboxes == nullptr: off)
   T*             speed_max;
   int            stage, multi, my_rank;
+  const int32_t* blist;   // MODE 3: ids of the partition-boundary chunks
   int            dense;   // every chunk of the plan is structured: chunk b = elements [256 b, 256 b + 256), one area
   int            area0;
   int            wave;    // CTAs resident at once (distance of the next-wave L2 prefetch), 0: off
@@ -76,16 +77,23 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 #define T8B_S_OWNREG 1
 #endif
 
-// MULTI: plans with ghosts (peer tables, owner ranks, self-ordering against the peers); its own instantiation so that
-// single-rank launches do not carry its registers (the kernel sits at the 80-register cap of 3 CTAs per SM)
-template <typename T, class L, bool SMAX, bool MULTI>
+// MODE (its own instantiations, so that single-rank launches do not carry the others' registers: the kernel sits at the
+// 80-register cap of 3 CTAs per SM):
+//   0  every chunk of the launch, no peer memory (one rank, or a ghost-tail plan)
+//   1  plans with ghosts read in place: peer tables, owner ranks, self-ordering against the peers
+//   2  "interior pass" of a ghost-tail plan: every chunk is launched, the partition-boundary ones leave at once (their
+//      ghost copies are still being pulled on another stream)
+//   3  "boundary pass": the launch covers the partition-boundary chunks only, chunk id from the compact list
+template <typename T, class L, bool SMAX, int MODE>
 __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const __grid_constant__ SArgs<T> A) {
+  constexpr bool MULTI = MODE == 1;
   constexpr int NS = L::NSLOT, NF = BoxCommon::NFLUX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* const cq = reinterpret_cast<T*>(smem_raw);   // [7][NS]
   T* const fl = cq + NCELLQ * NS;                 // [5][NF]
   __shared__ T red[8];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int b   = MODE == 3 ? __ldg(A.blist + blockIdx.x) : (int)blockIdx.x;
 
   // ---- phase 0: every independent global load first
   int  e0 = b * 256, area_idx = A.area0;
@@ -102,6 +110,9 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
   int       hrk  = A.my_rank;
   if (MULTI) hrk = __ldg(A.hrank + b * 256 + tid);
   const T u0 = A.in[0][e], u1 = A.in[1][e], u2 = A.in[2][e], u3 = A.in[3][e], u4 = A.in[4][e];
+  if (MODE == 2) {   // the flag was requested with everything else; a boundary chunk belongs to the other pass
+    if (__ldg(reinterpret_cast<const int*>(A.rec + b) + 3) != 0) return;
+  }
   if (A.pf_ok && (tid & 31) == 0) {
     // L2 prefetch hints, one or two per warp: the phase-2 operands of this chunk (rows of U^n, volume) and the streams
     // of the chunk that takes over this CTA slot about one wave later (CTAs are dispatched in index order)
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
     if (w < 5) { if (A.stage != 1) s_prefetch_l2(A.prev[w] + e0, 256u * sizeof(T)); }
     else if (w == 5 && A.vol_shift == 0) s_prefetch_l2(A.vol + e0, 256u * sizeof(T));
     const int bw = b + A.wave;
-    if (A.dense && A.wave > 0 && bw < (int)gridDim.x) {
+    if (MODE != 3 && A.dense && A.wave > 0 && bw < (int)gridDim.x) {
       if (w < 5) s_prefetch_l2(A.in[w] + bw * 256, 256u * sizeof(T));
       else if (w == 5) s_prefetch_l2(A.halo + bw * 256, 1024u);
     }
@@ -203,9 +214,9 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
   }
 }
 
-template <typename T, class L, bool SMAX, bool MULTI>
+template <typename T, class L, bool SMAX, int MODE>
 static int s_launch(const t8b200_plan* P, SArgs<T>& A, cudaStream_t st) {
-  auto             k    = structured_stage_kernel<T, L, SMAX, MULTI>;
+  auto             k    = structured_stage_kernel<T, L, SMAX, MODE>;
   constexpr size_t smem = sizeof(T) * ((size_t)NCELLQ * L::NSLOT + 5 * (size_t)BoxCommon::NFLUX);
   // the opt-in above 48 KB is per device: cached per device id (not once per process)
   static int resident[64];
@@ -221,16 +232,18 @@ static int s_launch(const t8b200_plan* P, SArgs<T>& A, cudaStream_t st) {
   }
   static const int wave_knob = getenv("T8B200_WAVE") ? atoi(getenv("T8B200_WAVE")) : -1;
   A.wave = wave_knob >= 0 ? wave_knob : resident[dev];
-  k<<<P->n_struct, 256, smem, st>>>(A);
+  const int grid = MODE == 3 ? P->nb_struct : P->n_struct;
+  if (grid > 0) k<<<grid, 256, smem, st>>>(A);
   return cudaGetLastError();
 }
 
 template <typename T>
 int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
                              const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
-                             const T* dt_dev, const StageSync* sync) {
+                             const T* dt_dev, const StageSync* sync, int part) {
   if (P->n_struct == 0) return cudaSuccess;
   SArgs<T> A{};
+  A.blist = P->blist;
   A.dt_ptr = dt_dev;
   if (sync) A.sync = *sync;
   A.rec = reinterpret_cast<const int4*>(P->s_rec); A.halo = P->s_halo; A.hrank = P->s_hrank;
@@ -253,14 +266,17 @@ int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in
   cudaStream_t st = (cudaStream_t)stream;
   auto pick = [&](auto layout) {
     using L = decltype(layout);
-    if (A.multi) return speed_max ? s_launch<T, L, true, true>(P, A, st) : s_launch<T, L, false, true>(P, A, st);
-    return speed_max ? s_launch<T, L, true, false>(P, A, st) : s_launch<T, L, false, false>(P, A, st);
+    if (part == 1) return speed_max ? s_launch<T, L, true, 2>(P, A, st) : s_launch<T, L, false, 2>(P, A, st);
+    if (part == 2) return speed_max ? s_launch<T, L, true, 3>(P, A, st) : s_launch<T, L, false, 3>(P, A, st);
+    if (A.multi) return speed_max ? s_launch<T, L, true, 1>(P, A, st) : s_launch<T, L, false, 1>(P, A, st);
+    return speed_max ? s_launch<T, L, true, 0>(P, A, st) : s_launch<T, L, false, 0>(P, A, st);
   };
   return P->box_layout == 1 ? pick(SubgridBox{}) : pick(MortonBox{});
 }
 template int t8b_structured_stage_run<float>(const t8b200_plan*, int, const float* const*, const float* const* const*,
                                              const float* const*, float* const*, const float*, float, float*, void*,
-                                             const float*, const StageSync*);
+                                             const float*, const StageSync*, int);
 template int t8b_structured_stage_run<double>(const t8b200_plan*, int, const double* const*,
                                               const double* const* const*, const double* const*, double* const*,
-                                              const double*, double, double*, void*, const double*, const StageSync*);
+                                              const double*, double, double*, void*, const double*, const StageSync*,
+                                              int);

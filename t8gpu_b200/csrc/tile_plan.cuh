@@ -57,6 +57,7 @@ struct t8b200_plan_host {
   std::vector<double>   area_tab, fnx, fny, fnz, farea;
   std::vector<int32_t>  s_rec, s_halo, s_hrank, g_list;   // structured chunks (box_layout.cuh)
   std::vector<int32_t>  pull_rank, pull_idx;              // ghost tail
+  std::vector<int32_t>  blist;                            // partition-boundary structured chunks
 };
 
 struct t8b200_plan {
@@ -95,6 +96,7 @@ struct t8b200_plan {
   // multi: partition-boundary chunks (some halo element lives on another rank) come first in s_rec / s_halo / s_hrank
   // and in g_list, so that the stage kernels can wait for / signal the peers from those chunks alone (peer_sync.cuh)
   int      nb_struct = 0, nb_generic = 0;
+  int32_t* blist = nullptr;     // ids of the partition-boundary structured chunks (nb_struct entries; dense plans)
   // volume lookup of the stage kernel: volume of element e = vol[e >> vol_shift] * vol_scale (subgrid cells share
   // their element's volume: shift 6 / 4, scale 1/64 / 1/16, ssp_runge_kutta.inl:116)
   int    vol_shift = 0;
@@ -616,7 +618,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     });
   }
   // structured chunks: records and halo lists in chunk order, the other chunk ids for the generic kernel
-  std::vector<int32_t> s_rec, s_halo, s_hrank, g_list;
+  std::vector<int32_t> s_rec, s_halo, s_hrank, g_list, blist;
   {
     int c = 0;
     for (auto& B : builders_flags) {
@@ -688,6 +690,8 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
       if (P->nb_struct + P->nb_generic == 0 && nchunks > 0) {   // no ghosts at all: one nominal boundary chunk
         if (P->n_struct) { s_rec[3] = 1; P->nb_struct = 1; } else { g_list[0] |= 1 << 30; P->nb_generic = 1; }
       }
+      for (int q = 0; q < P->n_struct; q++)
+        if (s_rec[(size_t)q * 4 + 3]) blist.push_back(q);   // position in the structured launch (== chunk id when dense)
     }
   }
   // ghost tail: distinct (owner rank, remote index) pairs of the halo entries that live on other ranks, sorted ->
@@ -743,7 +747,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     Hc->fnx.assign(fnx.begin(), fnx.end()); Hc->fny.assign(fny.begin(), fny.end());
     Hc->fnz.assign(fnz.begin(), fnz.end()); Hc->farea.assign(far.begin(), far.end());
     Hc->s_rec.swap(s_rec); Hc->s_halo.swap(s_halo); Hc->s_hrank.swap(s_hrank); Hc->g_list.swap(g_list);
-    Hc->pull_rank.swap(pull_rank); Hc->pull_idx.swap(pull_idx);
+    Hc->pull_rank.swap(pull_rank); Hc->pull_idx.swap(pull_idx); Hc->blist.swap(blist);
     P->host = Hc;
     return cudaSuccess;
   }
@@ -772,6 +776,7 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
     if (P->multi) P->s_hrank = upload(s_hrank, P->dev_bytes, err);
   }
   if (!g_list.empty()) P->g_list = upload(g_list, P->dev_bytes, err);
+  if (!blist.empty()) P->blist = upload(blist, P->dev_bytes, err);
   if (P->n_pull) {
     P->pull_rank = upload(pull_rank, P->dev_bytes, err);
     P->pull_idx  = upload(pull_idx, P->dev_bytes, err);
@@ -791,5 +796,5 @@ int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, con
 template <typename T>
 int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
                              const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
-                             const T* dt_dev, const t8b200::StageSync* sync);
+                             const T* dt_dev, const t8b200::StageSync* sync, int part = 0);
 void t8b_plan_free(t8b200_plan* P);

@@ -112,3 +112,63 @@ def test_meshes_outside_the_device_builder_are_reported(cuda):
     q, _ = np.linalg.qr(np.random.default_rng(7).normal(size=(3, 3)))
     conn["face_normals"] = (conn["face_normals"].view(-1, 3) @ torch.as_tensor(q.T).to(cuda)).reshape(-1).contiguous()
     assert tb.Plan.from_device(conn, torch.float64) is None
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_split_stage_passes_equal_the_single_launch(cuda, dtype):
+    """t8b200_fused_stage_part: interior pass + boundary pass of a ghost-tail plan write bitwise what the single launch
+    writes (two emulated ranks of the brick (2,1,1), every stage, wave-speed maximum included); the boundary list of
+    the device-built plan equals the host builder's; plans that are not structured-only report NotSupported."""
+    import t8gpu_b200 as tb
+    from t8gpu_b200.solver import NB_STEPS, NVAR
+    P, L, brick = 2, 4, (2, 1, 1)
+    dt = 0.1 * 2.0 ** -L
+    conns = [tb.cartesian_uniform_connectivity(3, L, dtype, P, r, device=cuda, brick=brick) for r in range(P)]
+    plans = [tb.Plan.from_device(c, dtype, ghost_tail=True) for c in conns]
+    ns = [int(c["n_local"]) for c in conns]
+    for r in range(P):
+        host = host_arrays(tb.conn_to_host(conns[r]), dtype, True)
+        bl = plans[r].device_array(19)
+        flags = plans[r].device_array(13).reshape(-1, 4)[:, 3]
+        assert np.array_equal(bl, np.nonzero(flags)[0]) and len(bl) > 0
+
+    def run(split):
+        bufs = []
+        for r in range(P):
+            b = torch.zeros((NVAR * NB_STEPS + 1, ns[r] + plans[r].n_tail), dtype=dtype, device=cuda)
+            b[NVAR * NB_STEPS, :ns[r]] = conns[r]["volumes"]
+            tb.init_kelvin_helmholtz(3, conns[r]["centroids"], [b[k, :ns[r]] for k in range(5)])
+            bufs.append(b)
+        tabs = {s: tb.RankTables([[bufs[r][s * NVAR + k] for k in range(NVAR)] for r in range(P)], cuda)
+                for s in range(NB_STEPS)}
+        vmax = [torch.zeros(1, dtype=dtype, device=cuda) for _ in range(P)]
+        nxt, prv = 0, 3
+        for it in range(3):
+            nxt, prv = prv, nxt
+            for stage, sin, sout in ((1, prv, 1), (2, 1, 2), (3, 2, nxt)):
+                for r in range(P):
+                    plans[r].pull([bufs[r][sin * NVAR + k] for k in range(NVAR)], tabs[sin])
+                for r in range(P):
+                    v = lambda s: [bufs[r][s * NVAR + k, :ns[r]] for k in range(NVAR)]  # noqa: E731
+                    sm = vmax[r] if stage == 3 else None
+                    if split:
+                        if sm is not None:
+                            sm.zero_()
+                        assert plans[r].stage_part(stage, 2, v(sin), v(prv), v(sout), bufs[r][NVAR * NB_STEPS], dt, speed_max=sm)
+                        assert plans[r].stage_part(stage, 1, v(sin), v(prv), v(sout), bufs[r][NVAR * NB_STEPS], dt, speed_max=sm)
+                    else:
+                        plans[r].stage(stage, v(sin), v(prv), v(sout), bufs[r][NVAR * NB_STEPS], dt, speed_max=sm)
+        torch.cuda.synchronize()
+        return [b[nxt * NVAR:(nxt + 1) * NVAR, :ns[r]].clone() for r, b in enumerate(bufs)], [float(x) for x in vmax]
+
+    whole, vm0 = run(False)
+    parts, vm1 = run(True)
+    for r in range(P):
+        assert torch.equal(whole[r], parts[r])
+    assert vm0 == vm1 and min(vm0) > 0
+    # a plan with generic chunks (level 3: a tree 8 elements across is its own neighbour) does not support the split
+    c3 = tb.cartesian_uniform_connectivity(3, 3, dtype, P, 0, device=cuda, brick=brick)
+    p3 = tb.Plan(tb.conn_to_host(c3), dtype, ghost_tail=True)
+    b3 = torch.zeros((NVAR * NB_STEPS + 1, int(c3["n_local"]) + p3.n_tail), dtype=dtype, device=cuda)
+    v3 = lambda s: [b3[s * NVAR + k, :int(c3["n_local"])] for k in range(NVAR)]  # noqa: E731
+    assert p3.stage_part(1, 1, v3(0), None, v3(1), b3[NVAR * NB_STEPS], dt) is False
