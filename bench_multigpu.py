@@ -6,7 +6,11 @@ live state arrays through peer-mapped pointers (NVLink); every rank evaluates al
 (owner computes, no remote atomics).
 
 Stage ordering across ranks (T8B200_SYNC):
-  pull (default)    ghost tail: every rank keeps local copies of its ghosts behind its own elements; per stage one
+  push (default)    ghost tail as in `pull`, filled from the OTHER side: after each stage every rank pushes the elements
+                    its peers hold copies of into their tails (t8b200_ghost_push: scattered local gather, consecutive
+                    remote stores), then the mailbox barrier publishes them; the next stage kernel starts right behind
+                    the barrier.
+  pull              ghost tail: every rank keeps local copies of its ghosts behind its own elements; per stage one
                     mailbox barrier kernel, one bandwidth-bound pull kernel that copies the ghosts from the peers' rows
                     over NVLink (no pack / unpack on the owner's side), then the SINGLE-rank stage kernel, which reads
                     no peer memory (direct peer loads inside the stage kernel cost +8 % per step: the NVLink latency
@@ -61,7 +65,7 @@ class MultiGpuEuler:
         import t8gpu_b200 as tb
         from t8gpu_b200.solver import NB_STEPS, NVAR
         self.tb, self.rank, self.world, self.device, self.dtype = tb, rank, world, device, dtype
-        self.sync = sync or os.environ.get("T8B200_SYNC", "pull")
+        self.sync = sync or os.environ.get("T8B200_SYNC", "push")
         brick = brick or BRICK[world]
         esz = 8 if dtype == torch.float64 else 4
         conn = tb.cartesian_uniform_connectivity(3, level, dtype, world, rank, device=device, brick=brick)
@@ -69,9 +73,9 @@ class MultiGpuEuler:
         self.n_faces = int(conn["n_faces"]) + int(conn["n_xfaces"])
         self.n_ghost = int(conn["n_ghost"])
         t0 = time.time()
-        self.plan = tb.Plan.from_device(conn, dtype, ghost_tail=self.sync in ("pull", "overlap"))     # no D2H
+        self.plan = tb.Plan.from_device(conn, dtype, ghost_tail=self.sync in ("push", "pull", "overlap"))     # no D2H
         if self.plan is None:
-            self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync in ("pull", "overlap"))
+            self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync in ("push", "pull", "overlap"))
         torch.cuda.synchronize()
         self.t_plan = time.time() - t0
         self.cap = (self.n + self.plan.n_tail + 31) // 32 * 32     # own elements, then the ghost tail
@@ -86,11 +90,14 @@ class MultiGpuEuler:
         rows = row_pointers(bases, caps, NVAR, NB_STEPS, esz)
         self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
         self.mail = None
-        if self.sync in ("overlap", "pull", "kernel", "peer", "none"):
+        if self.sync in ("push", "overlap", "pull", "kernel", "peer", "none"):
             self.mail = tb.PeerMailboxes(rank, world, device)
             mw = exchange_wires(dist, self.mail.handle, 0, world, device)
             self.mail.exchange([h for h, _ in mw])
         self.speed_loc = torch.zeros(1, dtype=dtype, device=device)
+        if self.sync == "push":
+            from t8gpu_b200.multi import send_lists
+            self.send = send_lists(dist, self.plan, self.n, rank, world, device)
         tb.init_kelvin_helmholtz(3, conn["centroids"], self.variables(0))
         self.next, self.prev = 0, 3
         self.speed_max = torch.zeros(1, dtype=dtype, device=device)
@@ -110,7 +117,10 @@ class MultiGpuEuler:
         """The state was written outside the stage kernels (initial data, upload): a full barrier before any rank reads
         ghosts, which also starts the stage-epoch sequence the self-ordering kernels continue."""
         if self.mail is not None and self.sync != "none":
-            if self.sync in ("pull", "overlap"):    # same class as the barrier that ends a step (precedes the first pull)
+            if self.sync == "push":     # the state was written by other means: push its ghost copies, then publish
+                self.tb.ghost_push(*self.send, self.variables(self.next), self.tables[self.next])
+                self.mail.barrier(self.speed_loc, self.speed_max)
+            elif self.sync in ("pull", "overlap"):    # same class as the barrier that ends a step (precedes the first pull)
                 self.mail.barrier(self.speed_loc, self.speed_max)
                 if self.sync == "overlap":          # the second stream continues from here
                     ev = torch.cuda.Event()
@@ -138,6 +148,20 @@ class MultiGpuEuler:
         prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
         vol, T = self.volume(), self.tables
         dtd = self.dt_dev if adaptive else None
+        if self.sync == "push":
+            m, P, push = self.mail, self.plan, self.tb.ghost_push
+            P.stage(1, prev, None, s1, vol, dt, dt_dev=dtd)
+            push(*self.send, s1, T[1])                    # the peers' copies of this rank's boundary elements
+            m.barrier()
+            P.stage(2, s1, prev, s2, vol, dt, dt_dev=dtd)
+            push(*self.send, s2, T[2])
+            m.barrier()
+            P.stage(3, s2, prev, nxt, vol, dt, speed_max=self.speed_loc, dt_dev=dtd)
+            push(*self.send, nxt, T[self.next])
+            m.barrier(self.speed_loc, self.speed_max)     # stage barrier + CFL max over the ranks
+            if adaptive:
+                self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
+            return 9 + int(adaptive)                      # 3 x (stage, push, barrier)
         if self.sync == "overlap":
             m, P, main, side = self.mail, self.plan, torch.cuda.current_stream(), self.side
             for stage, sin, vin, vout in ((1, self.prev, prev, s1), (2, 1, s1, s2), (3, 2, s2, nxt)):
@@ -375,7 +399,11 @@ def run_multi(args, rank, world, device):
         ms_per_step = ms / args.steps
         achieved = alg * n / (ms_per_step * 1e-3) / 1e9   # per GPU
         state_bytes = 5 * n * esz
-        sync_text = {"overlap": "ghost tail; every stage in two passes: the chunks without ghosts on the compute stream right "
+        sync_text = {"push": "ghost tail; after each stage every rank pushes the elements its peers hold copies of into "
+                             "their tails over NVLink (consecutive remote stores), one mailbox barrier kernel publishes "
+                             "them, the single-rank stage kernel follows (no peer memory inside it); the stage-3 barrier "
+                             "carries the CFL max",
+                     "overlap": "ghost tail; every stage in two passes: the chunks without ghosts on the compute stream right "
                                 "behind the previous stage, on a second stream mailbox barrier -> pull kernel (ghost "
                                 "copies from the peers' rows over NVLink) -> the partition-boundary chunks; the stage-3 "
                                 "barrier carries the CFL max",

@@ -188,6 +188,18 @@ int t8b200_plan_create_device(t8b200_plan** out, int is_f64, int ghost_tail, int
  * 18 as t8b200_plan_host_array numbers them); returns the element count (host_out may be NULL), -1 on error */
 int64_t t8b200_plan_device_array(const t8b200_plan* plan, int which, int32_t* host_out, int64_t capacity);
 
+/* The same exchange pushed by the owner: rows_all[k][dst_rank[e]][dst_idx[e]] = rows[k][src_idx[e]] for the n_send
+ * entries of this rank's send list (DEVICE arrays; the pull lists of the peers -- host arrays 17 / 18 of their plans --
+ * regrouped by owner and sorted by destination: what rank p pulls from this rank, with dst_idx = n_local(p) + j).  The
+ * remote stores are consecutive (whole lines over NVLink, posted), only the local gather is scattered; a
+ * t8b200_peer_barrier behind it publishes the copies.  rows: HOST array of nvar DEVICE pointers (this rank's rows of the
+ * step that was just written); rows_all: HOST array of nvar DEVICE tables of the same step. */
+int t8b200_ghost_push_f32(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
+                          const int32_t* dst_idx, const float* const* rows, float* const* const* rows_all, void* stream);
+int t8b200_ghost_push_f64(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
+                          const int32_t* dst_idx, const double* const* rows, double* const* const* rows_all,
+                          void* stream);
+
 /* One fused RK stage.  in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's arrays (stage input, U^n, stage
  * output).  in_all: HOST array of 5 DEVICE tables (one pointer per rank) for ghost reads, or NULL when the plan has
  * no ghosts.  vol: device, per element.  speed_max_dev: device scalar receiving max(|uHat|+aHat) over the faces of

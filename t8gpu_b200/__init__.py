@@ -465,6 +465,14 @@ def subgrid_criteria(dim, rho, vol, out=None, stream=None):
     return out
 
 
+def ghost_push(src_idx, dst_rank, dst_idx, rows, rows_all, stream=None):
+    """Owner-side push of the ghost copies (t8b200_ghost_push): rows_all[k][dst_rank[e]][dst_idx[e]] = rows[k][src_idx[e]]."""
+    s, _ = _sfx(rows[0].dtype)
+    check(getattr(lib(), "t8b200_ghost_push_" + s)(len(rows), C.c_int64(src_idx.numel()), C.c_void_p(src_idx.data_ptr()),
+                                                   C.c_void_p(dst_rank.data_ptr()), C.c_void_p(dst_idx.data_ptr()),
+                                                   ptrs(rows), rows_all.host, stream_ptr(stream)), "ghost_push")
+
+
 def subgrid_z_order(dim, cells, out=None, stream=None):
     """column_major_to_z_order + widening to double (output path of SubgridMeshManager::save_variable_to_vtk): cells =
     device tensor of n_elements * 64 (16) values of one variable -> float64 tensor in the Morton order of the cells."""

@@ -21,6 +21,8 @@ template <typename T>
 struct PtrsC { const T* p[MAXV]; };
 template <typename T>
 struct TablesC { const T* const* p[MAXV]; };
+template <typename T>
+struct Tables { T* const* p[MAXV]; };
 
 // adapt_data[i] = first old element behind new element i (n_new + 1 entries, mesh_manager.inl:258-281):
 //   diff = adapt_data[i+1] - adapt_data[i] : 0 -> i is a child of a refined element (not the last one),
@@ -128,6 +130,23 @@ ghost_pull_kernel(int nvar, int64_t n_pull, int64_t tail, const int32_t* __restr
     if (k == l) own.p[k][tail + j] = all.p[k][rk[j]][idx[j]];
 }
 
+// The same exchange as a PUSH from the owner: entry e of the send list, rows_all[k][dst_rank[e]][dst_idx[e]] =
+// rows_own[k][src_idx[e]].  The list is sorted by destination, so the remote stores of a warp are consecutive (whole
+// 128-byte lines over NVLink, posted writes) and only the local gather is scattered -- the pull reads isolated 8-byte
+// values out of 32-byte sectors of the peer's memory and waits for each of them.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ghost_push_kernel(int nvar, int64_t n_send, const int32_t* __restrict__ src, const int32_t* __restrict__ drk,
+                  const int32_t* __restrict__ dix, PtrsC<T> own, Tables<T> all) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_send * nvar) return;
+  const int64_t e = g % n_send;
+  const int     l = (int)(g / n_send);
+#pragma unroll
+  for (int k = 0; k < MAXV; k++)
+    if (k == l) all.p[k][drk[e]][dix[e]] = own.p[k][src[e]];
+}
+
 template <typename T>
 int adapt_impl(int dim_subgrid, int nvar, int64_t n_new, const int32_t* ad, const T* const* uo, T* const* un,
                const T* vo, T* vn, void* stream) {
@@ -179,7 +198,30 @@ static int ghost_pull_impl(const t8b200_plan* P, int nvar, T* const* rows, const
   return cudaGetLastError();
 }
 
+template <typename T>
+static int ghost_push_impl(int nvar, int64_t n_send, const int32_t* src, const int32_t* drk, const int32_t* dix,
+                           const T* const* rows, T* const* const* rows_all, void* stream) {
+  if (nvar < 1 || nvar > MAXV || n_send < 0) return cudaErrorInvalidValue;
+  if (n_send == 0) return 0;
+  if (!src || !drk || !dix || !rows || !rows_all) return cudaErrorInvalidValue;
+  PtrsC<T>  o{};
+  Tables<T> a{};
+  for (int k = 0; k < nvar; k++) { o.p[k] = rows[k]; a.p[k] = rows_all[k]; }
+  const int64_t total = n_send * nvar;
+  ghost_push_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nvar, n_send, src, drk, dix, o, a);
+  return cudaGetLastError();
+}
+
 extern "C" {
+int t8b200_ghost_push_f32(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
+                          const int32_t* dst_idx, const float* const* rows, float* const* const* rows_all, void* stream) {
+  return ghost_push_impl<float>(nvar, n_send, src_idx, dst_rank, dst_idx, rows, rows_all, stream);
+}
+int t8b200_ghost_push_f64(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
+                          const int32_t* dst_idx, const double* const* rows, double* const* const* rows_all,
+                          void* stream) {
+  return ghost_push_impl<double>(nvar, n_send, src_idx, dst_rank, dst_idx, rows, rows_all, stream);
+}
 int t8b200_ghost_pull_f32(const t8b200_plan* plan, int nvar, float* const* rows, const float* const* const* rows_all,
                           void* stream) {
   return ghost_pull_impl<float>(plan, nvar, rows, rows_all, stream);

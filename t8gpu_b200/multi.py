@@ -63,3 +63,34 @@ def timestep(vmax, cfl, max_level, dt_cap=None):
     """CompressibleEulerSolver::compute_timestep (solver.cu:225-228): cfl * 0.5^max_level / vmax, optionally capped."""
     dt = cfl * 0.5 ** max_level / vmax
     return dt if dt_cap is None else min(dt_cap, dt)
+
+
+def send_lists(dist, plan, n_local, rank, world, device):
+    """Push lists of this rank from the pull lists of all ranks: what every peer p pulls from `rank` (p's plan arrays 17 /
+    18), with its destination n_local(p) + j in p's rows.  Returns device int32 tensors (src_idx, dst_rank, dst_idx),
+    sorted by destination.  One all-gather of the padded pull lists at set-up."""
+    import numpy as np
+    import torch
+    pr, pi = plan.device_array(17), plan.device_array(18)
+    meta = torch.tensor([len(pr), n_local], dtype=torch.int64, device=device)
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    metas = [m.cpu().tolist() for m in metas]
+    cap = max(1, max(m[0] for m in metas))
+    mine = torch.zeros((2, cap), dtype=torch.int32, device=device)
+    mine[0, :len(pr)] = torch.as_tensor(pr)
+    mine[1, :len(pi)] = torch.as_tensor(pi)
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    src, drk, dix = [], [], []
+    for p in range(world):
+        if p == rank:
+            continue
+        n, nl = metas[p]
+        rk, ix = every[p][0, :n].cpu().numpy(), every[p][1, :n].cpu().numpy()
+        sel = np.nonzero(rk == rank)[0]
+        src.append(ix[sel])
+        drk.append(np.full(len(sel), p, np.int32))
+        dix.append((nl + sel).astype(np.int32))
+    cat = lambda a: torch.as_tensor(np.concatenate(a) if a else np.zeros(0, np.int32)).to(torch.int32).to(device)  # noqa: E731
+    return cat(src), cat(drk), cat(dix)
