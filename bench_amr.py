@@ -23,6 +23,8 @@ import time
 import numpy as np
 import torch
 
+from t8gpu_b200.multi import adapt_partition_ranges
+
 CRIT_SCALE, THRESHOLD = 10.0 / 0.5, 10.0   # the example's threshold (mesh_manager.inl:141) with the criterion scaled so
                                            # that the Cartesian shear layers refine (as tests/perf_amr.py)
 
@@ -191,15 +193,14 @@ class AmrRun:
         f2 = f.adapt(crit_h, threshold, 1, self.max_level, nranks=world)
         amap = f.adapt_map(f2)
         n_new = f2.num_elements
-        lo = np.searchsorted(amap[:-1], m.off, side="left")      # adapted, not yet repartitioned: rank q holds [lo[q], lo[q+1])
-        lo[world] = n_new
         off2 = f2.partition_offsets(world)
+        lo, ad_h, owner, index = adapt_partition_ranges(amap, m.off, off2, rank)
         T["forest_host(t8code stand-in)"] += time.time() - t
         # ---- adapt remap into a peer-visible intermediate (5 variables + volume)
         t = time.time()
         n_mid = int(lo[rank + 1] - lo[rank])
         mid = RankMidBuffer(n_mid, rank, world, dev, self.dtype, dist, tb, m.S)
-        ad = torch.as_tensor((amap[lo[rank]:lo[rank + 1] + 1] - m.off[rank]).astype(np.int32)).to(dev)
+        ad = torch.as_tensor(ad_h).to(dev)
         tb.adapt_remap(ad, m.vars(self.next), mid.vars(), m.volume(), mid.volume(), 3 if self.subgrid else 0)
         torch.cuda.synchronize()
         if world > 1:
@@ -211,9 +212,6 @@ class AmrRun:
         T["tile_plan"] += new.t_plan
         # ---- partition remap: pull the new elements from the ranks that hold them
         t = time.time()
-        g = np.arange(off2[rank], off2[rank + 1])
-        owner = (np.searchsorted(lo, g, side="right") - 1).astype(np.int32)
-        index = (g - lo[owner]).astype(np.int32)
         tb.partition_remap(torch.as_tensor(owner).to(dev), torch.as_tensor(index).to(dev), new.vars(0), mid.tables(),
                            new.volume(), mid.volume_table(), m.S)
         torch.cuda.synchronize()

@@ -94,3 +94,28 @@ def send_lists(dist, plan, n_local, rank, world, device):
         dix.append((nl + sel).astype(np.int32))
     cat = lambda a: torch.as_tensor(np.concatenate(a) if a else np.zeros(0, np.int32)).to(torch.int32).to(device)  # noqa: E731
     return cat(src), cat(drk), cat(dix)
+
+
+def adapt_partition_ranges(amap, off_old, off_new, rank):
+    """Index arithmetic of one adapt + repartition cycle for `rank` (host side; the forest work itself is t8code's).
+
+    amap: the global old -> new element map of the adapted forest (n_new + 1 entries, mesh_manager.inl:258-281);
+    off_old / off_new: partition offsets before the adapt / after the repartition (nranks + 1 entries).
+    t8code adapts every rank's elements in place (a family is only coarsened inside one rank), so the adapted, not yet
+    repartitioned forest keeps rank q's elements in [lo[q], lo[q+1]).  Returns
+      lo          those ranges (nranks + 1),
+      adapt_data  this rank's local map for t8b200_adapt_remap (n_mid + 1 entries, relative to its old elements),
+      owner, index  for every element of this rank's NEW partition: the rank that holds it after the adapt and its
+                  index there (what t8_forest_partition_data delivers, mesh_manager.inl:655-676) for
+                  t8b200_partition_remap."""
+    import numpy as np
+    amap = np.asarray(amap, np.int64)
+    off_old, off_new = np.asarray(off_old, np.int64), np.asarray(off_new, np.int64)
+    n_new = len(amap) - 1
+    lo = np.searchsorted(amap[:-1], off_old, side="left").astype(np.int64)
+    lo[-1] = n_new
+    adapt_data = (amap[lo[rank]:lo[rank + 1] + 1] - off_old[rank]).astype(np.int32)
+    g = np.arange(off_new[rank], off_new[rank + 1])
+    owner = (np.searchsorted(lo, g, side="right") - 1).astype(np.int32)
+    index = (g - lo[owner]).astype(np.int32)
+    return lo, adapt_data, owner, index

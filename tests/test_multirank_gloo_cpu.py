@@ -118,6 +118,42 @@ def _worker(rank, world, port, q):
         dts = [None] * world
         dist.all_gather_object(dts, out["dt"])
         assert dts[0] == dts[1] > 0
+
+        # ---- 5. push lists = the peers' pull lists regrouped by owner (send_lists over an all-gather)
+        class FakePlan:      # arrays 17 / 18 of a ghost-tail plan: sorted distinct (owner, index) pairs of the ghosts
+            def __init__(self, ranks, idx):
+                self.a = {17: np.asarray(ranks, np.int32), 18: np.asarray(idx, np.int32)}
+
+            def device_array(self, which):
+                return self.a[which]
+        gh = sorted(set((int(conn["ranks"][nl + g]), int(conn["indices"][nl + g])) for g in range(ng)))
+        plan = FakePlan([r for r, _ in gh], [i for _, i in gh])
+        src, drk, dix = multi.send_lists(dist, plan, nl, rank, world, "cpu")
+        lists = [None] * world
+        dist.all_gather_object(lists, (gh, nl, src.tolist(), drk.tolist(), dix.tolist()))
+        other = 1 - rank
+        o_gh, o_nl = lists[other][0], lists[other][1]
+        want = [(i, other, o_nl + j) for j, (r, i) in enumerate(o_gh) if r == rank]     # what the other rank pulls from me
+        assert list(zip(src.tolist(), drk.tolist(), dix.tolist())) == want and len(want) > 0
+
+        # ---- 6. one adapt + repartition cycle: the per-rank index arithmetic (adapt_partition_ranges) drives the
+        # restated remaps (oracle.adapt_remap / partition_remap) to exactly the one-rank result
+        lv, cent, vol, _ = f.elements()
+        crit = np.where(np.abs(cent[:, 0] - 0.5) < 0.2, 20.0, 0.0)
+        f2 = f.adapt(crit, 10.0, 1, 4, nranks=world)
+        amap = f.adapt_map(f2)
+        off2 = f2.partition_offsets(world)
+        u_glob, vol_glob = oracle.adapt_remap(amap, u0, volT, 0)                  # one rank: the whole forest at once
+        lo, ad, owner, index = multi.adapt_partition_ranges(amap, off, off2, rank)
+        assert lo[0] == 0 and lo[-1] == f2.num_elements and ad[0] == 0 and ad[-1] == off[rank + 1] - off[rank]
+        u_mid, vol_mid = oracle.adapt_remap(ad, np.ascontiguousarray(u0[:, off[rank]:off[rank + 1]]),
+                                            np.ascontiguousarray(volT[off[rank]:off[rank + 1]]), 0)
+        mids = [None] * world
+        dist.all_gather_object(mids, (u_mid, vol_mid))                            # stands for the peer tables
+        u_new, vol_new = oracle.partition_remap(owner, index, [m[0] for m in mids], [m[1] for m in mids])
+        assert np.array_equal(u_new, u_glob[:, off2[rank]:off2[rank + 1]])
+        assert np.array_equal(vol_new, vol_glob[off2[rank]:off2[rank + 1]])
+        assert np.array_equal(vol_new, f2.elements()[2][off2[rank]:off2[rank + 1]])
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
