@@ -246,6 +246,89 @@ T8B_HD T kepes_flux_n(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[
   return au + aHat;
 }
 
+#ifdef __CUDACC__
+// ---- two x-normal faces at once in packed fp32 (sm_100a: fma.rn.f32x2 / mul / add on register pairs) -------------
+// fp32 is bound by issue slots (~80 % busy, half of the instructions are FP32 arithmetic): evaluating two faces of a
+// thread in the two halves of a register pair halves the FP32 instruction count of the flux.  Same formulas as
+// kepes_flux_n<float, 0> (series branch) with the multiply-adds written out (results agree to rounding; the two lanes
+// are independent, so a face gives the same bits whichever lane or thread evaluates it); a strong jump on either face
+// (the reference's log branch) is reported through the return value and the caller re-evaluates both faces with the
+// scalar function.  The caller permutes the velocity components so that each face's normal is
+// "x" in its own frame and permutes the momentum fluxes back.
+struct F2 {
+  float2 v;
+};
+__device__ __forceinline__ F2 f2(float a, float b) { return F2{make_float2(a, b)}; }
+__device__ __forceinline__ F2 f2(float a) { return F2{make_float2(a, a)}; }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return F2{__fadd2_rn(a.v, b.v)}; }
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return F2{__fmul2_rn(a.v, b.v)}; }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return F2{__ffma2_rn(a.v, b.v, c.v)}; }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return fma2(b, f2(-1.f), a); }       // a - b
+__device__ __forceinline__ F2 fnma2(F2 a, F2 b, F2 c) { return fma2(F2{make_float2(-a.v.x, -a.v.y)}, b, c); }   // c - a b
+__device__ __forceinline__ F2 abs2(F2 a) { return F2{make_float2(fabsf(a.v.x), fabsf(a.v.y))}; }
+
+// L0 / R0: first face, L1 / R1: second face (both with normal +x in their own frame).  Fa / Fb: the five fluxes of
+// each, sa / sb: the wave-speed estimates.  Returns false when one of the faces needs the log branch (outputs invalid).
+__device__ __forceinline__ bool kepes_flux_x_pair(const Cell<float>& L0, const Cell<float>& R0, const Cell<float>& L1,
+                                                  const Cell<float>& R1, float Fa[5], float Fb[5], float& sa,
+                                                  float& sb_) {
+  const float kappa = 1.4f, km1 = kappa - 1.f, ikm1s = 1.f / km1;
+  const F2 ikm1 = f2(ikm1s), one = f2(1.f), half = f2(0.5f), two = f2(2.f);
+  const F2 c3 = f2(float(1.0 / 3.0)), c5 = f2(float(1.0 / 5.0)), c7 = f2(float(1.0 / 7.0));
+  const F2 Lrho = f2(L0.rho, L1.rho), Rrho = f2(R0.rho, R1.rho), Lb = f2(L0.b, L1.b), Rb = f2(R0.b, R1.b);
+  const F2 Lhx = f2(L0.hx, L1.hx), Lhy = f2(L0.hy, L1.hy), Lhz = f2(L0.hz, L1.hz);
+  const F2 Rhx = f2(R0.hx, R1.hx), Rhy = f2(R0.hy, R1.hy), Rhz = f2(R0.hz, R1.hz);
+  const F2 sr = Lrho + Rrho, dr = Rrho - Lrho, sb = Lb + Rb, db = Rb - Lb;
+  const F2 kps = f2(L0.kp, L1.kp) + f2(R0.kp, R1.kp), dq = f2(R0.q, R1.q) - f2(L0.q, L1.q);
+  // one reciprocal per face: MUFU seed per lane, the Newton step packed
+  const F2 x = sr * sb;
+  F2       r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.v.x) : "f"(x.v.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.v.y) : "f"(x.v.y));
+  const F2 rr  = fma2(r, fnma2(x, r, one), r);
+  const F2 isr = rr * sb, isb = rr * sr, hs = half * sr;
+  const F2 fr = dr * isr, ur = fr * fr, fb = db * isb, ub = fb * fb;
+  if (!(fmaxf(fmaxf(ur.v.x, ub.v.x), fmaxf(ur.v.y, ub.v.y)) < 1.0e-4f)) return false;   // strong jump: scalar path
+  const F2 xr = ur * fma2(ur, fma2(ur, c7, c5), c3);
+  const F2 xb = ub * fma2(ub, fma2(ub, c7, c5), c3);
+  const F2 rhoHat = hs * fnma2(xr, fnma2(xr, fnma2(xr, one, one), one), one);   // 1 - x (1 - x (1 - x))
+  const F2 hir = fma2(isr, xr, isr), hlr = fma2(fr, xr, fr), hib = fma2(isb, xb, isb), hlb = fma2(fb, xb, fb);
+  const F2 ax = Lhx + Rhx, ay = Lhy + Rhy, az = Lhz + Rhz;
+  const F2 uHat = ax;
+  const F2 vv   = fma2(az, az, fma2(ay, ay, ax * ax));
+  const F2 hvv  = half * vv;
+  const F2 dhh  = fma2(Lhz, Rhz, fma2(Lhy, Rhy, Lhx * Rhx));
+  // square root: rsqrt seed per lane, one packed correction (fast_sqrt(float))
+  const F2 sx = kps * hir;
+  F2       y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.v.x) : "f"(sx.v.x));
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.v.y) : "f"(sx.v.y));
+  const F2 s0   = sx * y;
+  const F2 aHat = fma2(fnma2(s0, s0, sx), half * y, s0);
+  const F2 ibk = hib * ikm1, tt = fma2(two, dhh, ibk), HHat = tt + hib, p1Hat = hs * isb;
+  const F2 F0 = rhoHat * uHat, Fs4 = fma2(F0, tt, uHat * p1Hat);
+  const F2 J0 = fma2(ikm1, hlb, hlr) - dq;
+  const F2 jx = fnma2(Lb, Lhx, Rb * Rhx), jy = fnma2(Lb, Lhy, Rb * Rhy), jz = fnma2(Lb, Lhz, Rb * Rhz);
+  const F2 aj = fma2(az, jz, fma2(ay, jy, ax * jx));
+  const F2 g  = fnma2(uHat, db, two * jx);
+  const F2 b  = fma2(two, aj, J0), c = fnma2(HHat, db, b), e = aHat * g, a1 = fnma2(hvv, db, b);
+  const F2 au = abs2(uHat);
+  const F2 k0 = rhoHat * f2(0.5f / kappa);
+  const F2 d0 = abs2(uHat - aHat) * k0 * (c - e), d4 = abs2(uHat + aHat) * k0 * (c + e);
+  const F2 d1 = au * (rhoHat * f2(km1 / kappa)) * a1, D2 = au * p1Hat;
+  const F2 s04 = d0 + d4, sum = s04 + d1, dif = aHat * (d4 - d0);
+  const F2 inr = fnma2(uHat, g, fnma2(vv, db, two * aj));
+  const F2 f0  = F0 - sum;
+  const F2 f4  = fnma2(D2, inr, fnma2(hvv, d1, fnma2(uHat, dif, fnma2(HHat, s04, Fs4))));
+  const F2 ca = fma2(D2, db, f0), cn = fma2(D2, g, p1Hat - dif), D22 = D2 + D2;
+  const F2 f1 = fnma2(D22, jx, ca * ax) + cn, f2_ = fnma2(D22, jy, ca * ay), f3 = fnma2(D22, jz, ca * az);
+  const F2 sp = au + aHat;
+  Fa[0] = f0.v.x; Fa[1] = f1.v.x; Fa[2] = f2_.v.x; Fa[3] = f3.v.x; Fa[4] = f4.v.x; sa  = sp.v.x;
+  Fb[0] = f0.v.y; Fb[1] = f1.v.y; Fb[2] = f2_.v.y; Fb[3] = f3.v.y; Fb[4] = f4.v.y; sb_ = sp.v.y;
+  return true;
+}
+#endif
+
 // general-normal entry point used by the reference-shaped kernels
 template <typename T>
 T8B_HD T kepes_flux(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[5]) {

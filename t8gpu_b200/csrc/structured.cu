@@ -73,6 +73,16 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 #ifndef T8B_S_MINB
 #define T8B_S_MINB 3
 #endif
+#ifndef T8B_S_MINB32   // fp32: resident CTAs per SM the register budget is sized for (48 registers come out anyway)
+#define T8B_S_MINB32 3
+#endif
+// 1: fp32 evaluates two faces per packed fp32x2 flux (fma.rn.f32x2, euler_flux.cuh: kepes_flux_x_pair).  Parity green,
+// measured SLOWER on the level-8 hex forest (1.50 ms per step at 64 registers / 4 CTAs per SM, 1.57 at 48 / 5 with
+// spills, 1.69 at 68 / 3, against 1.46 for the scalar flux at 48 / 5): the 210 packed instructions replace ~330 scalar
+// ones, but packing / unpacking moves, the rotated cell copies and the lost occupancy cost more.  Off.
+#ifndef T8B_S_PAIR
+#define T8B_S_PAIR 0
+#endif
 #ifndef T8B_S_OWNREG   // 1: the thread's own cell stays in registers through the face phase; 0: re-read per face
 #define T8B_S_OWNREG 1
 #endif
@@ -85,7 +95,8 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 //      ghost copies are still being pulled on another stream)
 //   3  "boundary pass": the launch covers the partition-boundary chunks only, chunk id from the compact list
 template <typename T, class L, bool SMAX, int MODE>
-__global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const __grid_constant__ SArgs<T> A) {
+__global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB32)
+    structured_stage_kernel(const __grid_constant__ SArgs<T> A) {
   constexpr bool MULTI = MODE == 1;
   constexpr int NS = L::NSLOT, NF = BoxCommon::NFLUX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -141,6 +152,58 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
 
   // ---- phase 1
   T smax = T(0);
+#if T8B_S_PAIR
+  if constexpr (sizeof(T) == 4) {
+    // fp32: two faces per packed evaluation (kepes_flux_x_pair): (x, y) of this element, then z together with one of
+    // the 128 faces on the upper box boundary (threads 0-127; the other threads duplicate their z face in that lane).
+    // Each face is rotated into its own frame by a cyclic permutation of the velocity components.
+    auto rot = [](const Cell<T>& c, int p0) {   // frame of a face with normal +e_p0: (h_p0, h_p0+1, h_p0+2)
+      Cell<T> q = c;
+      q.hx = p0 == 0 ? c.hx : p0 == 1 ? c.hy : c.hz;
+      q.hy = p0 == 0 ? c.hy : p0 == 1 ? c.hz : c.hx;
+      q.hz = p0 == 0 ? c.hz : p0 == 1 ? c.hx : c.hy;
+      return q;
+    };
+    auto store = [&](int j, const T F[5], int p0) {   // momentum fluxes back to xyz
+      fl[j] = F[0]; fl[4 * NF + j] = F[4];
+      fl[(1 + p0) * NF + j] = F[1];
+      fl[(1 + (p0 == 2 ? 0 : p0 + 1)) * NF + j] = F[2];
+      fl[(1 + (p0 == 0 ? 2 : p0 - 1)) * NF + j] = F[3];
+    };
+    const int sl0 = L::at_lower(tid, 0) ? L::halo_slot(0, 0, L::compact(tid, 0)) : L::lower_own(tid, 0);
+    const int sl1 = L::at_lower(tid, 1) ? L::halo_slot(1, 0, L::compact(tid, 1)) : L::lower_own(tid, 1);
+    const int sl2 = L::at_lower(tid, 2) ? L::halo_slot(2, 0, L::compact(tid, 2)) : L::lower_own(tid, 2);
+    T Fa[5], Fb[5], sa, sb;
+    {
+      const Cell<T> L0 = s_load_cell<T, NS>(cq, sl0), L1 = rot(s_load_cell<T, NS>(cq, sl1), 1), R1 = rot(C, 1);
+      if (!kepes_flux_x_pair(L0, C, L1, R1, Fa, Fb, sa, sb)) {
+        sa = kepes_flux_n<T, 0>(L0, C, T(0), T(0), T(0), Fa);
+        sb = kepes_flux_n<T, 0>(L1, R1, T(0), T(0), T(0), Fb);
+      }
+      if (SMAX) smax = fmax_(smax, fmax_(sa, sb));
+      store(tid, Fa, 0);
+      store(256 + tid, Fb, 1);
+    }
+    {
+      const bool up = tid < 128;
+      const int  d = tid < 64 ? tid >> 5 : 2, idx = tid < 64 ? tid & 31 : tid - 64;
+      const Cell<T> L0 = rot(s_load_cell<T, NS>(cq, sl2), 2), R0 = rot(C, 2);
+      Cell<T>       L1 = L0, R1 = R0;
+      if (up) {
+        L1 = rot(s_load_cell<T, NS>(cq, L::upper_elem(idx, d)), d);
+        R1 = rot(s_load_cell<T, NS>(cq, L::halo_slot(d, 1, idx)), d);
+      }
+      if (!kepes_flux_x_pair(L0, R0, L1, R1, Fa, Fb, sa, sb)) {
+        sa = kepes_flux_n<T, 0>(L0, R0, T(0), T(0), T(0), Fa);
+        sb = kepes_flux_n<T, 0>(L1, R1, T(0), T(0), T(0), Fb);
+      }
+      if (SMAX) smax = fmax_(smax, fmax_(sa, sb));
+      store(512 + tid, Fa, 2);
+      if (up) store(768 + tid, Fb, d);
+    }
+  } else
+#endif
+  {
 #define T8B_S_FACE(D)                                                                                              \
   {                                                                                                                \
     const int sl = L::at_lower(tid, D) ? L::halo_slot(D, 0, L::compact(tid, D)) : L::lower_own(tid, D);            \
@@ -170,6 +233,8 @@ __global__ void __launch_bounds__(256, T8B_S_MINB) structured_stage_kernel(const
     const int j = 768 + tid;   // == BoxCommon::upper_flux(d, idx)
     fl[j] = F[0]; fl[(1 + p0) * NF + j] = F[1]; fl[(1 + p1) * NF + j] = F[2]; fl[(1 + p2) * NF + j] = F[3];
     fl[4 * NF + j] = F[4];
+  }
+
   }
 
   // ---- phase 2: operands requested before the barrier
