@@ -47,6 +47,7 @@ struct SArgs {
   T*             speed_max;
   int            stage, multi, my_rank;
   const int32_t* blist;   // MODE 3: ids of the partition-boundary chunks
+  const uint4*   slots;   // T8B_S_TABLE: per thread (lower slots x | y << 16, z | ux << 16, uy | uz << 16, halo slot)
   int            dense;   // every chunk of the plan is structured: chunk b = elements [256 b, 256 b + 256), one area
   int            area0;
   int            wave;    // CTAs resident at once (distance of the next-wave L2 prefetch), 0: off
@@ -83,6 +84,9 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 #ifndef T8B_S_PAIR
 #define T8B_S_PAIR 0
 #endif
+#ifndef T8B_S_TABLE    // 1: slot indices of a thread from a 256-entry table instead of the layout's bit arithmetic
+#define T8B_S_TABLE 0
+#endif
 #ifndef T8B_S_OWNREG   // 1: the thread's own cell stays in registers through the face phase; 0: re-read per face
 #define T8B_S_OWNREG 1
 #endif
@@ -117,6 +121,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
     bnd = __ldg(reinterpret_cast<const int*>(A.rec + b) + 3) != 0;   // off the critical path: only the flag is read
   }
   const int e    = e0 + tid;
+  uint4     tab  = make_uint4(0u, 0u, 0u, 0u);
+  if (T8B_S_TABLE) tab = __ldg(A.slots + tid);   // the thread's slot indices: the same for every chunk (L1 / L2 resident)
   const int hidx = __ldg(A.halo + b * 256 + tid);
   int       hrk  = A.my_rank;
   if (MULTI) hrk = __ldg(A.hrank + b * 256 + tid);
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
   }
   const Cell<T> C = to_cell(u0, u1, u2, u3, u4);
   s_store_cell<T, NS>(cq, tid, C);
-  s_store_cell<T, NS>(cq, L::thread_slot(tid), to_cell(g0, g1, g2, g3, g4));
+  s_store_cell<T, NS>(cq, T8B_S_TABLE ? (int)tab.w : L::thread_slot(tid), to_cell(g0, g1, g2, g3, g4));
   __syncthreads();
 
   // ---- phase 1
@@ -206,7 +212,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
   {
 #define T8B_S_FACE(D)                                                                                              \
   {                                                                                                                \
-    const int sl = L::at_lower(tid, D) ? L::halo_slot(D, 0, L::compact(tid, D)) : L::lower_own(tid, D);            \
+    const int sl = T8B_S_TABLE ? (D == 0 ? (int)(tab.x & 0xFFFFu) : D == 1 ? (int)(tab.x >> 16) : (int)(tab.y & 0xFFFFu)) \
+                 : (L::at_lower(tid, D) ? L::halo_slot(D, 0, L::compact(tid, D)) : L::lower_own(tid, D));           \
     const Cell<T> Lc = s_load_cell<T, NS>(cq, sl);                                                                 \
     const Cell<T> Rc = T8B_S_OWNREG ? C : s_load_cell<T, NS>(cq, tid);                                             \
     T       F[5];                                                                                                  \
@@ -252,9 +259,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
   if (stage == 2) sc *= T(0.25);
   if (stage == 3) sc *= T(0.66666666666666);
   sc *= A.area_tab[area_idx];
-  const int ux = L::at_upper(tid, 0) ? BoxCommon::upper_flux(0, L::compact(tid, 0)) : L::upper_own(tid, 0);
-  const int uy = L::at_upper(tid, 1) ? BoxCommon::upper_flux(1, L::compact(tid, 1)) : 256 + L::upper_own(tid, 1);
-  const int uz = L::at_upper(tid, 2) ? BoxCommon::upper_flux(2, L::compact(tid, 2)) : 512 + L::upper_own(tid, 2);
+  const int ux = T8B_S_TABLE ? (int)(tab.y >> 16)
+                             : (L::at_upper(tid, 0) ? BoxCommon::upper_flux(0, L::compact(tid, 0)) : L::upper_own(tid, 0));
+  const int uy = T8B_S_TABLE ? (int)(tab.z & 0xFFFFu)
+                             : (L::at_upper(tid, 1) ? BoxCommon::upper_flux(1, L::compact(tid, 1)) : 256 + L::upper_own(tid, 1));
+  const int uz = T8B_S_TABLE ? (int)(tab.z >> 16)
+                             : (L::at_upper(tid, 2) ? BoxCommon::upper_flux(2, L::compact(tid, 2)) : 512 + L::upper_own(tid, 2));
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 5; k++) {
@@ -279,6 +289,25 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
   }
 }
 
+template <class L>
+static const uint4* slot_table(int dev) {
+  static uint4* tabs[64];
+  if (!tabs[dev]) {
+    uint4 h[256];
+    for (int t = 0; t < 256; t++) {
+      auto lower = [&](int d) { return L::at_lower(t, d) ? L::halo_slot(d, 0, L::compact(t, d)) : L::lower_own(t, d); };
+      const unsigned ux = L::at_upper(t, 0) ? BoxCommon::upper_flux(0, L::compact(t, 0)) : L::upper_own(t, 0);
+      const unsigned uy = L::at_upper(t, 1) ? BoxCommon::upper_flux(1, L::compact(t, 1)) : 256 + L::upper_own(t, 1);
+      const unsigned uz = L::at_upper(t, 2) ? BoxCommon::upper_flux(2, L::compact(t, 2)) : 512 + L::upper_own(t, 2);
+      h[t] = make_uint4((unsigned)lower(0) | (unsigned)lower(1) << 16, (unsigned)lower(2) | ux << 16, uy | uz << 16,
+                        (unsigned)L::thread_slot(t));
+    }
+    if (cudaMalloc(&tabs[dev], sizeof(h)) != cudaSuccess) return nullptr;
+    cudaMemcpy(tabs[dev], h, sizeof(h), cudaMemcpyHostToDevice);
+  }
+  return tabs[dev];
+}
+
 template <typename T, class L, bool SMAX, int MODE>
 static int s_launch(const t8b200_plan* P, SArgs<T>& A, cudaStream_t st) {
   auto             k    = structured_stage_kernel<T, L, SMAX, MODE>;
@@ -297,6 +326,10 @@ static int s_launch(const t8b200_plan* P, SArgs<T>& A, cudaStream_t st) {
   }
   static const int wave_knob = getenv("T8B200_WAVE") ? atoi(getenv("T8B200_WAVE")) : -1;
   A.wave = wave_knob >= 0 ? wave_knob : resident[dev];
+  if (T8B_S_TABLE) {
+    A.slots = slot_table<L>(dev);
+    if (!A.slots) return cudaErrorMemoryAllocation;
+  }
   const int grid = MODE == 3 ? P->nb_struct : P->n_struct;
   if (grid > 0) k<<<grid, 256, smem, st>>>(A);
   return cudaGetLastError();
