@@ -61,7 +61,10 @@ class SubgridBrick:
         self.vol = conn["volumes"]
         self.sync = os.environ.get("T8B200_SYNC", "pull") if world > 1 else "single"
         t0 = time.time()
-        self.plan = tb.SubgridPlan(tb.conn_to_host(conn), self.vol.cpu().numpy(), dtype, ghost_tail=self.sync == "pull")
+        self.plan = tb.SubgridPlan.from_device(conn, self.vol, dtype, ghost_tail=self.sync == "pull")   # no D2H
+        if self.plan is None:
+            self.plan = tb.SubgridPlan(tb.conn_to_host(conn), self.vol.cpu().numpy(), dtype, ghost_tail=self.sync == "pull")
+        torch.cuda.synchronize()
         self.t_plan = time.time() - t0
         self.cap = (self.n + self.plan.n_tail + 31) // 32 * 32     # own cells, then the ghost-cell tail
         self.shared = tb.SharedBuffer(NVAR * NB_STEPS * self.cap * esz, device)

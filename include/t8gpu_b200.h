@@ -246,6 +246,18 @@ int t8b200_subgrid_plan_create_ghost_tail(t8b200_subgrid_plan** out, int is_f64,
                                           int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
                                           const void* x_face_surfaces, const int32_t* x_level_difference,
                                           const int32_t* x_neighbor_offset);
+/* Cell-level plan built on the device from DEVICE arrays (see t8b200_plan_create_device): Subgrid<4,4,4> on forests
+ * whose every group of 4 consecutive elements is a 2 x 2 x 1 block of same-size siblings surrounded by single same-level
+ * elements (uniform forests and brick partitions); cudaErrorNotSupported otherwise (dim 2, hanging faces, walls ...).
+ * volumes: device, per element.  The neighbour offsets are not needed (same-level faces: the cell across a face has the
+ * same tangential coordinates). */
+int t8b200_subgrid_plan_create_device(t8b200_subgrid_plan** out, int is_f64, int dim, int ghost_tail, int64_t n_local,
+                                      int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* face_neighbors,
+                                      const void* face_normals, const void* face_surfaces,
+                                      const int32_t* face_level_difference, const void* volumes, const int32_t* ranks,
+                                      const int32_t* indices, int32_t n_xfaces, const int32_t* x_face_neighbors,
+                                      const void* x_face_normals, const void* x_face_surfaces,
+                                      const int32_t* x_level_difference, void* stream);
 const t8b200_plan* t8b200_subgrid_plan_base(const t8b200_subgrid_plan* plan);
 /* as t8b200_plan_info, counted in cells */
 int t8b200_subgrid_plan_info(const t8b200_subgrid_plan* plan, int64_t info[8]);

@@ -341,6 +341,50 @@ class SubgridPlan:
         self.info = dict(n_chunks=info[0], max_halo=info[1], max_faces=info[2], smem_bytes=info[3],
                          device_bytes=info[4], face_records=info[5], halo_entries=info[6], chunk=info[7])
 
+    @classmethod
+    def from_device(cls, conn, volumes, dtype, ghost_tail=False, stream=None):
+        """Cell-level plan built on the device from DEVICE tensors (t8b200_subgrid_plan_create_device); None when the
+        forest is not made of structured chunks only (then use SubgridPlan(conn_to_host(conn), ...))."""
+        _torch()
+        s, _ = _sfx(dtype)
+
+        def p(k):
+            t = conn.get(k)
+            return None if t is None or t.numel() == 0 else C.c_void_p(t.data_ptr())
+
+        nx, ng = int(conn.get("n_xfaces", 0)), int(conn.get("n_ghost", 0))
+        h = C.c_void_p()
+        rc = lib().t8b200_subgrid_plan_create_device(
+            C.byref(h), int(s == "f64"), int(conn["dim"]), int(bool(ghost_tail)), C.c_int64(int(conn["n_local"])),
+            C.c_int64(ng), int(conn["n_faces"]), int(conn["n_bfaces"]), p("face_neighbors"), p("face_normals"),
+            p("face_areas"), p("level_diff"), C.c_void_p(volumes.data_ptr()), p("ranks") if ng else None,
+            p("indices") if ng else None, nx, p("x_face_neighbors") if nx else None, p("x_face_normals") if nx else None,
+            p("x_face_areas") if nx else None, p("x_level_diff") if nx else None, stream_ptr(stream))
+        if rc == 801:
+            return None
+        check(rc, "subgrid_plan_create_device")
+        self = cls.__new__(cls)
+        self.dtype, self._h = dtype, h
+        lib().t8b200_subgrid_plan_base.restype = C.c_void_p
+        self._base = C.c_void_p(lib().t8b200_subgrid_plan_base(h))
+        self.n_tail = int(lib().t8b200_plan_ghost_tail_count(self._base))
+        info = (C.c_int64 * 8)()
+        check(lib().t8b200_subgrid_plan_info(self._h, info), "subgrid_plan_info")
+        self.info = dict(n_chunks=info[0], max_halo=info[1], max_faces=info[2], smem_bytes=info[3],
+                         device_bytes=info[4], face_records=info[5], halo_entries=info[6], chunk=info[7],
+                         built_on="device")
+        return self
+
+    def device_array(self, which):
+        import numpy as np
+        n = lib().t8b200_plan_device_array(self._base, which, None, C.c_int64(0))
+        if n < 0:
+            raise CudaError("plan_device_array(%d)" % which)
+        a = np.zeros(n, np.int32)
+        if n:
+            lib().t8b200_plan_device_array(self._base, which, a.ctypes.data_as(C.c_void_p), C.c_int64(n))
+        return a
+
     def __del__(self):
         if getattr(self, "_h", None) and lib is not None:
             lib().t8b200_subgrid_plan_destroy(self._h)

@@ -264,6 +264,13 @@ struct t8b200_subgrid_plan {
   int          dim  = 3;
 };
 
+t8b200_subgrid_plan* t8b_wrap_subgrid_plan(t8b200_plan* P, int dim) {
+  auto* SP = new t8b200_subgrid_plan();
+  SP->plan = P;
+  SP->dim  = dim;
+  return SP;
+}
+
 namespace {
 // cell index inside an element from (axis, x along the axis, tangential a, b)
 inline int cell_ax(int dim, int ax, int x, int a, int b) {

@@ -798,3 +798,5 @@ int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in
                              const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
                              const T* dt_dev, const t8b200::StageSync* sync, int part = 0);
 void t8b_plan_free(t8b200_plan* P);
+// defined in subgrid.cu: wraps a cell-level plan (device_plan.cu builds them too)
+t8b200_subgrid_plan* t8b_wrap_subgrid_plan(t8b200_plan* P, int dim);

@@ -172,3 +172,75 @@ def test_split_stage_passes_equal_the_single_launch(cuda, dtype):
     b3 = torch.zeros((NVAR * NB_STEPS + 1, int(c3["n_local"]) + p3.n_tail), dtype=dtype, device=cuda)
     v3 = lambda s: [b3[s * NVAR + k, :int(c3["n_local"])] for k in range(NVAR)]  # noqa: E731
     assert p3.stage_part(1, 1, v3(0), None, v3(1), b3[NVAR * NB_STEPS], dt) is False
+
+
+def subgrid_host_arrays(conn_host, volumes, dtype):
+    import t8gpu_b200 as tb
+    lib = tb.lib()
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+
+    def arr(k, dt):
+        v = conn_host.get(k)
+        return None if v is None or len(v) == 0 else np.ascontiguousarray(v, dtype=dt)
+
+    def p(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    keep = [arr("face_neighbors", np.int32), arr("face_normals", npdt), arr("face_areas", npdt),
+            arr("level_diff", np.int32), arr("offsets", np.int32), np.ascontiguousarray(volumes, dtype=npdt),
+            arr("ranks", np.int32), arr("indices", np.int32), arr("x_face_neighbors", np.int32),
+            arr("x_face_normals", npdt), arr("x_face_areas", npdt), arr("x_level_diff", np.int32),
+            arr("x_offsets", np.int32)]
+    ng = int(conn_host.get("n_ghost", 0))
+    sh = C.c_void_p()
+    assert lib.t8b200_subgrid_plan_create_host(
+        C.byref(sh), int(dtype == torch.float64), 3, C.c_int64(int(conn_host["n_local"])), C.c_int64(ng),
+        int(conn_host["n_faces"]), int(conn_host["n_bfaces"]), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]), p(keep[4]),
+        p(keep[5]), p(keep[6]) if ng else None, p(keep[7]) if ng else None, int(conn_host.get("n_xfaces", 0)), p(keep[8]),
+        p(keep[9]), p(keep[10]), p(keep[11]), p(keep[12])) == 0
+    lib.t8b200_subgrid_plan_base.restype = C.c_void_p
+    base = C.c_void_p(lib.t8b200_subgrid_plan_base(sh))
+    out = {}
+    for which in (13, 14, 15):
+        data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
+        assert lib.t8b200_plan_host_array(base, which, C.byref(data), C.byref(count), C.byref(eb)) == 0
+        n = count.value
+        out[which] = (np.frombuffer((C.c_char * (n * 4)).from_address(data.value), dtype=np.int32).copy() if n
+                      else np.zeros(0, np.int32))
+    lib.t8b200_subgrid_plan_destroy(sh)
+    return out
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("P", [1, 2])
+def test_subgrid_cell_plan_equals_host_builder(cuda, P, dtype):
+    """t8b200_subgrid_plan_create_device: Subgrid<4,4,4> cell-level plan from device arrays == the host builder's
+    (records, halo lists in thread order, owner ranks), same states bit for bit; an adapted forest is reported."""
+    import t8gpu_b200 as tb
+    from bench_subgrid import subgrid_connectivity
+    brick = (2, 1, 1) if P == 2 else (1, 1, 1)
+    for r in range(P):
+        conn = subgrid_connectivity(3, dtype, r, P, cuda, brick)
+        plan = tb.SubgridPlan.from_device(conn, conn["volumes"], dtype)
+        assert plan is not None and plan.info["n_chunks"] == int(conn["n_local"]) // 4
+        host = subgrid_host_arrays(tb.conn_to_host(conn), conn["volumes"].cpu().numpy(), dtype)
+        for which in (13, 14, 15):
+            assert np.array_equal(plan.device_array(which), host[which]), (which, r)
+    if P == 1:
+        f = oracle.Forest(3, 3)
+        npdt = np.float64 if dtype == torch.float64 else np.float32
+        lv, cent, vol, _ = f.elements()
+        a = tb.SubgridEulerSolver(f.connectivity(subgrid=True, dtype=npdt), vol.astype(npdt), dtype, device=cuda, mode="fused")
+        b = tb.SubgridEulerSolver(f.connectivity(subgrid=True, dtype=npdt), vol.astype(npdt), dtype, device=cuda, mode="fused")
+        b.plan = plan
+        u0 = oracle.subgrid_init_kh(3, cent.astype(npdt), lv, npdt)
+        a.set_state(u0)
+        b.set_state(u0)
+        for _ in range(3):
+            a.iterate(1e-3)
+            b.iterate(1e-3)
+        assert torch.equal(a.state(), b.state())
+        amr = f.adapt(np.where(cent[:, 2] < 0.25, 1.0, 0.0), 0.02, 1, 4)
+        ca = tb.conn_to_device(amr.connectivity(subgrid=True, dtype=npdt), dtype, cuda)
+        va = torch.as_tensor(amr.elements()[2].astype(npdt)).to(cuda)
+        assert tb.SubgridPlan.from_device(ca, va, dtype) is None
