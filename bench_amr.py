@@ -11,8 +11,9 @@ Per cycle, on every rank:
   adapt remap   t8b200_adapt_remap: old local elements -> the adapted, not yet repartitioned elements (device)
   partition     t8b200_partition_remap: every rank PULLS its new elements from the ranks that hold them, through the
                 peer tables over NVLink (mesh_manager.inl:625-643 does it through MPI + CUDA-IPC on one GPU)
-  connectivity  the reference-layout arrays of the new partition (host, mini-forest) + tile plan rebuild (device builder
-                when every chunk is structured, host builder otherwise)
+  connectivity  the reference-layout arrays of the new partition: built on the device from the leaf list
+                (t8b200_forest_connectivity; the subgrid variant still takes the host loop) + tile plan rebuild (device
+                builder when every chunk is structured, host builder otherwise)
 `--check`: every rank also steps the whole forest alone on its GPU and compares its partition after every cycle (the
 N-rank run must agree with the one-rank run of the same forest sequence within the north-star tolerance per step).
 """
@@ -46,25 +47,30 @@ class RankMesh:
         esz = 8 if dtype == torch.float64 else 4
         t0 = time.time()
         self.off = forest.partition_offsets(world)
-        conn = forest.connectivity(world, rank, subgrid=subgrid, dtype=npdt)
-        self.t_conn = time.time() - t0
-        self.n = int(conn["n_local"])
+        lv, cent = forest.elements()[:2]
         self.S = 64 if subgrid else 1
-        self.nc = self.n * self.S                          # entries of a variable row (cells)
-        t0 = time.time()
-        self.plan = None
-        lv = forest.elements()[0]
+        self.plan, conn_dev = None, None
         if subgrid:
+            # element-level connectivity of the subgrid manager (level differences, neighbour offsets): host loop of the
+            # t8code stand-in; the cell-level plan from the host builder
+            conn = forest.connectivity(world, rank, subgrid=True, dtype=npdt)
+            self.t_conn, self.conn_on = time.time() - t0, "host (t8code stand-in)"
+            self.n = int(conn["n_local"])
+            t0 = time.time()
             lvol = forest.elements()[2][self.off[rank]:self.off[rank + 1]].astype(npdt)
             self.plan = tb.SubgridPlan(conn, lvol, dtype, ghost_tail=world > 1)
-        elif lv.min() == lv.max() and self.n % 256 == 0:     # uniform: the device builder applies
-            keys = ("face_neighbors", "face_normals", "face_areas", "ranks", "indices", "x_face_neighbors",
-                    "x_face_normals", "x_face_areas")
-            cd = tb.conn_to_device({k: conn[k] for k in keys}, dtype, device)
-            cd.update({k: conn[k] for k in ("n_local", "n_ghost", "n_faces", "n_bfaces", "n_xfaces")})
-            self.plan = tb.Plan.from_device(cd, dtype, ghost_tail=world > 1)
-        if self.plan is None:
-            self.plan = tb.Plan(conn, dtype, ghost_tail=world > 1)
+        else:
+            # MeshManager connectivity on the device from the leaf list (t8b200_forest_connectivity): no host face loop
+            conn_dev = tb.forest_connectivity(3, True, tb.morton_keys(3, lv, cent), lv, dtype, world, rank, device=device)
+            torch.cuda.synchronize()
+            self.t_conn, self.conn_on = time.time() - t0, "device"
+            self.n = int(conn_dev["n_local"])
+            t0 = time.time()
+            if lv.min() == lv.max():                      # uniform: every chunk is structured, plan on the device too
+                self.plan = tb.Plan.from_device(conn_dev, dtype, ghost_tail=world > 1)
+            if self.plan is None:
+                self.plan = tb.Plan(tb.conn_to_host(conn_dev), dtype, ghost_tail=world > 1)
+        self.nc = self.n * self.S                          # entries of a variable row (cells)
         torch.cuda.synchronize()
         self.t_plan = time.time() - t0
         self.cap = pad32(self.nc + self.plan.n_tail)
@@ -208,7 +214,7 @@ class AmrRun:
         T["adapt_remap_device"] += time.time() - t
         # ---- new partition: connectivity (host) + plan + rows
         new = RankMesh(f2, rank, world, dev, self.dtype, dist, subgrid=self.subgrid)
-        T["connectivity_host(t8code stand-in)"] += new.t_conn
+        T["connectivity (%s)" % new.conn_on] = T.get("connectivity (%s)" % new.conn_on, 0.0) + new.t_conn
         T["tile_plan"] += new.t_plan
         # ---- partition remap: pull the new elements from the ranks that hold them
         t = time.time()
@@ -333,8 +339,8 @@ def run_amr(args, rank, world, device, dist=None, emit=True):
     run = AmrRun(level, max_level, dtype, rank, world, device, dist, subgrid=subgrid)
     shadow = OneRankShadow(run) if args.check else None
     dt = 0.1 * 2.0 ** -(max_level + (2 if subgrid else 0))
-    T = {k: 0.0 for k in ("criteria_device+gather", "forest_host(t8code stand-in)", "adapt_remap_device",
-                          "connectivity_host(t8code stand-in)", "tile_plan", "partition_remap_device")}
+    T = {k: 0.0 for k in ("criteria_device+gather", "forest_host(t8code stand-in)", "adapt_remap_device", "tile_plan",
+                          "partition_remap_device")}
     hist, t_step, updates, checks = [], 0.0, 0, []
     for _ in range(3):
         run.iterate(dt)

@@ -297,6 +297,17 @@ int  t8b200_cartesian_uniform_connectivity(t8b200_cart_conn* out, int is_f64, in
 int  t8b200_cartesian_brick_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int level, int bx, int by, int bz,
                                          int nranks, int rank, void* stream);
 void t8b200_cartesian_connectivity_free(t8b200_cart_conn* c);
+/* The same arrays for an ADAPTIVE, 2:1 face-balanced one-tree quad / hex forest, from its leaves: keys_dev = Morton key
+ * of every leaf's anchor at resolution 2^-20 per axis (bit b of coordinate d at position dim * b + d), levels_dev = its
+ * level, both DEVICE arrays over all n_leaves leaves in SFC order (what t8_forest_get_element_in_tree enumerates;
+ * 12 bytes per leaf instead of the face arrays).  Replaces the host loop of
+ * MeshManager::compute_connectivity_information (t8gpu/mesh/mesh_manager.inl:358-440: t8_forest_leaf_face_neighbors per
+ * face) bit for bit: hanging faces from the fine side (:411-424), ghost faces first and owned by the lower rank with
+ * area / num_neighbors (:396-409), boundary faces behind the interior ones (:431-440), ghosts in SFC order; periodic = 0:
+ * walls on the unit cube.  Rank `rank` of `nranks` holds the leaves [floor(N rank / P), floor(N (rank + 1) / P)).
+ * Free with t8b200_cartesian_connectivity_free. */
+int t8b200_forest_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int periodic, int64_t n_leaves,
+                               const uint64_t* keys_dev, const int32_t* levels_dev, int nranks, int rank, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
  * 4. Cross-GPU sharing of the variable buffers, one process per GPU.  Replaces the MPI_Allgather of

@@ -462,6 +462,53 @@ def cartesian_uniform_connectivity(dim, level, dtype, nranks=1, rank=0, device=N
     return out
 
 
+def morton_keys(dim, levels, centroids):
+    """Morton keys (numpy uint64) of the leaves' anchors at resolution 2^-20 per axis, from their levels and centroids --
+    the input of forest_connectivity (with t8code: the anchor coordinates of the elements)."""
+    import numpy as np
+    lv = np.asarray(levels, np.int64)
+    h = np.ldexp(1.0, -lv)
+    key = np.zeros(len(lv), np.uint64)
+    for d in range(dim):
+        c = np.rint((np.asarray(centroids)[:, d] - 0.5 * h) * (1 << 20)).astype(np.uint64)
+        for b in range(20):
+            key |= ((c >> np.uint64(b)) & np.uint64(1)) << np.uint64(dim * b + d)
+    return key
+
+
+def forest_connectivity(dim, periodic, keys, levels, dtype, nranks=1, rank=0, device=None):
+    """Device-built connectivity of an adaptive 2:1-balanced one-tree forest (t8b200_forest_connectivity) in the
+    reference layout -> dict of torch tensors.  keys: uint64 / int64 array or tensor, levels: int32, over ALL leaves."""
+    import numpy as np
+    torch = _torch()
+    s, _ = _sfx(dtype)
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    k = keys if isinstance(keys, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(keys).view(np.int64))
+    lv = levels if isinstance(levels, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(levels, dtype=np.int32))
+    k, lv = k.to(device), lv.to(torch.int32).to(device)
+    c = _CartConn()
+    check(lib().t8b200_forest_connectivity(C.byref(c), int(s == "f64"), dim, int(bool(periodic)), C.c_int64(k.numel()),
+                                           C.c_void_p(k.data_ptr()), C.c_void_p(lv.data_ptr()), nranks, rank,
+                                           stream_ptr()), "forest_connectivity")
+
+    def grab(ptr, n, dt):
+        if n == 0:
+            return torch.empty(0, dtype=dt, device=device)
+        return torch.as_tensor(_RawDeviceArray(ptr, n, dt), device=device).clone()
+
+    nl, ng, nf, nb, nx = c.n_local, c.n_ghost, c.n_faces, c.n_bfaces, c.n_xfaces
+    out = dict(dim=dim, n_local=nl, n_ghost=ng, n_faces=nf, n_bfaces=nb, n_xfaces=nx, rank=rank, nranks=nranks,
+               ranks=grab(c.ranks, nl + ng, torch.int32), indices=grab(c.indices, nl + ng, torch.int32),
+               face_neighbors=grab(c.face_neighbors, 2 * nf + nb, torch.int32),
+               face_normals=grab(c.face_normals, 3 * (nf + nb), dtype), face_areas=grab(c.face_surfaces, nf + nb, dtype),
+               volumes=grab(c.volumes, nl, dtype), centroids=grab(c.centroids, 3 * nl, dtype),
+               x_face_neighbors=grab(c.x_face_neighbors, 2 * nx, torch.int32),
+               x_face_normals=grab(c.x_face_normals, 3 * nx, dtype), x_face_areas=grab(c.x_face_surfaces, nx, dtype))
+    torch.cuda.synchronize()
+    lib().t8b200_cartesian_connectivity_free(C.byref(c))
+    return out
+
+
 def adapt_remap(adapt_data, vars_old, vars_new, vol_old, vol_new, subgrid_dim=0, stream=None):
     """adapt_variables_and_volume (subgrid_dim = 0) / subgrid adapt_variables + adapt_volume (3 or 2): device-side remap
     after t8code adapt.  adapt_data: device int32 tensor (n_new + 1); vars_*: lists of per-variable device tensors."""

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libt8gpu_b200.so")
-SOURCES = ["unstructured.cu", "fused.cu", "structured.cu", "cartesian.cu", "subgrid.cu", "remap.cu", "criteria.cu", "shared.cu", "output.cu", "device_plan.cu"]
+SOURCES = ["unstructured.cu", "fused.cu", "structured.cu", "cartesian.cu", "subgrid.cu", "remap.cu", "criteria.cu", "shared.cu", "output.cu", "device_plan.cu", "adaptive_conn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
