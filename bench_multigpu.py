@@ -256,6 +256,43 @@ class MultiGpuEuler:
             self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
         return 3
 
+    def breakdown(self, dt, steps=5):
+        """Where a multi-GPU step goes (push mode): CUDA events around every launch of `steps` steps, per rank.  Stands
+        in for a profiler capture of a multi-process run (ncu on one rank of a torchrun job hangs in the IPC set-up):
+        stage kernels, ghost pushes (with the NVLink bytes they move) and barrier kernels (launch + wait for the
+        slowest rank), averaged per launch."""
+        if self.sync != "push":
+            return None
+        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+        marks, st = [], torch.cuda.current_stream()
+        for _ in range(steps):
+            self.next, self.prev = self.prev, self.next
+            prev, s1, s2, nxt = (self.variables(s) for s in (self.prev, 1, 2, self.next))
+            vol, T = self.volume(), self.tables
+            for stage, vin, vout, so in ((1, prev, s1, 1), (2, s1, s2, 2), (3, s2, nxt, self.next)):
+                e = [ev() for _ in range(4)]
+                e[0].record(st)
+                self.plan.stage(stage, vin, prev if stage > 1 else None, vout, vol, dt,
+                                speed_max=self.speed_loc if stage == 3 else None)
+                e[1].record(st)
+                self.tb.ghost_push(*self.send, vout, T[so])
+                e[2].record(st)
+                if stage == 3:
+                    self.mail.barrier(self.speed_loc, self.speed_max)
+                else:
+                    self.mail.barrier()
+                e[3].record(st)
+                marks.append(e)
+        torch.cuda.synchronize()
+        n = len(marks)
+        t = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / n * 1e3 for i in range(3)]
+        n_send = int(self.send[0].numel())
+        esz = 8 if self.dtype == torch.float64 else 4
+        return {"stage_kernel_us": round(t[0], 1), "ghost_push_us": round(t[1], 1), "barrier_us": round(t[2], 1),
+                "ghost_push_bytes": n_send * 5 * esz, "ghost_push_gbs": round(n_send * 5 * esz / (t[1] * 1e-6) / 1e9, 1),
+                "elements_pushed": n_send, "note": "per launch, this rank, events between the launches (they serialise "
+                "the stream a little: the sum is above the timed ms_per_step / 3)"}
+
     def drain(self):
         """Joins the side stream (the last CFL reduction) into the compute stream."""
         if self.side_done is not None:
@@ -373,6 +410,7 @@ def run_multi(args, rank, world, device):
     assert bool((hist[:, 0] > 0).all()) and bool((hist[:, 0] <= dt).all()) and bool((hist[:, 1] > 0).all())
 
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    breakdown = sol.breakdown(dt)
     info = sol.plan.info
     nfaces, nghost, sync, t_plan = sol.n_faces, sol.n_ghost, sol.sync, sol.t_plan
     sol.close()
@@ -433,6 +471,7 @@ def run_multi(args, rank, world, device):
                            "host_setup_s": round(t_setup, 2), "tile_plan_s": round(t_plan, 3),
                            "tile_plan_built_on": info.get("built_on", "host"), "host_cores": os.cpu_count(),
                            "host_cpus_bound_to_gpu_numa_node": ncpu, "per_rank_ms_per_step": per_rank_ms,
+                           "step_breakdown_rank0": breakdown,
                            "plan": info},
                 "clocks": clocks, "parity": parity, "secondary": secondary,
                 "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",
