@@ -84,6 +84,9 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 #ifndef T8B_S_PAIR
 #define T8B_S_PAIR 0
 #endif
+#ifndef T8B_S_BULK     // 1: own elements through cp.async.bulk + mbarrier instead of LDG
+#define T8B_S_BULK 0
+#endif
 #ifndef T8B_S_TABLE    // 1: slot indices of a thread from a 256-entry table instead of the layout's bit arithmetic
 #define T8B_S_TABLE 0
 #endif
@@ -126,7 +129,31 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
   const int hidx = __ldg(A.halo + b * 256 + tid);
   int       hrk  = A.my_rank;
   if (MULTI) hrk = __ldg(A.hrank + b * 256 + tid);
+#if T8B_S_BULK
+  // own elements: five bulk copies global -> shared (UBLKCP, completion on an mbarrier) issued by one thread into the
+  // flux array, which is free until phase 1: no LSU issue slots and no landing registers for the 5 x 256 state values
+  __shared__ __align__(8) unsigned long long mbar;
+  const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(&mbar);
+  const bool     bulk   = A.pf_ok != 0 && MODE != 2;   // (the interior pass may leave before the copies have landed)
+  if (bulk) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      constexpr unsigned row_bytes = 256u * sizeof(T);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(5u * row_bytes) : "memory");
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(fl + k * 256)),
+                     "l"(A.in[k] + e0), "r"(row_bytes), "r"(mbar_a)
+                     : "memory");
+    }
+  }
+  T u0, u1, u2, u3, u4;
+  if (!bulk) { u0 = A.in[0][e]; u1 = A.in[1][e]; u2 = A.in[2][e]; u3 = A.in[3][e]; u4 = A.in[4][e]; }
+#else
   const T u0 = A.in[0][e], u1 = A.in[1][e], u2 = A.in[2][e], u3 = A.in[3][e], u4 = A.in[4][e];
+#endif
   if (MODE == 2) {   // the flag was requested with everything else; a boundary chunk belongs to the other pass
     if (__ldg(reinterpret_cast<const int*>(A.rec + b) + 3) != 0) return;
   }
@@ -151,6 +178,17 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
   } else {
     g0 = A.in[0][hidx]; g1 = A.in[1][hidx]; g2 = A.in[2][hidx]; g3 = A.in[3][hidx]; g4 = A.in[4][hidx];
   }
+#if T8B_S_BULK
+  if (bulk) {
+    __syncthreads();   // the barrier object is initialised before anybody waits on it
+    unsigned done;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(mbar_a) : "memory");
+    } while (!done);
+    u0 = fl[tid]; u1 = fl[256 + tid]; u2 = fl[512 + tid]; u3 = fl[768 + tid]; u4 = fl[1024 + tid];
+  }
+#endif
   const Cell<T> C = to_cell(u0, u1, u2, u3, u4);
   s_store_cell<T, NS>(cq, tid, C);
   s_store_cell<T, NS>(cq, T8B_S_TABLE ? (int)tab.w : L::thread_slot(tid), to_cell(g0, g1, g2, g3, g4));
