@@ -384,6 +384,20 @@ int t8b200_fused_stage_part_f32(const t8b200_plan* plan, int stage, int part, co
 int t8b200_fused_stage_part_f64(const t8b200_plan* plan, int stage, int part, const double* const* in,
                                 const double* const* prev, double* const* out, const double* vol, double dt,
                                 const double* dt_dev, double* speed_max_dev, void* stream);
+/* A stage of a ghost-tail plan with the PUSH folded into the stage kernel: the thread that writes an element other ranks
+ * hold a ghost copy of also stores the new values into those copies (posted NVLink stores from the kernel's epilogue; no
+ * push kernel, nothing to wait for inside the kernel).  out_all: HOST array of 5 DEVICE tables of the OUTPUT step;
+ * send_off (n_local + 1) / send_rank / send_idx: DEVICE, CSR by element of the destinations (rank, index in that rank's
+ * rows) -- the send list of t8b200_ghost_push_* grouped by source element.  A t8b200_peer_barrier behind the launch
+ * publishes the copies.  For ghost-tail plans whose chunks are all structured; otherwise cudaErrorNotSupported. */
+int t8b200_fused_stage_push_f32(const t8b200_plan* plan, int stage, const float* const* in, const float* const* prev,
+                                float* const* out, float* const* const* out_all, const float* vol, float dt,
+                                const float* dt_dev, float* speed_max_dev, const int32_t* send_off,
+                                const int32_t* send_rank, const int32_t* send_idx, void* stream);
+int t8b200_fused_stage_push_f64(const t8b200_plan* plan, int stage, const double* const* in, const double* const* prev,
+                                double* const* out, double* const* const* out_all, const double* vol, double dt,
+                                const double* dt_dev, double* speed_max_dev, const int32_t* send_off,
+                                const int32_t* send_rank, const int32_t* send_idx, void* stream);
 /* the same for the subgrid stage (no wave-speed reduction: the reference's subgrid solver has none) */
 int t8b200_subgrid_fused_stage_sync_f32(const t8b200_subgrid_plan* plan, int stage, const float* const* in,
                                         const float* const* const* in_all, const float* const* prev,

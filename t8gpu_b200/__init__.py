@@ -266,6 +266,20 @@ class Plan:
         check(getattr(lib(), "t8b200_ghost_pull_" + s)(self._h, len(rows), ptrs(rows), rows_all.host,
                                                        stream_ptr(stream)), "ghost_pull")
 
+    def stage_push(self, stage, inp, prev, out, out_all, vol, dt, send_csr, speed_max=None, stream=None, dt_dev=None):
+        """A stage with the ghost push folded into the kernel (t8b200_fused_stage_push): out_all = tables of the output
+        step, send_csr = (send_off, send_rank, send_idx) device int32 tensors (multi.send_csr).  False: not supported."""
+        s, ft = _sfx(self.dtype)
+        rc = getattr(lib(), "t8b200_fused_stage_push_" + s)(
+            self._h, stage, ptrs(inp), ptrs(prev) if prev is not None else None, ptrs(out), out_all.host,
+            C.c_void_p(vol.data_ptr()), ft(dt), C.c_void_p(dt_dev.data_ptr() if dt_dev is not None else None),
+            C.c_void_p(speed_max.data_ptr() if speed_max is not None else None), C.c_void_p(send_csr[0].data_ptr()),
+            C.c_void_p(send_csr[1].data_ptr()), C.c_void_p(send_csr[2].data_ptr()), stream_ptr(stream))
+        if rc == 801:
+            return False
+        check(rc, "fused_stage_push")
+        return True
+
     def stage_part(self, stage, part, inp, prev, out, vol, dt, speed_max=None, stream=None, dt_dev=None):
         """One pass of a stage split in two (t8b200_fused_stage_part): part 1 = the chunks that read no ghost copy,
         part 2 = the partition-boundary chunks.  Returns False when the plan does not support the split."""

@@ -616,6 +616,23 @@ static int fused_stage_part_impl(const t8b200_plan* P, int stage, int part, cons
   return t8b_structured_stage_run<T>(P, stage, in, nullptr, prev, out, vol, dt, speed_max, stream, dt_dev, nullptr, part);
 }
 
+// A stage of a ghost-tail plan whose chunks are all structured, with the push folded into the kernel.
+template <typename T>
+static int fused_stage_push_impl(const t8b200_plan* P, int stage, const T* const* in, const T* const* prev, T* const* out,
+                                 T* const* const* out_all, const T* vol, T dt, const T* dt_dev, T* speed_max,
+                                 const int32_t* send_off, const int32_t* send_rank, const int32_t* send_idx, void* stream) {
+  if (!P || stage < 1 || stage > 3 || !in || !out || !out_all || !vol || (stage > 1 && !prev) || !send_off) return cudaErrorInvalidValue;
+  if (P->is_f64 != (sizeof(T) == 8) || P->host_only) return cudaErrorInvalidValue;
+  if (!P->multi || !P->ghost_tail || P->n_struct != P->n_chunks || P->split) return cudaErrorNotSupported;
+  for (int k = 0; k < 5; k++)
+    if (!in[k] || !out[k] || !out_all[k] || out[k] == in[k] || (stage > 1 && (!prev[k] || out[k] == prev[k]))) return cudaErrorInvalidValue;
+  if (speed_max) T8B_TRY(cudaMemsetAsync(speed_max, 0, sizeof(T), (cudaStream_t)stream));
+  t8b_push_args pa{};
+  for (int k = 0; k < 5; k++) pa.out_all[k] = (const void* const*)out_all[k];
+  pa.send_off = send_off; pa.send_rank = send_rank; pa.send_idx = send_idx;
+  return t8b_structured_stage_run<T>(P, stage, in, nullptr, prev, out, vol, dt, speed_max, stream, dt_dev, nullptr, 0, &pa);
+}
+
 // Face source over the arrays behind MeshConnectivityAccessor<float_type,3> (t8gpu/mesh/mesh_manager.h:159-166):
 // global face ids [0,nf) interior, [nf,nf+nb) boundary, then the extra partition-boundary faces.
 template <typename T>
@@ -787,6 +804,20 @@ int t8b200_fused_stage_f64(const t8b200_plan* plan, int stage, const double* con
                            const double* const* const* in_all, const double* const* prev, double* const* out,
                            const double* vol, double dt, double* speed_max_dev, void* stream) {
   return fused_stage_impl<double>(plan, stage, in, in_all, prev, out, vol, dt, speed_max_dev, stream);
+}
+int t8b200_fused_stage_push_f32(const t8b200_plan* plan, int stage, const float* const* in, const float* const* prev,
+                                float* const* out, float* const* const* out_all, const float* vol, float dt,
+                                const float* dt_dev, float* speed_max_dev, const int32_t* send_off,
+                                const int32_t* send_rank, const int32_t* send_idx, void* stream) {
+  return fused_stage_push_impl<float>(plan, stage, in, prev, out, out_all, vol, dt, dt_dev, speed_max_dev, send_off,
+                                      send_rank, send_idx, stream);
+}
+int t8b200_fused_stage_push_f64(const t8b200_plan* plan, int stage, const double* const* in, const double* const* prev,
+                                double* const* out, double* const* const* out_all, const double* vol, double dt,
+                                const double* dt_dev, double* speed_max_dev, const int32_t* send_off,
+                                const int32_t* send_rank, const int32_t* send_idx, void* stream) {
+  return fused_stage_push_impl<double>(plan, stage, in, prev, out, out_all, vol, dt, dt_dev, speed_max_dev, send_off,
+                                       send_rank, send_idx, stream);
 }
 int t8b200_fused_stage_part_f32(const t8b200_plan* plan, int stage, int part, const float* const* in,
                                 const float* const* prev, float* const* out, const float* vol, float dt,

@@ -47,6 +47,9 @@ struct SArgs {
   T*             speed_max;
   int            stage, multi, my_rank;
   const int32_t* blist;   // MODE 3: ids of the partition-boundary chunks
+  // MODE 4: the elements other ranks hold ghost copies of are pushed into those copies by the thread that writes them
+  T* const*      out_all[5];   // [var][rank] tables of the OUTPUT step
+  const int32_t *send_off, *send_rank, *send_idx;   // CSR by element: destinations (rank, index in that rank's rows)
   const uint4*   slots;   // T8B_S_TABLE: per thread (lower slots x | y << 16, z | ux << 16, uy | uz << 16, halo slot)
   int            dense;   // every chunk of the plan is structured: chunk b = elements [256 b, 256 b + 256), one area
   int            area0;
@@ -101,6 +104,8 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 //   2  "interior pass" of a ghost-tail plan: every chunk is launched, the partition-boundary ones leave at once (their
 //      ghost copies are still being pulled on another stream)
 //   3  "boundary pass": the launch covers the partition-boundary chunks only, chunk id from the compact list
+//   4  ghost-tail plan with the push folded in: a thread of a partition-boundary chunk also stores its new values into
+//      the ghost copies the peers hold of its element (posted NVLink stores from the epilogue, no push kernel)
 template <typename T, class L, bool SMAX, int MODE>
 __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB32)
     structured_stage_kernel(const __grid_constant__ SArgs<T> A) {
@@ -119,8 +124,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
   if (!A.dense) {
     const int4 r = __ldg(A.rec + b);
     e0 = r.x; area_idx = r.y;
-    bnd = MULTI && r.w != 0 && A.sync.mailboxes != nullptr;
-  } else if (MULTI && A.sync.mailboxes != nullptr) {
+    bnd = (MODE == 4 || (MULTI && A.sync.mailboxes != nullptr)) && r.w != 0;
+  } else if ((MULTI && A.sync.mailboxes != nullptr) || MODE == 4) {
     bnd = __ldg(reinterpret_cast<const int*>(A.rec + b) + 3) != 0;   // off the critical path: only the flag is read
   }
   const int e    = e0 + tid;
@@ -308,7 +313,15 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? T8B_S_MINB : T8B_S_MINB3
   for (int k = 0; k < 5; k++) {
     const T* f = fl + k * NF;
     const T  acc = ((f[tid] + f[256 + tid]) + f[512 + tid]) - ((f[ux] + f[uy]) + f[uz]);
-    A.out[k][e] = base[k] + sc * acc;
+    base[k] = base[k] + sc * acc;
+    A.out[k][e] = base[k];
+  }
+  if (MODE == 4 && bnd) {   // the peers' copies of this element (0-3 of them), through the tables of the output step
+    for (int q = __ldg(A.send_off + e), q1 = __ldg(A.send_off + e + 1); q < q1; q++) {
+      const int rk = __ldg(A.send_rank + q), ix = __ldg(A.send_idx + q);
+#pragma unroll
+      for (int k = 0; k < 5; k++) A.out_all[k][rk][ix] = base[k];
+    }
   }
   if (SMAX) {
     smax = warp_max(smax);
@@ -376,10 +389,14 @@ static int s_launch(const t8b200_plan* P, SArgs<T>& A, cudaStream_t st) {
 template <typename T>
 int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
                              const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
-                             const T* dt_dev, const StageSync* sync, int part) {
+                             const T* dt_dev, const StageSync* sync, int part, const t8b_push_args* push) {
   if (P->n_struct == 0) return cudaSuccess;
   SArgs<T> A{};
   A.blist = P->blist;
+  if (push) {
+    for (int k = 0; k < 5; k++) A.out_all[k] = (T* const*)push->out_all[k];
+    A.send_off = push->send_off; A.send_rank = push->send_rank; A.send_idx = push->send_idx;
+  }
   A.dt_ptr = dt_dev;
   if (sync) A.sync = *sync;
   A.rec = reinterpret_cast<const int4*>(P->s_rec); A.halo = P->s_halo; A.hrank = P->s_hrank;
@@ -402,6 +419,7 @@ int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in
   cudaStream_t st = (cudaStream_t)stream;
   auto pick = [&](auto layout) {
     using L = decltype(layout);
+    if (push) return speed_max ? s_launch<T, L, true, 4>(P, A, st) : s_launch<T, L, false, 4>(P, A, st);
     if (part == 1) return speed_max ? s_launch<T, L, true, 2>(P, A, st) : s_launch<T, L, false, 2>(P, A, st);
     if (part == 2) return speed_max ? s_launch<T, L, true, 3>(P, A, st) : s_launch<T, L, false, 3>(P, A, st);
     if (A.multi) return speed_max ? s_launch<T, L, true, 1>(P, A, st) : s_launch<T, L, false, 1>(P, A, st);
@@ -411,8 +429,8 @@ int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in
 }
 template int t8b_structured_stage_run<float>(const t8b200_plan*, int, const float* const*, const float* const* const*,
                                              const float* const*, float* const*, const float*, float, float*, void*,
-                                             const float*, const StageSync*, int);
+                                             const float*, const StageSync*, int, const t8b_push_args*);
 template int t8b_structured_stage_run<double>(const t8b200_plan*, int, const double* const*,
                                               const double* const* const*, const double* const*, double* const*,
                                               const double*, double, double*, void*, const double*, const StageSync*,
-                                              int);
+                                              int, const t8b_push_args*);

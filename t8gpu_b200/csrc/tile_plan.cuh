@@ -786,6 +786,11 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
 }
 
 namespace t8b200 { struct StageSync; }
+// push folded into the stage kernel (t8b200_fused_stage_push_*): tables of the output step + CSR of the destinations
+struct t8b_push_args {
+  const void* const* out_all[5];
+  const int32_t *    send_off, *send_rank, *send_idx;
+};
 // defined in fused.cu (explicitly instantiated for float and double); dt_dev / sync: see t8b200_fused_stage_sync_*
 template <typename T>
 int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
@@ -796,7 +801,8 @@ int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, con
 template <typename T>
 int t8b_structured_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
                              const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
-                             const T* dt_dev, const t8b200::StageSync* sync, int part = 0);
+                             const T* dt_dev, const t8b200::StageSync* sync, int part = 0,
+                             const t8b_push_args* push = nullptr);
 void t8b_plan_free(t8b200_plan* P);
 // defined in subgrid.cu: wraps a cell-level plan (device_plan.cu builds them too)
 t8b200_subgrid_plan* t8b_wrap_subgrid_plan(t8b200_plan* P, int dim);

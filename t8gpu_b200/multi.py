@@ -119,3 +119,19 @@ def adapt_partition_ranges(amap, off_old, off_new, rank):
     owner = (np.searchsorted(lo, g, side="right") - 1).astype(np.int32)
     index = (g - lo[owner]).astype(np.int32)
     return lo, adapt_data, owner, index
+
+
+def send_csr(send, n_local, device):
+    """The send list (src_idx, dst_rank, dst_idx) of send_lists grouped by source element: (send_off[n_local + 1],
+    send_rank, send_idx) device int32 tensors for t8b200_fused_stage_push_*."""
+    import numpy as np
+    import torch
+    src, drk, dix = (t.cpu().numpy() for t in send)
+    order = np.argsort(src, kind="stable")
+    off = np.zeros(n_local + 1, np.int64)
+    np.add.at(off, src[order].astype(np.int64) + 1, 1)
+    off = np.cumsum(off).astype(np.int32)
+    mk = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(device)  # noqa: E731
+    if len(src) == 0:
+        return mk(off), mk(np.zeros(1)), mk(np.zeros(1))
+    return mk(off), mk(drk[order]), mk(dix[order])

@@ -166,6 +166,52 @@ def test_split_stage_passes_equal_the_single_launch(cuda, dtype):
     for r in range(P):
         assert torch.equal(whole[r], parts[r])
     assert vm0 == vm1 and min(vm0) > 0
+
+    # t8b200_fused_stage_push: the push folded into the stage kernel (no pull / push kernel at all) == the pulled run
+    from t8gpu_b200 import multi
+
+    class OneProcess:        # send_lists gathers the pull lists of all ranks: here they are all in this process
+        def __init__(self):
+            self.calls = []
+
+        def all_gather(self, out, mine):
+            self.calls.append((out, mine))
+
+    def lists_for(rank):
+        src, drk, dix = [], [], []
+        for p in range(P):
+            if p == rank:
+                continue
+            rk, ix = plans[p].device_array(17), plans[p].device_array(18)
+            sel = np.nonzero(rk == rank)[0]
+            src.append(ix[sel]); drk.append(np.full(len(sel), p, np.int32)); dix.append((ns[p] + sel).astype(np.int32))
+        cat = lambda a: torch.as_tensor(np.concatenate(a)).to(torch.int32).to(cuda)  # noqa: E731
+        return cat(src), cat(drk), cat(dix)
+
+    csr = [multi.send_csr(lists_for(r), ns[r], cuda) for r in range(P)]
+    bufs = []
+    for r in range(P):
+        b = torch.zeros((NVAR * NB_STEPS + 1, ns[r] + plans[r].n_tail), dtype=dtype, device=cuda)
+        b[NVAR * NB_STEPS, :ns[r]] = conns[r]["volumes"]
+        tb.init_kelvin_helmholtz(3, conns[r]["centroids"], [b[k, :ns[r]] for k in range(5)])
+        bufs.append(b)
+    tabs = {s: tb.RankTables([[bufs[r][s * NVAR + k] for k in range(NVAR)] for r in range(P)], cuda)
+            for s in range(NB_STEPS)}
+    for r in range(P):      # the initial state reaches the peers' copies through the stand-alone push kernel
+        tb.ghost_push(*lists_for(r), [bufs[r][k] for k in range(NVAR)], tabs[0])
+    vmax = [torch.zeros(1, dtype=dtype, device=cuda) for _ in range(P)]
+    nxt, prv = 0, 3
+    for it in range(3):
+        nxt, prv = prv, nxt
+        for stage, sin, sout in ((1, prv, 1), (2, 1, 2), (3, 2, nxt)):
+            for r in range(P):
+                v = lambda s: [bufs[r][s * NVAR + k, :ns[r]] for k in range(NVAR)]  # noqa: E731
+                assert plans[r].stage_push(stage, v(sin), v(prv), v(sout), tabs[sout], bufs[r][NVAR * NB_STEPS], dt,
+                                           csr[r], speed_max=vmax[r] if stage == 3 else None)
+    torch.cuda.synchronize()
+    for r in range(P):
+        assert torch.equal(bufs[r][nxt * NVAR:(nxt + 1) * NVAR, :ns[r]], whole[r])
+    assert [float(x) for x in vmax] == vm0
     # a plan with generic chunks (level 3: a tree 8 elements across is its own neighbour) does not support the split
     c3 = tb.cartesian_uniform_connectivity(3, 3, dtype, P, 0, device=cuda, brick=brick)
     p3 = tb.Plan(tb.conn_to_host(c3), dtype, ghost_tail=True)
