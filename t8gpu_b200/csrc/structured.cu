@@ -77,8 +77,8 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 #ifndef T8B_S_MINB
 #define T8B_S_MINB 3
 #endif
-#ifndef T8B_S_MINB32   // fp32: resident CTAs per SM the register budget is sized for (48 registers come out anyway)
-#define T8B_S_MINB32 3
+#ifndef T8B_S_MINB32   // fp32: resident CTAs per SM the register budget is sized for.  6 (40 registers, 12 bytes of spills; 6 x
+#define T8B_S_MINB32 6 // 34 KB of shared memory is all an SM holds) measured 1.428 ms per step against 1.463 at 5 x 48 registers
 #endif
 // 1: fp32 evaluates two faces per packed fp32x2 flux (fma.rn.f32x2, euler_flux.cuh: kepes_flux_x_pair).  Parity green,
 // measured SLOWER on the level-8 hex forest (1.50 ms per step at 64 registers / 4 CTAs per SM, 1.57 at 48 / 5 with
@@ -90,9 +90,14 @@ __device__ __forceinline__ void s_store_cell(T* cq, int s, const Cell<T>& q) {
 #ifndef T8B_S_BULK     // 1: own elements through cp.async.bulk + mbarrier instead of LDG
 #define T8B_S_BULK 0
 #endif
-#ifndef T8B_S_TABLE    // 1: slot indices of a thread from a 256-entry table instead of the layout's bit arithmetic
-#define T8B_S_TABLE 0
+// slot indices of a thread from a 256-entry table (one 16-byte load, L1 / L2 resident) instead of the layout's bit
+// arithmetic: 0 off, 1 both precisions, 2 fp32 only.  fp32 is bound by issue slots and 40 % of its instructions are
+// integer work: with the table 1.396 instead of 1.428 ms per step; fp64 loses 2.5 % (one more live register at the
+// 80-register cap), so fp32 only.
+#ifndef T8B_S_TABLE_SEL
+#define T8B_S_TABLE_SEL 2
 #endif
+#define T8B_S_TABLE (T8B_S_TABLE_SEL == 1 || (T8B_S_TABLE_SEL == 2 && sizeof(T) == 4))
 #ifndef T8B_S_OWNREG   // 1: the thread's own cell stays in registers through the face phase; 0: re-read per face
 #define T8B_S_OWNREG 1
 #endif

@@ -80,3 +80,17 @@ def test_partitions_reproduce_the_one_rank_step():
     nxt = stage(3, s2, prev)
     got = np.concatenate(nxt, axis=1)
     assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_send_csr_groups_the_send_list_by_source_element():
+    """multi.send_csr: (src, dst_rank, dst_idx) sorted by destination -> CSR by source element, stable."""
+    import torch
+    from t8gpu_b200 import multi
+    src = torch.tensor([5, 2, 5, 0, 2, 7], dtype=torch.int32)
+    drk = torch.tensor([1, 1, 2, 2, 3, 3], dtype=torch.int32)
+    dix = torch.tensor([10, 11, 20, 21, 30, 31], dtype=torch.int32)
+    off, rk, ix = multi.send_csr((src, drk, dix), 8, "cpu")
+    assert off.tolist() == [0, 1, 1, 3, 3, 3, 5, 5, 6]
+    assert rk.tolist() == [2, 1, 3, 1, 2, 3] and ix.tolist() == [21, 11, 30, 10, 20, 31]
+    off, rk, ix = multi.send_csr((src[:0], drk[:0], dix[:0]), 3, "cpu")
+    assert off.tolist() == [0, 0, 0, 0]
