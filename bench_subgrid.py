@@ -46,24 +46,25 @@ def cell_centers(centroids, level, dtype):
 
 
 class SubgridBrick:
-    def __init__(self, level, dtype, rank, world, device):
+    def __init__(self, level, dtype, rank, world, device, brick=None):
         import t8gpu_b200 as tb
         import torch.distributed as dist
         from t8gpu_b200.multi import BRICK, exchange_wires, row_pointers
         from t8gpu_b200.solver import NB_STEPS, NVAR
         self.rank, self.world, self.device, self.dtype = rank, world, device, dtype
         esz = 8 if dtype == torch.float64 else 4
-        conn = subgrid_connectivity(level, dtype, rank, world, device, BRICK[world])
+        conn = subgrid_connectivity(level, dtype, rank, world, device, brick or BRICK[world])
         self.ne = int(conn["n_local"])
         self.n = self.ne * 64
         self.n_faces = int(conn["n_faces"]) + int(conn["n_xfaces"])
         self.n_ghost = int(conn["n_ghost"])
         self.vol = conn["volumes"]
-        self.sync = os.environ.get("T8B200_SYNC", "pull") if world > 1 else "single"
+        self.sync = os.environ.get("T8B200_SYNC", "push") if world > 1 else "single"
+        tail = self.sync in ("push", "pull")
         t0 = time.time()
-        self.plan = tb.SubgridPlan.from_device(conn, self.vol, dtype, ghost_tail=self.sync == "pull")   # no D2H
+        self.plan = tb.SubgridPlan.from_device(conn, self.vol, dtype, ghost_tail=tail)   # no D2H of the connectivity
         if self.plan is None:
-            self.plan = tb.SubgridPlan(tb.conn_to_host(conn), self.vol.cpu().numpy(), dtype, ghost_tail=self.sync == "pull")
+            self.plan = tb.SubgridPlan(tb.conn_to_host(conn), self.vol.cpu().numpy(), dtype, ghost_tail=tail)
         torch.cuda.synchronize()
         self.t_plan = time.time() - t0
         self.cap = (self.n + self.plan.n_tail + 31) // 32 * 32     # own cells, then the ghost-cell tail
@@ -77,6 +78,9 @@ class SubgridBrick:
             self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
             self.mail = tb.PeerMailboxes(rank, world, device)
             self.mail.exchange([h for h, _ in exchange_wires(dist, self.mail.handle, 0, world, device)])
+            if self.sync == "push":        # what the peers hold copies of, sorted by destination (one all-gather)
+                from t8gpu_b200.multi import send_lists
+                self.send = send_lists(dist, self.plan, self.n, rank, world, device)
         tb.init_kelvin_helmholtz(3, cell_centers(conn["centroids"], level, dtype), self.variables(0))
         self.next, self.prev = 0, 3
         torch.cuda.synchronize()
@@ -88,6 +92,9 @@ class SubgridBrick:
         """State written outside the stage kernels: full barrier before any rank reads ghosts (starts / continues the
         stage-epoch sequence of the self-ordering kernels)."""
         if self.mail is not None:
+            if self.sync == "push":
+                import t8gpu_b200 as tb
+                tb.ghost_push(*self.send, self.variables(self.next), self.tables[self.next])
             self.mail.barrier()
 
     def variables(self, step):
@@ -102,13 +109,18 @@ class SubgridBrick:
         T, launches = self.tables, 0
         own_order = self.mail is not None and self.sync == "kernel"   # the stage kernels order themselves
         pull = self.mail is not None and self.sync == "pull"          # ghost-cell tail, single-rank stage kernels
-        for stage, sin, vin, vout in ((1, self.prev, prev, s1), (2, 1, s1, s2), (3, 2, s2, nxt)):
+        push = self.mail is not None and self.sync == "push"          # ... filled by the owner right behind the stage
+        for stage, sin, sout, vin, vout in ((1, self.prev, 1, prev, s1), (2, 1, 2, s1, s2), (3, 2, self.next, s2, nxt)):
             if pull:
                 self.plan.pull(vin, T[sin])
                 launches += 1
             self.plan.stage(stage, vin, prev if stage > 1 else None, vout, self.vol, dt,
-                            in_all=None if pull else T[sin], sync=self.mail if own_order else None)
+                            in_all=None if (pull or push) else T[sin], sync=self.mail if own_order else None)
             launches += 1
+            if push:
+                import t8gpu_b200 as tb
+                tb.ghost_push(*self.send, vout, T[sout])
+                launches += 1
             if self.mail is not None and not own_order:   # barrier kernel per stage
                 self.mail.barrier()
                 launches += 1
@@ -190,6 +202,31 @@ def measure_subgrid(level, dtype_name, steps, warmup, device, parity=True):
     return out
 
 
+def bitwise_parity(dtype, rank, world, device, level=2, steps=3):
+    """The N-rank Subgrid<4,4,4> run must be bitwise the one-rank run of the same brick (see bench_multigpu)."""
+    import torch.distributed as dist
+    from t8gpu_b200.multi import BRICK
+    dt = 0.1 * 2.0 ** -(level + 2)
+    sol = SubgridBrick(level, dtype, rank, world, device)
+    sub = torch.cuda.Stream()            # the one-rank brick needs no collectives: built with world = 1
+    one = SubgridBrick(level, dtype, 0, 1, device, brick=BRICK[world])
+    n1 = one.n
+    off = [(n1 // 64) * r // world * 64 for r in range(world + 1)]
+    same = bool(torch.equal(one.state()[:, off[rank]:off[rank + 1]], sol.state()))
+    for _ in range(steps):
+        one.iterate(dt)
+        sol.iterate(dt)
+    torch.cuda.synchronize()
+    same = same and bool(torch.equal(one.state()[:, off[rank]:off[rank + 1]], sol.state()))
+    flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    one.close()
+    sol.close()
+    del sub
+    return {"vs": "one-rank run of the same brick (level %d trees, %d cells)" % (level, n1), "steps": steps,
+            "bitwise_equal": bool(flag.item() == 1.0)}
+
+
 def run_subgrid(args, rank, world, device):
     import torch.distributed as dist
     from bench import ClockSampler, measured_peak
@@ -209,6 +246,10 @@ def run_subgrid(args, rank, world, device):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    parity = None
+    if world > 1:
+        parity = bitwise_parity(dtype, rank, world, device)
+        assert parity["bitwise_equal"], "the %d-rank subgrid run differs from the one-rank run of the same brick" % world
     t0 = time.time()
     sol = SubgridBrick(level, dtype, rank, world, device)
     t_setup = time.time() - t0
@@ -271,13 +312,13 @@ def run_subgrid(args, rank, world, device):
                                        "adaptation" % (BRICK[world], level, ne, n, total, args.dtype),
                            "cells_per_gpu": n, "element_faces_per_gpu": nfaces, "ghost_elements_per_gpu": nghost,
                            "partition": "one tree per GPU; ghost cells read from peer GPUs over NVLink, owner-computes "
-                                        "boundary faces; per stage a mailbox barrier kernel, a pull kernel filling the local "
-                                        "ghost-cell copies, then the single-rank stage kernel" if world > 1 else
+                                        "boundary faces; per stage the single-rank stage kernel, an owner-side push of the "
+                                        "ghost-cell copies, one mailbox barrier kernel" if world > 1 else
                                         "one rank", "l2": "inputs larger than L2 (%.0f MB of state per stage)" %
                                                           (2 * state_bytes / 1e6),
                            "host_setup_s": round(t_setup, 2), "tile_plan_host_s": round(t_plan, 2),
                            "host_cores": os.cpu_count(), "plan": info},
-                "clocks": clocks,
+                "clocks": clocks, "parity": parity,
                 "e2e": {"value": total * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",
                         "h2d_bytes_per_step": state_bytes / args.steps * world,
                         "d2h_bytes_per_step": (state_bytes / args.steps + esz) * world,
