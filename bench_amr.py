@@ -51,10 +51,11 @@ class RankMesh:
         self.S = 64 if subgrid else 1
         self.plan, conn_dev = None, None
         if subgrid:
-            # element-level connectivity of the subgrid manager (level differences, neighbour offsets): host loop of the
-            # t8code stand-in; the cell-level plan from the host builder
-            conn = forest.connectivity(world, rank, subgrid=True, dtype=npdt)
-            self.t_conn, self.conn_on = time.time() - t0, "host (t8code stand-in)"
+            # element-level connectivity of the subgrid manager (level differences, neighbour offsets) on the device
+            # from the leaf list (t8b200_forest_subgrid_connectivity); the cell-level plan from the host builder
+            conn = tb.conn_to_host(tb.forest_connectivity(3, True, tb.morton_keys(3, lv, cent), lv, dtype, world, rank,
+                                                          device=device, subgrid=True))
+            self.t_conn, self.conn_on = time.time() - t0, "device"
             self.n = int(conn["n_local"])
             t0 = time.time()
             lvol = forest.elements()[2][self.off[rank]:self.off[rank + 1]].astype(npdt)

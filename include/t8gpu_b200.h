@@ -308,6 +308,22 @@ void t8b200_cartesian_connectivity_free(t8b200_cart_conn* c);
  * Free with t8b200_cartesian_connectivity_free. */
 int t8b200_forest_connectivity(t8b200_cart_conn* out, int is_f64, int dim, int periodic, int64_t n_leaves,
                                const uint64_t* keys_dev, const int32_t* levels_dev, int nranks, int rank, void* stream);
+/* The same forest in the layout of SubgridMeshManager::compute_connectivity_information
+ * (t8gpu/mesh/subgrid_mesh_manager.inl:788-905, add_face :560-786): `dim` normal components per face, and per interior /
+ * x-face the level difference (<= 0: second element finer by that many levels) and the `dim` cell offsets of the face
+ * inside the coarser element's 4^dim grid; the pair is swapped (normal flipped) when the neighbour is the finer one.
+ * out->volumes are ELEMENT volumes.  Free `out` with t8b200_cartesian_connectivity_free and `info` with
+ * t8b200_subgrid_face_info_free. */
+typedef struct {
+  int32_t* level_diff;   /* n_faces */
+  int32_t* offsets;      /* n_faces * dim */
+  int32_t* x_level_diff; /* n_xfaces */
+  int32_t* x_offsets;    /* n_xfaces * dim */
+} t8b200_subgrid_face_info;
+int  t8b200_forest_subgrid_connectivity(t8b200_cart_conn* out, t8b200_subgrid_face_info* info, int is_f64, int dim,
+                                        int periodic, int64_t n_leaves, const uint64_t* keys_dev,
+                                        const int32_t* levels_dev, int nranks, int rank, void* stream);
+void t8b200_subgrid_face_info_free(t8b200_subgrid_face_info* info);
 
 /* -------------------------------------------------------------------------------------------------------------
  * 4. Cross-GPU sharing of the variable buffers, one process per GPU.  Replaces the MPI_Allgather of

@@ -490,8 +490,14 @@ def morton_keys(dim, levels, centroids):
     return key
 
 
-def forest_connectivity(dim, periodic, keys, levels, dtype, nranks=1, rank=0, device=None):
-    """Device-built connectivity of an adaptive 2:1-balanced one-tree forest (t8b200_forest_connectivity) in the
+class _SubgridFaceInfo(C.Structure):
+    _fields_ = [("level_diff", C.c_void_p), ("offsets", C.c_void_p), ("x_level_diff", C.c_void_p),
+                ("x_offsets", C.c_void_p)]
+
+
+def forest_connectivity(dim, periodic, keys, levels, dtype, nranks=1, rank=0, device=None, subgrid=False):
+    """Device-built connectivity of an adaptive 2:1-balanced one-tree forest (t8b200_forest_connectivity, or
+    t8b200_forest_subgrid_connectivity with subgrid=True: `dim` normal components, level_diff / offsets per face) in the
     reference layout -> dict of torch tensors.  keys: uint64 / int64 array or tensor, levels: int32, over ALL leaves."""
     import numpy as np
     torch = _torch()
@@ -500,10 +506,13 @@ def forest_connectivity(dim, periodic, keys, levels, dtype, nranks=1, rank=0, de
     k = keys if isinstance(keys, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(keys).view(np.int64))
     lv = levels if isinstance(levels, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(levels, dtype=np.int32))
     k, lv = k.to(device), lv.to(torch.int32).to(device)
-    c = _CartConn()
-    check(lib().t8b200_forest_connectivity(C.byref(c), int(s == "f64"), dim, int(bool(periodic)), C.c_int64(k.numel()),
-                                           C.c_void_p(k.data_ptr()), C.c_void_p(lv.data_ptr()), nranks, rank,
-                                           stream_ptr()), "forest_connectivity")
+    c, info = _CartConn(), _SubgridFaceInfo()
+    args = (int(s == "f64"), dim, int(bool(periodic)), C.c_int64(k.numel()), C.c_void_p(k.data_ptr()),
+            C.c_void_p(lv.data_ptr()), nranks, rank, stream_ptr())
+    if subgrid:
+        check(lib().t8b200_forest_subgrid_connectivity(C.byref(c), C.byref(info), *args), "forest_subgrid_connectivity")
+    else:
+        check(lib().t8b200_forest_connectivity(C.byref(c), *args), "forest_connectivity")
 
     def grab(ptr, n, dt):
         if n == 0:
@@ -511,15 +520,21 @@ def forest_connectivity(dim, periodic, keys, levels, dtype, nranks=1, rank=0, de
         return torch.as_tensor(_RawDeviceArray(ptr, n, dt), device=device).clone()
 
     nl, ng, nf, nb, nx = c.n_local, c.n_ghost, c.n_faces, c.n_bfaces, c.n_xfaces
+    nd = dim if subgrid else 3
     out = dict(dim=dim, n_local=nl, n_ghost=ng, n_faces=nf, n_bfaces=nb, n_xfaces=nx, rank=rank, nranks=nranks,
                ranks=grab(c.ranks, nl + ng, torch.int32), indices=grab(c.indices, nl + ng, torch.int32),
                face_neighbors=grab(c.face_neighbors, 2 * nf + nb, torch.int32),
-               face_normals=grab(c.face_normals, 3 * (nf + nb), dtype), face_areas=grab(c.face_surfaces, nf + nb, dtype),
+               face_normals=grab(c.face_normals, nd * (nf + nb), dtype), face_areas=grab(c.face_surfaces, nf + nb, dtype),
                volumes=grab(c.volumes, nl, dtype), centroids=grab(c.centroids, 3 * nl, dtype),
                x_face_neighbors=grab(c.x_face_neighbors, 2 * nx, torch.int32),
-               x_face_normals=grab(c.x_face_normals, 3 * nx, dtype), x_face_areas=grab(c.x_face_surfaces, nx, dtype))
+               x_face_normals=grab(c.x_face_normals, nd * nx, dtype), x_face_areas=grab(c.x_face_surfaces, nx, dtype))
+    if subgrid:
+        out.update(level_diff=grab(info.level_diff, nf, torch.int32), offsets=grab(info.offsets, dim * nf, torch.int32),
+                   x_level_diff=grab(info.x_level_diff, nx, torch.int32),
+                   x_offsets=grab(info.x_offsets, dim * nx, torch.int32))
     torch.cuda.synchronize()
     lib().t8b200_cartesian_connectivity_free(C.byref(c))
+    lib().t8b200_subgrid_face_info_free(C.byref(info))
     return out
 
 

@@ -113,35 +113,69 @@ __device__ inline int64_t ghost_pos(const int64_t* ghosts, int64_t ng, int64_t k
   return lo;
 }
 
-// MODE 0: faces per element (interior, boundary, x);  MODE 1: fill at the scanned offsets
-template <typename T, int MODE>
+struct FaceOut {   // interior / owned faces and x-faces; ld / off only for the subgrid layout
+  int32_t *nbr, *xnbr, *ld, *off, *xld, *xoff;
+  void *   normals, *areas, *xnormals, *xareas;
+};
+
+// MODE 0: faces per element (interior, boundary, x);  MODE 1: fill at the scanned offsets.  SUB: the layout of
+// SubgridMeshManager (subgrid_mesh_manager.inl:560-786 add_face): dim normal components, level difference and
+// neighbour offset per face, the finer element second (normal flipped when the pair is swapped).
+template <typename T, int MODE, bool SUB>
 __global__ void faces_kernel(Forest f, const int64_t* __restrict__ ghosts, int64_t ng, int64_t* cnt, int64_t* bcnt,
-                             int64_t* xcnt, int64_t nf_total, int32_t* nbr, T* normals, T* areas, int32_t* xnbr,
-                             T* xnormals, T* xareas) {
+                             int64_t* xcnt, int64_t nf_total, FaceOut out) {
   const int64_t nl = f.hi - f.lo, ei = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (ei >= nl) return;
   const int64_t e = f.lo + ei;
-  const int     l = f.level[e];
+  const int     l = f.level[e], nd = SUB ? f.dim : 3, E = 4;
   const double  h = ldexp(1.0, -l), area = f.dim == 3 ? h * h : h;
   int64_t o = MODE ? cnt[ei] : 0, bo = MODE ? bcnt[ei] : 0, xo = MODE ? xcnt[ei] : 0;
-  auto emit = [&](int32_t* pn, T* pr, T* pa, int64_t at, int32_t right, int face, double a) {
-    pn[2 * at] = (int32_t)ei; pn[2 * at + 1] = right;
-    pr[3 * at] = T(0); pr[3 * at + 1] = T(0); pr[3 * at + 2] = T(0);
-    pr[3 * at + (face >> 1)] = (face & 1) ? T(1) : T(-1);
+  auto emit = [&](bool x, int64_t at, int64_t n_global, int32_t nid, int face, double a) {
+    int32_t* pn = x ? out.xnbr : out.nbr;
+    T*       pr = (T*)(x ? out.xnormals : out.normals);
+    T*       pa = (T*)(x ? out.xareas : out.areas);
+    T        sgn = (face & 1) ? T(1) : T(-1);
+    int32_t  left = (int32_t)ei, right = nid;
+    if (SUB) {
+      int32_t*  pl = x ? out.xld : out.ld;
+      int32_t*  po = x ? out.xoff : out.off;
+      const int nlev = f.level[n_global], ax = face >> 1;
+      int       ofs[3] = {0, 0, 0}, ldiff = 0;
+      if (nlev == l) {
+        ofs[ax] = (face & 1) ? 0 : E - 1;
+      } else if (nlev < l) {   // coarser neighbour: which quadrant of its face this element touches
+        const int child = (int)((f.key[e] >> (f.dim * (MAXL - l))) & ((1u << f.dim) - 1));
+        for (int d = 0; d < f.dim; d++) ofs[d] = E / 2 * ((child >> d) & 1);
+        ofs[ax] = (face & 1) ? 0 : E - 1;
+        ldiff   = nlev - l;
+      } else {                 // finer neighbour: swap so that the finer element comes second
+        const int child = (int)((f.key[n_global] >> (f.dim * (MAXL - nlev))) & ((1u << f.dim) - 1));
+        for (int d = 0; d < f.dim; d++) ofs[d] = E / 2 * ((child >> d) & 1);
+        ofs[ax] = (face & 1) ? E - 1 : 0;
+        ldiff   = l - nlev;
+        left = nid; right = (int32_t)ei; sgn = -sgn;
+      }
+      pl[at] = ldiff;
+      for (int d = 0; d < f.dim; d++) po[f.dim * at + d] = ofs[d];
+    }
+    pn[2 * at] = left; pn[2 * at + 1] = right;
+    for (int d = 0; d < nd; d++) pr[nd * at + d] = T(0);
+    pr[nd * at + (face >> 1)] = sgn;
     pa[at] = (T)a;
   };
   for (int face = 0; face < 2 * f.dim; face++) {
     int64_t   nb[4];
     const int nn = face_neighbors(f, e, face, nb);
-    // ghost neighbours first (mesh_manager.inl:396-409): the lower rank owns the face, area / num_neighbors
+    // ghost neighbours first (mesh_manager.inl:396-409, subgrid_mesh_manager.inl:859-877): the lower rank owns the
+    // face, area / num_neighbors
     for (int i = 0; i < nn; i++) {
       if (nb[i] >= f.lo && nb[i] < f.hi) continue;
       const int32_t nid = (int32_t)(nl + ghost_pos(ghosts, ng, nb[i]));
       if (f.rank < owner_of(f, nb[i])) {
-        if (MODE) emit(nbr, normals, areas, o, nid, face, area / (double)nn);
+        if (MODE) emit(false, o, nb[i], nid, face, area / (double)nn);
         o++;
       } else {
-        if (MODE) emit(xnbr, xnormals, xareas, xo, nid, face, area / (double)nn);
+        if (MODE) emit(true, xo, nb[i], nid, face, area / (double)nn);
         xo++;
       }
     }
@@ -149,17 +183,18 @@ __global__ void faces_kernel(Forest f, const int64_t* __restrict__ ghosts, int64
     if (nn == 1 && nb[0] >= f.lo && nb[0] < f.hi) {
       const int64_t nid = nb[0] - f.lo;
       if (nid > ei || (nid < ei && f.level[nb[0]] < l)) {
-        if (MODE) emit(nbr, normals, areas, o, (int32_t)nid, face, area);
+        if (MODE) emit(false, o, nb[0], (int32_t)nid, face, area);
         o++;
       }
     }
     if (nn == 0) {   // domain boundary (mesh_manager.inl:431-440): behind the interior faces
       if (MODE) {
         const int64_t at = nf_total + bo;
-        nbr[2 * nf_total + bo] = (int32_t)ei;
-        normals[3 * at] = T(0); normals[3 * at + 1] = T(0); normals[3 * at + 2] = T(0);
-        normals[3 * at + (face >> 1)] = (face & 1) ? T(1) : T(-1);
-        areas[at] = (T)area;
+        T*            pr = (T*)out.normals;
+        out.nbr[2 * nf_total + bo] = (int32_t)ei;
+        for (int d = 0; d < nd; d++) pr[nd * at + d] = T(0);
+        pr[nd * at + (face >> 1)] = (face & 1) ? T(1) : T(-1);
+        ((T*)out.areas)[at] = (T)area;
       }
       bo++;
     }
@@ -187,8 +222,8 @@ __global__ void elements_kernel(Forest f, const int64_t* __restrict__ ghosts, in
   }
 }
 
-template <typename T>
-int build(t8b200_cart_conn* out, Forest f, cudaStream_t st) {
+template <typename T, bool SUB>
+int build(t8b200_cart_conn* out, t8b200_subgrid_face_info* info, Forest f, cudaStream_t st) {
   const int64_t  nl     = f.hi - f.lo;
   const unsigned blocks = (unsigned)((nl + 255) / 256);
   auto           pol    = thrust::cuda::par.on(st);
@@ -216,8 +251,7 @@ int build(t8b200_cart_conn* out, Forest f, cudaStream_t st) {
   T8B_TRY(cudaMemsetAsync(cnt, 0, 3 * (nl + 1) * sizeof(int64_t), st));
   int64_t *bcnt = cnt + (nl + 1), *xcnt = cnt + 2 * (nl + 1);
   if (nl > 0)
-    faces_kernel<T, 0><<<blocks, 256, 0, st>>>(f, ghosts, ng, cnt, bcnt, xcnt, 0, nullptr, nullptr, nullptr, nullptr,
-                                               nullptr, nullptr);
+    faces_kernel<T, 0, SUB><<<blocks, 256, 0, st>>>(f, ghosts, ng, cnt, bcnt, xcnt, 0, FaceOut{});
   thrust::exclusive_scan(pol, cnt, cnt + nl + 1, cnt);
   thrust::exclusive_scan(pol, bcnt, bcnt + nl + 1, bcnt);
   thrust::exclusive_scan(pol, xcnt, xcnt + nl + 1, xcnt);
@@ -232,17 +266,24 @@ int build(t8b200_cart_conn* out, Forest f, cudaStream_t st) {
   T8B_TRY(alloc((void**)&out->ranks, (nl + ng) * 4));
   T8B_TRY(alloc((void**)&out->indices, (nl + ng) * 4));
   T8B_TRY(alloc((void**)&out->face_neighbors, (2 * nf + nb) * 4));
-  T8B_TRY(alloc(&out->face_normals, (nf + nb) * 3 * sizeof(T)));
+  const int nd = SUB ? f.dim : 3;
+  T8B_TRY(alloc(&out->face_normals, (nf + nb) * nd * sizeof(T)));
   T8B_TRY(alloc(&out->face_surfaces, (nf + nb) * sizeof(T)));
   T8B_TRY(alloc(&out->volumes, nl * sizeof(T)));
   T8B_TRY(alloc(&out->centroids, nl * 3 * sizeof(T)));
   T8B_TRY(alloc((void**)&out->x_face_neighbors, nx * 8));
-  T8B_TRY(alloc(&out->x_face_normals, nx * 3 * sizeof(T)));
+  T8B_TRY(alloc(&out->x_face_normals, nx * nd * sizeof(T)));
   T8B_TRY(alloc(&out->x_face_surfaces, nx * sizeof(T)));
-  if (nl > 0)
-    faces_kernel<T, 1><<<blocks, 256, 0, st>>>(f, ghosts, ng, cnt, bcnt, xcnt, nf, out->face_neighbors,
-                                               (T*)out->face_normals, (T*)out->face_surfaces, out->x_face_neighbors,
-                                               (T*)out->x_face_normals, (T*)out->x_face_surfaces);
+  FaceOut fo{out->face_neighbors, out->x_face_neighbors, nullptr, nullptr, nullptr, nullptr,
+             out->face_normals,   out->face_surfaces,    out->x_face_normals, out->x_face_surfaces};
+  if (SUB) {
+    T8B_TRY(alloc((void**)&info->level_diff, nf * 4));
+    T8B_TRY(alloc((void**)&info->offsets, nf * f.dim * 4));
+    T8B_TRY(alloc((void**)&info->x_level_diff, nx * 4));
+    T8B_TRY(alloc((void**)&info->x_offsets, nx * f.dim * 4));
+    fo.ld = info->level_diff; fo.off = info->offsets; fo.xld = info->x_level_diff; fo.xoff = info->x_offsets;
+  }
+  if (nl > 0) faces_kernel<T, 1, SUB><<<blocks, 256, 0, st>>>(f, ghosts, ng, cnt, bcnt, xcnt, nf, fo);
   if (nl + ng > 0)
     elements_kernel<T><<<(unsigned)((nl + ng + 255) / 256), 256, 0, st>>>(f, ghosts, ng, out->ranks, out->indices,
                                                                            (T*)out->volumes, (T*)out->centroids);
@@ -262,5 +303,26 @@ extern "C" int t8b200_forest_connectivity(t8b200_cart_conn* out, int is_f64, int
   *out = t8b200_cart_conn{};
   Forest f{dim, periodic ? 1 : 0, nranks, rank, n_leaves, part_off(n_leaves, nranks, rank),
            part_off(n_leaves, nranks, rank + 1), keys_dev, levels_dev};
-  return is_f64 ? build<double>(out, f, (cudaStream_t)stream) : build<float>(out, f, (cudaStream_t)stream);
+  return is_f64 ? build<double, false>(out, nullptr, f, (cudaStream_t)stream)
+                : build<float, false>(out, nullptr, f, (cudaStream_t)stream);
+}
+
+extern "C" int t8b200_forest_subgrid_connectivity(t8b200_cart_conn* out, t8b200_subgrid_face_info* info, int is_f64,
+                                                  int dim, int periodic, int64_t n_leaves, const uint64_t* keys_dev,
+                                                  const int32_t* levels_dev, int nranks, int rank, void* stream) {
+  if (!out || !info || (dim != 2 && dim != 3) || n_leaves < 0 || nranks < 1 || rank < 0 || rank >= nranks)
+    return cudaErrorInvalidValue;
+  if (n_leaves > 0 && (!keys_dev || !levels_dev)) return cudaErrorInvalidValue;
+  *out  = t8b200_cart_conn{};
+  *info = t8b200_subgrid_face_info{};
+  Forest f{dim, periodic ? 1 : 0, nranks, rank, n_leaves, part_off(n_leaves, nranks, rank),
+           part_off(n_leaves, nranks, rank + 1), keys_dev, levels_dev};
+  return is_f64 ? build<double, true>(out, info, f, (cudaStream_t)stream)
+                : build<float, true>(out, info, f, (cudaStream_t)stream);
+}
+
+extern "C" void t8b200_subgrid_face_info_free(t8b200_subgrid_face_info* info) {
+  if (!info) return;
+  cudaFree(info->level_diff); cudaFree(info->offsets); cudaFree(info->x_level_diff); cudaFree(info->x_offsets);
+  *info = t8b200_subgrid_face_info{};
 }
