@@ -139,6 +139,13 @@ int t8b200_plan_create_host(t8b200_plan** out, int is_f64, int64_t n_local, int6
                             const int32_t* face_neighbors, const void* face_normals, const void* face_surfaces,
                             const int32_t* ranks, const int32_t* indices, int32_t n_xfaces,
                             const int32_t* x_face_neighbors, const void* x_face_normals, const void* x_face_surfaces);
+/* Check access to the DEVICE builder's logic without a device: a host-only plan produced by the per-block program the
+ * CUDA threads of t8b200_plan_create_device run (csrc/plan_block.cuh), driven by host loops.  Same arguments and arrays
+ * as t8b200_plan_create_host; multi-rank plans stop at the chunk arrays (arrays 0-12). */
+int t8b200_plan_create_block_program_host(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
+                                          int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
+                                          const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                                          const void* xnormals, const void* xareas);
 int t8b200_plan_host_array(const t8b200_plan* plan, int which, const void** data, int64_t* count, int* elem_bytes);
 
 /* Ghost tail.  The reference keeps no ghost layer: kernels dereference the owner's arrays directly

@@ -18,7 +18,9 @@
 #include "../../include/t8gpu_b200.h"
 #include "common.cuh"
 #include "euler_flux.cuh"
+#include "mesh_faces.cuh"
 #include "peer_sync.cuh"
+#include "plan_emulate.cuh"
 #include "tile_plan.cuh"
 
 using namespace t8b200;
@@ -633,30 +635,6 @@ static int fused_stage_push_impl(const t8b200_plan* P, int stage, const T* const
   return t8b_structured_stage_run<T>(P, stage, in, nullptr, prev, out, vol, dt, speed_max, stream, dt_dev, nullptr, 0, &pa);
 }
 
-// Face source over the arrays behind MeshConnectivityAccessor<float_type,3> (t8gpu/mesh/mesh_manager.h:159-166):
-// global face ids [0,nf) interior, [nf,nf+nb) boundary, then the extra partition-boundary faces.
-template <typename T>
-struct MeshFaces {
-  int32_t        nf, nb, nx;
-  const int32_t* nbr;
-  const T *      normals, *areas;
-  const int32_t *ranks, *indices, *xnbr;
-  const T *      xnormals, *xareas;
-  int64_t num_faces() const { return (int64_t)nf + nb + nx; }
-  void endpoints(int64_t f, int32_t& l, int32_t& r) const {
-    if (f < nf) { l = nbr[2 * f]; r = nbr[2 * f + 1]; }
-    else if (f < (int64_t)nf + nb) { l = nbr[2 * (int64_t)nf + (f - nf)]; r = -1; }
-    else { int64_t g = f - nf - nb; l = xnbr[2 * g]; r = xnbr[2 * g + 1]; }
-  }
-  void geometry(int64_t f, T nrm[3], T& a) const {
-    const T* n;
-    if (f < (int64_t)nf + nb) { n = normals + 3 * f; a = areas[f]; }
-    else { int64_t g = f - nf - nb; n = xnormals + 3 * g; a = xareas[g]; }
-    nrm[0] = n[0]; nrm[1] = n[1]; nrm[2] = n[2];
-  }
-  void owner(int32_t id, int32_t& rk, int32_t& ix) const { rk = ranks[id]; ix = indices[id]; }
-};
-
 template <typename T>
 int t8b_fused_stage_run(const t8b200_plan* P, int stage, const T* const* in, const T* const* const* in_all,
                         const T* const* prev, T* const* out, const T* vol, T dt, T* speed_max, void* stream,
@@ -688,17 +666,18 @@ static int plan_create_impl(t8b200_plan** out, int host_only, int is_f64, int64_
   if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
   t8b200_plan* P = new t8b200_plan();
   P->is_f64      = is_f64 ? 1 : 0;
-  P->host_only   = host_only & 1;   // flags: bit 0 host-only plan, bit 1 ghost tail
+  P->host_only   = host_only & 1;   // flags: bit 0 host-only plan, bit 1 ghost tail, bit 2 block program on the host
   P->ghost_tail  = (host_only >> 1) & 1;
+  const bool emulate = (host_only & 5) == 5;   // plan_emulate.cuh: the device builder's per-block program, host loops
   int rc;
   if (is_f64) {
     MeshFaces<double> src{nf, nb, nx, nbr, (const double*)normals, (const double*)areas, ranks, indices, xnbr,
                           (const double*)xnormals, (const double*)xareas};
-    rc = plan_build<double>(P, n_local, n_ghost > 0, src);
+    rc = emulate ? plan_build_emulated<double>(P, n_local, n_ghost > 0, src) : plan_build<double>(P, n_local, n_ghost > 0, src);
   } else {
     MeshFaces<float> src{nf, nb, nx, nbr, (const float*)normals, (const float*)areas, ranks, indices, xnbr,
                          (const float*)xnormals, (const float*)xareas};
-    rc = plan_build<float>(P, n_local, n_ghost > 0, src);
+    rc = emulate ? plan_build_emulated<float>(P, n_local, n_ghost > 0, src) : plan_build<float>(P, n_local, n_ghost > 0, src);
   }
   if (rc != 0) {
     t8b200_plan_destroy(P);
@@ -720,6 +699,14 @@ int t8b200_plan_create_host(t8b200_plan** out, int is_f64, int64_t n_local, int6
                             const int32_t* indices, int32_t nx, const int32_t* xnbr, const void* xnormals,
                             const void* xareas) {
   return plan_create_impl(out, 1, is_f64, n_local, n_ghost, nf, nb, nbr, normals, areas, ranks, indices, nx, xnbr,
+                          xnormals, xareas);
+}
+
+int t8b200_plan_create_block_program_host(t8b200_plan** out, int is_f64, int64_t n_local, int64_t n_ghost, int32_t nf,
+                                          int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
+                                          const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                                          const void* xnormals, const void* xareas) {
+  return plan_create_impl(out, 5, is_f64, n_local, n_ghost, nf, nb, nbr, normals, areas, ranks, indices, nx, xnbr,
                           xnormals, xareas);
 }
 

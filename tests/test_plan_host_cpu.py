@@ -448,3 +448,85 @@ def test_host_plan_is_not_launchable():
     data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
     assert L.t8b200_plan_host_array(h, 99, C.byref(data), C.byref(count), C.byref(eb)) != 0
     L.t8b200_plan_destroy(h)
+
+
+# ---- the device builder's per-block program (csrc/plan_block.cuh) run on the host == the host builder, bit for bit ----
+def _plan_with(fn, conn, dtype):
+    keep = [_arr(conn, "face_neighbors", np.int32), _arr(conn, "face_normals", dtype), _arr(conn, "face_areas", dtype),
+            _arr(conn, "ranks", np.int32), _arr(conn, "indices", np.int32), _arr(conn, "x_face_neighbors", np.int32),
+            _arr(conn, "x_face_normals", dtype), _arr(conn, "x_face_areas", dtype)]
+    h = C.c_void_p()
+    rc = fn(C.byref(h), int(dtype == np.float64), C.c_int64(int(conn["n_local"])), C.c_int64(int(conn.get("n_ghost", 0))),
+            int(conn["n_faces"]), int(conn["n_bfaces"]), _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), _p(keep[4]),
+            int(conn.get("n_xfaces", 0)), _p(keep[5]), _p(keep[6]), _p(keep[7]))
+    assert rc == 0, rc
+    return h, keep
+
+
+def _int_arrays(L, h, which):
+    out = {}
+    for w in which:
+        data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
+        assert L.t8b200_plan_host_array(h, w, C.byref(data), C.byref(count), C.byref(eb)) == 0
+        n = count.value
+        out[w] = (np.frombuffer((C.c_char * (n * 4)).from_address(data.value), dtype=np.int32).copy() if n
+                  else np.zeros(0, np.int32))
+    return out
+
+
+def _same_plan(L, conn, dtype, multi):
+    h1, k1 = _plan_with(L.t8b200_plan_create_host, conn, dtype)
+    h2, k2 = _plan_with(L.t8b200_plan_create_block_program_host, conn, dtype)
+    A, B = arrays(L, h1), arrays(L, h2)
+    assert A["info"] == B["info"]
+    for k in A:
+        if k != "info":
+            assert np.array_equal(A[k], B[k]), k
+    if not multi:   # chunk lists of the structured / generic kernels (multi: device post-pass, tests/test_device_plan_gpu.py)
+        X, Y = _int_arrays(L, h1, (13, 14, 15, 16)), _int_arrays(L, h2, (13, 14, 15, 16))
+        for k in X:
+            assert np.array_equal(X[k], Y[k]), k
+    L.t8b200_plan_destroy(h1)
+    L.t8b200_plan_destroy(h2)
+    return A
+
+
+def _twice_adapted():
+    f = oracle.Forest(3, 3)
+    for width in (0.2, 0.1):
+        lv, cent, vol, _ = f.elements()
+        f = f.adapt(np.where(np.abs(cent[:, 2] - 0.5) < width, 20.0, 0.0), 10.0, 1, 5)
+    return f
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_block_program_equals_host_builder(dtype):
+    L = _lib()
+    A = _same_plan(L, oracle.Forest(3, 4).connectivity(dtype=dtype), dtype, False)
+    assert A["info"][0] == 16                                             # all structured
+    _same_plan(L, oracle.Forest(3, 3, periodic=False).connectivity(dtype=dtype), dtype, False)   # walls
+    _same_plan(L, oracle.Forest(2, 5).connectivity(dtype=dtype), dtype, False)                   # quads
+    f = _twice_adapted()
+    A = _same_plan(L, f.connectivity(dtype=dtype), dtype, False)
+    assert len(A["ovf_ent"]) > 0                                          # elements with more than 8 faces
+    for P in (2, 3):
+        for r in range(P):
+            _same_plan(L, f.connectivity(P, r, dtype=dtype), dtype, True)
+    for per in (True, False):                                             # general normals, shuffled numbering
+        A = _same_plan(L, hybrid_mesh(12, per, dtype, seed=3, shuffle=not per)[0], dtype, False)
+        assert len(A["fnx"]) > 0
+
+
+def test_block_program_splits_like_host_builder(monkeypatch):
+    monkeypatch.setenv("T8B200_TEST_MAX_HALO", "40")
+    L = _lib()
+    f = oracle.Forest(3, 4)
+    A = _same_plan(L, f.connectivity(dtype=np.float64), np.float64, False)
+    assert A["info"][0] > 16
+    for r in range(2):
+        _same_plan(L, f.connectivity(2, r, dtype=np.float64), np.float64, True)
+    f = oracle.Forest(3, 2)
+    for _ in range(3):
+        lv, cent, vol, _v = f.elements()
+        f = f.adapt(np.where(np.abs(cent[:, 0] - 0.5) + np.abs(cent[:, 1] - 0.5) < 0.3, 20.0, 0.0), 10.0, 1, 5)
+    _same_plan(L, f.connectivity(dtype=np.float32), np.float32, False)
