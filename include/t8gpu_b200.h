@@ -178,13 +178,17 @@ int t8b200_ghost_pull_f64(const t8b200_plan* plan, int nvar, double* const* rows
                           void* stream);
 
 /* The plan built ON THE DEVICE from DEVICE connectivity arrays (same arguments as t8b200_plan_create, all pointers device
- * pointers): no device -> host copy of the connectivity, no host loop -- for the meshes whose every block of 256
- * consecutive elements is an 8 x 8 x 4 box of same-size hexahedra with 256 single same-size face neighbours (uniform
- * forests and brick partitions: the arrays t8b200_cartesian_*_connectivity leaves on the device).  Returns
- * cudaErrorNotSupported (801) for any other mesh (hanging faces, walls, general normals, n_local not a multiple of 256):
- * the caller then copies the arrays to the host and uses t8b200_plan_create.  The plan holds the halo lists of its
- * chunks (equal, entry for entry, to arrays 13-15 / 17-18 of the host builder) and serves t8b200_fused_stage_*,
- * t8b200_ghost_pull_* and t8b200_gradient_criteria_*.  ghost_tail != 0: as t8b200_plan_create_ghost_tail.
+ * pointers): no device -> host copy of the connectivity, no host loop over the faces.
+ *   - Meshes whose every block of 256 consecutive elements is an 8 x 8 x 4 box of same-size hexahedra with 256 single
+ *     same-size face neighbours (uniform forests and brick partitions: the arrays t8b200_cartesian_*_connectivity leaves
+ *     on the device): three kernels and a sort of the ghost keys.
+ *   - Any other mesh (hanging faces, walls, general normals, ragged ends, blocks that must be split): one CUDA thread
+ *     per block of 256 elements runs the block program of csrc/plan_block.cuh between data-parallel passes over the
+ *     faces and the chunks; device -> host traffic is counters, the <= 256 distinct areas and two flag bytes per chunk.
+ * Every array of the plan equals the host builder's, entry for entry (t8b200_plan_device_bytes, numbered as
+ * t8b200_plan_host_array).  Returns cudaErrorNotSupported (801) only for n_local == 0.  The plan serves
+ * t8b200_fused_stage_*, t8b200_ghost_pull_* and t8b200_gradient_criteria_*.  ghost_tail != 0: as
+ * t8b200_plan_create_ghost_tail.
  * Replaces the upload half of MeshManager::compute_connectivity_information (t8gpu/mesh/mesh_manager.inl:442-480). */
 int t8b200_plan_create_device(t8b200_plan** out, int is_f64, int ghost_tail, int64_t n_local, int64_t n_ghost,
                               int32_t nf, int32_t nb, const int32_t* face_neighbors, const void* face_normals,
@@ -194,6 +198,9 @@ int t8b200_plan_create_device(t8b200_plan** out, int is_f64, int ghost_tail, int
 /* test access: one of the structured / ghost-tail DEVICE arrays of a plan copied to the host (which = 13, 14, 15, 17,
  * 18 as t8b200_plan_host_array numbers them); returns the element count (host_out may be NULL), -1 on error */
 int64_t t8b200_plan_device_array(const t8b200_plan* plan, int which, int32_t* host_out, int64_t capacity);
+/* test access to EVERY device array of a plan (which = 0 ... 19 as t8b200_plan_host_array), raw bytes in the device
+ * element type; returns the byte count (host_out may be NULL), -1 on error */
+int64_t t8b200_plan_device_bytes(const t8b200_plan* plan, int which, void* host_out, int64_t capacity_bytes);
 
 /* The same exchange pushed by the owner: rows_all[k][dst_rank[e]][dst_idx[e]] = rows[k][src_idx[e]] for the n_send
  * entries of this rank's send list (DEVICE arrays; the pull lists of the peers -- host arrays 17 / 18 of their plans --

@@ -212,8 +212,9 @@ class Plan:
     @classmethod
     def from_device(cls, conn, dtype, ghost_tail=False, stream=None):
         """Plan built on the device from DEVICE connectivity tensors (t8b200_plan_create_device): no copy of the
-        connectivity to the host.  Returns None when the mesh is not made of structured chunks only (the caller then
-        uses Plan(conn_to_host(conn), ...))."""
+        connectivity to the host: the three-kernel builder for structured-only meshes, else one CUDA thread per block
+        of 256 elements (csrc/plan_block.cuh).  Returns None only for a rank without elements (the caller then uses
+        Plan(conn_to_host(conn), ...))."""
         _torch()
         s, _ = _sfx(dtype)
 
@@ -229,7 +230,7 @@ class Plan:
             int(conn["n_faces"]), int(conn["n_bfaces"]), p("face_neighbors"), p("face_normals"), p("face_areas"),
             p("ranks") if ng else None, p("indices") if ng else None, nx, p("x_face_neighbors") if nx else None,
             p("x_face_normals") if nx else None, p("x_face_areas") if nx else None, stream_ptr(stream))
-        if rc == 801:   # cudaErrorNotSupported: not a structured-only mesh
+        if rc == 801:   # cudaErrorNotSupported: nothing to build
             return None
         check(rc, "plan_create_device")
         self = cls.__new__(cls)

@@ -14,14 +14,19 @@
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/scan.h>
 #include <thrust/sort.h>
 #include <thrust/unique.h>
 
+#include <algorithm>
 #include <cmath>
+#include <vector>
 
 #include "../../include/t8gpu_b200.h"
 #include "box_layout.cuh"
 #include "common.cuh"
+#include "mesh_faces.cuh"
+#include "plan_block.cuh"
 #include "tile_plan.cuh"
 
 using namespace t8b200;
@@ -188,13 +193,13 @@ __global__ void uniform_check_kernel(int64_t n_elem, const T* __restrict__ vol, 
 __global__ void ghost_keys_kernel(int64_t n, const int32_t* __restrict__ halo, const int32_t* __restrict__ hrank, int me,
                                   unsigned long long* __restrict__ keys, unsigned long long* count) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || hrank[i] == me) return;
+  if (i >= n || halo[i] < 0 || hrank[i] == me) return;
   keys[atomicAdd(count, 1ull)] = ((unsigned long long)(uint32_t)hrank[i] << 32) | (uint32_t)halo[i];
 }
 __global__ void redirect_kernel(int64_t n, int32_t* __restrict__ halo, int32_t* __restrict__ hrank, int me,
                                 const unsigned long long* __restrict__ keys, int64_t nkeys, int64_t n_local) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || hrank[i] == me) return;
+  if (i >= n || halo[i] < 0 || hrank[i] == me) return;
   const unsigned long long k = ((unsigned long long)(uint32_t)hrank[i] << 32) | (uint32_t)halo[i];
   int64_t lo = 0, hi = nkeys;   // lower bound
   while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
@@ -349,6 +354,362 @@ int device_plan_impl(t8b200_plan** out, int flags_in, int64_t n_local, int64_t n
   return 0;
 }
 
+
+// =====================================================================================================================
+// Any other mesh (hanging faces, walls, general normals, ragged ends, blocks that must be split): the generic builder.
+// One CUDA thread runs the per-block program of plan_block.cuh for one block of 256 elements -- the programs are
+// independent, branchy integer work over ~1000 faces each, latency-bound; thousands of them in flight hide it -- between
+// data-parallel passes over the faces (classification, bucketing) and over the chunks (launch lists, ghost tail).
+// Device -> host traffic: counters, the <= 256 distinct areas and two flag bytes per chunk; never the connectivity.
+// Every array equals the host builder's (tests/test_device_plan_gpu.py).
+// =====================================================================================================================
+enum GFlag { G_NOT_AXIS = 0, G_MANY_AREAS, G_BAD_FACE, G_PROGRAM_ERROR, G_MY_RANK, G_N };
+constexpr unsigned long long AREA_EMPTY = ~0ull;
+constexpr int                AREA_SLOTS = 257;
+
+template <typename T>
+__device__ inline unsigned long long area_bits(T a) {
+  if constexpr (sizeof(T) == 8) return (unsigned long long)__double_as_longlong((double)a);
+  else return (unsigned long long)__float_as_uint((float)a);
+}
+
+// per face: normal class and area into the set of distinct areas (lock-free insert), faces per block
+template <typename T, class Src>
+__global__ void __launch_bounds__(256) classify_kernel(Src src, int64_t ntot, int64_t n_local, int multi,
+                                                       unsigned long long* area_set, int* flags,
+                                                       unsigned long long* blk_cnt) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f == 0 && n_local > 0 && multi) { int32_t rk = 0, ix = 0; src.owner(0, rk, ix); flags[G_MY_RANK] = rk; }
+  if (f >= ntot) return;
+  T nrm[3], a;
+  src.geometry(f, nrm, a);
+  if (pb::axis_code_hd(nrm) < 0) flags[G_NOT_AXIS] = 1;
+  else {
+    const unsigned long long bits = area_bits(a);
+    int i = 0;
+    for (; i < AREA_SLOTS; i++) {
+      unsigned long long v = *(volatile unsigned long long*)(area_set + i);
+      if (v == bits) break;
+      if (v == AREA_EMPTY) {
+        v = atomicCAS(area_set + i, AREA_EMPTY, bits);
+        if (v == AREA_EMPTY || v == bits) break;
+      }
+    }
+    if (i == AREA_SLOTS) flags[G_MANY_AREAS] = 1;
+  }
+  int32_t l, r;
+  src.endpoints(f, l, r);
+  const int64_t cl = l < n_local ? l / pb::EC : -1, cr = (r >= 0 && r < n_local) ? r / pb::EC : -1;
+  if (cl < 0 && cr < 0) { flags[G_BAD_FACE] = 1; return; }
+  if (cl >= 0) atomicAdd(blk_cnt + cl, 1ull);
+  if (cr >= 0 && cr != cl) atomicAdd(blk_cnt + cr, 1ull);
+}
+
+template <class Src>
+__global__ void __launch_bounds__(256) bucket_kernel(Src src, int64_t ntot, int64_t n_local, const unsigned long long* face_off,
+                                                     unsigned long long* cursor, int64_t* rec) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= ntot) return;
+  int32_t l, r;
+  src.endpoints(f, l, r);
+  const int64_t cl = l < n_local ? l / pb::EC : -1, cr = (r >= 0 && r < n_local) ? r / pb::EC : -1;
+  if (cl >= 0) rec[face_off[cl] + atomicAdd(cursor + cl, 1ull)] = f;
+  if (cr >= 0 && cr != cl) rec[face_off[cr] + atomicAdd(cursor + cr, 1ull)] = f;
+}
+
+template <typename T, class Src, bool FILL>
+__global__ void __launch_bounds__(64) block_pass_kernel(Src src, pb::Params<T> pr, unsigned char* arena, int64_t nprog,
+                                                        int64_t blk0, int64_t nblocks, const unsigned long long* face_off,
+                                                        int64_t* rec, pb::Counts* cn, const unsigned long long* bases,
+                                                        pb::Out<T> out, int* flags) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, blk = blk0 + t;
+  if (t >= nprog || blk >= nblocks) return;
+  const pb::Ws w = pb::Ws::carve(arena, nprog, t, true);
+  pb::Counts   c;
+  pb::block_program<T, Src, FILL>(src, pr, w, blk, rec + face_off[blk], (int64_t)(face_off[blk + 1] - face_off[blk]), c,
+                                  FILL ? (int64_t)bases[blk] : 0, FILL ? (int64_t)bases[(nblocks + 1) + blk] : 0,
+                                  FILL ? (int64_t)bases[2 * (nblocks + 1) + blk] : 0, out);
+  if (c.rc || (FILL && c.chunks != cn[blk].chunks)) flags[G_PROGRAM_ERROR] = 1;
+  if (!FILL) cn[blk] = c;
+}
+
+// counts of the blocks -> three arrays for the scans (chunks, overflow offsets, overflow entries) + totals
+__global__ void __launch_bounds__(256) counts_kernel(int64_t nblocks, const pb::Counts* cn, unsigned long long* bases,
+                                                     unsigned long long* totals) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const pb::Counts c = cn[b];
+  bases[b] = c.chunks; bases[(nblocks + 1) + b] = c.ovf_off; bases[2 * (nblocks + 1) + b] = c.ovf_ent;
+  atomicMax(totals + 0, (unsigned long long)c.max_halo);
+  atomicMax(totals + 1, (unsigned long long)c.max_faces);
+  atomicAdd(totals + 2, (unsigned long long)c.sum_halo);
+  atomicAdd(totals + 3, (unsigned long long)c.sum_faces);
+  if (c.chunks > 1) totals[4] = 1;
+}
+
+// CTA = chunk: does it read another rank's elements?  (structured chunks: their 256-entry list, else the halo list)
+__global__ void __launch_bounds__(256) chunk_flags_kernel(int HS, const int32_t* __restrict__ halo_elem,
+                                                          const int32_t* __restrict__ halo_rank,
+                                                          const uint8_t* __restrict__ s_flag, int me, uint8_t* bflag) {
+  const int64_t c = blockIdx.x;
+  bool          b = false;
+  for (int h = threadIdx.x; h < HS; h += 256) b = b || (halo_elem[c * HS + h] >= 0 && halo_rank[c * HS + h] != me);
+  const int any = __syncthreads_or(b ? 1 : 0);
+  if (threadIdx.x == 0) bflag[c] = (uint8_t)any;
+  (void)s_flag;
+}
+
+// CTA = structured chunk at launch position q: record + its 256-entry halo list from the per-chunk scratch
+__global__ void __launch_bounds__(256) gather_structured_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ hdr,
+                                                                const int32_t* __restrict__ s_halo_tmp,
+                                                                const int32_t* __restrict__ s_hrank_tmp, int32_t* s_rec,
+                                                                int32_t* s_halo, int32_t* s_hrank) {
+  const int64_t q = blockIdx.x;
+  const int32_t o = order[q], c = o & 0x3FFFFFFF;
+  s_halo[q * 256 + threadIdx.x] = s_halo_tmp[(int64_t)c * 256 + threadIdx.x];
+  if (s_hrank) s_hrank[q * 256 + threadIdx.x] = s_hrank_tmp[(int64_t)c * 256 + threadIdx.x];
+  if (threadIdx.x == 0) {
+    s_rec[4 * q] = hdr[8 * (int64_t)c]; s_rec[4 * q + 1] = hdr[8 * (int64_t)c + 7]; s_rec[4 * q + 2] = c;
+    s_rec[4 * q + 3] = (o >> 30) & 1;
+  }
+}
+
+template <typename T, class Src>
+int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& src, cudaStream_t st) {
+  static_assert(pb::EC == EC && pb::MS == MS && pb::MF == MF && pb::ELL == ELL, "plan_block.cuh constants");
+  const int64_t nblocks = (n_local + EC - 1) / EC, ntot = src.num_faces();
+  auto          pol     = thrust::cuda::par.on(st);
+  P->n_local = n_local; P->multi = multi ? 1 : 0;
+  auto dev_alloc = [&](auto** p, size_t bytes, int fill) {
+    cudaError_t e = cudaMalloc(p, bytes + 32);
+    if (e != cudaSuccess) return e;
+    P->dev_bytes += (int64_t)bytes + 32;
+    return cudaMemsetAsync(*p, fill, bytes + 32, st);
+  };
+  // ---- faces: classes, distinct areas, buckets per block
+  DevFree<unsigned long long> area_set, blk, totals;
+  DevFree<int>                flags;
+  T8B_TRY(cudaMalloc(&area_set.p, 8 * AREA_SLOTS));
+  T8B_TRY(cudaMemsetAsync(area_set.p, 0xFF, 8 * AREA_SLOTS, st));
+  T8B_TRY(cudaMalloc(&flags.p, sizeof(int) * G_N));
+  T8B_TRY(cudaMemsetAsync(flags.p, 0, sizeof(int) * G_N, st));
+  // blk: [0, nb+1) face offsets, then the cursors; after the count pass 3 x (nb+1) bases
+  T8B_TRY(cudaMalloc(&blk.p, 8 * 3 * (size_t)(nblocks + 1)));
+  T8B_TRY(cudaMemsetAsync(blk.p, 0, 8 * 3 * (size_t)(nblocks + 1), st));
+  DevFree<unsigned long long> face_off;
+  T8B_TRY(cudaMalloc(&face_off.p, 8 * (size_t)(nblocks + 1)));
+  T8B_TRY(cudaMemsetAsync(face_off.p, 0, 8 * (size_t)(nblocks + 1), st));
+  const unsigned fgrid = (unsigned)((ntot + 255) / 256);
+  if (ntot > 0) classify_kernel<T, Src><<<fgrid, 256, 0, st>>>(src, ntot, n_local, multi ? 1 : 0, area_set.p, flags.p, face_off.p);
+  thrust::device_ptr<unsigned long long> fo(face_off.p);
+  thrust::exclusive_scan(pol, fo, fo + nblocks + 1, fo);
+  unsigned long long n_rec_all = 0;
+  T8B_TRY(cudaMemcpyAsync(&n_rec_all, face_off.p + nblocks, 8, cudaMemcpyDeviceToHost, st));
+  T8B_TRY(cudaStreamSynchronize(st));
+  DevFree<int64_t> rec;
+  T8B_TRY(cudaMalloc(&rec.p, 8 * (size_t)std::max<unsigned long long>(n_rec_all, 1)));
+  if (ntot > 0) bucket_kernel<Src><<<fgrid, 256, 0, st>>>(src, ntot, n_local, face_off.p, blk.p, rec.p);
+  // ---- COUNT pass: one program per block, in batches that bound the workspace
+  const int64_t nprog = std::min<int64_t>(nblocks, 65536);
+  DevFree<unsigned char> arena;
+  DevFree<pb::Counts>    cn;
+  T8B_TRY(cudaMalloc(&arena.p, (size_t)pb::Ws::bytes_per_program * (size_t)nprog + 64));
+  T8B_TRY(cudaMalloc(&cn.p, sizeof(pb::Counts) * (size_t)nblocks));
+  int max_halo_allowed = MS - EC;
+  if (const char* t = getenv("T8B200_TEST_MAX_HALO")) max_halo_allowed = std::min(max_halo_allowed, std::max(8, atoi(t)));
+  const int box_layout = P->vol_shift == 6 ? 1 : P->vol_shift == 0 ? 0 : -1;
+  P->box_layout        = box_layout;
+  int16_t inv_h[SubgridBox::NSLOT];
+  for (int i = 0; i < SubgridBox::NSLOT; i++) inv_h[i] = -1;
+  for (int h = 0; h < 256; h++) inv_h[box_layout == 1 ? SubgridBox::thread_slot(h) : MortonBox::thread_slot(h)] = (int16_t)h;
+  DevFree<int16_t> inv;
+  T8B_TRY(cudaMalloc(&inv.p, sizeof(inv_h)));
+  T8B_TRY(cudaMemcpyAsync(inv.p, inv_h, sizeof(inv_h), cudaMemcpyHostToDevice, st));
+  pb::Params<T> pr{n_local, multi ? 1 : 0, 0, 0, box_layout, max_halo_allowed, MF - 1, nullptr, inv.p};
+  pb::Out<T>    out{};
+  T8B_TRY(cudaMemsetAsync(blk.p, 0, 8 * 3 * (size_t)(nblocks + 1), st));   // cursors done; now the bases
+  for (int64_t b0 = 0; b0 < nblocks; b0 += nprog)
+    block_pass_kernel<T, Src, false><<<(unsigned)((nprog + 63) / 64), 64, 0, st>>>(src, pr, arena.p, nprog, b0, nblocks,
+                                                                                  face_off.p, rec.p, cn.p, blk.p, out, flags.p);
+  T8B_TRY(cudaMalloc(&totals.p, 8 * 8));
+  T8B_TRY(cudaMemsetAsync(totals.p, 0, 8 * 8, st));
+  counts_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(nblocks, cn.p, blk.p, totals.p);
+  thrust::device_ptr<unsigned long long> bp(blk.p);
+  for (int k = 0; k < 3; k++) thrust::exclusive_scan(pol, bp + k * (nblocks + 1), bp + (k + 1) * (nblocks + 1), bp + k * (nblocks + 1));
+  unsigned long long tot[8], ends[3], aset[AREA_SLOTS];
+  int                fl[G_N];
+  T8B_TRY(cudaMemcpyAsync(tot, totals.p, sizeof(tot), cudaMemcpyDeviceToHost, st));
+  for (int k = 0; k < 3; k++) T8B_TRY(cudaMemcpyAsync(&ends[k], blk.p + k * (nblocks + 1) + nblocks, 8, cudaMemcpyDeviceToHost, st));
+  T8B_TRY(cudaMemcpyAsync(aset, area_set.p, sizeof(aset), cudaMemcpyDeviceToHost, st));
+  T8B_TRY(cudaMemcpyAsync(fl, flags.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  T8B_TRY(cudaGetLastError());
+  T8B_TRY(cudaStreamSynchronize(st));
+  if (fl[G_BAD_FACE] || fl[G_PROGRAM_ERROR]) return cudaErrorInvalidValue;
+  if (multi) P->my_rank = fl[G_MY_RANK];
+  const int64_t nchunks = (int64_t)ends[0], n_oo = (int64_t)ends[1], n_oe = (int64_t)ends[2];
+  if (n_local > 0x7FFFFF00LL || nchunks * MF > 0x7FFFFF00LL || n_oo > 0x7FFFFF00LL || n_oe > 0x7FFFFF00LL) return cudaErrorInvalidValue;
+  std::vector<T> area_tab;
+  bool           cmp = !fl[G_NOT_AXIS] && !fl[G_MANY_AREAS];
+  if (cmp) {
+    for (int i = 0; i < AREA_SLOTS && aset[i] != AREA_EMPTY; i++) {
+      T a;
+      if constexpr (sizeof(T) == 8) memcpy(&a, &aset[i], 8); else { const uint32_t u = (uint32_t)aset[i]; memcpy(&a, &u, 4); }
+      area_tab.push_back(a);
+    }
+    if (area_tab.size() > 256) cmp = false;
+    std::sort(area_tab.begin(), area_tab.end());
+  }
+  const int max_halo = (int)tot[0], max_faces = (int)tot[1];
+  const int HS = std::max(32, (max_halo + 31) / 32 * 32), FS = std::max(32, (max_faces + 31) / 32 * 32);
+  P->n_chunks = (int)nchunks; P->split = tot[4] ? 1 : 0; P->hs = HS; P->fs = FS; P->max_halo = max_halo; P->max_faces = max_faces;
+  P->n_halo = (int64_t)tot[2]; P->n_records = (int64_t)tot[3]; P->ms = MS; P->mf = MF;
+  P->smem_bytes = sizeof(T) == 8 ? 8 * ((size_t)NCELLQ * MS + 5 * (size_t)MF) : 32 * (size_t)MS + 20 * (size_t)MF;
+  P->cmp = cmp ? 1 : 0; P->n_areas = cmp ? (int)area_tab.size() : 0;
+  // ---- plan arrays (padding: halo -1, everything else 0, element -> face table 0xFFFF)
+  T8B_TRY(dev_alloc(&P->hdr, 4 * 8 * (size_t)nchunks, 0));
+  T8B_TRY(dev_alloc(&P->halo_elem, 4 * (size_t)nchunks * HS, 0xFF));
+  if (multi) T8B_TRY(dev_alloc(&P->halo_rank, 4 * (size_t)nchunks * HS, 0));
+  T8B_TRY(dev_alloc(&P->face_lr, 4 * (size_t)nchunks * FS, 0));
+  if (cmp) {
+    T8B_TRY(dev_alloc(&P->face_ai, (size_t)nchunks * FS, 0));
+    T8B_TRY(dev_alloc((T**)&P->area_tab, sizeof(T) * std::max<size_t>(area_tab.size(), 1), 0));
+    T8B_TRY(cudaMemcpyAsync(P->area_tab, area_tab.data(), sizeof(T) * area_tab.size(), cudaMemcpyHostToDevice, st));
+  } else {
+    T8B_TRY(dev_alloc((T**)&P->fnx, sizeof(T) * (size_t)nchunks * FS, 0));
+    T8B_TRY(dev_alloc((T**)&P->fny, sizeof(T) * (size_t)nchunks * FS, 0));
+    T8B_TRY(dev_alloc((T**)&P->fnz, sizeof(T) * (size_t)nchunks * FS, 0));
+    T8B_TRY(dev_alloc((T**)&P->farea, sizeof(T) * (size_t)nchunks * FS, 0));
+  }
+  T8B_TRY(dev_alloc((uint16_t**)&P->ell, 2 * (size_t)std::max<int64_t>(n_local, 1) * ELL, 0xFF));
+  T8B_TRY(dev_alloc(&P->ovf_off, 2 * (size_t)std::max<int64_t>(n_oo, 1), 0));
+  T8B_TRY(dev_alloc(&P->ovf_ent, 2 * (size_t)std::max<int64_t>(n_oe, 1), 0));
+  P->n_ovf_off = n_oo; P->n_ovf_ent = n_oe;
+  DevFree<uint8_t> s_flag, bflag;
+  DevFree<int32_t> s_halo_tmp, s_hrank_tmp;
+  T8B_TRY(cudaMalloc(&s_flag.p, (size_t)nchunks + 1));
+  T8B_TRY(cudaMalloc(&bflag.p, (size_t)nchunks + 1));
+  T8B_TRY(cudaMalloc(&s_halo_tmp.p, 4 * 256 * (size_t)nchunks + 4));
+  if (multi) T8B_TRY(cudaMalloc(&s_hrank_tmp.p, 4 * 256 * (size_t)nchunks + 4));
+  // ---- FILL pass
+  pr.cmp = cmp ? 1 : 0; pr.n_areas = (int)area_tab.size(); pr.area_tab = (const T*)P->area_tab;
+  out = pb::Out<T>{HS, FS, P->hdr, P->halo_elem, P->halo_rank, P->face_lr, P->face_ai, (T*)P->fnx, (T*)P->fny, (T*)P->fnz,
+                   (T*)P->farea, (uint16_t*)P->ell, P->ovf_off, P->ovf_ent, s_flag.p, s_halo_tmp.p, s_hrank_tmp.p};
+  for (int64_t b0 = 0; b0 < nblocks; b0 += nprog)
+    block_pass_kernel<T, Src, true><<<(unsigned)((nprog + 63) / 64), 64, 0, st>>>(src, pr, arena.p, nprog, b0, nblocks,
+                                                                                 face_off.p, rec.p, cn.p, blk.p, out, flags.p);
+  const int me = P->my_rank;
+  if (multi && nchunks > 0) chunk_flags_kernel<<<(unsigned)nchunks, 256, 0, st>>>(HS, P->halo_elem, P->halo_rank, s_flag.p, me, bflag.p);
+  else T8B_TRY(cudaMemsetAsync(bflag.p, 0, (size_t)nchunks + 1, st));
+  // ---- launch lists: two flag bytes per chunk to the host, the order back (tile_plan.cuh: arrange)
+  std::vector<uint8_t> sf((size_t)nchunks), bf((size_t)nchunks);
+  T8B_TRY(cudaMemcpyAsync(sf.data(), s_flag.p, (size_t)nchunks, cudaMemcpyDeviceToHost, st));
+  T8B_TRY(cudaMemcpyAsync(bf.data(), bflag.p, (size_t)nchunks, cudaMemcpyDeviceToHost, st));
+  T8B_TRY(cudaMemcpyAsync(fl, flags.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  T8B_TRY(cudaGetLastError());
+  T8B_TRY(cudaStreamSynchronize(st));
+  if (fl[G_PROGRAM_ERROR]) return cudaErrorInvalidValue;
+  std::vector<int32_t> s_list, g_list, blist;
+  for (int64_t c = 0; c < nchunks; c++) (sf[c] ? s_list : g_list).push_back((int32_t)c);
+  P->n_struct  = (int)s_list.size();
+  P->n_generic = P->n_struct ? (int)g_list.size() : (int)nchunks;
+  if (!P->n_struct && !multi) g_list.clear();
+  if (multi) {
+    static const int order_mode = getenv("T8B200_BND_ORDER") ? (getenv("T8B200_BND_ORDER")[0] == 'f' ? 1 : getenv("T8B200_BND_ORDER")[0] == 'n' ? 2 : 0) : 0;
+    const bool keep_order = order_mode == 2 || (P->n_struct == nchunks && !P->split);
+    auto arrange = [&](std::vector<int32_t>& list, int& n_bnd) {
+      const size_t n = list.size();
+      std::vector<int32_t> bl, il, order;
+      for (int32_t c : list) (bf[c] ? bl : il).push_back(c);
+      n_bnd = (int)bl.size();
+      order.reserve(n);
+      if (keep_order) order = list;
+      else if (order_mode == 1 || bl.empty()) { order = bl; order.insert(order.end(), il.begin(), il.end()); }
+      else {
+        const size_t nb = bl.size(), W = std::max(nb, n / 2);
+        size_t ib = 0, ii = 0;
+        for (size_t pos = 0; pos < n; pos++) {
+          const bool want_b = ib < nb && (pos >= W || ib * W / nb <= pos || ii >= il.size());
+          order.push_back(want_b ? bl[ib++] : il[ii++]);
+        }
+      }
+      for (auto& c : order) if (bf[c]) c |= 1 << 30;
+      list.swap(order);
+    };
+    arrange(s_list, P->nb_struct);
+    arrange(g_list, P->nb_generic);
+    if (P->nb_struct + P->nb_generic == 0 && nchunks > 0) {   // no ghosts at all: one nominal boundary chunk
+      if (P->n_struct) { s_list[0] |= 1 << 30; P->nb_struct = 1; } else { g_list[0] |= 1 << 30; P->nb_generic = 1; }
+    }
+    for (int q = 0; q < P->n_struct; q++) if (s_list[q] >> 30 & 1) blist.push_back(q);
+  }
+  if (P->n_struct) {
+    DevFree<int32_t> order;
+    T8B_TRY(cudaMalloc(&order.p, 4 * s_list.size()));
+    T8B_TRY(cudaMemcpyAsync(order.p, s_list.data(), 4 * s_list.size(), cudaMemcpyHostToDevice, st));
+    T8B_TRY(dev_alloc(&P->s_rec, 4 * 4 * s_list.size(), 0));
+    T8B_TRY(dev_alloc(&P->s_halo, 4 * 256 * s_list.size(), 0));
+    if (multi) T8B_TRY(dev_alloc(&P->s_hrank, 4 * 256 * s_list.size(), 0));
+    gather_structured_kernel<<<(unsigned)s_list.size(), 256, 0, st>>>(order.p, P->hdr, s_halo_tmp.p, s_hrank_tmp.p, P->s_rec,
+                                                                     P->s_halo, P->s_hrank);
+    int32_t a0 = 0;
+    T8B_TRY(cudaMemcpyAsync(&a0, P->s_rec + 1, 4, cudaMemcpyDeviceToHost, st));
+    T8B_TRY(cudaStreamSynchronize(st));
+    P->s_area0 = a0;
+  }
+  if (!g_list.empty()) {
+    T8B_TRY(dev_alloc(&P->g_list, 4 * g_list.size(), 0));
+    T8B_TRY(cudaMemcpyAsync(P->g_list, g_list.data(), 4 * g_list.size(), cudaMemcpyHostToDevice, st));
+  }
+  if (!blist.empty()) {
+    T8B_TRY(dev_alloc(&P->blist, 4 * blist.size(), 0));
+    T8B_TRY(cudaMemcpyAsync(P->blist, blist.data(), 4 * blist.size(), cudaMemcpyHostToDevice, st));
+  }
+  // ---- ghost tail over the halo lists and the structured lists
+  if (P->ghost_tail && multi) {
+    const int64_t n1 = nchunks * HS, n2 = (int64_t)P->n_struct * 256;
+    DevFree<unsigned long long> keys, count;
+    T8B_TRY(cudaMalloc(&keys.p, 8 * (size_t)std::max<int64_t>(n1 + n2, 1)));
+    T8B_TRY(cudaMalloc(&count.p, 8));
+    T8B_TRY(cudaMemsetAsync(count.p, 0, 8, st));
+    if (n1) ghost_keys_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(n1, P->halo_elem, P->halo_rank, me, keys.p, count.p);
+    if (n2) ghost_keys_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(n2, P->s_halo, P->s_hrank, me, keys.p, count.p);
+    unsigned long long nk = 0;
+    T8B_TRY(cudaMemcpyAsync(&nk, count.p, 8, cudaMemcpyDeviceToHost, st));
+    T8B_TRY(cudaStreamSynchronize(st));
+    thrust::device_ptr<unsigned long long> kb(keys.p);
+    thrust::sort(pol, kb, kb + nk);
+    const int64_t nu = thrust::unique(pol, kb, kb + nk) - kb;
+    if (nu + n_local > 0x7FFFFF00LL) return cudaErrorInvalidValue;
+    if (nu > 0) {
+      if (n1) redirect_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(n1, P->halo_elem, P->halo_rank, me, keys.p, nu, n_local);
+      if (n2) redirect_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(n2, P->s_halo, P->s_hrank, me, keys.p, nu, n_local);
+      T8B_TRY(dev_alloc(&P->pull_rank, 4 * (size_t)nu, 0));
+      T8B_TRY(dev_alloc(&P->pull_idx, 4 * (size_t)nu, 0));
+      split_keys_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, st>>>(nu, keys.p, P->pull_rank, P->pull_idx);
+    }
+    P->n_pull = nu;
+  }
+  T8B_TRY(cudaGetLastError());
+  T8B_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+template <typename T>
+int generic_mesh_plan(t8b200_plan** out, int ghost_tail, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
+                      const int32_t* nbr, const T* normals, const T* areas, const int32_t* ranks, const int32_t* indices,
+                      int32_t nx, const int32_t* xnbr, const T* xnormals, const T* xareas, void* stream) {
+  if (n_local <= 0 || n_local + n_ghost > 0x7FFFFF00LL) return cudaErrorNotSupported;
+  t8b200_plan* P = new t8b200_plan();
+  struct Guard { t8b200_plan* p; ~Guard() { if (p) t8b200_plan_destroy(p); } } guard{P};
+  P->is_f64 = sizeof(T) == 8; P->ghost_tail = ghost_tail ? 1 : 0;
+  MeshFaces<T> src{nf, nb, nx, nbr, normals, areas, n_ghost > 0 ? ranks : nullptr, indices, xnbr, xnormals, xareas};
+  const int rc = generic_device_plan<T>(P, n_local, n_ghost > 0, src, (cudaStream_t)stream);
+  if (rc) return rc;
+  guard.p = nullptr;
+  *out    = P;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -357,12 +718,26 @@ int t8b200_plan_create_device(t8b200_plan** out, int is_f64, int ghost_tail, int
                               const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
                               const void* xnormals, const void* xareas, void* stream) {
   const int flags = ghost_tail ? 2 : 0;
-  if (is_f64)
-    return device_plan_impl<double>(out, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
-                                    (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
-                                    (const double*)xareas, stream);
-  return device_plan_impl<float>(out, flags, n_local, n_ghost, nf, nb, nbr, (const float*)normals, (const float*)areas,
-                                 ranks, indices, nx, xnbr, (const float*)xnormals, (const float*)xareas, stream);
+  const bool generic_only = getenv("T8B200_DEVICE_PLAN") && getenv("T8B200_DEVICE_PLAN")[0] == 'g';   // tests
+  int rc = cudaErrorNotSupported;
+  if (!generic_only)
+    rc = is_f64 ? device_plan_impl<double>(out, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
+                                           (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
+                                           (const double*)xareas, stream)
+                : device_plan_impl<float>(out, flags, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
+                                          (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
+                                          (const float*)xareas, stream);
+  if (rc != cudaErrorNotSupported) return rc;
+  // not a structured-only mesh: the generic builder (one program per block of 256 elements)
+  if (!out || n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0) return cudaErrorInvalidValue;
+  if ((nf + nb > 0 && (!nbr || !normals || !areas)) || (nx > 0 && (!xnbr || !xnormals || !xareas))) return cudaErrorInvalidValue;
+  if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
+  return is_f64 ? generic_mesh_plan<double>(out, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
+                                            (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
+                                            (const double*)xareas, stream)
+                : generic_mesh_plan<float>(out, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
+                                           (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
+                                           (const float*)xareas, stream);
 }
 
 int t8b200_subgrid_plan_create_device(t8b200_subgrid_plan** out, int is_f64, int dim, int ghost_tail, int64_t n_local,
@@ -386,6 +761,42 @@ int t8b200_subgrid_plan_create_device(t8b200_subgrid_plan** out, int is_f64, int
   if (rc) return rc;
   *out = t8b_wrap_subgrid_plan(P, 3);
   return 0;
+}
+
+// test access to every DEVICE array of a plan, numbered as t8b200_plan_host_array does (0 hdr ... 19 blist), as raw bytes in
+// the device element type (float plans: area table / normals as float); returns the byte count, -1 on error
+int64_t t8b200_plan_device_bytes(const t8b200_plan* P, int which, void* host_out, int64_t capacity_bytes) {
+  if (!P || P->host_only) return -1;
+  const int64_t nc = P->n_chunks, ts = P->is_f64 ? 8 : 4;
+  const void*   src = nullptr;
+  int64_t       n   = 0;
+  switch (which) {
+    case 0: src = P->hdr; n = 32 * nc; break;
+    case 1: src = P->halo_elem; n = 4 * nc * P->hs; break;
+    case 2: src = P->halo_rank; n = 4 * nc * P->hs; break;
+    case 3: src = P->face_lr; n = 4 * nc * P->fs; break;
+    case 4: src = P->face_ai; n = nc * P->fs; break;
+    case 5: src = P->ell; n = 2 * 8 * std::max<int64_t>(P->n_local, 1); break;
+    case 6: src = P->ovf_off; n = 2 * P->n_ovf_off; break;
+    case 7: src = P->ovf_ent; n = 2 * P->n_ovf_ent; break;
+    case 8: src = P->area_tab; n = ts * P->n_areas; break;
+    case 9: src = P->fnx; n = ts * nc * P->fs; break;
+    case 10: src = P->fny; n = ts * nc * P->fs; break;
+    case 11: src = P->fnz; n = ts * nc * P->fs; break;
+    case 12: src = P->farea; n = ts * nc * P->fs; break;
+    case 13: src = P->s_rec; n = 16 * (int64_t)P->n_struct; break;
+    case 14: src = P->s_halo; n = 1024 * (int64_t)P->n_struct; break;
+    case 15: src = P->s_hrank; n = 1024 * (int64_t)P->n_struct; break;
+    case 16: src = P->g_list; n = 4 * (int64_t)P->n_generic; break;
+    case 17: src = P->pull_rank; n = 4 * P->n_pull; break;
+    case 18: src = P->pull_idx; n = 4 * P->n_pull; break;
+    case 19: src = P->blist; n = 4 * (int64_t)P->nb_struct; break;
+    default: return -1;
+  }
+  if (!src) return 0;
+  if (host_out && n > 0 && cudaMemcpy(host_out, src, (size_t)std::min(n, capacity_bytes), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return n;
 }
 
 // test access: copies one of the structured / ghost-tail DEVICE arrays of a plan to the host (which: 13 s_rec, 14 s_halo,

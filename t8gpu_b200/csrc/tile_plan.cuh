@@ -85,6 +85,7 @@ struct t8b200_plan {
   uint4*    ell      = nullptr;  // n_chunks * EC
   uint16_t* ovf_off  = nullptr;  // (EC + 1) per chunk that has overflow entries
   uint16_t* ovf_ent  = nullptr;
+  int64_t   n_ovf_off = 0, n_ovf_ent = 0;
   // structured chunks (box_layout.cuh, structured.cu): 8 x 8 x 4 boxes with 256 single same-size neighbours
   int      box_layout = -1;     // layout the builder tested the chunks against: 0 MortonBox, 1 SubgridBox, -1 none
   int      n_struct = 0, n_generic = 0;
@@ -727,6 +728,8 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
   }
   P->n_halo     = n_halo;
   P->n_records  = n_rec;
+  P->n_ovf_off  = (int64_t)n_ovf_off;
+  P->n_ovf_ent  = (int64_t)n_ovf_ent;
   P->hs = HS;
   P->fs = FS;
   P->max_halo   = max_halo;

@@ -95,23 +95,155 @@ def test_partitioned_brick_plan_equals_host_builder(cuda, brick, P, ghost_tail):
             assert plan.device_array(13).reshape(-1, 4)[:, 3].sum() > 0      # partition-boundary chunks are flagged
 
 
-def test_meshes_outside_the_device_builder_are_reported(cuda):
-    """Hanging faces, walls, general normals: cudaErrorNotSupported -> None, the caller falls back to the host builder."""
+HOST_DT = {1: np.uint8, 2: np.uint16, 4: np.int32, 8: np.float64}
+
+
+def host_all(conn_host, dtype, ghost_tail):
+    """All 20 arrays of the HOST builder + plan info (floating-point arrays in the plan's precision)."""
     import t8gpu_b200 as tb
-    f = oracle.Forest(3, 4)
+    lib = tb.lib()
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+
+    def arr(k, dt):
+        v = conn_host.get(k)
+        return None if v is None or len(v) == 0 else np.ascontiguousarray(v, dtype=dt)
+
+    def p(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    keep = [arr("face_neighbors", np.int32), arr("face_normals", npdt), arr("face_areas", npdt), arr("ranks", np.int32),
+            arr("indices", np.int32), arr("x_face_neighbors", np.int32), arr("x_face_normals", npdt),
+            arr("x_face_areas", npdt)]
+    ng = int(conn_host.get("n_ghost", 0))
+    h = C.c_void_p()
+    fn = lib.t8b200_plan_create_ghost_tail_host if ghost_tail else lib.t8b200_plan_create_host
+    assert fn(C.byref(h), int(dtype == torch.float64), C.c_int64(int(conn_host["n_local"])), C.c_int64(ng),
+              int(conn_host["n_faces"]), int(conn_host["n_bfaces"]), p(keep[0]), p(keep[1]), p(keep[2]),
+              p(keep[3]) if ng else None, p(keep[4]) if ng else None, int(conn_host.get("n_xfaces", 0)), p(keep[5]),
+              p(keep[6]), p(keep[7])) == 0
+    out = {}
+    for which in range(20):
+        data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
+        assert lib.t8b200_plan_host_array(h, which, C.byref(data), C.byref(count), C.byref(eb)) == 0
+        n = count.value
+        a = (np.frombuffer((C.c_char * (n * eb.value)).from_address(data.value), dtype=HOST_DT[eb.value]).copy() if n
+             else np.zeros(0, HOST_DT[eb.value]))
+        out[which] = a.astype(npdt) if which in (8, 9, 10, 11, 12) else a
+    info = (C.c_int64 * 8)()
+    assert lib.t8b200_plan_info(h, info) == 0
+    out["info"] = [info[i] for i in (0, 1, 2, 3, 5, 6, 7)]          # without the device byte count
+    lib.t8b200_plan_destroy(h)
+    return out
+
+
+def device_all(plan, dtype):
+    import t8gpu_b200 as tb
+    lib = tb.lib()
+    lib.t8b200_plan_device_bytes.restype = C.c_int64
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    dts = {0: np.int32, 1: np.int32, 2: np.int32, 3: np.int32, 4: np.uint8, 5: np.uint16, 6: np.uint16, 7: np.uint16}
+    out = {}
+    for which in range(20):
+        dt = npdt if which in (8, 9, 10, 11, 12) else dts.get(which, np.int32)
+        n = lib.t8b200_plan_device_bytes(plan._h, which, None, C.c_int64(0))
+        assert n >= 0, which
+        a = np.zeros(n // np.dtype(dt).itemsize, dt)
+        if n:
+            assert lib.t8b200_plan_device_bytes(plan._h, which, a.ctypes.data_as(C.c_void_p), C.c_int64(n)) == n
+        out[which] = a
+    i = plan.info
+    out["info"] = [i["n_chunks"], i["max_halo"], i["max_faces"], i["smem_bytes"], i["face_records"], i["halo_entries"],
+                   i["chunk"]]
+    return out
+
+
+def assert_same_plan(conn_host, dtype, ghost_tail, cuda, tag=""):
+    import t8gpu_b200 as tb
+    H = host_all(conn_host, dtype, ghost_tail)
+    plan = tb.Plan.from_device(tb.conn_to_device(conn_host, dtype, cuda), dtype, ghost_tail=ghost_tail)
+    assert plan is not None, tag
+    D = device_all(plan, dtype)
+    assert D["info"] == H["info"], (tag, D["info"], H["info"])
+    for which in range(20):
+        assert D[which].size == H[which].size and np.array_equal(D[which].view(H[which].dtype), H[which]), (tag, which)
+    return plan, H
+
+
+def _amr_forest(level=3):
+    f = oracle.Forest(3, level)
+    for width in (0.2, 0.1):
+        lv, cent, vol, _ = f.elements()
+        f = f.adapt(np.where(np.abs(cent[:, 2] - 0.5) < width, 20.0, 0.0), 10.0, 1, level + 2)
+    return f
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_generic_device_builder_equals_host_builder(cuda, dtype, monkeypatch):
+    """Hanging faces (overflow entries), walls, quads, boxes that are their own neighbours, general normals: the plan
+    built by one CUDA thread per block (csrc/plan_block.cuh) equals the host builder's in all 20 arrays."""
+    from util import hybrid_mesh
+    monkeypatch.setenv("T8B200_DEVICE_PLAN", "generic")          # not the three-kernel builder of structured-only meshes
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    amr = _amr_forest()
+    plan, H = assert_same_plan(amr.connectivity(dtype=npdt), dtype, False, cuda, "amr")
+    assert H[7].size > 0                                          # overflow CSR in use
+    assert_same_plan(oracle.Forest(3, 4, periodic=False).connectivity(dtype=npdt), dtype, False, cuda, "walls")
+    assert_same_plan(oracle.Forest(3, 3).connectivity(dtype=npdt), dtype, False, cuda, "level 3")
+    assert_same_plan(oracle.Forest(2, 5).connectivity(dtype=npdt), dtype, False, cuda, "quads")
+    for per in (True, False):
+        _, H = assert_same_plan(hybrid_mesh(12, per, npdt, seed=3, shuffle=not per)[0], dtype, False, cuda, "hybrid")
+        assert H[9].size > 0                                      # general geometry arrays
+    # the uniform forest through the generic builder: every chunk structured
+    _, H = assert_same_plan(oracle.Forest(3, 4).connectivity(dtype=npdt), dtype, False, cuda, "uniform")
+    assert H[13].size == 4 * 16 and H[16].size == 0
+    monkeypatch.setenv("T8B200_TEST_MAX_HALO", "40")              # blocks split into 8+ chunks each
+    _, H = assert_same_plan(oracle.Forest(3, 4).connectivity(dtype=npdt), dtype, False, cuda, "split")
+    assert H["info"][0] > 16
+
+
+@pytest.mark.parametrize("ghost_tail", [False, True])
+@pytest.mark.parametrize("P", [2, 3])
+def test_generic_device_builder_multi_rank(cuda, P, ghost_tail, monkeypatch):
+    """Partitioned adaptive forest: owner ranks, partition-boundary flags and launch order, ghost-tail redirection and
+    pull lists as the host builder's."""
+    monkeypatch.setenv("T8B200_DEVICE_PLAN", "generic")
+    amr = _amr_forest()
+    for dtype, npdt in ((torch.float64, np.float64), (torch.float32, np.float32)):
+        for r in range(P):
+            plan, H = assert_same_plan(amr.connectivity(P, r, dtype=npdt), dtype, ghost_tail, cuda, "P%d r%d" % (P, r))
+            if ghost_tail:
+                assert plan.n_tail == H[17].size > 0
+    # a partition of a uniform forest whose boxes are not all structured (level 3) and one that is (level 4, ragged cut)
+    for level in (3, 4):
+        f = oracle.Forest(3, level)
+        for r in range(P):
+            assert_same_plan(f.connectivity(P, r, dtype=np.float64), torch.float64, ghost_tail, cuda, "uniform")
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_generic_device_plan_steps_like_the_host_plan(cuda, dtype):
+    """leaves -> device connectivity -> device plan -> 3 steps: bitwise the states of the host-built plan."""
+    import t8gpu_b200 as tb
+    from util import perturbed_kh
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    f = _amr_forest()
     lv, cent, vol, _ = f.elements()
-    amr = f.adapt(np.where(np.abs(cent[:, 2] - 0.5) < 0.2, 20.0, 0.0), 10.0, 1, 5)
-    walls = oracle.Forest(3, 4, periodic=False)
-    small = tb.conn_to_device(oracle.Forest(3, 3).connectivity(dtype=np.float64), torch.float64, cuda)
-    assert tb.Plan.from_device(small, torch.float64) is None     # 8 elements across: a box is its own neighbour
-    for forest in (amr, walls):
-        conn = tb.conn_to_device(forest.connectivity(dtype=np.float64), torch.float64, cuda)
-        assert tb.Plan.from_device(conn, torch.float64) is None
-    conn = tb.conn_to_device(f.connectivity(dtype=np.float64), torch.float64, cuda)
-    assert tb.Plan.from_device(conn, torch.float64) is not None
-    q, _ = np.linalg.qr(np.random.default_rng(7).normal(size=(3, 3)))
-    conn["face_normals"] = (conn["face_normals"].view(-1, 3) @ torch.as_tensor(q.T).to(cuda)).reshape(-1).contiguous()
-    assert tb.Plan.from_device(conn, torch.float64) is None
+    conn = tb.forest_connectivity(3, True, tb.morton_keys(3, lv, cent), lv, dtype, device=cuda)
+    plan = tb.Plan.from_device(conn, dtype)
+    assert plan is not None and plan.info["built_on"] == "device"
+    host = tb.conn_to_host(conn)
+    a = tb.EulerSolver(host, conn["volumes"], dtype, device=cuda)
+    b = tb.EulerSolver(host, conn["volumes"], dtype, device=cuda, plan=plan)
+    u0, _ = perturbed_kh(f, npdt, seed=5)
+    a.set_state(u0)
+    b.set_state(u0)
+    for _ in range(3):
+        a.iterate(1e-3)
+        b.iterate(1e-3)
+    assert torch.isfinite(a.state()).all() and torch.equal(a.state(), b.state())
+    ca = tb.gradient_criteria(a.plan, a.state()[0], a.volume())
+    cb = tb.gradient_criteria(plan, b.state()[0], b.volume())
+    assert torch.equal(ca, cb)
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
