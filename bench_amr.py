@@ -67,9 +67,9 @@ class RankMesh:
             self.t_conn, self.conn_on = time.time() - t0, "device"
             self.n = int(conn_dev["n_local"])
             t0 = time.time()
-            if lv.min() == lv.max():                      # uniform: every chunk is structured, plan on the device too
-                self.plan = tb.Plan.from_device(conn_dev, dtype, ghost_tail=world > 1)
-            if self.plan is None:
+            # tile plan on the device as well (structured-only meshes: three kernels; else one thread per block)
+            self.plan = tb.Plan.from_device(conn_dev, dtype, ghost_tail=world > 1)
+            if self.plan is None:                         # a rank without elements
                 self.plan = tb.Plan(tb.conn_to_host(conn_dev), dtype, ghost_tail=world > 1)
         self.nc = self.n * self.S                          # entries of a variable row (cells)
         torch.cuda.synchronize()

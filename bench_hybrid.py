@@ -38,7 +38,11 @@ class HybridRank:
         self.t_mesh = time.time() - t0
         self.n = int(conn["n_local"])
         t0 = time.time()
-        self.plan = tb.Plan(conn, dtype, ghost_tail=world > 1)
+        # the mesh generator is host code (stand-in for a t8code cmesh): upload its arrays once, plan on the device
+        self.plan = tb.Plan.from_device(tb.conn_to_device(conn, dtype, device), dtype, ghost_tail=world > 1)
+        if self.plan is None:
+            self.plan = tb.Plan(conn, dtype, ghost_tail=world > 1)
+        torch.cuda.synchronize()
         self.t_plan = time.time() - t0
         self.conn = conn
         self.cap = pad32(self.n + self.plan.n_tail)

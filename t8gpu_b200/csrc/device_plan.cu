@@ -377,7 +377,7 @@ __device__ inline unsigned long long area_bits(T a) {
 template <typename T, class Src>
 __global__ void __launch_bounds__(256) classify_kernel(Src src, int64_t ntot, int64_t n_local, int multi,
                                                        unsigned long long* area_set, int* flags,
-                                                       unsigned long long* blk_cnt) {
+                                                       unsigned long long* blk_cnt, unsigned long long* keys) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (f == 0 && n_local > 0 && multi) { int32_t rk = 0, ix = 0; src.owner(0, rk, ix); flags[G_MY_RANK] = rk; }
   if (f >= ntot) return;
@@ -400,21 +400,18 @@ __global__ void __launch_bounds__(256) classify_kernel(Src src, int64_t ntot, in
   int32_t l, r;
   src.endpoints(f, l, r);
   const int64_t cl = l < n_local ? l / pb::EC : -1, cr = (r >= 0 && r < n_local) ? r / pb::EC : -1;
+  if (keys) {   // block << 40 | face: sorted, the candidates of every block in ascending face order; ~0 = none
+    keys[2 * f]     = cl >= 0 ? ((unsigned long long)cl << 40) | (unsigned long long)f : ~0ull;
+    keys[2 * f + 1] = (cr >= 0 && cr != cl) ? ((unsigned long long)cr << 40) | (unsigned long long)f : ~0ull;
+  }
   if (cl < 0 && cr < 0) { flags[G_BAD_FACE] = 1; return; }
   if (cl >= 0) atomicAdd(blk_cnt + cl, 1ull);
   if (cr >= 0 && cr != cl) atomicAdd(blk_cnt + cr, 1ull);
 }
 
-template <class Src>
-__global__ void __launch_bounds__(256) bucket_kernel(Src src, int64_t ntot, int64_t n_local, const unsigned long long* face_off,
-                                                     unsigned long long* cursor, int64_t* rec) {
-  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= ntot) return;
-  int32_t l, r;
-  src.endpoints(f, l, r);
-  const int64_t cl = l < n_local ? l / pb::EC : -1, cr = (r >= 0 && r < n_local) ? r / pb::EC : -1;
-  if (cl >= 0) rec[face_off[cl] + atomicAdd(cursor + cl, 1ull)] = f;
-  if (cr >= 0 && cr != cl) rec[face_off[cr] + atomicAdd(cursor + cr, 1ull)] = f;
+__global__ void __launch_bounds__(256) mask_keys_kernel(int64_t n, unsigned long long* keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keys[i] != ~0ull) keys[i] &= (1ull << 40) - 1;
 }
 
 template <typename T, class Src, bool FILL>
@@ -431,6 +428,322 @@ __global__ void __launch_bounds__(64) block_pass_kernel(Src src, pb::Params<T> p
                                   FILL ? (int64_t)bases[2 * (nblocks + 1) + blk] : 0, out);
   if (c.rc || (FILL && c.chunks != cn[blk].chunks)) flags[G_PROGRAM_ERROR] = 1;
   if (!FILL) cn[blk] = c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The block program of plan_block.cuh executed by one WARP with its workspace in shared memory (the default; the
+// thread-per-block kernel above stays selectable with T8B200_DEVICE_PLAN=serial and is the form the host emulation
+// runs).  Step by step the same program, each loop in its data-parallel form:
+//   faces of the range        ballot + prefix compaction over the block's (sorted) candidate list
+//   distinct outside elements atomicCAS inserts into the open-addressing table; sorted by counting ranks
+//   records in kernel order   bitonic sort of the (group, left slot, right slot, position) keys
+//   element -> face table     bitonic sort of the (slot, entry) pairs; rank inside the slot's run = entry position
+//   structured test           atomicCAS fills of the lower / upper neighbour tables, then one lane per element
+// ---------------------------------------------------------------------------------------------------------------------
+namespace wp {
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr unsigned long long FACE_MASK = (1ull << 40) - 1;   // candidate key = block << 40 | face id
+
+struct Smem {
+  unsigned long long key[pb::MF];
+  int32_t            ends[2 * pb::MF];   // endpoints; then the (slot, entry) pairs; then the neighbour tables
+  int32_t            pos[pb::MF];
+  int32_t            ht_key[pb::HT];
+  uint16_t           ht_val[pb::HT];
+  int32_t            halo[pb::MS - pb::EC], halo_sorted[pb::MS - pb::EC];
+  int32_t            el_cnt[pb::EC], el_off[pb::EC], ovf_loc[pb::EC];
+  int                nh, seg[4], flag;
+};
+
+template <typename U>
+__device__ inline void warp_bitonic(U* a, int n, int lane) {   // n: power of two >= 32
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n; i += 32) {
+        const int p = i ^ j;
+        if (p > i) {
+          const U x = a[i], y = a[p];
+          if (((i & k) == 0) == (x > y)) { a[i] = y; a[p] = x; }
+        }
+      }
+      __syncwarp();
+    }
+}
+
+template <typename T, class Src, bool FILL>
+__device__ int chunk_warp(const Src& src, const pb::Params<T>& pr, Smem& sm, const unsigned long long* cand, int64_t ncand,
+                          bool whole, int64_t b0, int64_t b1, pb::Counts& cn, int64_t c, int64_t oo_at, int64_t oe_at,
+                          const pb::Out<T>& out) {
+  constexpr int EC = pb::EC, MS = pb::MS, MF = pb::MF, HT = pb::HT, ELL = pb::ELL, MAXH = pb::MS - pb::EC;
+  const int lane = threadIdx.x & 31;
+  // the faces of the range, ascending in the face id
+  int nfc = 0;
+  for (int64_t q0 = 0; q0 < ncand; q0 += 32) {
+    const int64_t q = q0 + lane;
+    bool          keep = false;
+    int32_t       l = 0, r = 0;
+    if (q < ncand) {
+      src.endpoints((int64_t)(cand[q] & FACE_MASK), l, r);
+      keep = whole || (l >= b0 && l < b1) || (r >= b0 && r < b1);
+    }
+    const unsigned m  = __ballot_sync(FULL, keep);
+    const int      at = nfc + __popc(m & ((1u << lane) - 1u));
+    if (keep && at < MF) { sm.pos[at] = (int32_t)q; sm.ends[2 * at] = l; sm.ends[2 * at + 1] = r; }
+    nfc += __popc(m);
+    if (nfc > pr.max_faces_allowed) return 1;
+  }
+  // distinct elements outside the range
+  for (int i = lane; i < HT; i += 32) sm.ht_key[i] = -1;
+  if (lane == 0) sm.nh = 0;
+  __syncwarp();
+  for (int j = lane; j < 2 * nfc; j += 32) {
+    const int32_t id = sm.ends[j];
+    if (id < 0 || (id >= b0 && id < b1)) continue;
+    unsigned k = pb::halo_hash(id);
+    while (*(volatile int*)&sm.nh <= MAXH) {   // more than MAXH distinct: the chunk does not fit, stop filling the table
+      const int32_t old = atomicCAS(&sm.ht_key[k], -1, id);
+      if (old == -1) {
+        const int s = atomicAdd(&sm.nh, 1);
+        if (s < MAXH) sm.halo[s] = id;
+        break;
+      }
+      if (old == id) break;
+      k = (k + 1) & (HT - 1);
+    }
+  }
+  __syncwarp();
+  const int nh = sm.nh;
+  if (nh > pr.max_halo_allowed) return 1;
+  // entries per own slot, their exclusive prefix sums (all entries / entries beyond ELL)
+  for (int i = lane; i < EC; i += 32) sm.el_cnt[i] = 0;
+  __syncwarp();
+  for (int j = lane; j < 2 * nfc; j += 32) {
+    const int32_t id = sm.ends[j];
+    if (id >= b0 && id < b1) atomicAdd(&sm.el_cnt[id - b0], 1);
+  }
+  __syncwarp();
+  int s1 = 0, s2 = 0;
+  for (int i = 0; i < 8; i++) { const int v = sm.el_cnt[lane * 8 + i]; s1 += v; s2 += v > ELL ? v - ELL : 0; }
+  int p1 = s1, p2 = s2;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t1 = __shfl_up_sync(FULL, p1, d), t2 = __shfl_up_sync(FULL, p2, d);
+    if (lane >= d) { p1 += t1; p2 += t2; }
+  }
+  const int n_pairs = __shfl_sync(FULL, p1, 31), n_ovf = __shfl_sync(FULL, p2, 31);
+  {
+    int e1 = p1 - s1, e2 = p2 - s2;
+    for (int i = 0; i < 8; i++) {
+      const int v = sm.el_cnt[lane * 8 + i];
+      sm.el_off[lane * 8 + i] = e1; sm.ovf_loc[lane * 8 + i] = e2;
+      e1 += v; e2 += v > ELL ? v - ELL : 0;
+    }
+  }
+  __syncwarp();
+  if (!FILL) {
+    cn.chunks++;
+    cn.max_halo  = nh > cn.max_halo ? nh : cn.max_halo;
+    cn.max_faces = nfc > cn.max_faces ? nfc : cn.max_faces;
+    cn.sum_halo += nh;
+    cn.sum_faces += nfc;
+    if (n_ovf) { cn.ovf_off += EC + 1; cn.ovf_ent += n_ovf; }
+    return 0;
+  }
+
+  int32_t* H = out.hdr + 8 * c;
+  // halo: sorted by counting ranks (ids are distinct), owners, slot of every id
+  for (int i = lane; i < nh; i += 32) {
+    const int32_t id = sm.halo[i];
+    int           rk = 0;
+    for (int j = 0; j < nh; j++) rk += sm.halo[j] < id;
+    sm.halo_sorted[rk] = id;
+  }
+  __syncwarp();
+  int bad = 0;
+  for (int h = lane; h < nh; h += 32) {
+    const int32_t id = sm.halo_sorted[h];
+    int32_t       rk = 0, ix = id;
+    if (pr.multi) src.owner(id, rk, ix);
+    else if (id >= pr.n_local) bad = 1;
+    out.halo_elem[c * out.HS + h] = ix;
+    if (pr.multi) out.halo_rank[c * out.HS + h] = rk;
+    unsigned k = pb::halo_hash(id);
+    while (sm.ht_key[k] != id) k = (k + 1) & (HT - 1);
+    sm.ht_val[k] = (uint16_t)(EC + h);
+  }
+  if (__any_sync(FULL, bad)) return -1;
+  if (lane < 4) sm.seg[lane] = 0;
+  __syncwarp();
+  auto slot_of = [&](int32_t id) -> int {
+    if (id >= b0 && id < b1) return (int)(id - b0);
+    unsigned k = pb::halo_hash(id);
+    while (sm.ht_key[k] != id) k = (k + 1) & (HT - 1);
+    return sm.ht_val[k];
+  };
+  // records in kernel order
+  int n2 = 32;
+  while (n2 < nfc) n2 <<= 1;
+  for (int j = lane; j < n2; j += 32) {
+    if (j >= nfc) { sm.key[j] = ~0ull; continue; }
+    const int32_t l = sm.ends[2 * j], r = sm.ends[2 * j + 1];
+    int           sl = slot_of(l), sr = r < 0 ? 0xFFFF : slot_of(r), grp = 0;
+    if (pr.cmp) {
+      T nrm[3], a;
+      src.geometry((int64_t)(cand[sm.pos[j]] & FACE_MASK), nrm, a);
+      const int code = pb::axis_code_hd(nrm);
+      grp = r < 0 ? 3 : code >> 1;
+      if (r < 0) sr = 0xFFF8 | code;
+      else if (!(code & 1)) { const int t = sl; sl = sr; sr = t; }
+      atomicAdd(&sm.seg[grp], 1);
+    }
+    sm.key[j] = ((unsigned long long)(grp * MS + sl) << 32) | ((unsigned long long)sr << 16) | (unsigned long long)j;
+  }
+  __syncwarp();
+  warp_bitonic(sm.key, n2, lane);
+  if (lane == 0) {
+    H[0] = (int32_t)b0;
+    H[1] = (int32_t)(b1 - b0);
+    H[2] = nh | (nfc << 16);
+    H[3] = sm.seg[0] | ((sm.seg[0] + sm.seg[1]) << 16);
+    H[4] = sm.seg[0] + sm.seg[1] + sm.seg[2];
+    H[5] = n_ovf ? (int32_t)oo_at : -1;
+    H[6] = n_ovf ? (int32_t)oe_at : 0;
+  }
+  if (n_ovf) {
+    for (int i = lane; i < EC; i += 32) out.ovf_off[oo_at + i] = (uint16_t)sm.ovf_loc[i];
+    if (lane == 0) out.ovf_off[oo_at + EC] = (uint16_t)n_ovf;
+  }
+  // emission: records, geometry, (slot, entry) pairs
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(sm.ends);
+  int       n2p   = 64;
+  while (n2p < 2 * nfc) n2p <<= 1;
+  for (int i = 2 * nfc + lane; i < n2p; i += 32) pairs[i] = 0xFFFFFFFFu;
+  auto area_index = [&](T a) {
+    int lo = 0, hi = pr.n_areas - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (pr.area_tab[mid] < a) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  int area0 = -1;
+  if (pr.cmp && nfc > 0) {
+    T nrm[3], a;
+    src.geometry((int64_t)(cand[sm.pos[(int)(sm.key[0] & 0xFFFFu)]] & FACE_MASK), nrm, a);
+    area0 = area_index(a);
+  }
+  int mismatch = 0;
+  for (int jj = lane; jj < nfc; jj += 32) {
+    const unsigned long long kk = sm.key[jj];
+    const int j = (int)(kk & 0xFFFFu), sr = (int)((kk >> 16) & 0xFFFFu), gs = (int)(kk >> 32), grp = gs / MS, sl = gs % MS;
+    T         nrm[3], a;
+    src.geometry((int64_t)(cand[sm.pos[j]] & FACE_MASK), nrm, a);
+    if (pr.cmp) {
+      const int ai = area_index(a);
+      out.face_ai[c * out.FS + jj] = (uint8_t)ai;
+      mismatch |= ai != area0;
+    } else {
+      out.fnx[c * out.FS + jj] = nrm[0]; out.fny[c * out.FS + jj] = nrm[1]; out.fnz[c * out.FS + jj] = nrm[2];
+      out.far[c * out.FS + jj] = a;
+    }
+    const uint32_t axis_bits = (pr.cmp && grp < 3) ? (uint32_t)grp << 14 : 0u;
+    out.face_lr[c * out.FS + jj] = (uint32_t)sl | axis_bits | ((uint32_t)sr << 16);
+    pairs[2 * jj]     = sl < EC ? ((uint32_t)sl << 16) | (uint32_t)(jj << 1) : 0xFFFFFFFFu;
+    pairs[2 * jj + 1] = sr < EC ? ((uint32_t)sr << 16) | (uint32_t)((jj << 1) | 1) : 0xFFFFFFFFu;
+  }
+  const bool uniform = pr.cmp && !__any_sync(FULL, mismatch);
+  __syncwarp();
+  warp_bitonic(pairs, n2p, lane);
+  for (int i = lane; i < n_pairs; i += 32) {
+    const uint32_t p = pairs[i];
+    const int      slot = (int)(p >> 16), k = i - sm.el_off[slot];
+    const uint16_t en = (uint16_t)(p & 0xFFFFu);
+    if (k < ELL) out.ell[(b0 + slot) * ELL + k] = en;
+    else out.ovf_ent[oe_at + sm.ovf_loc[slot] + (k - ELL)] = en;
+  }
+  if (lane == 0) H[7] = (uniform && area0 >= 0) ? area0 : -1;
+  __syncwarp();
+  // structured?
+  int structured = 0;
+  if (pr.box_layout >= 0 && pr.cmp && uniform && area0 >= 0 && b1 - b0 == 256 && (b0 & 255) == 0 && sm.seg[3] == 0 &&
+      nh == 256 && nfc == BoxCommon::NFLUX) {
+    int32_t *lo = sm.ends, *hi = sm.ends + 3 * EC;
+    for (int i = lane; i < 6 * EC; i += 32) sm.ends[i] = -1;
+    if (lane == 0) sm.flag = 1;
+    __syncwarp();
+    for (int jj = lane; jj < nfc; jj += 32) {
+      const unsigned long long kk = sm.key[jj];
+      const int sr = (int)((kk >> 16) & 0xFFFFu), gs = (int)(kk >> 32), d = gs / MS, sl = gs % MS;
+      if (sl < 256 && atomicCAS(&hi[d * EC + sl], -1, sr) != -1) sm.flag = 0;
+      if (sr < 256 && atomicCAS(&lo[d * EC + sr], -1, sl) != -1) sm.flag = 0;
+    }
+    __syncwarp();
+    auto test = [&](auto tag) {
+      using L = decltype(tag);
+      for (int t = lane; t < 256; t += 32)
+        for (int d = 0; d < 3; d++) {
+          const int l = lo[d * EC + t], u = hi[d * EC + t];
+          if ((L::at_lower(t, d) ? l < 256 : l != L::lower_own(t, d)) || (L::at_upper(t, d) ? u < 256 : u != L::upper_own(t, d))) {
+            sm.flag = 0;
+            continue;
+          }
+          if (L::at_lower(t, d)) {
+            const int h = pr.thread_of_slot[L::halo_slot(d, 0, L::compact(t, d))];
+            out.s_halo[c * 256 + h] = out.halo_elem[c * out.HS + (l - 256)];
+            if (pr.multi) out.s_hrank[c * 256 + h] = out.halo_rank[c * out.HS + (l - 256)];
+          }
+          if (L::at_upper(t, d)) {
+            const int h = pr.thread_of_slot[L::halo_slot(d, 1, L::compact(t, d))];
+            out.s_halo[c * 256 + h] = out.halo_elem[c * out.HS + (u - 256)];
+            if (pr.multi) out.s_hrank[c * 256 + h] = out.halo_rank[c * out.HS + (u - 256)];
+          }
+        }
+    };
+    if (sm.flag) { if (pr.box_layout == 1) test(SubgridBox{}); else test(MortonBox{}); }
+    __syncwarp();
+    structured = sm.flag;
+  }
+  if (lane == 0) out.s_flag[c] = (uint8_t)structured;
+  __syncwarp();
+  cn.chunks++;
+  if (n_ovf) { cn.ovf_off += EC + 1; cn.ovf_ent += n_ovf; }
+  return 0;
+}
+}  // namespace wp
+
+// CTA = one warp; walks the blocks blockIdx.x, blockIdx.x + gridDim.x, ...
+template <typename T, class Src, bool FILL>
+__global__ void __launch_bounds__(32) block_warp_kernel(Src src, pb::Params<T> pr, int64_t nblocks,
+                                                        const unsigned long long* face_off, const unsigned long long* keys,
+                                                        pb::Counts* cn, const unsigned long long* bases, pb::Out<T> out,
+                                                        int* flags) {
+  __shared__ wp::Smem sm;
+  struct Range { int64_t b0, b1; };
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    Range         todo[40];
+    int           sp = 0;
+    const int64_t blk_b0 = blk * pb::EC, blk_b1 = blk * pb::EC + pb::EC < pr.n_local ? blk * pb::EC + pb::EC : pr.n_local;
+    const unsigned long long* cand  = keys + face_off[blk];
+    const int64_t             ncand = (int64_t)(face_off[blk + 1] - face_off[blk]);
+    const int64_t cb = FILL ? (int64_t)bases[blk] : 0, ob = FILL ? (int64_t)bases[(nblocks + 1) + blk] : 0,
+                  eb = FILL ? (int64_t)bases[2 * (nblocks + 1) + blk] : 0;
+    pb::Counts c{0, 0, 0, 0, 0, 0, 0, 0};
+    todo[sp++] = {blk_b0, blk_b1};
+    while (sp > 0) {
+      const Range rg = todo[--sp];
+      const int   rc = wp::chunk_warp<T, Src, FILL>(src, pr, sm, cand, ncand, rg.b1 - rg.b0 == blk_b1 - blk_b0, rg.b0, rg.b1, c,
+                                                    cb + c.chunks, ob + c.ovf_off, eb + c.ovf_ent, out);
+      __syncwarp();
+      if (rc == 1 && rg.b1 - rg.b0 > 1) {
+        const int64_t mid = (rg.b0 + rg.b1) / 2;
+        todo[sp++] = {mid, rg.b1};
+        todo[sp++] = {rg.b0, mid};
+        continue;
+      }
+      if (rc) { c.rc = 1; break; }
+    }
+    if (threadIdx.x == 0) {
+      if (c.rc || (FILL && c.chunks != cn[blk].chunks)) flags[G_PROGRAM_ERROR] = 1;
+      if (!FILL) cn[blk] = c;
+    }
+    __syncwarp();
+  }
 }
 
 // counts of the blocks -> three arrays for the scans (chunks, overflow offsets, overflow entries) + totals
@@ -479,6 +792,8 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   static_assert(pb::EC == EC && pb::MS == MS && pb::MF == MF && pb::ELL == ELL, "plan_block.cuh constants");
   const int64_t nblocks = (n_local + EC - 1) / EC, ntot = src.num_faces();
   auto          pol     = thrust::cuda::par.on(st);
+  // T8B200_DEVICE_PLAN=serial: one THREAD per block runs pb::block_program (the form the host emulation checks)
+  const bool serial = getenv("T8B200_DEVICE_PLAN") && getenv("T8B200_DEVICE_PLAN")[0] == 's';
   P->n_local = n_local; P->multi = multi ? 1 : 0;
   auto dev_alloc = [&](auto** p, size_t bytes, int fill) {
     cudaError_t e = cudaMalloc(p, bytes + 32);
@@ -500,20 +815,22 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   T8B_TRY(cudaMalloc(&face_off.p, 8 * (size_t)(nblocks + 1)));
   T8B_TRY(cudaMemsetAsync(face_off.p, 0, 8 * (size_t)(nblocks + 1), st));
   const unsigned fgrid = (unsigned)((ntot + 255) / 256);
-  if (ntot > 0) classify_kernel<T, Src><<<fgrid, 256, 0, st>>>(src, ntot, n_local, multi ? 1 : 0, area_set.p, flags.p, face_off.p);
-  thrust::device_ptr<unsigned long long> fo(face_off.p);
+  // candidate faces of every block: keys block << 40 | face (a face between two blocks appears in both), sorted
+  if (nblocks >= (1LL << 23) || ntot >= (1LL << 40)) return cudaErrorInvalidValue;
+  DevFree<unsigned long long> keys;
+  T8B_TRY(cudaMalloc(&keys.p, 16 * (size_t)std::max<int64_t>(ntot, 1)));
+  if (ntot > 0) classify_kernel<T, Src><<<fgrid, 256, 0, st>>>(src, ntot, n_local, multi ? 1 : 0, area_set.p, flags.p, face_off.p, keys.p);
+  thrust::device_ptr<unsigned long long> fo(face_off.p), kp(keys.p);
   thrust::exclusive_scan(pol, fo, fo + nblocks + 1, fo);
-  unsigned long long n_rec_all = 0;
-  T8B_TRY(cudaMemcpyAsync(&n_rec_all, face_off.p + nblocks, 8, cudaMemcpyDeviceToHost, st));
-  T8B_TRY(cudaStreamSynchronize(st));
-  DevFree<int64_t> rec;
-  T8B_TRY(cudaMalloc(&rec.p, 8 * (size_t)std::max<unsigned long long>(n_rec_all, 1)));
-  if (ntot > 0) bucket_kernel<Src><<<fgrid, 256, 0, st>>>(src, ntot, n_local, face_off.p, blk.p, rec.p);
+  thrust::sort(pol, kp, kp + 2 * ntot);
+  int64_t* rec = reinterpret_cast<int64_t*>(keys.p);   // serial mode: the face ids alone
+  if (serial && ntot > 0) mask_keys_kernel<<<(unsigned)((2 * ntot + 255) / 256), 256, 0, st>>>(2 * ntot, keys.p);
   // ---- COUNT pass: one program per block, in batches that bound the workspace
   const int64_t nprog = std::min<int64_t>(nblocks, 65536);
+  const unsigned wgrid = (unsigned)std::min<int64_t>(nblocks, 148 * 32);
   DevFree<unsigned char> arena;
   DevFree<pb::Counts>    cn;
-  T8B_TRY(cudaMalloc(&arena.p, (size_t)pb::Ws::bytes_per_program * (size_t)nprog + 64));
+  if (serial) T8B_TRY(cudaMalloc(&arena.p, (size_t)pb::Ws::bytes_per_program * (size_t)nprog + 64));
   T8B_TRY(cudaMalloc(&cn.p, sizeof(pb::Counts) * (size_t)nblocks));
   int max_halo_allowed = MS - EC;
   if (const char* t = getenv("T8B200_TEST_MAX_HALO")) max_halo_allowed = std::min(max_halo_allowed, std::max(8, atoi(t)));
@@ -527,10 +844,12 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   T8B_TRY(cudaMemcpyAsync(inv.p, inv_h, sizeof(inv_h), cudaMemcpyHostToDevice, st));
   pb::Params<T> pr{n_local, multi ? 1 : 0, 0, 0, box_layout, max_halo_allowed, MF - 1, nullptr, inv.p};
   pb::Out<T>    out{};
-  T8B_TRY(cudaMemsetAsync(blk.p, 0, 8 * 3 * (size_t)(nblocks + 1), st));   // cursors done; now the bases
-  for (int64_t b0 = 0; b0 < nblocks; b0 += nprog)
-    block_pass_kernel<T, Src, false><<<(unsigned)((nprog + 63) / 64), 64, 0, st>>>(src, pr, arena.p, nprog, b0, nblocks,
-                                                                                  face_off.p, rec.p, cn.p, blk.p, out, flags.p);
+  if (serial)
+    for (int64_t b0 = 0; b0 < nblocks; b0 += nprog)
+      block_pass_kernel<T, Src, false><<<(unsigned)((nprog + 63) / 64), 64, 0, st>>>(src, pr, arena.p, nprog, b0, nblocks,
+                                                                                    face_off.p, rec, cn.p, blk.p, out, flags.p);
+  else
+    block_warp_kernel<T, Src, false><<<wgrid, 32, 0, st>>>(src, pr, nblocks, face_off.p, keys.p, cn.p, blk.p, out, flags.p);
   T8B_TRY(cudaMalloc(&totals.p, 8 * 8));
   T8B_TRY(cudaMemsetAsync(totals.p, 0, 8 * 8, st));
   counts_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(nblocks, cn.p, blk.p, totals.p);
@@ -594,9 +913,12 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   pr.cmp = cmp ? 1 : 0; pr.n_areas = (int)area_tab.size(); pr.area_tab = (const T*)P->area_tab;
   out = pb::Out<T>{HS, FS, P->hdr, P->halo_elem, P->halo_rank, P->face_lr, P->face_ai, (T*)P->fnx, (T*)P->fny, (T*)P->fnz,
                    (T*)P->farea, (uint16_t*)P->ell, P->ovf_off, P->ovf_ent, s_flag.p, s_halo_tmp.p, s_hrank_tmp.p};
-  for (int64_t b0 = 0; b0 < nblocks; b0 += nprog)
-    block_pass_kernel<T, Src, true><<<(unsigned)((nprog + 63) / 64), 64, 0, st>>>(src, pr, arena.p, nprog, b0, nblocks,
-                                                                                 face_off.p, rec.p, cn.p, blk.p, out, flags.p);
+  if (serial)
+    for (int64_t b0 = 0; b0 < nblocks; b0 += nprog)
+      block_pass_kernel<T, Src, true><<<(unsigned)((nprog + 63) / 64), 64, 0, st>>>(src, pr, arena.p, nprog, b0, nblocks,
+                                                                                   face_off.p, rec, cn.p, blk.p, out, flags.p);
+  else
+    block_warp_kernel<T, Src, true><<<wgrid, 32, 0, st>>>(src, pr, nblocks, face_off.p, keys.p, cn.p, blk.p, out, flags.p);
   const int me = P->my_rank;
   if (multi && nchunks > 0) chunk_flags_kernel<<<(unsigned)nchunks, 256, 0, st>>>(HS, P->halo_elem, P->halo_rank, s_flag.p, me, bflag.p);
   else T8B_TRY(cudaMemsetAsync(bflag.p, 0, (size_t)nchunks + 1, st));
@@ -718,7 +1040,8 @@ int t8b200_plan_create_device(t8b200_plan** out, int is_f64, int ghost_tail, int
                               const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
                               const void* xnormals, const void* xareas, void* stream) {
   const int flags = ghost_tail ? 2 : 0;
-  const bool generic_only = getenv("T8B200_DEVICE_PLAN") && getenv("T8B200_DEVICE_PLAN")[0] == 'g';   // tests
+  const char* mode_env     = getenv("T8B200_DEVICE_PLAN");   // tests: "generic" / "serial" skip the three-kernel builder
+  const bool  generic_only = mode_env && (mode_env[0] == 'g' || mode_env[0] == 's');
   int rc = cudaErrorNotSupported;
   if (!generic_only)
     rc = is_f64 ? device_plan_impl<double>(out, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,

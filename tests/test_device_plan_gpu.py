@@ -177,12 +177,14 @@ def _amr_forest(level=3):
     return f
 
 
+@pytest.mark.parametrize("mode", ["generic", "serial"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_generic_device_builder_equals_host_builder(cuda, dtype, monkeypatch):
+def test_generic_device_builder_equals_host_builder(cuda, dtype, mode, monkeypatch):
     """Hanging faces (overflow entries), walls, quads, boxes that are their own neighbours, general normals: the plan
-    built by one CUDA thread per block (csrc/plan_block.cuh) equals the host builder's in all 20 arrays."""
+    built by one warp per block (mode generic: device_plan.cu block_warp_kernel) or one thread per block (mode serial:
+    the program of csrc/plan_block.cuh as the host emulation runs it) equals the host builder's in all 20 arrays."""
     from util import hybrid_mesh
-    monkeypatch.setenv("T8B200_DEVICE_PLAN", "generic")          # not the three-kernel builder of structured-only meshes
+    monkeypatch.setenv("T8B200_DEVICE_PLAN", mode)               # not the three-kernel builder of structured-only meshes
     npdt = np.float64 if dtype == torch.float64 else np.float32
     amr = _amr_forest()
     plan, H = assert_same_plan(amr.connectivity(dtype=npdt), dtype, False, cuda, "amr")
