@@ -250,6 +250,14 @@ int t8b200_subgrid_plan_create_host(t8b200_subgrid_plan** out, int is_f64, int d
                                     const int32_t* indices, int32_t n_xfaces, const int32_t* x_face_neighbors,
                                     const void* x_face_normals, const void* x_face_surfaces,
                                     const int32_t* x_level_difference, const int32_t* x_neighbor_offset);
+/* as t8b200_plan_create_block_program_host: the device builder's per-block program over the cell faces, on the host */
+int t8b200_subgrid_plan_create_block_program_host(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local,
+                                                  int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* nbr,
+                                                  const void* normals, const void* areas, const int32_t* level_diff,
+                                                  const int32_t* offsets, const void* volumes, const int32_t* ranks,
+                                                  const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                                                  const void* xnormals, const void* xareas, const int32_t* xld,
+                                                  const int32_t* xoff);
 /* ghost-tail variant (see t8b200_plan_create_ghost_tail); tail entries are CELLS: rows need n_local * 64 (16) +
  * t8b200_plan_ghost_tail_count(t8b200_subgrid_plan_base(plan)) entries, pulled with t8b200_ghost_pull_* on the base plan */
 int t8b200_subgrid_plan_create_ghost_tail(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local,
@@ -260,18 +268,28 @@ int t8b200_subgrid_plan_create_ghost_tail(t8b200_subgrid_plan** out, int is_f64,
                                           int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
                                           const void* x_face_surfaces, const int32_t* x_level_difference,
                                           const int32_t* x_neighbor_offset);
-/* Cell-level plan built on the device from DEVICE arrays (see t8b200_plan_create_device): Subgrid<4,4,4> on forests
+/* host-only variant of t8b200_subgrid_plan_create_ghost_tail (CPU-side checks, see t8b200_plan_create_host) */
+int t8b200_subgrid_plan_create_ghost_tail_host(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local,
+                                               int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* nbr,
+                                               const void* normals, const void* areas, const int32_t* level_diff,
+                                               const int32_t* offsets, const void* volumes, const int32_t* ranks,
+                                               const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                                               const void* xnormals, const void* xareas, const int32_t* xld,
+                                               const int32_t* xoff);
+/* Cell-level plan built on the device from DEVICE arrays (see t8b200_plan_create_device).  Subgrid<4,4,4> on forests
  * whose every group of 4 consecutive elements is a 2 x 2 x 1 block of same-size siblings surrounded by single same-level
- * elements (uniform forests and brick partitions); cudaErrorNotSupported otherwise (dim 2, hanging faces, walls ...).
- * volumes: device, per element.  The neighbour offsets are not needed (same-level faces: the cell across a face has the
- * same tangential coordinates). */
+ * elements (uniform forests and brick partitions): three kernels.  Any other forest (hanging faces, walls, Subgrid<4,4>):
+ * the generic builder over the cell faces (16 / 4 per element face, 144 / 24 inside an element), one warp per 256
+ * cells; every array equals t8b200_subgrid_plan_create's.  volumes: device, per element; offsets / x_offsets: dim per
+ * face (same-level faces do not read them).  Arguments otherwise as t8b200_subgrid_plan_create. */
 int t8b200_subgrid_plan_create_device(t8b200_subgrid_plan** out, int is_f64, int dim, int ghost_tail, int64_t n_local,
                                       int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* face_neighbors,
                                       const void* face_normals, const void* face_surfaces,
-                                      const int32_t* face_level_difference, const void* volumes, const int32_t* ranks,
-                                      const int32_t* indices, int32_t n_xfaces, const int32_t* x_face_neighbors,
-                                      const void* x_face_normals, const void* x_face_surfaces,
-                                      const int32_t* x_level_difference, void* stream);
+                                      const int32_t* face_level_difference, const int32_t* face_neighbor_offset,
+                                      const void* volumes, const int32_t* ranks, const int32_t* indices,
+                                      int32_t n_xfaces, const int32_t* x_face_neighbors, const void* x_face_normals,
+                                      const void* x_face_surfaces, const int32_t* x_level_difference,
+                                      const int32_t* x_neighbor_offset, void* stream);
 const t8b200_plan* t8b200_subgrid_plan_base(const t8b200_subgrid_plan* plan);
 /* as t8b200_plan_info, counted in cells */
 int t8b200_subgrid_plan_info(const t8b200_subgrid_plan* plan, int64_t info[8]);

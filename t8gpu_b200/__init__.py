@@ -358,8 +358,9 @@ class SubgridPlan:
 
     @classmethod
     def from_device(cls, conn, volumes, dtype, ghost_tail=False, stream=None):
-        """Cell-level plan built on the device from DEVICE tensors (t8b200_subgrid_plan_create_device); None when the
-        forest is not made of structured chunks only (then use SubgridPlan(conn_to_host(conn), ...))."""
+        """Cell-level plan built on the device from DEVICE tensors (t8b200_subgrid_plan_create_device: three kernels
+        for structured-only forests, else the generic builder over the cell faces); None only for a rank without
+        elements (then use SubgridPlan(conn_to_host(conn), ...))."""
         _torch()
         s, _ = _sfx(dtype)
 
@@ -372,9 +373,10 @@ class SubgridPlan:
         rc = lib().t8b200_subgrid_plan_create_device(
             C.byref(h), int(s == "f64"), int(conn["dim"]), int(bool(ghost_tail)), C.c_int64(int(conn["n_local"])),
             C.c_int64(ng), int(conn["n_faces"]), int(conn["n_bfaces"]), p("face_neighbors"), p("face_normals"),
-            p("face_areas"), p("level_diff"), C.c_void_p(volumes.data_ptr()), p("ranks") if ng else None,
+            p("face_areas"), p("level_diff"), p("offsets"), C.c_void_p(volumes.data_ptr()), p("ranks") if ng else None,
             p("indices") if ng else None, nx, p("x_face_neighbors") if nx else None, p("x_face_normals") if nx else None,
-            p("x_face_areas") if nx else None, p("x_level_diff") if nx else None, stream_ptr(stream))
+            p("x_face_areas") if nx else None, p("x_level_diff") if nx else None, p("x_offsets") if nx else None,
+            stream_ptr(stream))
         if rc == 801:
             return None
         check(rc, "subgrid_plan_create_device")

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "mesh_faces.cuh"
 #include "plan_block.cuh"
+#include "subgrid_faces.cuh"
 #include "tile_plan.cuh"
 
 using namespace t8b200;
@@ -1032,6 +1033,39 @@ int generic_mesh_plan(t8b200_plan** out, int ghost_tail, int64_t n_local, int64_
   return 0;
 }
 
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256) inner_area_kernel(int64_t n, const T* __restrict__ vol, T* __restrict__ inner) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) inner[e] = subgrid_inner_area<T, DIM>(vol[e]);
+}
+
+// cell-level plan of Subgrid<4,4,4> / <4,4> over the cell faces (subgrid_faces.cuh), n_local / n_ghost in ELEMENTS
+template <typename T, int DIM>
+int generic_subgrid_plan(t8b200_plan** out, int ghost_tail, int64_t n_local, int64_t n_ghost, int32_t nf, int32_t nb,
+                         const int32_t* nbr, const T* normals, const T* areas, const int32_t* ld, const int32_t* off,
+                         const T* vol, const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                         const T* xnormals, const T* xareas, const int32_t* xld, const int32_t* xoff, void* stream) {
+  constexpr int S = DIM == 3 ? 64 : 16;
+  if (n_local <= 0) return cudaErrorNotSupported;
+  if ((n_local + n_ghost) * S > 0x7FFFFFF0LL) return cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  DevFree<T>   inner;
+  T8B_TRY(cudaMalloc(&inner.p, sizeof(T) * (size_t)n_local));
+  inner_area_kernel<T, DIM><<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(n_local, vol, inner.p);
+  t8b200_plan* P = new t8b200_plan();
+  struct Guard { t8b200_plan* p; ~Guard() { if (p) t8b200_plan_destroy(p); } } guard{P};
+  P->is_f64 = sizeof(T) == 8; P->ghost_tail = ghost_tail ? 1 : 0;
+  P->vol_shift = DIM == 3 ? 6 : 4; P->vol_scale = DIM == 3 ? 1.0 / 64.0 : 1.0 / 16.0;
+  SubgridFaces<T, DIM> src{n_local, nf, nb, nx, nbr, normals, areas, ld, off, vol, ranks, indices, xnbr, xnormals, xareas,
+                           xld, xoff, inner.p};
+  const int rc = generic_device_plan<T>(P, n_local * S, n_ghost > 0, src, st);
+  if (rc) return rc;
+  guard.p = nullptr;
+  *out    = P;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1065,24 +1099,39 @@ int t8b200_plan_create_device(t8b200_plan** out, int is_f64, int ghost_tail, int
 
 int t8b200_subgrid_plan_create_device(t8b200_subgrid_plan** out, int is_f64, int dim, int ghost_tail, int64_t n_local,
                                       int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* nbr, const void* normals,
-                                      const void* areas, const int32_t* level_diff, const void* volumes,
-                                      const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
-                                      const void* xnormals, const void* xareas, const int32_t* x_level_diff,
-                                      void* stream) {
-  if (!out) return cudaErrorInvalidValue;
-  if (dim != 3) return cudaErrorNotSupported;     // Subgrid<4,4>: host builder
+                                      const void* areas, const int32_t* level_diff, const int32_t* offsets,
+                                      const void* volumes, const int32_t* ranks, const int32_t* indices, int32_t nx,
+                                      const int32_t* xnbr, const void* xnormals, const void* xareas,
+                                      const int32_t* x_level_diff, const int32_t* x_offsets, void* stream) {
+  if (!out || (dim != 2 && dim != 3)) return cudaErrorInvalidValue;
   const int    flags = ghost_tail ? 2 : 0;
   t8b200_plan* P     = nullptr;
-  const int rc = is_f64 ? device_plan_impl<double>(&P, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
-                                                   (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
-                                                   (const double*)xareas, stream, true, (const double*)volumes, level_diff,
-                                                   x_level_diff)
-                        : device_plan_impl<float>(&P, flags, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
-                                                  (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
-                                                  (const float*)xareas, stream, true, (const float*)volumes, level_diff,
-                                                  x_level_diff);
+  const char*  mode_env     = getenv("T8B200_DEVICE_PLAN");
+  const bool   generic_only = mode_env && (mode_env[0] == 'g' || mode_env[0] == 's');
+  int          rc           = cudaErrorNotSupported;
+  if (dim == 3 && !generic_only)   // Subgrid<4,4,4> on structured-only forests: three kernels
+    rc = is_f64 ? device_plan_impl<double>(&P, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
+                                           (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
+                                           (const double*)xareas, stream, true, (const double*)volumes, level_diff,
+                                           x_level_diff)
+                : device_plan_impl<float>(&P, flags, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
+                                          (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
+                                          (const float*)xareas, stream, true, (const float*)volumes, level_diff,
+                                          x_level_diff);
+  if (rc == cudaErrorNotSupported) {   // any other forest: the generic builder over the cell faces
+    if (n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0 || !volumes) return cudaErrorInvalidValue;
+    if ((nf + nb > 0 && (!nbr || !normals || !areas)) || (nf > 0 && (!level_diff || !offsets))) return cudaErrorInvalidValue;
+    if (nx > 0 && (!xnbr || !xnormals || !xareas || !x_level_diff || !x_offsets)) return cudaErrorInvalidValue;
+    if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
+#define T8B_SG(TT, DD)                                                                                                    \
+  generic_subgrid_plan<TT, DD>(&P, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const TT*)normals, (const TT*)areas,       \
+                               level_diff, offsets, (const TT*)volumes, ranks, indices, nx, xnbr, (const TT*)xnormals,    \
+                               (const TT*)xareas, x_level_diff, x_offsets, stream)
+    rc = is_f64 ? (dim == 3 ? T8B_SG(double, 3) : T8B_SG(double, 2)) : (dim == 3 ? T8B_SG(float, 3) : T8B_SG(float, 2));
+#undef T8B_SG
+  }
   if (rc) return rc;
-  *out = t8b_wrap_subgrid_plan(P, 3);
+  *out = t8b_wrap_subgrid_plan(P, dim);
   return 0;
 }
 

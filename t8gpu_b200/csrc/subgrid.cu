@@ -14,6 +14,8 @@
 #include "../../include/t8gpu_b200.h"
 #include "common.cuh"
 #include "euler_flux.cuh"
+#include "plan_emulate.cuh"
+#include "subgrid_faces.cuh"
 #include "tile_plan.cuh"
 
 using namespace t8b200;
@@ -271,132 +273,6 @@ t8b200_subgrid_plan* t8b_wrap_subgrid_plan(t8b200_plan* P, int dim) {
   return SP;
 }
 
-namespace {
-// cell index inside an element from (axis, x along the axis, tangential a, b)
-inline int cell_ax(int dim, int ax, int x, int a, int b) {
-  if (dim == 2) return ax == 0 ? x + 4 * a : a + 4 * x;
-  return ax == 0 ? x + 4 * a + 16 * b : (ax == 1 ? a + 4 * x + 16 * b : a + 4 * b + 16 * x);
-}
-
-// DIM is a template parameter: the plan builder asks for the endpoints of every cell face several times, and with
-// compile-time cell / face counts the decoding of a face id needs no integer division by a run-time value
-template <typename T, int DIM>
-struct SubgridFaces {
-  static constexpr int dim = DIM;
-  int64_t        n_local;  // elements
-  int32_t        nf, nb, nx;
-  const int32_t* nbr;
-  const T *      normals, *areas;   // normals: dim components per face
-  const int32_t *ld, *off;          // off: dim components per face
-  const T*       vol;
-  const int32_t *ranks, *indices, *xnbr;
-  const T *      xnormals, *xareas;
-  const int32_t *xld, *xoff;
-  std::vector<T> inner_area;   // per element: area of the faces between its cells (prepare())
-  static constexpr int S() { return DIM == 3 ? 64 : 16; }
-  static constexpr int TPF() { return DIM == 3 ? 16 : 4; }
-  static constexpr int IPE() { return DIM * 3 * TPF(); }   // inner faces per element: dim axes x 3 planes x TPF
-  int64_t n_inner() const { return n_local * IPE(); }
-  int64_t num_faces() const { return n_inner() + ((int64_t)nf + nb + nx) * TPF(); }
-
-  // element face F (0..nf+nb+nx), sub-face s -> left / right cell inside their elements
-  void sub_cells(const T* n, const int32_t* o, int dstride, int s, int& lc, int& rc) const {
-    const int i = s & 3, j = s >> 2;
-    int al[3] = {0, 0, 0}, si[3] = {0, 0, 0}, sj[3] = {0, 0, 0};
-    if (n[0] == T(1)) { al[0] = 3; si[1] = 1; sj[2] = 1; }
-    if (n[0] == T(-1)) { si[1] = 1; sj[2] = 1; }
-    if (n[1] == T(1)) { al[1] = 3; si[0] = 1; sj[2] = 1; }
-    if (n[1] == T(-1)) { si[0] = 1; sj[2] = 1; }
-    if (dim == 3) {
-      if (n[2] == T(1)) { al[2] = 3; si[0] = 1; sj[1] = 1; }
-      if (n[2] == T(-1)) { si[0] = 1; sj[1] = 1; }
-    }
-    int l[3], r[3];
-    for (int d = 0; d < 3; d++) {
-      l[d] = al[d] + i * si[d] + j * sj[d];
-      r[d] = (o && d < dim ? o[d] : 0) + dstride * (i * si[d] + j * sj[d]) / 2;
-    }
-    lc = l[0] + 4 * l[1] + 16 * l[2];
-    rc = r[0] + 4 * r[1] + 16 * r[2];
-  }
-  void outer(int64_t g, int64_t& F, int& s, const int32_t*& pn, const T*& n, const T*& ar, const int32_t*& l_d,
-             const int32_t*& o, bool& wall) const {
-    F = g / TPF();
-    s = (int)(g % TPF());
-    wall = false;
-    if (F < nf) { pn = nbr + 2 * F; n = normals + dim * F; ar = areas + F; l_d = ld + F; o = off + dim * F; }
-    else if (F < (int64_t)nf + nb) {
-      wall = true;
-      pn = nbr + 2 * (int64_t)nf + (F - nf); n = normals + dim * F; ar = areas + F; l_d = nullptr; o = nullptr;
-    } else {
-      const int64_t x = F - nf - nb;
-      pn = xnbr + 2 * x; n = xnormals + dim * x; ar = xareas + x; l_d = xld + x; o = xoff + dim * x;
-    }
-  }
-  void endpoints(int64_t f, int32_t& l, int32_t& r) const {
-    if (f < n_inner()) {
-      const int64_t e = f / IPE();
-      const int     q = (int)(f % IPE()), ax = q / (3 * TPF()), t = q % (3 * TPF()), p = t / TPF(), s = t % TPF();
-      l = (int32_t)(e * S() + cell_ax(dim, ax, p, s & 3, s >> 2));
-      r = (int32_t)(e * S() + cell_ax(dim, ax, p + 1, s & 3, s >> 2));
-      return;
-    }
-    int64_t        F;
-    int            s, lc, rc;
-    const int32_t *pn, *l_d, *o;
-    const T *      n, *ar;
-    bool           wall;
-    outer(f - n_inner(), F, s, pn, n, ar, l_d, o, wall);
-    sub_cells(n, o, (l_d && *l_d != 0) ? 1 : 2, s, lc, rc);
-    l = (int32_t)((int64_t)pn[0] * S() + lc);
-    r = wall ? -1 : (int32_t)((int64_t)pn[1] * S() + rc);
-  }
-  void geometry(int64_t f, T nrm[3], T& a) const {
-    nrm[0] = nrm[1] = nrm[2] = T(0);
-    if (f < n_inner()) {
-      const int64_t e  = f / IPE();
-      const int     ax = (int)(f % IPE()) / (3 * TPF());
-      nrm[ax] = T(1);
-      a = inner_area[e];
-      return;
-    }
-    int64_t        F;
-    int            s;
-    const int32_t *pn, *l_d, *o;
-    const T *      n, *ar;
-    bool           wall;
-    outer(f - n_inner(), F, s, pn, n, ar, l_d, o, wall);
-    for (int d = 0; d < dim; d++) nrm[d] = n[d];
-    a = *ar / T(TPF());
-  }
-  // surface = (cbrt(vol)/4)^2 (kernels.inl:352-354) resp. sqrt(vol)/4 (2-D, :542-544), once per element (the plan
-  // asks for the geometry of every cell face several times)
-  void prepare() {
-    inner_area.resize((size_t)n_local);
-    parallel_ranges(n_local, plan_threads(), [&](int, int64_t e0, int64_t e1) {
-      for (int64_t e = e0; e < e1; e++) {
-        if (dim == 3) {
-          // libm's cbrt is off by an ulp on exact cubes (dyadic Cartesian volumes): take the exact root when there is
-          // one, so that the faces inside an element and between elements get the same area entry
-          T c = std::cbrt(vol[e]);
-          for (T t : {std::nextafter(c, T(0)), std::nextafter(c, T(2) * c)})
-            if (t * t * t == vol[e]) c = t;
-          const T edge = c / T(4);
-          inner_area[e] = edge * edge;
-        } else {
-          inner_area[e] = std::sqrt(vol[e]) / T(4);
-        }
-      }
-    });
-  }
-  void owner(int32_t id, int32_t& rk, int32_t& ix) const {
-    const int32_t e = id / S(), c = id % S();
-    rk = ranks[e];
-    ix = indices[e] * S() + c;
-  }
-};
-}  // namespace
-
 template <typename T, int DIM>
 static int sg_plan_build_dim(t8b200_subgrid_plan* SP, int host_only, int64_t n_local, int64_t n_ghost, int32_t nf,
                              int32_t nb, const int32_t* nbr, const T* normals, const T* areas,
@@ -423,17 +299,22 @@ static int sg_plan_build_dim(t8b200_subgrid_plan* SP, int host_only, int64_t n_l
                              const int32_t* indices, int32_t nx, const int32_t* xnbr, const T* xnormals,
                              const T* xareas, const int32_t* xld, const int32_t* xoff) {
   constexpr int dim = DIM;
+  // area of the faces between the cells, once per element (the plan asks for the geometry of a face several times)
+  std::vector<T> inner((size_t)n_local);
+  parallel_ranges(n_local, plan_threads(), [&](int, int64_t e0, int64_t e1) {
+    for (int64_t e = e0; e < e1; e++) inner[e] = subgrid_inner_area<T, DIM>(vol[e]);
+  });
   SubgridFaces<T, DIM> src{n_local, nf, nb, nx, nbr, normals, areas, level_diff, offsets, vol, ranks, indices, xnbr,
-                           xnormals, xareas, xld, xoff, {}};
-  src.prepare();
+                           xnormals, xareas, xld, xoff, inner.data()};
   if ((n_local + n_ghost) * src.S() > 0x7FFFFFF0LL) return cudaErrorInvalidValue;
   t8b200_plan* P = new t8b200_plan();
   SP->plan       = P;
   P->is_f64      = sizeof(T) == 8;
-  P->host_only   = host_only & 1;   // flags: bit 0 host-only plan, bit 1 ghost tail
+  P->host_only   = host_only & 1;   // flags: bit 0 host-only plan, bit 1 ghost tail, bit 2 block program on the host
   P->ghost_tail  = (host_only >> 1) & 1;
   P->vol_shift   = dim == 3 ? 6 : 4;
   P->vol_scale   = dim == 3 ? 1.0 / 64.0 : 1.0 / 16.0;
+  if ((host_only & 5) == 5) return plan_build_emulated<T>(P, n_local * src.S(), n_ghost > 0, src);
   return plan_build<T>(P, n_local * src.S(), n_ghost > 0, src);
 }
 
@@ -483,6 +364,16 @@ int t8b200_subgrid_plan_create_host(t8b200_subgrid_plan** out, int is_f64, int d
   return sg_plan_create_impl(out, 1, is_f64, dim, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets,
                              volumes, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
 }
+int t8b200_subgrid_plan_create_block_program_host(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local,
+                                                  int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* nbr,
+                                                  const void* normals, const void* areas, const int32_t* level_diff,
+                                                  const int32_t* offsets, const void* volumes, const int32_t* ranks,
+                                                  const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                                                  const void* xnormals, const void* xareas, const int32_t* xld,
+                                                  const int32_t* xoff) {
+  return sg_plan_create_impl(out, 5, is_f64, dim, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets,
+                             volumes, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
+}
 int t8b200_subgrid_plan_create_ghost_tail(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local,
                                           int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* nbr,
                                           const void* normals, const void* areas, const int32_t* level_diff,
@@ -490,6 +381,16 @@ int t8b200_subgrid_plan_create_ghost_tail(t8b200_subgrid_plan** out, int is_f64,
                                           const int32_t* indices, int32_t nx, const int32_t* xnbr, const void* xnormals,
                                           const void* xareas, const int32_t* xld, const int32_t* xoff) {
   return sg_plan_create_impl(out, 2, is_f64, dim, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets,
+                             volumes, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
+}
+int t8b200_subgrid_plan_create_ghost_tail_host(t8b200_subgrid_plan** out, int is_f64, int dim, int64_t n_local,
+                                               int64_t n_ghost, int32_t nf, int32_t nb, const int32_t* nbr,
+                                               const void* normals, const void* areas, const int32_t* level_diff,
+                                               const int32_t* offsets, const void* volumes, const int32_t* ranks,
+                                               const int32_t* indices, int32_t nx, const int32_t* xnbr,
+                                               const void* xnormals, const void* xareas, const int32_t* xld,
+                                               const int32_t* xoff) {
+  return sg_plan_create_impl(out, 3, is_f64, dim, n_local, n_ghost, nf, nb, nbr, normals, areas, level_diff, offsets,
                              volumes, ranks, indices, nx, xnbr, xnormals, xareas, xld, xoff);
 }
 const t8b200_plan* t8b200_subgrid_plan_base(const t8b200_subgrid_plan* SP) { return SP ? SP->plan : nullptr; }

@@ -420,7 +420,87 @@ def test_subgrid_cell_plan_equals_host_builder(cuda, P, dtype):
             a.iterate(1e-3)
             b.iterate(1e-3)
         assert torch.equal(a.state(), b.state())
-        amr = f.adapt(np.where(cent[:, 2] < 0.25, 1.0, 0.0), 0.02, 1, 4)
-        ca = tb.conn_to_device(amr.connectivity(subgrid=True, dtype=npdt), dtype, cuda)
-        va = torch.as_tensor(amr.elements()[2].astype(npdt)).to(cuda)
-        assert tb.SubgridPlan.from_device(ca, va, dtype) is None
+
+
+def subgrid_host_all(conn_host, volumes, dtype, dim, ghost_tail):
+    """All 20 arrays + info of the HOST builder's cell-level plan."""
+    import t8gpu_b200 as tb
+    lib = tb.lib()
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+
+    def arr(k, dt):
+        v = conn_host.get(k)
+        return None if v is None or len(v) == 0 else np.ascontiguousarray(v, dtype=dt)
+
+    def p(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    keep = [arr("face_neighbors", np.int32), arr("face_normals", npdt), arr("face_areas", npdt),
+            arr("level_diff", np.int32), arr("offsets", np.int32), np.ascontiguousarray(volumes, dtype=npdt),
+            arr("ranks", np.int32), arr("indices", np.int32), arr("x_face_neighbors", np.int32),
+            arr("x_face_normals", npdt), arr("x_face_areas", npdt), arr("x_level_diff", np.int32),
+            arr("x_offsets", np.int32)]
+    ng = int(conn_host.get("n_ghost", 0))
+    sh = C.c_void_p()
+    fn = lib.t8b200_subgrid_plan_create_ghost_tail_host if ghost_tail else lib.t8b200_subgrid_plan_create_host
+    assert fn(C.byref(sh), int(dtype == torch.float64), dim, C.c_int64(int(conn_host["n_local"])), C.c_int64(ng),
+              int(conn_host["n_faces"]), int(conn_host["n_bfaces"]), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]),
+              p(keep[4]), p(keep[5]), p(keep[6]) if ng else None, p(keep[7]) if ng else None,
+              int(conn_host.get("n_xfaces", 0)), p(keep[8]), p(keep[9]), p(keep[10]), p(keep[11]), p(keep[12])) == 0
+    lib.t8b200_subgrid_plan_base.restype = C.c_void_p
+    base = C.c_void_p(lib.t8b200_subgrid_plan_base(sh))
+    out = {}
+    for which in range(20):
+        data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
+        assert lib.t8b200_plan_host_array(base, which, C.byref(data), C.byref(count), C.byref(eb)) == 0
+        n = count.value
+        a = (np.frombuffer((C.c_char * (n * eb.value)).from_address(data.value), dtype=HOST_DT[eb.value]).copy() if n
+             else np.zeros(0, HOST_DT[eb.value]))
+        out[which] = a.astype(npdt) if which in (8, 9, 10, 11, 12) else a
+    info = (C.c_int64 * 8)()
+    assert lib.t8b200_plan_info(base, info) == 0
+    out["info"] = [info[i] for i in (0, 1, 2, 3, 5, 6, 7)]
+    lib.t8b200_subgrid_plan_destroy(sh)
+    return out
+
+
+class _Base:   # device_all() reads plan._h: the cell-level plan behind a subgrid plan
+    def __init__(self, plan):
+        self._h, self.info = plan._base, plan.info
+
+
+@pytest.mark.parametrize("ghost_tail", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_generic_device_builder_on_subgrid_cells(cuda, dtype, ghost_tail, monkeypatch):
+    """Cell-level plans of adapted / walled Subgrid<4,4,4> and Subgrid<4,4> forests built on the device (one warp per 256
+    cells over the cell faces) equal the host builder's in all 20 arrays, one rank and partitioned."""
+    import t8gpu_b200 as tb
+    monkeypatch.setenv("T8B200_DEVICE_PLAN", "generic")
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    cases = []
+    f = oracle.Forest(3, 2)
+    cases.append((f, 3))
+    lv, cent, vol, _ = f.elements()
+    cases.append((f.adapt(np.where(np.abs(cent[:, 2] - 0.5) < 0.3, 20.0, 0.0), 10.0, 1, 4), 3))
+    g = oracle.Forest(3, 1, periodic=False)
+    lv, cent, vol, _ = g.elements()
+    cases.append((g.adapt(np.where(cent[:, 2] < 0.5, 1.0, 0.0), 0.02, 1, 2), 3))
+    h = oracle.Forest(2, 2, periodic=False)
+    lv, cent, vol, _ = h.elements()
+    cases.append((h.adapt(np.where(cent[:, 1] < 0.5, 1.0, 0.0), 0.02, 1, 3), 2))
+    for forest, dim in cases:
+        vol = forest.elements()[2]
+        for P in ((1, 2) if not ghost_tail else (2,)):
+            off = forest.partition_offsets(P)
+            for r in range(P):
+                conn = forest.connectivity(P, r, subgrid=True, dtype=npdt)
+                lvol = vol[off[r]:off[r + 1]].astype(npdt)
+                H = subgrid_host_all(conn, lvol, dtype, dim, ghost_tail)
+                plan = tb.SubgridPlan.from_device(tb.conn_to_device(conn, dtype, cuda), torch.as_tensor(lvol).to(cuda),
+                                                  dtype, ghost_tail=ghost_tail)
+                assert plan is not None
+                D = device_all(_Base(plan), dtype)
+                assert D["info"] == H["info"], (dim, P, r, D["info"], H["info"])
+                for which in range(20):
+                    assert D[which].size == H[which].size and np.array_equal(D[which].view(H[which].dtype), H[which]), \
+                        (which, dim, P, r)

@@ -530,3 +530,56 @@ def test_block_program_splits_like_host_builder(monkeypatch):
         lv, cent, vol, _v = f.elements()
         f = f.adapt(np.where(np.abs(cent[:, 0] - 0.5) + np.abs(cent[:, 1] - 0.5) < 0.3, 20.0, 0.0), 10.0, 1, 5)
     _same_plan(L, f.connectivity(dtype=np.float32), np.float32, False)
+
+
+def _sg_plan_with(fn, L, conn, vol, dtype, dim):
+    keep = [_arr(conn, k, d) for k, d in (("face_neighbors", np.int32), ("face_normals", dtype), ("face_areas", dtype),
+                                          ("level_diff", np.int32), ("offsets", np.int32), ("ranks", np.int32),
+                                          ("indices", np.int32), ("x_face_neighbors", np.int32), ("x_face_normals", dtype),
+                                          ("x_face_areas", dtype), ("x_level_diff", np.int32), ("x_offsets", np.int32))]
+    vols = np.ascontiguousarray(vol, dtype)
+    ng, nx = int(conn.get("n_ghost", 0)), int(conn.get("n_xfaces", 0))
+    sh = C.c_void_p()
+    assert fn(C.byref(sh), int(dtype == np.float64), dim, C.c_int64(int(conn["n_local"])), C.c_int64(ng),
+              int(conn["n_faces"]), int(conn["n_bfaces"]), _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), _p(keep[4]),
+              _p(vols), _p(keep[5]) if ng else None, _p(keep[6]) if ng else None, nx, _p(keep[7]), _p(keep[8]),
+              _p(keep[9]), _p(keep[10]), _p(keep[11])) == 0
+    return sh, keep, vols
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_block_program_equals_host_builder_on_subgrid_cells(dtype):
+    """The cell-face source of Subgrid<4,4,4> / <4,4> through the device builder's block program (host loops)."""
+    L = _lib()
+    cases = []
+    f = oracle.Forest(3, 2)
+    cases.append((f, 3))                                                   # uniform: structured SubgridBox chunks
+    lv, cent, vol, _ = f.elements()
+    cases.append((f.adapt(np.where(np.abs(cent[:, 2] - 0.5) < 0.3, 20.0, 0.0), 10.0, 1, 4), 3))
+    g = oracle.Forest(3, 1, periodic=False)
+    lv, cent, vol, _ = g.elements()
+    cases.append((g.adapt(np.where(cent[:, 2] < 0.5, 1.0, 0.0), 0.02, 1, 2), 3))      # walls
+    h = oracle.Forest(2, 2, periodic=False)
+    lv, cent, vol, _ = h.elements()
+    cases.append((h.adapt(np.where(cent[:, 1] < 0.5, 1.0, 0.0), 0.02, 1, 3), 2))      # Subgrid<4,4>
+    for forest, dim in cases:
+        vol = forest.elements()[2]
+        for P in (1, 2):
+            off = forest.partition_offsets(P)
+            for r in range(P):
+                conn = forest.connectivity(P, r, subgrid=True, dtype=dtype)
+                lvol = vol[off[r]:off[r + 1]]
+                s1, k1, v1 = _sg_plan_with(L.t8b200_subgrid_plan_create_host, L, conn, lvol, dtype, dim)
+                s2, k2, v2 = _sg_plan_with(L.t8b200_subgrid_plan_create_block_program_host, L, conn, lvol, dtype, dim)
+                h1, h2 = C.c_void_p(L.t8b200_subgrid_plan_base(s1)), C.c_void_p(L.t8b200_subgrid_plan_base(s2))
+                A, B = arrays(L, h1), arrays(L, h2)
+                assert A["info"] == B["info"]
+                for k in A:
+                    if k != "info":
+                        assert np.array_equal(A[k], B[k]), (k, dim, P, r)
+                if P == 1:
+                    X, Y = _int_arrays(L, h1, (13, 14, 15, 16)), _int_arrays(L, h2, (13, 14, 15, 16))
+                    for k in X:
+                        assert np.array_equal(X[k], Y[k]), k
+                L.t8b200_subgrid_plan_destroy(s1)
+                L.t8b200_subgrid_plan_destroy(s2)
