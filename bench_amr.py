@@ -52,14 +52,17 @@ class RankMesh:
         self.plan, conn_dev = None, None
         if subgrid:
             # element-level connectivity of the subgrid manager (level differences, neighbour offsets) on the device
-            # from the leaf list (t8b200_forest_subgrid_connectivity); the cell-level plan from the host builder
-            conn = tb.conn_to_host(tb.forest_connectivity(3, True, tb.morton_keys(3, lv, cent), lv, dtype, world, rank,
-                                                          device=device, subgrid=True))
+            # from the leaf list (t8b200_forest_subgrid_connectivity), the cell-level plan on the device from it
+            conn_dev = tb.forest_connectivity(3, True, tb.morton_keys(3, lv, cent), lv, dtype, world, rank, device=device,
+                                              subgrid=True)
+            torch.cuda.synchronize()
             self.t_conn, self.conn_on = time.time() - t0, "device"
-            self.n = int(conn["n_local"])
+            self.n = int(conn_dev["n_local"])
             t0 = time.time()
-            lvol = forest.elements()[2][self.off[rank]:self.off[rank + 1]].astype(npdt)
-            self.plan = tb.SubgridPlan(conn, lvol, dtype, ghost_tail=world > 1)
+            self.plan = tb.SubgridPlan.from_device(conn_dev, conn_dev["volumes"], dtype, ghost_tail=world > 1)
+            if self.plan is None:                         # a rank without elements
+                self.plan = tb.SubgridPlan(tb.conn_to_host(conn_dev), conn_dev["volumes"].cpu().numpy(), dtype,
+                                           ghost_tail=world > 1)
         else:
             # MeshManager connectivity on the device from the leaf list (t8b200_forest_connectivity): no host face loop
             conn_dev = tb.forest_connectivity(3, True, tb.morton_keys(3, lv, cent), lv, dtype, world, rank, device=device)

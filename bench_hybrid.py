@@ -186,7 +186,7 @@ def run_hybrid(args, rank, world, device, dist=None, emit=True):
                                "x-faces; t8code hybrid cmeshes absent -> end-to-end parity blocked on t8code" % tiles,
                        "elements_per_gpu": sol.n, "ghosts_per_gpu": int(sol.conn["n_ghost"]),
                        "faces_per_element": f_tot / n_tot, "alg_bytes_per_element_step": alg,
-                       "host_setup_s": {"mesh+partition_numpy": round(sol.t_mesh, 2), "tile_plan_host": round(sol.t_plan, 2)},
+                       "host_setup_s": {"mesh+partition_numpy": round(sol.t_mesh, 2), "tile_plan (" + sol.plan.info.get("built_on", "host") + ", incl. upload)": round(sol.t_plan, 3)},
                        "plan": sol.plan.info, "l2": "state %.0f MB per stage per GPU" % (2 * 5 * sol.n * esz / 1e6)},
             "clocks": clocks, "gpu_launches": launches, "parity": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
