@@ -246,7 +246,7 @@ T8B_HD T kepes_flux_n(const Cell<T>& L, const Cell<T>& R, T nx, T ny, T nz, T F[
   return au + aHat;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && defined(T8B_ENABLE_F32X2)   // structured.cu with T8B_S_PAIR=1 only (needs sm_100a intrinsics)
 // ---- two x-normal faces at once in packed fp32 (sm_100a: fma.rn.f32x2 / mul / add on register pairs) -------------
 // fp32 is bound by issue slots (~80 % busy, half of the instructions are FP32 arithmetic): evaluating two faces of a
 // thread in the two halves of a register pair halves the FP32 instruction count of the flux.  Same formulas as

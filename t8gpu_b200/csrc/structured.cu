@@ -16,6 +16,9 @@
 // Reference behaviour replaced (not translated): one stage of CompressibleEulerSolver::iterate
 // (examples/compressible_euler/solver.cu:78-112) and of SubgridCompressibleEulerSolver::iterate
 // (examples/subgrid/solver.inl:156-194) on the uniform parts of the mesh.
+#if defined(T8B_S_PAIR) && T8B_S_PAIR
+#define T8B_ENABLE_F32X2 1   // euler_flux.cuh: the packed two-face flux (experiment, off by default)
+#endif
 #include <algorithm>
 #include <cstdlib>
 
