@@ -196,6 +196,23 @@ def measure_subgrid(level, dtype_name, steps, warmup, device, parity=True):
            "ms_per_step": ms_per_step, "value": sol.n / (ms_per_step * 1e-3), "clocks": clocks,
            "roofline_frac": achieved / peak, "roofline_achieved_gbs": achieved,
            "alg_bytes_per_cell_step": ALG_CELL_BYTES[dtype_name], "tile_plan_s": round(sol.t_plan, 2)}
+    if dtype_name == "f64":
+        # the FP64-pipe roofline beside the HBM one: the structured kernel evaluates the same 3.5 faces per cell as per
+        # element of the unstructured mesh (same template, SubgridBox layout), so the executed FP64 instructions per
+        # cell-stage are those of the committed capture of that kernel
+        try:
+            import json
+            from bench import ROOT, fp64_peak
+            rec = json.load(open(os.path.join(ROOT, "profiles", "traffic_f64.json")))
+            per_cell = rec["fp64_thread_inst_per_launch"] / rec.get("elements_per_launch", 16777216)
+            pk, pk_src = fp64_peak()
+            rate = per_cell * sol.n / (ms_per_step / 3.0 * 1e-3)
+            out["fp64_pipe"] = {"frac": rate / pk, "per_cell_stage": per_cell, "peak": pk, "peak_source": pk_src,
+                                "floor_ms_per_step": 3e3 * per_cell * sol.n / pk,
+                                "note": "HBM roofline counts state bytes only (328.3 B per cell-step): its FP64-pipe "
+                                        "ceiling sits at %.0f %% of that roofline" % (100 * ALG_CELL_BYTES["f64"] * sol.n / peak / 1e9 / (3e3 * per_cell * sol.n / pk * 1e-3))}
+        except (OSError, KeyError, ValueError):
+            pass
     if parity:
         out["parity"] = parity_subgrid(sol, level, dtype_name)
     sol.close()
