@@ -10,6 +10,8 @@ Stage ordering across ranks (T8B200_SYNC):
                     its peers hold copies of into their tails (t8b200_ghost_push: scattered local gather, consecutive
                     remote stores), then the mailbox barrier publishes them; the next stage kernel starts right behind
                     the barrier.
+  pushb             push and barrier in ONE launch (t8b200_ghost_push_barrier: the last CTA to finish its pushes signals
+                    and waits): two launches per stage instead of three.
   fpush             the push folded into the stage kernel (t8b200_fused_stage_push): the thread that writes an element
                     its peers hold a copy of also stores the new values into those copies from the kernel's epilogue.
                     Bitwise equal, but measured SLOWER than the separate push kernel on 2 GPUs (2.57 vs 2.46 ms per
@@ -78,9 +80,9 @@ class MultiGpuEuler:
         self.n_faces = int(conn["n_faces"]) + int(conn["n_xfaces"])
         self.n_ghost = int(conn["n_ghost"])
         t0 = time.time()
-        self.plan = tb.Plan.from_device(conn, dtype, ghost_tail=self.sync in ("fpush", "push", "pull", "overlap"))     # no D2H
+        self.plan = tb.Plan.from_device(conn, dtype, ghost_tail=self.sync in ("fpush", "push", "pushb", "pull", "overlap"))     # no D2H
         if self.plan is None:
-            self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync in ("fpush", "push", "pull", "overlap"))
+            self.plan = tb.Plan(tb.conn_to_host(conn), dtype, ghost_tail=self.sync in ("fpush", "push", "pushb", "pull", "overlap"))
         torch.cuda.synchronize()
         self.t_plan = time.time() - t0
         self.cap = (self.n + self.plan.n_tail + 31) // 32 * 32     # own elements, then the ghost tail
@@ -95,12 +97,12 @@ class MultiGpuEuler:
         rows = row_pointers(bases, caps, NVAR, NB_STEPS, esz)
         self.tables = {s: tb.PointerTables(rows[s], device) for s in range(NB_STEPS)}
         self.mail = None
-        if self.sync in ("fpush", "push", "overlap", "pull", "kernel", "peer", "none"):
+        if self.sync in ("fpush", "push", "pushb", "overlap", "pull", "kernel", "peer", "none"):
             self.mail = tb.PeerMailboxes(rank, world, device)
             mw = exchange_wires(dist, self.mail.handle, 0, world, device)
             self.mail.exchange([h for h, _ in mw])
         self.speed_loc = torch.zeros(1, dtype=dtype, device=device)
-        if self.sync in ("push", "fpush"):
+        if self.sync in ("push", "fpush", "pushb"):
             from t8gpu_b200.multi import send_csr, send_lists
             self.send = send_lists(dist, self.plan, self.n, rank, world, device)
             self.csr = send_csr(self.send, self.n, device)
@@ -123,7 +125,7 @@ class MultiGpuEuler:
         """The state was written outside the stage kernels (initial data, upload): a full barrier before any rank reads
         ghosts, which also starts the stage-epoch sequence the self-ordering kernels continue."""
         if self.mail is not None and self.sync != "none":
-            if self.sync in ("push", "fpush"):     # the state was written by other means: push its ghost copies, then publish
+            if self.sync in ("push", "fpush", "pushb"):     # the state was written by other means: push its ghost copies, then publish
                 self.tb.ghost_push(*self.send, self.variables(self.next), self.tables[self.next])
                 self.mail.barrier(self.speed_loc, self.speed_max)
             elif self.sync in ("pull", "overlap"):    # same class as the barrier that ends a step (precedes the first pull)
@@ -169,6 +171,17 @@ class MultiGpuEuler:
             if adaptive:
                 self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
             return 6 + int(adaptive)                      # 3 x (stage with push, barrier)
+        if self.sync == "pushb":
+            m, P = self.mail, self.plan
+            P.stage(1, prev, None, s1, vol, dt, dt_dev=dtd)
+            m.push_barrier(*self.send, s1, T[1])          # push + the barrier that publishes it, one launch
+            P.stage(2, s1, prev, s2, vol, dt, dt_dev=dtd)
+            m.push_barrier(*self.send, s2, T[2])
+            P.stage(3, s2, prev, nxt, vol, dt, speed_max=self.speed_loc, dt_dev=dtd)
+            m.push_barrier(*self.send, nxt, T[self.next], self.speed_loc, self.speed_max)   # + CFL max over the ranks
+            if adaptive:
+                self.tb.timestep(self.speed_max, CFL, self.length, dt, self.dt_dev)
+            return 6 + int(adaptive)                      # 3 x (stage, push + barrier)
         if self.sync == "push":
             m, P, push = self.mail, self.plan, self.tb.ghost_push
             P.stage(1, prev, None, s1, vol, dt, dt_dev=dtd)
@@ -282,7 +295,7 @@ class MultiGpuEuler:
         in for a profiler capture of a multi-process run (ncu on one rank of a torchrun job hangs in the IPC set-up):
         stage kernels, ghost pushes (with the NVLink bytes they move) and barrier kernels (launch + wait for the
         slowest rank), averaged per launch."""
-        if self.sync not in ("push", "fpush"):
+        if self.sync not in ("push", "fpush", "pushb"):
             return None
         ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
         marks, st = [], torch.cuda.current_stream()
@@ -476,6 +489,10 @@ def run_multi(args, rank, world, device):
                               "copy of also stores the new values into those copies over NVLink (posted stores from the "
                               "epilogue); one mailbox barrier kernel per stage publishes them; the stage-3 barrier "
                               "carries the CFL max",
+                     "pushb": "ghost tail; after each stage ONE kernel pushes the elements the peers hold copies of into "
+                              "their tails over NVLink (consecutive remote stores) and, from its last CTA, runs the "
+                              "mailbox barrier that publishes them; the single-rank stage kernel follows (no peer memory "
+                              "inside it); the stage-3 barrier carries the CFL max",
                      "push": "ghost tail; after each stage every rank pushes the elements its peers hold copies of into "
                              "their tails over NVLink (consecutive remote stores), one mailbox barrier kernel publishes "
                              "them, the single-rank stage kernel follows (no peer memory inside it); the stage-3 barrier "

@@ -213,6 +213,18 @@ int t8b200_ghost_push_f32(int nvar, int64_t n_send, const int32_t* src_idx, cons
 int t8b200_ghost_push_f64(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
                           const int32_t* dst_idx, const double* const* rows, double* const* const* rows_all,
                           void* stream);
+/* The push and the t8b200_peer_barrier that publishes it in ONE launch (the last CTA to finish its pushes runs the
+ * barrier protocol): arguments of t8b200_ghost_push_* + those of t8b200_peer_barrier (value_dev != NULL: CFL slots and
+ * maximum into out_max_dev, epoch from the CFL sequence; else stage slots / stage sequence).  counter_dev: DEVICE
+ * unsigned, zero before the first call, left at zero by every call.  A rank with n_send == 0 still takes part. */
+int t8b200_ghost_push_barrier_f32(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
+                                  const int32_t* dst_idx, const float* const* rows, float* const* const* rows_all,
+                                  unsigned* counter_dev, int nranks, int rank, long long epoch, void* const* mailboxes_dev,
+                                  const float* value_dev, float* out_max_dev, void* stream);
+int t8b200_ghost_push_barrier_f64(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
+                                  const int32_t* dst_idx, const double* const* rows, double* const* const* rows_all,
+                                  unsigned* counter_dev, int nranks, int rank, long long epoch, void* const* mailboxes_dev,
+                                  const double* value_dev, double* out_max_dev, void* stream);
 
 /* One fused RK stage.  in/prev/out: HOST arrays of 5 DEVICE pointers to this rank's arrays (stage input, U^n, stage
  * output).  in_all: HOST array of 5 DEVICE tables (one pointer per rank) for ghost reads, or NULL when the plan has

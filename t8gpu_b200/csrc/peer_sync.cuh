@@ -38,6 +38,34 @@ __device__ __forceinline__ long long peer_load_epoch(const PeerSlot* s) {
   return e;
 }
 
+// The barrier protocol of t8b200_peer_barrier for the first `nranks` lanes of ONE warp (all 32 lanes call it): lane p
+// stores (value, epoch) into this rank's slot of rank p's mailbox, then waits for rank p's slot of the own mailbox;
+// with out_max the maximum of the values goes to *out_max.  value == nullptr: stage slots, else CFL slots.
+__device__ __forceinline__ void peer_barrier_warp(int lane, int nranks, int rank, long long epoch, PeerSlot* const* mailboxes,
+                                                  const void* value, int value_is_f64, void* out_max) {
+  const int base = (value ? 2 * nranks : 0) + (int)(epoch & 1) * nranks;
+  double    v    = 0.0;
+  if (value) v = value_is_f64 ? *(const double*)value : (double)*(const float*)value;
+  if (lane < nranks) {
+    PeerSlot* s = mailboxes[lane] + base + rank;
+    // value first, then the epoch with release semantics at system scope (the reader acquires the epoch)
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&s->value), "d"(v) : "memory");
+    peer_store_epoch(s, epoch);
+  }
+  double m = 0.0;
+  if (lane < nranks) {
+    const PeerSlot* s = mailboxes[rank] + base + lane;
+    while (peer_load_epoch(s) < epoch) {}
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(m) : "l"(&s->value) : "memory");
+  }
+  if (out_max) {
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+      if (value_is_f64) *(double*)out_max = m; else *(float*)out_max = (float)m;
+    }
+  }
+}
+
 // Called by a THREAD about to read an element owned by rank `owner` (a ghost): waits until that rank has signalled
 // the awaited epoch.  The acquire is per thread and in front of the thread's own peer loads, so no CTA-wide step is
 // needed, threads that read this rank's own elements never wait, and a chunk only waits for the ranks it reads from.

@@ -10,6 +10,7 @@
 //   t8gpu/mesh/subgrid_mesh_manager.inl:1216-1283 partition_variable_data, partition_volume_data
 #include "../../include/t8gpu_b200.h"
 #include "common.cuh"
+#include "peer_sync.cuh"
 #include "tile_plan.cuh"
 
 namespace {
@@ -147,6 +148,40 @@ ghost_push_kernel(int nvar, int64_t n_send, const int32_t* __restrict__ src, con
     if (k == l) all.p[k][drk[e]][dix[e]] = own.p[k][src[e]];
 }
 
+// The push and the barrier that publishes it in ONE launch: every CTA pushes its entries, releases them at system
+// scope and counts itself; the last CTA to finish runs the barrier protocol of t8b200_peer_barrier (signal every
+// peer, wait for every peer).  One launch per stage instead of two between consecutive stage kernels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ghost_push_barrier_kernel(int nvar, int64_t n_send, const int32_t* __restrict__ src, const int32_t* __restrict__ drk,
+                          const int32_t* __restrict__ dix, PtrsC<T> own, Tables<T> all, unsigned* counter, int nranks,
+                          int rank, long long epoch, t8b200::PeerSlot* const* mailboxes, const void* value,
+                          int value_is_f64, void* out_max) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_send * nvar) {
+    const int64_t e = g % n_send;
+    const int     l = (int)(g / n_send);
+#pragma unroll
+    for (int k = 0; k < MAXV; k++)
+      if (k == l) all.p[k][drk[e]][dix[e]] = own.p[k][src[e]];
+  }
+  __shared__ int last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // one system-scope fence per CTA: the CTA barrier orders the other threads' remote stores before it (cumulativity),
+    // so they are visible before the CTA counts itself
+    __threadfence_system();
+    last = atomicAdd(counter, 1u) + 1u == gridDim.x;
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x < 32) {
+    __threadfence_system();   // acquire the counts of the other CTAs, release in front of the epoch stores
+    t8b200::peer_barrier_warp(threadIdx.x, nranks, rank, epoch, mailboxes, value, value_is_f64, out_max);
+    if (threadIdx.x == 0) *counter = 0u;   // the next launch on this stream starts from zero
+  }
+}
+
 template <typename T>
 int adapt_impl(int dim_subgrid, int nvar, int64_t n_new, const int32_t* ad, const T* const* uo, T* const* un,
                const T* vo, T* vn, void* stream) {
@@ -212,6 +247,23 @@ static int ghost_push_impl(int nvar, int64_t n_send, const int32_t* src, const i
   return cudaGetLastError();
 }
 
+template <typename T>
+static int ghost_push_barrier_impl(int nvar, int64_t n_send, const int32_t* src, const int32_t* drk, const int32_t* dix,
+                                   const T* const* rows, T* const* const* rows_all, unsigned* counter, int nranks, int rank,
+                                   long long epoch, void* const* mailboxes, const void* value, void* out_max, void* stream) {
+  if (nvar < 1 || nvar > MAXV || n_send < 0 || nranks < 1 || nranks > 32 || rank < 0 || rank >= nranks || epoch <= 0)
+    return cudaErrorInvalidValue;
+  if (!counter || !mailboxes || !rows || !rows_all || (n_send > 0 && (!src || !drk || !dix))) return cudaErrorInvalidValue;
+  PtrsC<T>  o{};
+  Tables<T> a{};
+  for (int k = 0; k < nvar; k++) { o.p[k] = rows[k]; a.p[k] = rows_all[k]; }
+  const int64_t total = std::max<int64_t>(n_send * nvar, 1);   // a rank with nothing to send still takes part in the barrier
+  ghost_push_barrier_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      nvar, n_send, src, drk, dix, o, a, counter, nranks, rank, epoch, (t8b200::PeerSlot* const*)mailboxes, value,
+      sizeof(T) == 8, out_max);
+  return cudaGetLastError();
+}
+
 extern "C" {
 int t8b200_ghost_push_f32(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
                           const int32_t* dst_idx, const float* const* rows, float* const* const* rows_all, void* stream) {
@@ -221,6 +273,20 @@ int t8b200_ghost_push_f64(int nvar, int64_t n_send, const int32_t* src_idx, cons
                           const int32_t* dst_idx, const double* const* rows, double* const* const* rows_all,
                           void* stream) {
   return ghost_push_impl<double>(nvar, n_send, src_idx, dst_rank, dst_idx, rows, rows_all, stream);
+}
+int t8b200_ghost_push_barrier_f32(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
+                                  const int32_t* dst_idx, const float* const* rows, float* const* const* rows_all,
+                                  unsigned* counter_dev, int nranks, int rank, long long epoch, void* const* mailboxes_dev,
+                                  const float* value_dev, float* out_max_dev, void* stream) {
+  return ghost_push_barrier_impl<float>(nvar, n_send, src_idx, dst_rank, dst_idx, rows, rows_all, counter_dev, nranks, rank,
+                                        epoch, mailboxes_dev, value_dev, out_max_dev, stream);
+}
+int t8b200_ghost_push_barrier_f64(int nvar, int64_t n_send, const int32_t* src_idx, const int32_t* dst_rank,
+                                  const int32_t* dst_idx, const double* const* rows, double* const* const* rows_all,
+                                  unsigned* counter_dev, int nranks, int rank, long long epoch, void* const* mailboxes_dev,
+                                  const double* value_dev, double* out_max_dev, void* stream) {
+  return ghost_push_barrier_impl<double>(nvar, n_send, src_idx, dst_rank, dst_idx, rows, rows_all, counter_dev, nranks,
+                                         rank, epoch, mailboxes_dev, value_dev, out_max_dev, stream);
 }
 int t8b200_ghost_pull_f32(const t8b200_plan* plan, int nvar, float* const* rows, const float* const* const* rows_all,
                           void* stream) {

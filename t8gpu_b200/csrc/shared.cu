@@ -47,28 +47,7 @@ using t8b200::PeerSlot;
 
 __global__ void peer_barrier_kernel(int nranks, int rank, long long epoch, PeerSlot* const* mailboxes, const void* value,
                                     int value_is_f64, void* out_max) {
-  const int lane = threadIdx.x;
-  const int base = (value ? 2 * nranks : 0) + (int)(epoch & 1) * nranks;
-  double    v    = 0.0;
-  if (value) v = value_is_f64 ? *(const double*)value : (double)*(const float*)value;
-  if (lane < nranks) {
-    PeerSlot* s = mailboxes[lane] + base + rank;
-    // value first, then the epoch with release semantics at system scope (the reader acquires the epoch)
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&s->value), "d"(v) : "memory");
-    t8b200::peer_store_epoch(s, epoch);
-  }
-  double m = 0.0;
-  if (lane < nranks) {
-    const PeerSlot* s = mailboxes[rank] + base + lane;
-    while (t8b200::peer_load_epoch(s) < epoch) {}
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(m) : "l"(&s->value) : "memory");
-  }
-  if (out_max) {
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) {
-      if (value_is_f64) *(double*)out_max = m; else *(float*)out_max = (float)m;
-    }
-  }
+  t8b200::peer_barrier_warp(threadIdx.x, nranks, rank, epoch, mailboxes, value, value_is_f64, out_max);
 }
 
 // CompressibleEulerSolver::compute_timestep (examples/compressible_euler/solver.cu:225-228) without leaving the device:

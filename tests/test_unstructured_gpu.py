@@ -447,6 +447,28 @@ def test_peer_barrier_single_rank(cuda):
         mb.barrier()
         torch.cuda.synchronize()
         assert float(out[0]) == 3.25
+    # push + barrier in one launch: one rank pushing into its own rows (many CTAs: the last one runs the barrier)
+    for dt in (torch.float64, torch.float32):
+        n, ns = 100000, 70001
+        rows = [torch.rand(2 * n, dtype=dt, device=cuda) for _ in range(5)]
+        want = [r.clone() for r in rows]
+        src = torch.randperm(n, device=cuda)[:ns].to(torch.int32)
+        dst = (n + torch.arange(ns, device=cuda)).to(torch.int32)
+        for k in range(5):
+            want[k][n:n + ns] = rows[k][src.long()]
+        tables = tb.RankTables([rows], cuda)
+        v = torch.tensor([1.5], dtype=dt, device=cuda)
+        out = torch.zeros(1, dtype=dt, device=cuda)
+        for rep in range(3):                               # the counter is left at zero by every call
+            mb.push_barrier(src, torch.zeros(ns, dtype=torch.int32, device=cuda), dst, rows, tables, v, out)
+            mb.push_barrier(src, torch.zeros(ns, dtype=torch.int32, device=cuda), dst, rows, tables)
+        torch.cuda.synchronize()
+        assert float(out[0]) == 1.5 and int(mb.push_counter[0]) == 0
+        for k in range(5):
+            assert torch.equal(rows[k], want[k])
+        empty = torch.zeros(0, dtype=torch.int32, device=cuda)
+        mb.push_barrier(empty, empty, empty, rows, tables)  # nothing to send: still a barrier
+        torch.cuda.synchronize()
     L = tb.lib()
     assert L.t8b200_peer_barrier(0, 0, C.c_longlong(1), None, None, 1, None, None) != 0
     assert L.t8b200_peer_barrier(2, 2, C.c_longlong(1), C.c_void_p(mb.table.data_ptr()), None, 1, None, None) != 0
