@@ -48,23 +48,36 @@ CFL = 0.7   # examples/compressible_euler/solver.h:37
 
 
 def pin_to_gpu_numa_node(device):
-    """Host threads (and the pinned staging buffers they first-touch) onto the CPUs next to this rank's GPU."""
+    """Host threads onto the CPUs next to this rank's GPU, and the memory policy of the process to the GPU's NUMA node
+    (set_mempolicy(MPOL_PREFERRED)): the pinned staging buffers allocated afterwards sit next to the GPU even when the
+    container owns no CPU of that socket.  Returns (local cpus bound, numa node or -1, policy set?)."""
+    ncpu, node, policy = 0, -1, False
     try:
-        bus = torch.cuda.get_device_properties(device).pci_bus_id
-        dom = torch.cuda.get_device_properties(device).pci_domain_id
-        dev = torch.cuda.get_device_properties(device).pci_device_id
-        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        props = torch.cuda.get_device_properties(device)
+        base = "/sys/bus/pci/devices/%04x:%02x:%02x.0/" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
         cpus = set()
-        for part in open(path).read().strip().split(","):
+        for part in open(base + "local_cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return len(cpus)
+            ncpu = len(cpus)
+        node = int(open(base + "numa_node").read().strip())
     except Exception:
         pass
-    return 0
+    if node >= 0 and os.environ.get("T8B200_MEMPOLICY", "1") != "0":
+        try:
+            import ctypes
+            import platform
+            if platform.machine() == "x86_64":
+                mask = (ctypes.c_ulong * 16)()
+                mask[node // 64] = 1 << (node % 64)
+                libc = ctypes.CDLL(None, use_errno=True)
+                policy = libc.syscall(238, 1, mask, 1024) == 0        # SYS_set_mempolicy, MPOL_PREFERRED
+        except Exception:
+            policy = False
+    return ncpu, node, policy
 
 
 class MultiGpuEuler:
@@ -374,7 +387,9 @@ def bitwise_parity(dtype, rank, world, device, level=4, steps=3):
 def run_multi(args, rank, world, device):
     from bench import ALG_BYTES, ClockSampler, measured_peak
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
-    ncpu = pin_to_gpu_numa_node(device)
+    ncpu, numa_node, mempolicy = pin_to_gpu_numa_node(device)
+    numa_all = [None] * world
+    dist.all_gather_object(numa_all, (ncpu, numa_node, mempolicy))
     parity = bitwise_parity(dtype, rank, world, device)
     if os.environ.get("T8B200_SYNC") != "none":   # (the timing experiment without stage ordering is expected to differ)
         assert parity["bitwise_equal"], "the %d-rank run differs from the one-rank run of the same brick" % world
@@ -526,7 +541,9 @@ def run_multi(args, rank, world, device):
                            "sync": sync_text, "l2": "inputs larger than L2", "settle_steps_before_warmup": settle,
                            "host_setup_s": round(t_setup, 2), "tile_plan_s": round(t_plan, 3),
                            "tile_plan_built_on": info.get("built_on", "host"), "host_cores": os.cpu_count(),
-                           "host_cpus_bound_to_gpu_numa_node": ncpu, "per_rank_ms_per_step": per_rank_ms,
+                           "host_cpus_bound_to_gpu_numa_node": ncpu,
+                           "per_rank_(local_cpus, numa_node, mempolicy_preferred_set)": numa_all,
+                           "per_rank_ms_per_step": per_rank_ms,
                            "step_breakdown_rank0": breakdown,
                            "plan": info},
                 "clocks": clocks, "parity": parity, "secondary": secondary,
