@@ -227,10 +227,12 @@ int build(t8b200_cart_conn* out, t8b200_subgrid_face_info* info, Forest f, cudaS
   const int64_t  nl     = f.hi - f.lo;
   const unsigned blocks = (unsigned)((nl + 255) / 256);
   auto           pol    = thrust::cuda::par.on(st);
-  int64_t*       ghosts = nullptr;
-  int64_t        ng     = 0;
+  T8bScratch<int64_t> ghosts_mem, cnt_mem;
+  int64_t*&           ghosts = ghosts_mem.p;
+  int64_t             ng     = 0;
   if (f.nranks > 1 && nl > 0) {
-    unsigned long long* counter;
+    T8bScratch<unsigned long long> counter_mem;
+    unsigned long long*&           counter = counter_mem.p;
     T8B_TRY(cudaMalloc(&counter, 8));
     T8B_TRY(cudaMemsetAsync(counter, 0, 8, st));
     ghost_candidates_kernel<<<blocks, 256, 0, st>>>(f, counter, nullptr);
@@ -244,9 +246,8 @@ int build(t8b200_cart_conn* out, t8b200_subgrid_face_info* info, Forest f, cudaS
       thrust::sort(pol, ghosts, ghosts + nc);
       ng = thrust::unique(pol, ghosts, ghosts + nc) - ghosts;
     }
-    cudaFree(counter);
   }
-  int64_t* cnt;   // three count arrays of nl + 1 entries
+  int64_t*& cnt = cnt_mem.p;   // three count arrays of nl + 1 entries
   T8B_TRY(cudaMalloc(&cnt, 3 * (nl + 1) * sizeof(int64_t)));
   T8B_TRY(cudaMemsetAsync(cnt, 0, 3 * (nl + 1) * sizeof(int64_t), st));
   int64_t *bcnt = cnt + (nl + 1), *xcnt = cnt + 2 * (nl + 1);
@@ -289,8 +290,26 @@ int build(t8b200_cart_conn* out, t8b200_subgrid_face_info* info, Forest f, cudaS
                                                                            (T*)out->volumes, (T*)out->centroids);
   T8B_TRY(cudaGetLastError());
   T8B_TRY(cudaStreamSynchronize(st));
-  cudaFree(cnt); cudaFree(ghosts);
   return 0;
+}
+
+// on failure nothing stays allocated behind `out` / `info`
+template <typename T, bool SUB>
+int build_or_release(t8b200_cart_conn* out, t8b200_subgrid_face_info* info, Forest f, cudaStream_t st) {
+  int rc;
+  try {
+    rc = build<T, SUB>(out, info, f, st);
+  } catch (const std::bad_alloc&) {
+    rc = cudaErrorMemoryAllocation;
+  } catch (...) {
+    cudaGetLastError();
+    rc = cudaErrorUnknown;
+  }
+  if (rc) {
+    t8b200_cartesian_connectivity_free(out);
+    if (info) t8b200_subgrid_face_info_free(info);
+  }
+  return rc;
 }
 
 }  // namespace
@@ -303,8 +322,8 @@ extern "C" int t8b200_forest_connectivity(t8b200_cart_conn* out, int is_f64, int
   *out = t8b200_cart_conn{};
   Forest f{dim, periodic ? 1 : 0, nranks, rank, n_leaves, part_off(n_leaves, nranks, rank),
            part_off(n_leaves, nranks, rank + 1), keys_dev, levels_dev};
-  return is_f64 ? build<double, false>(out, nullptr, f, (cudaStream_t)stream)
-                : build<float, false>(out, nullptr, f, (cudaStream_t)stream);
+  return is_f64 ? build_or_release<double, false>(out, nullptr, f, (cudaStream_t)stream)
+                : build_or_release<float, false>(out, nullptr, f, (cudaStream_t)stream);
 }
 
 extern "C" int t8b200_forest_subgrid_connectivity(t8b200_cart_conn* out, t8b200_subgrid_face_info* info, int is_f64,
@@ -317,8 +336,8 @@ extern "C" int t8b200_forest_subgrid_connectivity(t8b200_cart_conn* out, t8b200_
   *info = t8b200_subgrid_face_info{};
   Forest f{dim, periodic ? 1 : 0, nranks, rank, n_leaves, part_off(n_leaves, nranks, rank),
            part_off(n_leaves, nranks, rank + 1), keys_dev, levels_dev};
-  return is_f64 ? build<double, true>(out, info, f, (cudaStream_t)stream)
-                : build<float, true>(out, info, f, (cudaStream_t)stream);
+  return is_f64 ? build_or_release<double, true>(out, info, f, (cudaStream_t)stream)
+                : build_or_release<float, true>(out, info, f, (cudaStream_t)stream);
 }
 
 extern "C" void t8b200_subgrid_face_info_free(t8b200_subgrid_face_info* info) {

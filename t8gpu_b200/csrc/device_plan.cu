@@ -1073,28 +1073,35 @@ int t8b200_plan_create_device(t8b200_plan** out, int is_f64, int ghost_tail, int
                               int32_t nf, int32_t nb, const int32_t* nbr, const void* normals, const void* areas,
                               const int32_t* ranks, const int32_t* indices, int32_t nx, const int32_t* xnbr,
                               const void* xnormals, const void* xareas, void* stream) {
-  const int flags = ghost_tail ? 2 : 0;
-  const char* mode_env     = getenv("T8B200_DEVICE_PLAN");   // tests: "generic" / "serial" skip the three-kernel builder
-  const bool  generic_only = mode_env && (mode_env[0] == 'g' || mode_env[0] == 's');
-  int rc = cudaErrorNotSupported;
-  if (!generic_only)
-    rc = is_f64 ? device_plan_impl<double>(out, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
-                                           (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
-                                           (const double*)xareas, stream)
-                : device_plan_impl<float>(out, flags, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
-                                          (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
-                                          (const float*)xareas, stream);
-  if (rc != cudaErrorNotSupported) return rc;
-  // not a structured-only mesh: the generic builder (one program per block of 256 elements)
-  if (!out || n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0) return cudaErrorInvalidValue;
-  if ((nf + nb > 0 && (!nbr || !normals || !areas)) || (nx > 0 && (!xnbr || !xnormals || !xareas))) return cudaErrorInvalidValue;
-  if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
-  return is_f64 ? generic_mesh_plan<double>(out, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
-                                            (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
-                                            (const double*)xareas, stream)
-                : generic_mesh_plan<float>(out, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
-                                           (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
-                                           (const float*)xareas, stream);
+  try {
+    const int flags = ghost_tail ? 2 : 0;
+    const char* mode_env     = getenv("T8B200_DEVICE_PLAN");   // tests: "generic" / "serial" skip the three-kernel builder
+    const bool  generic_only = mode_env && (mode_env[0] == 'g' || mode_env[0] == 's');
+    int rc = cudaErrorNotSupported;
+    if (!generic_only)
+      rc = is_f64 ? device_plan_impl<double>(out, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
+                                             (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
+                                             (const double*)xareas, stream)
+                  : device_plan_impl<float>(out, flags, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
+                                            (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
+                                            (const float*)xareas, stream);
+    if (rc != cudaErrorNotSupported) return rc;
+    // not a structured-only mesh: the generic builder (one program per block of 256 elements)
+    if (!out || n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0) return cudaErrorInvalidValue;
+    if ((nf + nb > 0 && (!nbr || !normals || !areas)) || (nx > 0 && (!xnbr || !xnormals || !xareas))) return cudaErrorInvalidValue;
+    if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
+    return is_f64 ? generic_mesh_plan<double>(out, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
+                                              (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
+                                              (const double*)xareas, stream)
+                  : generic_mesh_plan<float>(out, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
+                                             (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
+                                             (const float*)xareas, stream);
+  } catch (const std::bad_alloc&) {
+    return cudaErrorMemoryAllocation;
+  } catch (...) {   // thrust reports failed temporary allocations / launches by exception
+    cudaGetLastError();
+    return cudaErrorUnknown;
+  }
 }
 
 int t8b200_subgrid_plan_create_device(t8b200_subgrid_plan** out, int is_f64, int dim, int ghost_tail, int64_t n_local,
@@ -1103,36 +1110,44 @@ int t8b200_subgrid_plan_create_device(t8b200_subgrid_plan** out, int is_f64, int
                                       const void* volumes, const int32_t* ranks, const int32_t* indices, int32_t nx,
                                       const int32_t* xnbr, const void* xnormals, const void* xareas,
                                       const int32_t* x_level_diff, const int32_t* x_offsets, void* stream) {
-  if (!out || (dim != 2 && dim != 3)) return cudaErrorInvalidValue;
-  const int    flags = ghost_tail ? 2 : 0;
-  t8b200_plan* P     = nullptr;
-  const char*  mode_env     = getenv("T8B200_DEVICE_PLAN");
-  const bool   generic_only = mode_env && (mode_env[0] == 'g' || mode_env[0] == 's');
-  int          rc           = cudaErrorNotSupported;
-  if (dim == 3 && !generic_only)   // Subgrid<4,4,4> on structured-only forests: three kernels
-    rc = is_f64 ? device_plan_impl<double>(&P, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
-                                           (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
-                                           (const double*)xareas, stream, true, (const double*)volumes, level_diff,
-                                           x_level_diff)
-                : device_plan_impl<float>(&P, flags, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
-                                          (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
-                                          (const float*)xareas, stream, true, (const float*)volumes, level_diff,
-                                          x_level_diff);
-  if (rc == cudaErrorNotSupported) {   // any other forest: the generic builder over the cell faces
-    if (n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0 || !volumes) return cudaErrorInvalidValue;
-    if ((nf + nb > 0 && (!nbr || !normals || !areas)) || (nf > 0 && (!level_diff || !offsets))) return cudaErrorInvalidValue;
-    if (nx > 0 && (!xnbr || !xnormals || !xareas || !x_level_diff || !x_offsets)) return cudaErrorInvalidValue;
-    if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
-#define T8B_SG(TT, DD)                                                                                                    \
-  generic_subgrid_plan<TT, DD>(&P, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const TT*)normals, (const TT*)areas,       \
-                               level_diff, offsets, (const TT*)volumes, ranks, indices, nx, xnbr, (const TT*)xnormals,    \
-                               (const TT*)xareas, x_level_diff, x_offsets, stream)
-    rc = is_f64 ? (dim == 3 ? T8B_SG(double, 3) : T8B_SG(double, 2)) : (dim == 3 ? T8B_SG(float, 3) : T8B_SG(float, 2));
-#undef T8B_SG
+  try {
+    if (!out || (dim != 2 && dim != 3)) return cudaErrorInvalidValue;
+    const int    flags = ghost_tail ? 2 : 0;
+    t8b200_plan* P     = nullptr;
+    const char*  mode_env     = getenv("T8B200_DEVICE_PLAN");
+    const bool   generic_only = mode_env && (mode_env[0] == 'g' || mode_env[0] == 's');
+    int          rc           = cudaErrorNotSupported;
+    if (dim == 3 && !generic_only)   // Subgrid<4,4,4> on structured-only forests: three kernels
+      rc = is_f64 ? device_plan_impl<double>(&P, flags, n_local, n_ghost, nf, nb, nbr, (const double*)normals,
+                                             (const double*)areas, ranks, indices, nx, xnbr, (const double*)xnormals,
+                                             (const double*)xareas, stream, true, (const double*)volumes, level_diff,
+                                             x_level_diff)
+                  : device_plan_impl<float>(&P, flags, n_local, n_ghost, nf, nb, nbr, (const float*)normals,
+                                            (const float*)areas, ranks, indices, nx, xnbr, (const float*)xnormals,
+                                            (const float*)xareas, stream, true, (const float*)volumes, level_diff,
+                                            x_level_diff);
+    if (rc == cudaErrorNotSupported) {   // any other forest: the generic builder over the cell faces
+      if (n_local < 0 || n_ghost < 0 || nf < 0 || nb < 0 || nx < 0 || !volumes) return cudaErrorInvalidValue;
+      if ((nf + nb > 0 && (!nbr || !normals || !areas)) || (nf > 0 && (!level_diff || !offsets))) return cudaErrorInvalidValue;
+      if (nx > 0 && (!xnbr || !xnormals || !xareas || !x_level_diff || !x_offsets)) return cudaErrorInvalidValue;
+      if (n_ghost > 0 && (!ranks || !indices)) return cudaErrorInvalidValue;
+  #define T8B_SG(TT, DD)                                                                                                    \
+    generic_subgrid_plan<TT, DD>(&P, ghost_tail, n_local, n_ghost, nf, nb, nbr, (const TT*)normals, (const TT*)areas,       \
+                                 level_diff, offsets, (const TT*)volumes, ranks, indices, nx, xnbr, (const TT*)xnormals,    \
+                                 (const TT*)xareas, x_level_diff, x_offsets, stream)
+      rc = is_f64 ? (dim == 3 ? T8B_SG(double, 3) : T8B_SG(double, 2)) : (dim == 3 ? T8B_SG(float, 3) : T8B_SG(float, 2));
+  #undef T8B_SG
+    }
+    if (rc) return rc;
+    *out = t8b_wrap_subgrid_plan(P, dim);
+    return 0;
+
+  } catch (const std::bad_alloc&) {
+    return cudaErrorMemoryAllocation;
+  } catch (...) {
+    cudaGetLastError();
+    return cudaErrorUnknown;
   }
-  if (rc) return rc;
-  *out = t8b_wrap_subgrid_plan(P, dim);
-  return 0;
 }
 
 // test access to every DEVICE array of a plan, numbered as t8b200_plan_host_array does (0 hdr ... 19 blist), as raw bytes in
