@@ -937,25 +937,14 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   P->n_generic = P->n_struct ? (int)g_list.size() : (int)nchunks;
   if (!P->n_struct && !multi) g_list.clear();
   if (multi) {
-    static const int order_mode = getenv("T8B200_BND_ORDER") ? (getenv("T8B200_BND_ORDER")[0] == 'f' ? 1 : getenv("T8B200_BND_ORDER")[0] == 'n' ? 2 : 0) : 0;
-    const bool keep_order = order_mode == 2 || (P->n_struct == nchunks && !P->split);
-    auto arrange = [&](std::vector<int32_t>& list, int& n_bnd) {
-      const size_t n = list.size();
-      std::vector<int32_t> bl, il, order;
-      for (int32_t c : list) (bf[c] ? bl : il).push_back(c);
-      n_bnd = (int)bl.size();
-      order.reserve(n);
-      if (keep_order) order = list;
-      else if (order_mode == 1 || bl.empty()) { order = bl; order.insert(order.end(), il.begin(), il.end()); }
-      else {
-        const size_t nb = bl.size(), W = std::max(nb, n / 2);
-        size_t ib = 0, ii = 0;
-        for (size_t pos = 0; pos < n; pos++) {
-          const bool want_b = ib < nb && (pos >= W || ib * W / nb <= pos || ii >= il.size());
-          order.push_back(want_b ? bl[ib++] : il[ii++]);
-        }
-      }
-      for (auto& c : order) if (bf[c]) c |= 1 << 30;
+    const bool keep_order = t8b_boundary_order_mode() == 2 || (P->n_struct == nchunks && !P->split);
+    auto arrange = [&](std::vector<int32_t>& list, int& n_bnd) {   // tile_plan.cuh: t8b_boundary_order
+      std::vector<uint8_t> flag(list.size());
+      n_bnd = 0;
+      for (size_t q = 0; q < list.size(); q++) { flag[q] = bf[list[q]]; n_bnd += flag[q]; }
+      std::vector<int32_t> order;
+      order.reserve(list.size());
+      for (size_t q : t8b_boundary_order(flag, keep_order)) order.push_back(list[q] | (flag[q] ? 1 << 30 : 0));
       list.swap(order);
     };
     arrange(s_list, P->nb_struct);

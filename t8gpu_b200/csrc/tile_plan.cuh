@@ -163,6 +163,34 @@ static void parallel_ranges(int64_t n, int nthreads, Fn&& fn) {   // fn(thread, 
   for (auto& x : th) x.join();
 }
 
+// Launch order of a chunk list of a multi-rank plan (shared by the host builder below and the device builder,
+// device_plan.cu).  flag[q] != 0: chunk q reads another rank's elements (partition-boundary chunk).  Boundary chunk j of
+// nb sits at position floor(j W / nb) of the first W = max(nb, n/2) positions, interior chunks fill the rest in element
+// order -- all boundary chunks are done (and signalled, peer_sync.cuh) about half way through the kernel, without a
+// first wave made of nothing but NVLink-latency-bound chunks.  T8B200_BND_ORDER=first: all of them first; =natural:
+// element order.  keep_order: plans whose chunks are all structured and unsplit keep the element order (chunk b =
+// elements [256 b, 256 b + 256) needs no record load in front of the kernel's first loads: +4.5 % per step with it).
+static inline int t8b_boundary_order_mode() {
+  static const int mode = getenv("T8B200_BND_ORDER") ? (getenv("T8B200_BND_ORDER")[0] == 'f' ? 1 : getenv("T8B200_BND_ORDER")[0] == 'n' ? 2 : 0) : 0;
+  return mode;
+}
+static inline std::vector<size_t> t8b_boundary_order(const std::vector<uint8_t>& flag, bool keep_order) {
+  const int    order_mode = t8b_boundary_order_mode();
+  const size_t n = flag.size();
+  std::vector<size_t> bl, il, order;
+  for (size_t q = 0; q < n; q++) (flag[q] ? bl : il).push_back(q);
+  order.reserve(n);
+  if (keep_order) { for (size_t q = 0; q < n; q++) order.push_back(q); return order; }
+  if (order_mode == 1 || bl.empty()) { order = bl; order.insert(order.end(), il.begin(), il.end()); return order; }
+  const size_t nb = bl.size(), W = std::max(nb, n / 2);
+  size_t ib = 0, ii = 0;
+  for (size_t pos = 0; pos < n; pos++) {
+    const bool want_b = ib < nb && (pos >= W || ib * W / nb <= pos || ii >= il.size());
+    if (want_b) order.push_back(bl[ib++]); else order.push_back(il[ii++]);
+  }
+  return order;
+}
+
 // Builds the plan from any face source `src` (its member functions are called concurrently, they must be const-safe):
 //   int64_t num_faces();                                  faces of this rank, every face of a local element exactly once
 //   void endpoints(int64_t f, int32_t& l, int32_t& r);    element ids; r = -1: wall; ids >= n_local: ghosts
@@ -649,31 +677,10 @@ static int plan_build(t8b200_plan* P, int64_t n_local, bool multi, Src& src) {
         for (int h = 0; h < HS; h++)
           if (halo_elem[c * HS + h] >= 0 && halo_rank[c * HS + h] != me) { gb[q] = 1; break; }
       }
-      // order of the launches: boundary chunk j of nb sits at position floor(j W / nb) of the first W = max(nb, n/2)
-      // positions, interior chunks fill the rest in element order -- all boundary chunks are done (and signalled) about
-      // half way through the kernel, without a first wave made of nothing but NVLink-latency-bound chunks
-      // (T8B200_BND_ORDER=first: all of them first; =natural: element order).  The flag travels with the chunk:
-      // s_rec[4 q + 3] = 1, g_list entry | 1 << 30.
-      static const int order_mode = getenv("T8B200_BND_ORDER") ? (getenv("T8B200_BND_ORDER")[0] == 'f' ? 1 : getenv("T8B200_BND_ORDER")[0] == 'n' ? 2 : 0) : 0;
-      // plans whose chunks are all structured and unsplit keep the element order: chunk b = elements [256 b, 256 b + 256)
-      // needs no record load in front of the kernel's first loads (measured: +4.5 % per step with it), and their
-      // boundary chunks are scattered over the launch by the Morton order anyway
-      const bool keep_order = order_mode == 2 || (P->n_struct == nchunks && !split);
-      auto arrange = [&](const std::vector<uint8_t>& flag) {
-        const size_t n = flag.size();
-        std::vector<size_t> bl, il, order;
-        for (size_t q = 0; q < n; q++) (flag[q] ? bl : il).push_back(q);
-        order.reserve(n);
-        if (keep_order) { for (size_t q = 0; q < n; q++) order.push_back(q); return order; }
-        if (order_mode == 1 || bl.empty()) { order = bl; order.insert(order.end(), il.begin(), il.end()); return order; }
-        const size_t nb = bl.size(), W = std::max(nb, n / 2);
-        size_t ib = 0, ii = 0;
-        for (size_t pos = 0; pos < n; pos++) {
-          const bool want_b = ib < nb && (pos >= W || ib * W / nb <= pos || ii >= il.size());
-          if (want_b) order.push_back(bl[ib++]); else order.push_back(il[ii++]);
-        }
-        return order;
-      };
+      // order of the launches: t8b_boundary_order above.  The flag travels with the chunk: s_rec[4 q + 3] = 1, g_list
+      // entry | 1 << 30.
+      const bool keep_order = t8b_boundary_order_mode() == 2 || (P->n_struct == nchunks && !split);
+      auto arrange = [&](const std::vector<uint8_t>& flag) { return t8b_boundary_order(flag, keep_order); };
       std::vector<int32_t> r2, h2, k2, g2;
       r2.reserve(s_rec.size()); h2.reserve(s_halo.size()); k2.reserve(s_hrank.size()); g2.reserve(g_list.size());
       for (size_t q : arrange(sb)) {
