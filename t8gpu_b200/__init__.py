@@ -673,6 +673,7 @@ class PeerMailboxes:
         self.cfl_epoch = 0
         self.table = None
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.push_counter = torch.zeros(1, dtype=torch.int32, device=device)   # CTAs of a push + barrier launch
         self.struct = None
 
     @property
@@ -714,7 +715,6 @@ class PeerMailboxes:
 
     def push_barrier(self, src_idx, dst_rank, dst_idx, rows, rows_all, value=None, out=None, stream=None):
         """ghost_push + barrier in one launch (t8b200_ghost_push_barrier_*); epochs as in `barrier`."""
-        torch = _torch()
         s, _ = _sfx(rows[0].dtype)
         if value is not None:
             self.cfl_epoch += 1
@@ -722,8 +722,6 @@ class PeerMailboxes:
         else:
             self.stage_epoch += 1
             epoch = self.stage_epoch
-        if getattr(self, "push_counter", None) is None:
-            self.push_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         check(getattr(lib(), "t8b200_ghost_push_barrier_" + s)(
             len(rows), C.c_int64(src_idx.numel()), C.c_void_p(src_idx.data_ptr()), C.c_void_p(dst_rank.data_ptr()),
             C.c_void_p(dst_idx.data_ptr()), ptrs(rows), rows_all.host, C.c_void_p(self.push_counter.data_ptr()),
