@@ -203,6 +203,27 @@ def test_generic_device_builder_equals_host_builder(cuda, dtype, mode, monkeypat
     assert H["info"][0] > 16
 
 
+def test_generic_device_builder_edge_cases(cuda, monkeypatch):
+    """More than 256 distinct areas on axis-aligned faces (the compressed geometry does not apply), a mesh smaller than
+    one block, a rank without elements."""
+    import t8gpu_b200 as tb
+    monkeypatch.setenv("T8B200_DEVICE_PLAN", "generic")
+    conn = oracle.Forest(3, 4).connectivity(dtype=np.float64)
+    rng = np.random.default_rng(5)
+    conn["face_areas"] = conn["face_areas"] * (1.0 + rng.integers(0, 300, conn["face_areas"].size) / 1024.0)
+    _, H = assert_same_plan(conn, torch.float64, False, cuda, "300 areas")
+    assert H[9].size > 0 and H[4].size == 0                       # general-geometry arrays, no area indices
+    conn = oracle.Forest(3, 4).connectivity(dtype=np.float64)
+    conn["face_areas"] = conn["face_areas"] * (1.0 + rng.integers(0, 200, conn["face_areas"].size) / 1024.0)
+    _, H = assert_same_plan(conn, torch.float64, False, cuda, "200 areas")
+    assert H[8].size == 200 and H[4].size > 0                     # area table in use, no chunk is structured
+    assert H[13].size == 0
+    assert_same_plan(oracle.Forest(3, 2).connectivity(dtype=np.float32), torch.float32, False, cuda, "64 elements")
+    assert_same_plan(oracle.Forest(2, 1).connectivity(dtype=np.float64), torch.float64, False, cuda, "4 quads")
+    empty = dict(n_local=0, n_ghost=0, n_faces=0, n_bfaces=0, n_xfaces=0)
+    assert tb.Plan.from_device(empty, torch.float64) is None      # cudaErrorNotSupported: the host builder's case
+
+
 @pytest.mark.parametrize("ghost_tail", [False, True])
 @pytest.mark.parametrize("P", [2, 3])
 def test_generic_device_builder_multi_rank(cuda, P, ghost_tail, monkeypatch):

@@ -583,3 +583,17 @@ def test_block_program_equals_host_builder_on_subgrid_cells(dtype):
                         assert np.array_equal(X[k], Y[k]), k
                 L.t8b200_subgrid_plan_destroy(s1)
                 L.t8b200_subgrid_plan_destroy(s2)
+
+
+def test_block_program_edge_cases():
+    """More than 256 distinct areas on axis-aligned faces (no compressed geometry), exactly-fitting area table, meshes
+    smaller than one block."""
+    L = _lib()
+    rng = np.random.default_rng(5)
+    for k in (300, 200):
+        conn = oracle.Forest(3, 4).connectivity(dtype=np.float64)
+        conn["face_areas"] = conn["face_areas"] * (1.0 + rng.integers(0, k, conn["face_areas"].size) / 1024.0)
+        A = _same_plan(L, conn, np.float64, False)
+        assert (len(A["area_tab"]), len(A["fnx"]) > 0) == ((0, True) if k > 256 else (k, False))
+    _same_plan(L, oracle.Forest(3, 2).connectivity(dtype=np.float32), np.float32, False)
+    _same_plan(L, oracle.Forest(2, 1).connectivity(dtype=np.float64), np.float64, False)
