@@ -531,6 +531,12 @@ int t8b200_subgrid_criteria_f64(int dim, int64_t n_elements, const double* rho, 
  * (device, 3 per point, float_type).  u: HOST array of 5 device pointers. */
 int t8b200_init_kelvin_helmholtz_f32(int dim, int64_t n, const float* centers, float* const* u, void* stream);
 int t8b200_init_kelvin_helmholtz_f64(int dim, int64_t n, const double* centers, double* const* u, void* stream);
+/* Kelvin-Helmholtz initial state on the globe of the unstructured example (examples/compressible_euler/solver.cu:17-72,
+ * a host lambda per element there) sampled at n element centroids (device, 3 per point, already cast to float_type as
+ * at :32-34; r > 0 and not on the z axis).  Same expression types as the reference; agrees with the host evaluation to
+ * the rounding of the device's sqrt / acos / asin / sin / cos / exp. */
+int t8b200_init_spherical_kelvin_helmholtz_f32(int64_t n, const float* centers, float* const* u, void* stream);
+int t8b200_init_spherical_kelvin_helmholtz_f64(int64_t n, const double* centers, double* const* u, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
  * 7. Output path of the subgrid manager (the step after the hot path when a run writes VTK)

@@ -211,6 +211,16 @@ def init_kh_points(dim, centers, dtype):
     return u
 
 
+def init_spherical_kh_points(centers, dtype):
+    """Kelvin-Helmholtz field on the globe (compressible_euler/solver.cu:17-72) at points already cast to dtype."""
+    s, _ = _sfx(dtype)
+    c = np.ascontiguousarray(centers, dtype=dtype)
+    n = c.shape[0]
+    u = np.zeros((5, n), dtype)
+    getattr(lib(), "orc_init_spherical_kh_points_" + s)(C.c_int64(n), _p(c), _p(u), C.c_int64(n))
+    return u
+
+
 def subgrid_init_kh(dim, centers, levels, dtype):
     s, _ = _sfx(dtype)
     c = np.ascontiguousarray(centers, dtype=dtype)

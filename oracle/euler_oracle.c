@@ -13,6 +13,9 @@
 #define MCBRT cbrt
 #define MEXP exp
 #define MPOW pow
+#define MACOS acos
+#define MASIN asin
+#define MCOS cos
 #include "euler_impl.inc"
 #undef REAL
 #undef SFX
@@ -22,6 +25,9 @@
 #undef MCBRT
 #undef MEXP
 #undef MPOW
+#undef MACOS
+#undef MASIN
+#undef MCOS
 
 #define REAL float
 #define SFX _f32
@@ -31,4 +37,7 @@
 #define MCBRT cbrtf
 #define MEXP expf
 #define MPOW powf
+#define MACOS acosf
+#define MASIN asinf
+#define MCOS cosf
 #include "euler_impl.inc"

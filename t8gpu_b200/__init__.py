@@ -761,6 +761,15 @@ def init_kelvin_helmholtz(dim, centers, u, stream=None):
                                                                ptrs(u), stream_ptr(stream)), "init_kh")
 
 
+def init_spherical_kelvin_helmholtz(centers, u, stream=None):
+    """Kelvin-Helmholtz state on the globe (compressible_euler/solver.cu:17-72) at `centers` (device tensor, 3 per
+    point) into the 5 tensors `u`."""
+    s, _ = _sfx(centers.dtype)
+    n = centers.numel() // 3
+    check(getattr(lib(), "t8b200_init_spherical_kelvin_helmholtz_" + s)(C.c_int64(n), C.c_void_p(centers.data_ptr()),
+                                                                         ptrs(u), stream_ptr(stream)), "init_spherical_kh")
+
+
 def conn_to_host(conn):
     """torch-tensor connectivity dict -> numpy dict (for Plan)."""
     import torch

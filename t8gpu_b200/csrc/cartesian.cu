@@ -182,6 +182,30 @@ __global__ void kh_kernel(int dim, int64_t n, const T* __restrict__ centers, Ptr
   u.p[4][i] = T(2.5) / (gamma - T(1.0)) + T(0.5) * (m1 * m1 + m2 * m2 + m3 * m3) / rho;
 }
 
+// The Kelvin-Helmholtz state on the globe of the unstructured example (examples/compressible_euler/solver.cu:17-72: a
+// host lambda per element in the reference) at n element centroids, same expression types: float_type square roots and
+// inverse trigonometric functions, double for the terms that involve the double literals (:54-61).
+template <typename T>
+__global__ void spherical_kh_kernel(int64_t n, const T* __restrict__ centers, Ptrs5<T> u) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T sigma = T(0.2) / sqrt(T(2.0)), gamma = T(1.4);
+  const T x = centers[3 * i], y = centers[3 * i + 1], z = centers[3 * i + 2];
+  const T r = sqrt(x * x + y * y + z * z);
+  const T er0 = x / r, er1 = y / r, er2 = z / r;
+  const T ep0 = er1 / sqrt(er1 * er1 + er0 * er0), ep1 = -er0 / sqrt(er1 * er1 + er0 * er0), ep2 = T(0.0);
+  const T et0 = er1 * ep2 - er2 * ep1, et1 = er2 * ep0 - er0 * ep2, et2 = er0 * ep1 - er1 * ep0;
+  const T phi   = (T)((y >= 0.0) ? (double)acos(x / sqrt(x * x + y * y)) : 2.0 * M_PI - acos(x / sqrt(x * x + y * y)));
+  const T theta = asin(z / r);
+  const T v_phi   = (T)(r * cos(theta) * (theta < 0 ? -0.5 : 0.5));
+  const T v_theta = (T)(0.5 * r * sin(2.0 * phi) * (exp(-(theta / (2 * sigma)) * (theta / (2 * sigma)))));
+  const T rho = (T)(theta < 0.0 ? 2.0 : 1.0);
+  const T m1 = rho * (v_phi * ep0 + v_theta * et0), m2 = rho * (v_phi * ep1 + v_theta * et1),
+          m3 = rho * (v_phi * ep2 + v_theta * et2);
+  u.p[0][i] = rho; u.p[1][i] = m1; u.p[2][i] = m2; u.p[3][i] = m3;
+  u.p[4][i] = T(2.5) / (gamma - T(1.0)) + T(0.5) * (m1 * m1 + m2 * m2 + m3 * m3) / rho;
+}
+
 template <typename T>
 int build(t8b200_cart_conn* out, Geo g, cudaStream_t st) {
   const int64_t nl = g.hi - g.lo;
@@ -255,6 +279,19 @@ int kh_impl(int dim, int64_t n, const T* centers, T* const* u, void* stream) {
   return cudaGetLastError();
 }
 
+template <typename T>
+int spherical_kh_impl(int64_t n, const T* centers, T* const* u, void* stream) {
+  if (n < 0 || (n > 0 && (!centers || !u))) return cudaErrorInvalidValue;
+  if (n == 0) return 0;
+  Ptrs5<T> p;
+  for (int k = 0; k < 5; k++) {
+    if (!u[k]) return cudaErrorInvalidValue;
+    p.p[k] = u[k];
+  }
+  spherical_kh_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, centers, p);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
@@ -290,6 +327,12 @@ void t8b200_cartesian_connectivity_free(t8b200_cart_conn* c) {
   *c = t8b200_cart_conn{};
 }
 
+int t8b200_init_spherical_kelvin_helmholtz_f32(int64_t n, const float* centers, float* const* u, void* stream) {
+  return spherical_kh_impl<float>(n, centers, u, stream);
+}
+int t8b200_init_spherical_kelvin_helmholtz_f64(int64_t n, const double* centers, double* const* u, void* stream) {
+  return spherical_kh_impl<double>(n, centers, u, stream);
+}
 int t8b200_init_kelvin_helmholtz_f32(int dim, int64_t n, const float* centers, float* const* u, void* stream) {
   return kh_impl<float>(dim, n, centers, u, stream);
 }

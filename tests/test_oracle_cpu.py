@@ -184,3 +184,26 @@ def test_product_flux_algebra_on_host_matches_oracle():
             worst[dt] = max(worst[dt], np.abs(F.astype(np.float64) - Fo).max() / scale, abs(s - so_) / so_)
     assert worst[np.float64] < 2e-14, worst
     assert worst[np.float32] < 2e-5, worst
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spherical_kh_restatement_properties(dtype):
+    """compressible_euler/solver.cu:17-72 restated: density 2 below / 1 above the equator, velocity tangent to the globe,
+    zonal speed 0.5 r cos(theta) away from the perturbation, energy = 2.5 / 0.4 + kinetic part (pinned against the
+    reference's own constructor in tests/test_initial_conditions_gpu.py)."""
+    rng = np.random.default_rng(1)
+    c = rng.uniform(-1.0, 1.0, (4000, 3))
+    c *= (0.6 + 0.4 * rng.random((4000, 1))) / np.linalg.norm(c, axis=1, keepdims=True)
+    c = c.astype(dtype)
+    u = oracle.init_spherical_kh_points(c, dtype).astype(np.float64)
+    cd = c.astype(np.float64)
+    r = np.linalg.norm(cd, axis=1)
+    theta = np.arcsin(cd[:, 2] / r)
+    eps = np.finfo(dtype).eps
+    assert np.array_equal(u[0], np.where(theta < 0, 2.0, 1.0))
+    v = u[1:4] / u[0]
+    assert np.abs((v * (cd / r[:, None]).T).sum(0)).max() < 50 * eps
+    far = np.abs(theta) > 1.2                                    # exp(-(theta / 0.283)^2) < 2e-8 there
+    speed = np.linalg.norm(v, axis=0)
+    assert np.abs(speed[far] - 0.5 * r[far] * np.cos(theta[far])).max() < 1e-6
+    assert np.abs(u[4] - (2.5 / 0.4 + 0.5 * (u[1:4] ** 2).sum(0) / u[0])).max() < 50 * eps * u[4].max()
