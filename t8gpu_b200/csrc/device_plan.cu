@@ -733,8 +733,8 @@ __global__ void __launch_bounds__(32) block_warp_kernel(Src src, pb::Params<T> p
       __syncwarp();
       if (rc == 1 && rg.b1 - rg.b0 > 1) {
         const int64_t mid = (rg.b0 + rg.b1) / 2;
-        todo[sp++] = {mid, rg.b1};
-        todo[sp++] = {rg.b0, mid};
+        todo[sp].b0 = mid;   todo[sp++].b1 = rg.b1;
+        todo[sp].b0 = rg.b0; todo[sp++].b1 = mid;
         continue;
       }
       if (rc) { c.rc = 1; break; }

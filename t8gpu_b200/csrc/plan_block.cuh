@@ -316,8 +316,8 @@ __host__ __device__ inline void block_program(const Src& src, const Params<T>& p
     if (rc == 1) {
       if (rg.b1 - rg.b0 <= 1) { cn.rc = 1; return; }   // one element exceeds a CTA
       const int64_t mid = (rg.b0 + rg.b1) / 2;
-      todo[sp++] = {mid, rg.b1};
-      todo[sp++] = {rg.b0, mid};
+      todo[sp].b0 = mid;   todo[sp++].b1 = rg.b1;
+      todo[sp].b0 = rg.b0; todo[sp++].b1 = mid;
       continue;
     }
     if (rc) { cn.rc = 1; return; }
