@@ -795,6 +795,15 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   auto          pol     = thrust::cuda::par.on(st);
   // T8B200_DEVICE_PLAN=serial: one THREAD per block runs pb::block_program (the form the host emulation checks)
   const bool serial = getenv("T8B200_DEVICE_PLAN") && getenv("T8B200_DEVICE_PLAN")[0] == 's';
+  static const bool timing = getenv("T8B200_PLAN_TIMING") != nullptr;   // phases to stderr (adds a synchronisation each)
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[t8b200 device plan] %-34s %.3f ms\n", what, 1e3 * std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
   P->n_local = n_local; P->multi = multi ? 1 : 0;
   auto dev_alloc = [&](auto** p, size_t bytes, int fill) {
     cudaError_t e = cudaMalloc(p, bytes + 32);
@@ -826,6 +835,7 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   thrust::sort(pol, kp, kp + 2 * ntot);
   int64_t* rec = reinterpret_cast<int64_t*>(keys.p);   // serial mode: the face ids alone
   if (serial && ntot > 0) mask_keys_kernel<<<(unsigned)((2 * ntot + 255) / 256), 256, 0, st>>>(2 * ntot, keys.p);
+  lap("classify + key sort");
   // ---- COUNT pass: one program per block, in batches that bound the workspace
   const int64_t nprog = std::min<int64_t>(nblocks, 65536);
   const unsigned wgrid = (unsigned)std::min<int64_t>(nblocks, 148 * 32);
@@ -851,6 +861,7 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
                                                                                     face_off.p, rec, cn.p, blk.p, out, flags.p);
   else
     block_warp_kernel<T, Src, false><<<wgrid, 32, 0, st>>>(src, pr, nblocks, face_off.p, keys.p, cn.p, blk.p, out, flags.p);
+  lap("count pass");
   T8B_TRY(cudaMalloc(&totals.p, 8 * 8));
   T8B_TRY(cudaMemsetAsync(totals.p, 0, 8 * 8, st));
   counts_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(nblocks, cn.p, blk.p, totals.p);
@@ -865,6 +876,7 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   T8B_TRY(cudaGetLastError());
   T8B_TRY(cudaStreamSynchronize(st));
   if (fl[G_BAD_FACE] || fl[G_PROGRAM_ERROR]) return cudaErrorInvalidValue;
+  lap("scans + counters to the host");
   if (multi) P->my_rank = fl[G_MY_RANK];
   const int64_t nchunks = (int64_t)ends[0], n_oo = (int64_t)ends[1], n_oe = (int64_t)ends[2];
   if (n_local > 0x7FFFFF00LL || nchunks * MF > 0x7FFFFF00LL || n_oo > 0x7FFFFF00LL || n_oe > 0x7FFFFF00LL) return cudaErrorInvalidValue;
@@ -920,6 +932,7 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
                                                                                    face_off.p, rec, cn.p, blk.p, out, flags.p);
   else
     block_warp_kernel<T, Src, true><<<wgrid, 32, 0, st>>>(src, pr, nblocks, face_off.p, keys.p, cn.p, blk.p, out, flags.p);
+  lap("allocations + fill pass");
   const int me = P->my_rank;
   if (multi && nchunks > 0) chunk_flags_kernel<<<(unsigned)nchunks, 256, 0, st>>>(HS, P->halo_elem, P->halo_rank, s_flag.p, me, bflag.p);
   else T8B_TRY(cudaMemsetAsync(bflag.p, 0, (size_t)nchunks + 1, st));
@@ -932,6 +945,7 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   T8B_TRY(cudaStreamSynchronize(st));
   if (fl[G_PROGRAM_ERROR]) return cudaErrorInvalidValue;
   std::vector<int32_t> s_list, g_list, blist;
+  lap("chunk flags to the host");
   for (int64_t c = 0; c < nchunks; c++) (sf[c] ? s_list : g_list).push_back((int32_t)c);
   P->n_struct  = (int)s_list.size();
   P->n_generic = P->n_struct ? (int)g_list.size() : (int)nchunks;
@@ -1003,6 +1017,7 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   }
   T8B_TRY(cudaGetLastError());
   T8B_TRY(cudaStreamSynchronize(st));
+  lap("launch lists + ghost tail");
   return 0;
 }
 
