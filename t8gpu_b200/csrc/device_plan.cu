@@ -788,6 +788,21 @@ __global__ void __launch_bounds__(256) gather_structured_kernel(const int32_t* _
   }
 }
 
+// One allocation carved into 256-byte aligned pieces (cudaMalloc / cudaFree cost far more than the kernels of a plan
+// build: measured 6-16 ms for the 14 plan arrays of a 0.7 M-element forest).  A Pool without base measures.
+struct Pool {
+  unsigned char* base = nullptr;
+  size_t         used = 0;
+  template <typename U>
+  U* take(size_t count) {
+    const size_t off = used;
+    used += (count * sizeof(U) + 32 + 255) & ~(size_t)255;   // 32 bytes of slack: 16-byte granular prefetch hints
+    return base ? reinterpret_cast<U*>(base + off) : nullptr;
+  }
+};
+template <typename U>
+struct Piece { U* p = nullptr; };   // a piece of a Pool (same `.p` access as DevFree, no ownership)
+
 template <typename T, class Src>
 int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& src, cudaStream_t st) {
   static_assert(pb::EC == EC && pb::MS == MS && pb::MF == MF && pb::ELL == ELL, "plan_block.cuh constants");
@@ -812,23 +827,36 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
     return cudaMemsetAsync(*p, fill, bytes + 32, st);
   };
   // ---- faces: classes, distinct areas, buckets per block
-  DevFree<unsigned long long> area_set, blk, totals;
-  DevFree<int>                flags;
-  T8B_TRY(cudaMalloc(&area_set.p, 8 * AREA_SLOTS));
+  if (nblocks >= (1LL << 23) || ntot >= (1LL << 40)) return cudaErrorInvalidValue;
+  Piece<unsigned long long> area_set, blk, totals, face_off, keys;   // blk: 3 x (nb+1) bases after the count pass
+  Piece<int>                flags;
+  Piece<pb::Counts>         cn;
+  Piece<int16_t>            inv;
+  auto carve_scratch = [&](Pool& pool) {
+    area_set.p = pool.take<unsigned long long>(AREA_SLOTS);
+    flags.p    = pool.take<int>(G_N);
+    blk.p      = pool.take<unsigned long long>(3 * (size_t)(nblocks + 1));
+    face_off.p = pool.take<unsigned long long>((size_t)(nblocks + 1));
+    totals.p   = pool.take<unsigned long long>(8);
+    cn.p       = pool.take<pb::Counts>((size_t)nblocks);
+    inv.p      = pool.take<int16_t>(SubgridBox::NSLOT);
+    keys.p     = pool.take<unsigned long long>(2 * (size_t)std::max<int64_t>(ntot, 1));
+  };
+  DevFree<unsigned char> scratch;
+  {
+    Pool measure;
+    carve_scratch(measure);
+    T8B_TRY(cudaMalloc(&scratch.p, measure.used));
+    Pool pool{scratch.p, 0};
+    carve_scratch(pool);
+  }
   T8B_TRY(cudaMemsetAsync(area_set.p, 0xFF, 8 * AREA_SLOTS, st));
-  T8B_TRY(cudaMalloc(&flags.p, sizeof(int) * G_N));
   T8B_TRY(cudaMemsetAsync(flags.p, 0, sizeof(int) * G_N, st));
-  // blk: [0, nb+1) face offsets, then the cursors; after the count pass 3 x (nb+1) bases
-  T8B_TRY(cudaMalloc(&blk.p, 8 * 3 * (size_t)(nblocks + 1)));
   T8B_TRY(cudaMemsetAsync(blk.p, 0, 8 * 3 * (size_t)(nblocks + 1), st));
-  DevFree<unsigned long long> face_off;
-  T8B_TRY(cudaMalloc(&face_off.p, 8 * (size_t)(nblocks + 1)));
   T8B_TRY(cudaMemsetAsync(face_off.p, 0, 8 * (size_t)(nblocks + 1), st));
+  T8B_TRY(cudaMemsetAsync(totals.p, 0, 8 * 8, st));
   const unsigned fgrid = (unsigned)((ntot + 255) / 256);
   // candidate faces of every block: keys block << 40 | face (a face between two blocks appears in both), sorted
-  if (nblocks >= (1LL << 23) || ntot >= (1LL << 40)) return cudaErrorInvalidValue;
-  DevFree<unsigned long long> keys;
-  T8B_TRY(cudaMalloc(&keys.p, 16 * (size_t)std::max<int64_t>(ntot, 1)));
   if (ntot > 0) classify_kernel<T, Src><<<fgrid, 256, 0, st>>>(src, ntot, n_local, multi ? 1 : 0, area_set.p, flags.p, face_off.p, keys.p);
   thrust::device_ptr<unsigned long long> fo(face_off.p), kp(keys.p);
   thrust::exclusive_scan(pol, fo, fo + nblocks + 1, fo);
@@ -840,9 +868,7 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   const int64_t nprog = std::min<int64_t>(nblocks, 65536);
   const unsigned wgrid = (unsigned)std::min<int64_t>(nblocks, 148 * 32);
   DevFree<unsigned char> arena;
-  DevFree<pb::Counts>    cn;
   if (serial) T8B_TRY(cudaMalloc(&arena.p, (size_t)pb::Ws::bytes_per_program * (size_t)nprog + 64));
-  T8B_TRY(cudaMalloc(&cn.p, sizeof(pb::Counts) * (size_t)nblocks));
   int max_halo_allowed = MS - EC;
   if (const char* t = getenv("T8B200_TEST_MAX_HALO")) max_halo_allowed = std::min(max_halo_allowed, std::max(8, atoi(t)));
   const int box_layout = P->vol_shift == 6 ? 1 : P->vol_shift == 0 ? 0 : -1;
@@ -850,8 +876,6 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   int16_t inv_h[SubgridBox::NSLOT];
   for (int i = 0; i < SubgridBox::NSLOT; i++) inv_h[i] = -1;
   for (int h = 0; h < 256; h++) inv_h[box_layout == 1 ? SubgridBox::thread_slot(h) : MortonBox::thread_slot(h)] = (int16_t)h;
-  DevFree<int16_t> inv;
-  T8B_TRY(cudaMalloc(&inv.p, sizeof(inv_h)));
   T8B_TRY(cudaMemcpyAsync(inv.p, inv_h, sizeof(inv_h), cudaMemcpyHostToDevice, st));
   pb::Params<T> pr{n_local, multi ? 1 : 0, 0, 0, box_layout, max_halo_allowed, MF - 1, nullptr, inv.p};
   pb::Out<T>    out{};
@@ -862,8 +886,6 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   else
     block_warp_kernel<T, Src, false><<<wgrid, 32, 0, st>>>(src, pr, nblocks, face_off.p, keys.p, cn.p, blk.p, out, flags.p);
   lap("count pass");
-  T8B_TRY(cudaMalloc(&totals.p, 8 * 8));
-  T8B_TRY(cudaMemsetAsync(totals.p, 0, 8 * 8, st));
   counts_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(nblocks, cn.p, blk.p, totals.p);
   thrust::device_ptr<unsigned long long> bp(blk.p);
   for (int k = 0; k < 3; k++) thrust::exclusive_scan(pol, bp + k * (nblocks + 1), bp + (k + 1) * (nblocks + 1), bp + k * (nblocks + 1));
@@ -897,31 +919,56 @@ int generic_device_plan(t8b200_plan* P, int64_t n_local, bool multi, const Src& 
   P->n_halo = (int64_t)tot[2]; P->n_records = (int64_t)tot[3]; P->ms = MS; P->mf = MF;
   P->smem_bytes = sizeof(T) == 8 ? 8 * ((size_t)NCELLQ * MS + 5 * (size_t)MF) : 32 * (size_t)MS + 20 * (size_t)MF;
   P->cmp = cmp ? 1 : 0; P->n_areas = cmp ? (int)area_tab.size() : 0;
-  // ---- plan arrays (padding: halo -1, everything else 0, element -> face table 0xFFFF)
-  T8B_TRY(dev_alloc(&P->hdr, 4 * 8 * (size_t)nchunks, 0));
-  T8B_TRY(dev_alloc(&P->halo_elem, 4 * (size_t)nchunks * HS, 0xFF));
-  if (multi) T8B_TRY(dev_alloc(&P->halo_rank, 4 * (size_t)nchunks * HS, 0));
-  T8B_TRY(dev_alloc(&P->face_lr, 4 * (size_t)nchunks * FS, 0));
-  if (cmp) {
-    T8B_TRY(dev_alloc(&P->face_ai, (size_t)nchunks * FS, 0));
-    T8B_TRY(dev_alloc((T**)&P->area_tab, sizeof(T) * std::max<size_t>(area_tab.size(), 1), 0));
-    T8B_TRY(cudaMemcpyAsync(P->area_tab, area_tab.data(), sizeof(T) * area_tab.size(), cudaMemcpyHostToDevice, st));
-  } else {
-    T8B_TRY(dev_alloc((T**)&P->fnx, sizeof(T) * (size_t)nchunks * FS, 0));
-    T8B_TRY(dev_alloc((T**)&P->fny, sizeof(T) * (size_t)nchunks * FS, 0));
-    T8B_TRY(dev_alloc((T**)&P->fnz, sizeof(T) * (size_t)nchunks * FS, 0));
-    T8B_TRY(dev_alloc((T**)&P->farea, sizeof(T) * (size_t)nchunks * FS, 0));
+  // ---- plan arrays in one allocation (padding: halo -1, element -> face table 0xFFFF, everything else 0) and the
+  // per-chunk scratch of the fill pass in another
+  size_t ones_end = 0;
+  auto carve_plan = [&](Pool& pool) {
+    P->halo_elem = pool.take<int32_t>((size_t)nchunks * HS);
+    P->ell       = reinterpret_cast<uint4*>(pool.take<uint16_t>((size_t)std::max<int64_t>(n_local, 1) * ELL));
+    ones_end     = pool.used;                                     // [0, ones_end): 0xFF, the rest: 0
+    P->hdr       = pool.take<int32_t>(8 * (size_t)nchunks);
+    if (multi) P->halo_rank = pool.take<int32_t>((size_t)nchunks * HS);
+    P->face_lr = pool.take<uint32_t>((size_t)nchunks * FS);
+    if (cmp) {
+      P->face_ai  = pool.take<uint8_t>((size_t)nchunks * FS);
+      P->area_tab = pool.take<T>(std::max<size_t>(area_tab.size(), 1));
+    } else {
+      P->fnx   = pool.take<T>((size_t)nchunks * FS);
+      P->fny   = pool.take<T>((size_t)nchunks * FS);
+      P->fnz   = pool.take<T>((size_t)nchunks * FS);
+      P->farea = pool.take<T>((size_t)nchunks * FS);
+    }
+    P->ovf_off = pool.take<uint16_t>((size_t)std::max<int64_t>(n_oo, 1));
+    P->ovf_ent = pool.take<uint16_t>((size_t)std::max<int64_t>(n_oe, 1));
+  };
+  {
+    Pool measure;
+    carve_plan(measure);
+    T8B_TRY(cudaMalloc(&P->pool, measure.used));
+    P->dev_bytes += (int64_t)measure.used;
+    Pool pool{static_cast<unsigned char*>(P->pool), 0};
+    carve_plan(pool);
+    T8B_TRY(cudaMemsetAsync(P->pool, 0xFF, ones_end, st));
+    T8B_TRY(cudaMemsetAsync(static_cast<unsigned char*>(P->pool) + ones_end, 0, measure.used - ones_end, st));
   }
-  T8B_TRY(dev_alloc((uint16_t**)&P->ell, 2 * (size_t)std::max<int64_t>(n_local, 1) * ELL, 0xFF));
-  T8B_TRY(dev_alloc(&P->ovf_off, 2 * (size_t)std::max<int64_t>(n_oo, 1), 0));
-  T8B_TRY(dev_alloc(&P->ovf_ent, 2 * (size_t)std::max<int64_t>(n_oe, 1), 0));
+  if (cmp) T8B_TRY(cudaMemcpyAsync(P->area_tab, area_tab.data(), sizeof(T) * area_tab.size(), cudaMemcpyHostToDevice, st));
   P->n_ovf_off = n_oo; P->n_ovf_ent = n_oe;
-  DevFree<uint8_t> s_flag, bflag;
-  DevFree<int32_t> s_halo_tmp, s_hrank_tmp;
-  T8B_TRY(cudaMalloc(&s_flag.p, (size_t)nchunks + 1));
-  T8B_TRY(cudaMalloc(&bflag.p, (size_t)nchunks + 1));
-  T8B_TRY(cudaMalloc(&s_halo_tmp.p, 4 * 256 * (size_t)nchunks + 4));
-  if (multi) T8B_TRY(cudaMalloc(&s_hrank_tmp.p, 4 * 256 * (size_t)nchunks + 4));
+  Piece<uint8_t> s_flag, bflag;
+  Piece<int32_t> s_halo_tmp, s_hrank_tmp;
+  auto carve_chunks = [&](Pool& pool) {
+    s_flag.p     = pool.take<uint8_t>((size_t)nchunks + 1);
+    bflag.p      = pool.take<uint8_t>((size_t)nchunks + 1);
+    s_halo_tmp.p = pool.take<int32_t>(256 * (size_t)nchunks + 1);
+    if (multi) s_hrank_tmp.p = pool.take<int32_t>(256 * (size_t)nchunks + 1);
+  };
+  DevFree<unsigned char> chunk_scratch;
+  {
+    Pool measure;
+    carve_chunks(measure);
+    T8B_TRY(cudaMalloc(&chunk_scratch.p, measure.used));
+    Pool pool{chunk_scratch.p, 0};
+    carve_chunks(pool);
+  }
   // ---- FILL pass
   pr.cmp = cmp ? 1 : 0; pr.n_areas = (int)area_tab.size(); pr.area_tab = (const T*)P->area_tab;
   out = pb::Out<T>{HS, FS, P->hdr, P->halo_elem, P->halo_rank, P->face_lr, P->face_ai, (T*)P->fnx, (T*)P->fny, (T*)P->fnz,

@@ -767,9 +767,13 @@ void t8b200_plan_destroy(t8b200_plan* P) {
     delete P;
     return;
   }
-  cudaFree(P->hdr); cudaFree(P->halo_elem); cudaFree(P->halo_rank);
-  cudaFree(P->face_lr); cudaFree(P->face_ai); cudaFree(P->fnx); cudaFree(P->fny); cudaFree(P->fnz); cudaFree(P->farea);
-  cudaFree(P->area_tab); cudaFree(P->ell); cudaFree(P->ovf_off); cudaFree(P->ovf_ent);
+  if (P->pool) {   // generic device builder: the chunk arrays are pieces of one allocation
+    cudaFree(P->pool);
+  } else {
+    cudaFree(P->hdr); cudaFree(P->halo_elem); cudaFree(P->halo_rank);
+    cudaFree(P->face_lr); cudaFree(P->face_ai); cudaFree(P->fnx); cudaFree(P->fny); cudaFree(P->fnz); cudaFree(P->farea);
+    cudaFree(P->area_tab); cudaFree(P->ell); cudaFree(P->ovf_off); cudaFree(P->ovf_ent);
+  }
   cudaFree(P->s_rec); cudaFree(P->s_halo); cudaFree(P->s_hrank); cudaFree(P->g_list);
   cudaFree(P->pull_rank); cudaFree(P->pull_idx); cudaFree(P->blist);
   delete P;

@@ -74,7 +74,8 @@ struct t8b200_plan {
   int64_t dev_bytes = 0, n_records = 0, n_halo = 0;
   int     cmp = 0, n_areas = 0;
   int     hs = 0, fs = 0;  // per-chunk strides of the halo and face arrays
-  // device arrays
+  // device arrays (plans of the generic device builder: pieces of `pool`, one allocation)
+  void*     pool      = nullptr;
   int32_t*  hdr       = nullptr;  // 8 per chunk
   int32_t*  halo_elem = nullptr;  // index into the owner's arrays
   int32_t*  halo_rank = nullptr;  // owner rank (multi only)
